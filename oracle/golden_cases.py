@@ -1,0 +1,40 @@
+"""Known-answer cases for the sampling hot path (shared by make_golden.py and tests/).
+
+Each case is regenerated from seeds by ``prodiff_b200.synth``; the ``.npz`` under
+``tests/golden/`` stores only what the *reference* produced (per-step x0 predictions and the
+final mel) plus a sha256 of the regenerated weights/inputs.
+"""
+from prodiff_b200.synth import DiffNetConfig
+
+# name -> dict(cfg, timesteps, schedule_type, max_beta, infer_step, B, T, out_init, wseed, iseed)
+SAMPLE_CASES = {
+    # BASELINE.json configs[0]: the reference's own CPU-runnable case, full-size DiffNet.
+    "cfg1_full": dict(cfg=DiffNetConfig(128, 256, 20, 256, 1), timesteps=4, schedule_type="vpsde", max_beta=40,
+                      infer_step=4, B=1, T=400, out_init="trained", wseed=1234, iseed=4321),
+    # dilation cycle 4 (dilations 1,2,4,8), ragged T (not a multiple of the 128-frame tile), B>1
+    "dil4_ragged": dict(cfg=DiffNetConfig(128, 256, 8, 256, 4), timesteps=4, schedule_type="vpsde", max_beta=40,
+                        infer_step=2, B=2, T=150, out_init="trained", wseed=11, iseed=12),
+    # 512 residual channels (BASELINE config 4 shape), 100-step teacher schedule, first 3 reverse steps
+    "c512_t100": dict(cfg=DiffNetConfig(128, 256, 4, 512, 4), timesteps=100, schedule_type="vpsde", max_beta=0.06,
+                      infer_step=3, B=1, T=200, out_init="trained", wseed=21, iseed=22),
+    # worst-case output scale (Kaiming output_projection), tiny T (shorter than every dilation halo sum)
+    "kaiming_short": dict(cfg=DiffNetConfig(128, 256, 6, 256, 3), timesteps=4, schedule_type="vpsde", max_beta=40,
+                          infer_step=4, B=3, T=7, out_init="kaiming", wseed=31, iseed=32),
+    # other schedules the constructor accepts (prodiff.py:28-44)
+    "linear_sched": dict(cfg=DiffNetConfig(128, 256, 2, 256, 1), timesteps=8, schedule_type="linear", max_beta=0.06,
+                         infer_step=8, B=1, T=64, out_init="trained", wseed=41, iseed=42),
+    "cosine_sched": dict(cfg=DiffNetConfig(128, 256, 2, 256, 2), timesteps=6, schedule_type="cosine", max_beta=0.06,
+                         infer_step=6, B=1, T=33, out_init="trained", wseed=51, iseed=52),
+}
+
+# Denoiser-only cases: WaveNet.forward with per-row (possibly float) diffusion steps, as the training
+# branch (prodiff.py:141-143) and the rectified-flow sampler (reflow.py:50) call it.
+DENOISE_CASES = {
+    "fwd_int_steps": dict(cfg=DiffNetConfig(128, 256, 4, 256, 2), B=3, T=130, steps=[0, 3, 1], out_init="trained",
+                          wseed=61, iseed=62),
+    "fwd_float_steps": dict(cfg=DiffNetConfig(128, 256, 3, 256, 1), B=2, T=257, steps=[250.0, 999.5],
+                            out_init="kaiming", wseed=71, iseed=72),
+    # PitchPredictor-shaped denoiser (in_dims = 64 repeat bins)
+    "fwd_in64": dict(cfg=DiffNetConfig(64, 256, 2, 256, 1), B=1, T=100, steps=[2], out_init="trained",
+                     wseed=81, iseed=82),
+}

@@ -1,0 +1,114 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference from /root/reference.
+
+Run in the build container (the reference cannot travel to the GPU box):
+
+    python oracle/make_golden.py            # writes tests/golden/<case>.npz
+
+The reference draws x_T with ``torch.rand`` (prodiff.py:147) and per-step noise with
+``torch.randn`` (prodiff.py:118); to feed it the injected tensors without editing it, the two
+functions are patched for the duration of one ``forward`` call.  Per-step
+x0 predictions are captured with a forward hook on the reference ``WaveNet``.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+REF = os.environ.get("PRODIFF_REFERENCE", "/root/reference")
+sys.path.insert(0, ROOT)
+sys.dont_write_bytecode = True
+
+
+def load_reference():
+    if not os.path.isdir(REF):
+        raise SystemExit(f"reference not found at {REF}")
+    sys.path.insert(0, REF)
+    from modules.decoder.wavenet import WaveNet            # noqa
+    from modules.diffusion.prodiff import GaussianDiffusion  # noqa
+    return WaveNet, GaussianDiffusion
+
+
+class injected_randomness:
+    """Patch torch.rand / torch.randn to pop pre-generated tensors (shape-checked)."""
+
+    def __init__(self, x_T, noise):
+        self.queue_rand = [x_T]
+        self.queue_randn = list(noise)
+
+    def __enter__(self):
+        self._rand, self._randn = torch.rand, torch.randn
+
+        def rand(*shape, **kw):
+            t = self.queue_rand.pop(0)
+            assert tuple(t.shape) == tuple(shape), (t.shape, shape)
+            return t.clone()
+
+        def randn(shape, **kw):
+            t = self.queue_randn.pop(0)
+            assert tuple(t.shape) == tuple(shape), (t.shape, shape)
+            return t.clone()
+
+        torch.rand, torch.randn = rand, randn
+        return self
+
+    def __exit__(self, *a):
+        torch.rand, torch.randn = self._rand, self._randn
+        assert not self.queue_rand and not self.queue_randn, "reference consumed less randomness than injected"
+
+
+def run_reference_sample(case):
+    from prodiff_b200 import synth
+    WaveNet, GaussianDiffusion = load_reference()
+    cfg = case["cfg"]
+    state = synth.make_state(cfg, case["wseed"], case["out_init"])
+    cond, x_T, noise = synth.make_inputs(cfg, case["B"], case["T"], case["infer_step"], case["iseed"])
+    wn = WaveNet(cfg.in_dims, cfg.hidden_size, cfg.residual_layers, cfg.residual_channels, cfg.dilation_cycle_length)
+    wn.load_state_dict(state, strict=True)
+    gd = GaussianDiffusion(cfg.in_dims, wn, timesteps=case["timesteps"], time_scale=1000,
+                           schedule_type=case["schedule_type"], max_beta=case["max_beta"],
+                           spec_min=[-12.0], spec_max=[0.0]).eval()
+    x0s = []
+    h = wn.register_forward_hook(lambda m, i, o: x0s.append(o.detach().clone()))
+    with torch.no_grad(), injected_randomness(x_T, noise):
+        mel = gd(cond, infer_step=case["infer_step"], infer=True)
+    h.remove()
+    return dict(mel=mel.contiguous().numpy(), x0=torch.stack(x0s).numpy(),
+                digest=np.array(synth.digest(state, cond, x_T, noise)),
+                coef1=gd.posterior_mean_coef1.numpy(), coef2=gd.posterior_mean_coef2.numpy(),
+                logvar=gd.posterior_log_variance_clipped.numpy())
+
+
+def run_reference_denoise(case):
+    from prodiff_b200 import synth
+    WaveNet, _ = load_reference()
+    cfg = case["cfg"]
+    state = synth.make_state(cfg, case["wseed"], case["out_init"])
+    cond, x_T, _ = synth.make_inputs(cfg, case["B"], case["T"], 1, case["iseed"])
+    wn = WaveNet(cfg.in_dims, cfg.hidden_size, cfg.residual_layers, cfg.residual_channels, cfg.dilation_cycle_length)
+    wn.load_state_dict(state, strict=True)
+    steps = torch.tensor(case["steps"])
+    with torch.no_grad():
+        out = wn(x_T, steps, cond.transpose(1, 2))
+    return dict(out=out.numpy(), digest=np.array(synth.digest(state, cond, x_T)))
+
+
+def main():
+    from oracle.golden_cases import SAMPLE_CASES, DENOISE_CASES
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    out_dir = os.path.join(ROOT, "tests", "golden")
+    os.makedirs(out_dir, exist_ok=True)
+    for name, case in SAMPLE_CASES.items():
+        r = run_reference_sample(case)
+        np.savez(os.path.join(out_dir, f"sample_{name}.npz"), **r)
+        print(f"sample_{name}: mel {r['mel'].shape} x0 {r['x0'].shape} |x0|max {np.abs(r['x0']).max():.3f}")
+    for name, case in DENOISE_CASES.items():
+        r = run_reference_denoise(case)
+        np.savez(os.path.join(out_dir, f"denoise_{name}.npz"), **r)
+        print(f"denoise_{name}: out {r['out'].shape} |out|max {np.abs(r['out']).max():.3f}")
+
+
+if __name__ == "__main__":
+    main()

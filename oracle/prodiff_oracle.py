@@ -1,0 +1,216 @@
+"""CPU fp32 oracle for the ProDiff sampling hot path.  TEST INFRASTRUCTURE ONLY.
+
+This file restates, op for op, the two reference files on the hot path
+
+    /root/reference/modules/decoder/wavenet.py      (DiffNet denoiser)
+    /root/reference/modules/diffusion/prodiff.py    (GaussianDiffusion sampler)
+
+as plain functions over a ``state`` dict of fp32 tensors (the reference's own
+``state_dict`` keys).  It exists so that the CUDA path can be checked on a GPU box where
+``/root/reference`` is not mounted.  Only ``tests/``, ``__graft_entry__.smoke()`` and
+``bench.py``'s CPU-baseline / ``--impl reference`` legs may import it; the product package
+``prodiff_b200`` never does (tests/test_no_oracle_in_product.py enforces that).
+
+Pinning: the reference ships no tests, golden vectors or checkpoints for this path
+(SURVEY.md §4, §8c), so the oracle is pinned against the *live reference modules* imported
+from /root/reference in the build container: ``tests/test_oracle_vs_reference.py`` demands
+bit-identical outputs, and ``oracle/make_golden.py`` (committed) ran the reference itself to
+produce the known-answer vectors under ``tests/golden/`` that travel to the GPU box.
+
+The only deliberate difference from the reference: ``x_T`` and the per-step Gaussian noise are
+*injected* tensors instead of ``torch.rand`` / ``torch.randn`` calls (prodiff.py:118,147), so two
+implementations can be compared on identical randomness.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+State = Dict[str, torch.Tensor]
+
+
+# --------------------------------------------------------------------------------------
+# noise schedules and posterior tables  (prodiff.py:18-46, 49-104)
+# --------------------------------------------------------------------------------------
+def vpsde_beta_t(t, T, min_beta, max_beta):
+    """prodiff.py:18-20"""
+    t_coef = (2 * t - 1) / (T ** 2)
+    return 1.0 - np.exp(-min_beta / T - 0.5 * (max_beta - min_beta) * t_coef)
+
+
+def logsnr_schedule_cosine(t, *, logsnr_min, logsnr_max):
+    """prodiff.py:22-25"""
+    b = np.arctan(np.exp(-0.5 * logsnr_max))
+    a = np.arctan(np.exp(-0.5 * logsnr_min)) - b
+    return -2.0 * np.log(np.tan(a * t + b))
+
+
+def get_noise_schedule_list(schedule_mode, timesteps, min_beta=0.0, max_beta=0.01, s=0.008):
+    """prodiff.py:27-46 (float64 numpy, same formulas, same error on unknown mode)."""
+    if schedule_mode == "linear":
+        return np.linspace(1e-4, max_beta, timesteps)
+    if schedule_mode == "cosine":
+        steps = timesteps + 1
+        x = np.linspace(0, steps, steps)
+        ac = np.cos(((x / steps) + s) / (1 + s) * np.pi * 0.5) ** 2
+        ac = ac / ac[0]
+        betas = 1 - (ac[1:] / ac[:-1])
+        return np.clip(betas, a_min=0, a_max=0.999)
+    if schedule_mode == "vpsde":
+        return np.array([vpsde_beta_t(t, timesteps, min_beta, max_beta) for t in range(1, timesteps + 1)])
+    if schedule_mode == "logsnr":
+        return np.array([logsnr_schedule_cosine(t / timesteps, logsnr_min=-20.0, logsnr_max=20.0)
+                         for t in range(1, timesteps + 1)])
+    raise NotImplementedError
+
+
+def diffusion_tables(timesteps=1000, schedule_type="vpsde", max_beta=0.02, betas=None) -> Dict[str, torch.Tensor]:
+    """The persistent buffers GaussianDiffusion.__init__ registers (prodiff.py:54-99).
+
+    All arithmetic in float64 numpy, cast to fp32 at the end, exactly as the reference does.
+    Every table has ``timesteps + 1`` entries.
+    """
+    if betas is None:
+        betas = get_noise_schedule_list(schedule_mode=schedule_type, timesteps=timesteps + 1,
+                                        min_beta=0.1, max_beta=max_beta, s=0.008)
+    betas = np.asarray(betas, dtype=np.float64)
+    alphas = 1.0 - betas
+    alphas_cumprod = np.cumprod(alphas, axis=0)
+    alphas_cumprod_prev = np.append(1.0, alphas_cumprod[:-1])
+    posterior_variance = betas * (1.0 - alphas_cumprod_prev) / (1.0 - alphas_cumprod)
+    f32 = lambda a: torch.tensor(a, dtype=torch.float32)
+    return {
+        "betas": f32(betas),
+        "alphas_cumprod": f32(alphas_cumprod),
+        "alphas_cumprod_prev": f32(alphas_cumprod_prev),
+        "sqrt_alphas_cumprod": f32(np.sqrt(alphas_cumprod)),
+        "sqrt_one_minus_alphas_cumprod": f32(np.sqrt(1.0 - alphas_cumprod)),
+        "log_one_minus_alphas_cumprod": f32(np.log(1.0 - alphas_cumprod)),
+        "sqrt_recip_alphas_cumprod": f32(np.sqrt(1.0 / alphas_cumprod)),
+        "sqrt_recipm1_alphas_cumprod": f32(np.sqrt(1.0 / alphas_cumprod - 1)),
+        "posterior_variance": f32(posterior_variance),
+        "posterior_log_variance_clipped": f32(np.log(np.maximum(posterior_variance, 1e-20))),
+        "posterior_mean_coef1": f32(betas * np.sqrt(alphas_cumprod_prev) / (1.0 - alphas_cumprod)),
+        "posterior_mean_coef2": f32((1.0 - alphas_cumprod_prev) * np.sqrt(alphas) / (1.0 - alphas_cumprod)),
+    }
+
+
+# --------------------------------------------------------------------------------------
+# DiffNet denoiser (wavenet.py)
+# --------------------------------------------------------------------------------------
+def sinusoidal_pos_emb(x: torch.Tensor, dim: int) -> torch.Tensor:
+    """wavenet.py:31-38.  x: [B] (int64 or float) -> [B, dim]."""
+    half_dim = dim // 2
+    emb = math.log(10000) / (half_dim - 1)
+    emb = torch.exp(torch.arange(half_dim, device=x.device) * -emb)
+    emb = x[:, None] * emb[None, :]
+    return torch.cat((emb.sin(), emb.cos()), dim=-1)
+
+
+def mish(x: torch.Tensor) -> torch.Tensor:
+    """wavenet.py:22-24"""
+    return x * torch.tanh(F.softplus(x))
+
+
+def num_layers(state: State) -> int:
+    n = 0
+    while f"residual_layers.{n}.dilated_conv.weight" in state:
+        n += 1
+    return n
+
+
+def residual_block(state: State, i: int, dilation: int, x, conditioner, diffusion_step):
+    """wavenet.py:60-72"""
+    p = f"residual_layers.{i}."
+    d = F.linear(diffusion_step, state[p + "diffusion_projection.weight"],
+                 state[p + "diffusion_projection.bias"]).unsqueeze(-1)
+    c = F.conv1d(conditioner, state[p + "conditioner_projection.weight"], state[p + "conditioner_projection.bias"])
+    y = x + d
+    y = F.conv1d(y, state[p + "dilated_conv.weight"], state[p + "dilated_conv.bias"],
+                 padding=dilation, dilation=dilation) + c
+    gate, filt = torch.chunk(y, 2, dim=1)
+    y = torch.sigmoid(gate) * torch.tanh(filt)
+    y = F.conv1d(y, state[p + "output_projection.weight"], state[p + "output_projection.bias"])
+    residual, skip = torch.chunk(y, 2, dim=1)
+    return (x + residual) / math.sqrt(2.0), skip
+
+
+def wavenet_forward(state: State, spec, diffusion_step, cond, dilation_cycle_length: int,
+                    trace: Optional[dict] = None):
+    """wavenet.py:100-123.  spec [B,1,M,T], diffusion_step [B], cond [B,H,T] -> [B,1,M,T]."""
+    L = num_layers(state)
+    C = state["input_projection.weight"].shape[0]
+    x = spec[:, 0]
+    x = F.conv1d(x, state["input_projection.weight"], state["input_projection.bias"])
+    x = F.relu(x)
+    e = sinusoidal_pos_emb(diffusion_step, C)
+    e = F.linear(e, state["mlp.0.weight"], state["mlp.0.bias"])
+    e = mish(e)
+    e = F.linear(e, state["mlp.2.weight"], state["mlp.2.bias"])
+    skip = []
+    if trace is not None:
+        trace["x_in"] = x
+        trace["x"] = []
+    for i in range(L):
+        x, s = residual_block(state, i, 2 ** (i % dilation_cycle_length), x, cond, e)
+        skip.append(s)
+        if trace is not None:
+            trace["x"].append(x)
+    x = torch.sum(torch.stack(skip), dim=0) / math.sqrt(L)
+    x = F.conv1d(x, state["skip_projection.weight"], state["skip_projection.bias"])
+    x = F.relu(x)
+    x = F.conv1d(x, state["output_projection.weight"], state["output_projection.bias"])
+    return x[:, None, :, :]
+
+
+# --------------------------------------------------------------------------------------
+# sampler (prodiff.py:13-16, 106-153)
+# --------------------------------------------------------------------------------------
+def extract(a, t, x_shape):
+    """prodiff.py:13-16"""
+    b, *_ = t.shape
+    out = a.gather(-1, t)
+    return out.reshape(b, *((1,) * (len(x_shape) - 1)))
+
+
+def q_posterior_sample(tables, x_0, x_t, t, noise):
+    """prodiff.py:106-121 with the ``torch.randn`` at :118 replaced by ``noise``."""
+    b = x_0.shape[0]
+    mean = (extract(tables["posterior_mean_coef1"], t, x_t.shape) * x_0 +
+            extract(tables["posterior_mean_coef2"], t, x_t.shape) * x_t)
+    log_var = extract(tables["posterior_log_variance_clipped"], t, x_t.shape)
+    nonzero_mask = (1 - (t == 0).float()).reshape(b, *((1,) * (len(x_0.shape) - 1)))
+    return mean + nonzero_mask * (0.5 * log_var).exp() * noise
+
+
+def q_sample(tables, x_0, t, x_T):
+    """prodiff.py:128-133"""
+    return (extract(tables["sqrt_alphas_cumprod"], t, x_0.shape) * x_0 +
+            extract(tables["sqrt_one_minus_alphas_cumprod"], t, x_0.shape) * x_T)
+
+
+@torch.no_grad()
+def sample(state: State, tables, cond, x_T, noise, infer_step: int, num_timesteps: int,
+           dilation_cycle_length: int) -> Tuple[torch.Tensor, List[torch.Tensor]]:
+    """GaussianDiffusion.forward(infer=True) (prodiff.py:136-138,145-153).
+
+    cond [B,T,H]; x_T [B,1,M,T] replaces torch.rand (:147); noise [K,B,1,M,T] replaces the
+    per-step torch.randn (:118), noise[j] being consumed by the j-th loop iteration
+    (t = K-1-j), including the masked one at t == 0.
+    Returns (mel [B,T,M] as the same transposed view the reference returns, [x0_pred per step]).
+    """
+    b = cond.shape[0]
+    cond = cond.transpose(1, 2)
+    infer_step = int(np.clip(infer_step, 1, num_timesteps))
+    x = x_T
+    x0s = []
+    for j, i in enumerate(range(infer_step - 1, -1, -1)):
+        t = torch.full((b,), i, dtype=torch.long)
+        x_0_pred = wavenet_forward(state, x, t, cond, dilation_cycle_length)
+        x0s.append(x_0_pred)
+        x = q_posterior_sample(tables, x_0_pred, x, t, noise[j])
+    return x[:, 0].transpose(1, 2), x0s

@@ -1,0 +1,37 @@
+"""Shared helpers for the test-suite (fixture loading, case regeneration)."""
+import os
+
+import numpy as np
+import torch
+
+from oracle import prodiff_oracle as oracle
+from oracle.golden_cases import SAMPLE_CASES, DENOISE_CASES
+from prodiff_b200 import synth
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load_golden(kind, name):
+    return np.load(os.path.join(GOLDEN, f"{kind}_{name}.npz"))
+
+
+def regen_sample_case(name):
+    case = SAMPLE_CASES[name]
+    cfg = case["cfg"]
+    state = synth.make_state(cfg, case["wseed"], case["out_init"])
+    cond, x_T, noise = synth.make_inputs(cfg, case["B"], case["T"], case["infer_step"], case["iseed"])
+    return case, cfg, state, cond, x_T, noise
+
+
+def regen_denoise_case(name):
+    case = DENOISE_CASES[name]
+    cfg = case["cfg"]
+    state = synth.make_state(cfg, case["wseed"], case["out_init"])
+    cond, x_T, _ = synth.make_inputs(cfg, case["B"], case["T"], 1, case["iseed"])
+    return case, cfg, state, cond, x_T, torch.tensor(case["steps"])
+
+
+def oracle_sample(case, cfg, state, cond, x_T, noise):
+    tables = oracle.diffusion_tables(case["timesteps"], case["schedule_type"], case["max_beta"])
+    return oracle.sample(state, tables, cond, x_T, noise, case["infer_step"], case["timesteps"],
+                         cfg.dilation_cycle_length)

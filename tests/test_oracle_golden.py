@@ -1,0 +1,77 @@
+"""The oracle restatement against the known-answer vectors the reference produced (CPU, no GPU).
+
+The fixtures were written by oracle/make_golden.py running the unmodified reference; this is the
+pin that lets the oracle stand in for the reference on the GPU box.  Tolerance is 2e-5 absolute, not
+bit-exact, only because mkldnn may pick a different conv algorithm / thread split on another host;
+bit-exactness against the live reference in one process is asserted in test_oracle_vs_reference.py.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import prodiff_oracle as oracle
+from oracle.golden_cases import SAMPLE_CASES, DENOISE_CASES
+from prodiff_b200 import synth
+from tests import helpers
+
+TOL = 2e-5
+
+
+@pytest.mark.parametrize("name", sorted(SAMPLE_CASES))
+def test_sample_matches_reference_fixture(name):
+    case, cfg, state, cond, x_T, noise = helpers.regen_sample_case(name)
+    g = helpers.load_golden("sample", name)
+    assert str(g["digest"]) == synth.digest(state, cond, x_T, noise), "regenerated inputs differ from the fixture's"
+    mel, x0s = helpers.oracle_sample(case, cfg, state, cond, x_T, noise)
+    assert mel.shape == (case["B"], case["T"], cfg.in_dims)
+    x0 = torch.stack(x0s).numpy()
+    assert x0.shape == g["x0"].shape
+    assert np.abs(x0 - g["x0"]).max() <= TOL
+    assert np.abs(mel.numpy() - g["mel"]).max() <= TOL
+    # outputs are not degenerate (H1): the denoiser output must carry signal, not just its bias
+    assert np.abs(g["x0"]).max() > 0.1
+
+
+@pytest.mark.parametrize("name", sorted(SAMPLE_CASES))
+def test_tables_match_reference_fixture(name):
+    case = SAMPLE_CASES[name]
+    g = helpers.load_golden("sample", name)
+    tb = oracle.diffusion_tables(case["timesteps"], case["schedule_type"], case["max_beta"])
+    for k_fix, k_tab in (("coef1", "posterior_mean_coef1"), ("coef2", "posterior_mean_coef2"),
+                         ("logvar", "posterior_log_variance_clipped")):
+        assert tb[k_tab].shape[0] == case["timesteps"] + 1
+        np.testing.assert_array_equal(tb[k_tab].numpy(), g[k_fix])
+
+
+@pytest.mark.parametrize("name", sorted(DENOISE_CASES))
+def test_denoise_matches_reference_fixture(name):
+    case, cfg, state, cond, x_T, steps = helpers.regen_denoise_case(name)
+    g = helpers.load_golden("denoise", name)
+    assert str(g["digest"]) == synth.digest(state, cond, x_T)
+    with torch.no_grad():
+        out = oracle.wavenet_forward(state, x_T, steps, cond.transpose(1, 2), cfg.dilation_cycle_length)
+    assert out.shape == (case["B"], 1, cfg.in_dims, case["T"])
+    assert np.abs(out.numpy() - g["out"]).max() <= TOL
+
+
+def test_default_schedule_values():
+    """SURVEY §8 a1/a2 probed values for the default config (vpsde, max_beta=40, timesteps=4)."""
+    tb = oracle.diffusion_tables(4, "vpsde", 40)
+    np.testing.assert_allclose(tb["betas"].numpy(), [.5587, .9105, .9819, .9963, .9993], atol=5e-5)
+    np.testing.assert_allclose(tb["posterior_mean_coef1"].numpy(), [1, .6297, .1952, .0267, .0016], atol=5e-5)
+    np.testing.assert_allclose(tb["posterior_mean_coef2"].numpy(), [0, .1740, .1294, .0606, .0273], atol=5e-5)
+
+
+def test_unknown_schedule_raises():
+    with pytest.raises(NotImplementedError):
+        oracle.get_noise_schedule_list("nope", 4)
+
+
+def test_t0_noise_is_masked():
+    """prodiff.py:119-121: the noise drawn at t == 0 must not reach the output."""
+    case, cfg, state, cond, x_T, noise = helpers.regen_sample_case("cosine_sched")
+    mel_a, _ = helpers.oracle_sample(case, cfg, state, cond, x_T, noise)
+    noise2 = noise.clone()
+    noise2[-1] += 100.0
+    mel_b, _ = helpers.oracle_sample(case, cfg, state, cond, x_T, noise2)
+    assert torch.equal(mel_a, mel_b)

@@ -1,0 +1,60 @@
+"""Bit-exact check of the oracle against the live reference (build container only).
+
+Skipped wherever /root/reference is absent (e.g. the GPU box): nothing that runs there may read it.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+REF = "/root/reference"
+pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "modules", "diffusion")),
+                                reason="reference not mounted")
+
+
+@pytest.fixture(scope="module")
+def mg():
+    import oracle.make_golden as mg
+    mg.load_reference()
+    yield mg
+    if REF in sys.path:
+        sys.path.remove(REF)
+
+
+@pytest.mark.parametrize("name", ["dil4_ragged", "kaiming_short", "cosine_sched"])
+def test_sample_bit_exact(mg, name):
+    from oracle.golden_cases import SAMPLE_CASES
+    from tests import helpers
+    case, cfg, state, cond, x_T, noise = helpers.regen_sample_case(name)
+    ref = mg.run_reference_sample(SAMPLE_CASES[name])
+    mel, x0s = helpers.oracle_sample(case, cfg, state, cond, x_T, noise)
+    assert np.array_equal(torch.stack(x0s).numpy(), ref["x0"])
+    assert np.array_equal(mel.contiguous().numpy(), ref["mel"])
+
+
+@pytest.mark.parametrize("name", ["fwd_int_steps", "fwd_float_steps", "fwd_in64"])
+def test_denoise_bit_exact(mg, name):
+    from oracle import prodiff_oracle as oracle
+    from oracle.golden_cases import DENOISE_CASES
+    from tests import helpers
+    case, cfg, state, cond, x_T, steps = helpers.regen_denoise_case(name)
+    ref = mg.run_reference_denoise(DENOISE_CASES[name])
+    with torch.no_grad():
+        out = oracle.wavenet_forward(state, x_T, steps, cond.transpose(1, 2), cfg.dilation_cycle_length)
+    assert np.array_equal(out.numpy(), ref["out"])
+
+
+def test_reference_init_distribution_matches_synth(mg):
+    """synth.make_state mirrors the reference's init *distributions* (not its torch RNG stream)."""
+    from prodiff_b200 import synth
+    WaveNet, _ = mg.load_reference()
+    torch.manual_seed(0)
+    ref = WaveNet(128, 256, 4, 256, 1).state_dict()
+    mine = synth.make_state(synth.DiffNetConfig(128, 256, 4, 256, 1), 0, out_init="zero")
+    assert set(ref) == set(mine)
+    for k in ref:
+        assert ref[k].shape == mine[k].shape, k
+        if ref[k].numel() >= 4096:
+            assert abs(float(ref[k].std()) - float(mine[k].std())) <= 0.08 * float(ref[k].std()) + 1e-8, k
