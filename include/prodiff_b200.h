@@ -1,0 +1,118 @@
+/* prodiff_b200 -- C ABI of the B200-native ProDiff sampling hot path.
+ *
+ * The reference (T1uTiu/ProDiff) is pure Python/PyTorch and has no FFI; the boundary it offers for this path is
+ * two nn.Module classes:
+ *
+ *   WaveNet.forward(spec, diffusion_step, cond)                       modules/decoder/wavenet.py:100-123
+ *   GaussianDiffusion.forward(cond, ..., infer_step, infer=True)      modules/diffusion/prodiff.py:136-153
+ *   GaussianDiffusion.p_sample / q_posterior_sample                   modules/diffusion/prodiff.py:106-126
+ *
+ * This header declares what a binding for those two classes calls.  Plain pointers and sizes only: no torch
+ * types, no C++ types.  All device pointers are CUDA device memory owned by the caller (in the Python host they
+ * are torch tensors); the library never allocates device memory and never keeps an input pointer after a call
+ * returns, except the `packed` and `workspace` blocks the caller hands to pd_model_create / pd_plan_create, which
+ * must outlive the handle.  Every function returns 0 on success and a non-zero code on failure;
+ * pd_last_error() then returns a thread-local message.  There is no CPU fallback: a device that is not
+ * compute capability 10.x is an error.
+ *
+ * Threading: a pd_model is immutable after creation; a pd_plan owns scratch buffers and must be used by one
+ * stream at a time.  All work is enqueued on the caller's stream and is asynchronous with respect to the host.
+ */
+#ifndef PRODIFF_B200_H
+#define PRODIFF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PD_ABI_VERSION 1
+
+enum { PD_BF16 = 0, PD_FP16 = 1 }; /* tensor-core operand type; accumulation is always fp32 */
+
+/* Constructor arguments of the reference WaveNet (wavenet.py:75) plus the operand type. */
+typedef struct pd_config {
+  int32_t in_dims;               /* M: mel bins; 64 or 128                              */
+  int32_t hidden_size;           /* H: condition channels; multiple of 64               */
+  int32_t residual_layers;       /* L                                                   */
+  int32_t residual_channels;     /* C: multiple of 256                                  */
+  int32_t dilation_cycle_length; /* dilation of layer i = 2^(i % cycle)  (wavenet.py:93) */
+  int32_t dtype;                 /* PD_BF16 / PD_FP16                                   */
+} pd_config;
+
+typedef struct pd_model pd_model; /* packed weights + weight tensor maps (per device)            */
+typedef struct pd_plan pd_plan;   /* scratch layout + activation tensor maps for one (B, T) shape */
+
+/* Number of entries pd_model_create expects in `state`: 10 + 8 * L. Order (all fp32, contiguous, on device):
+ *   0 input_projection.weight [C,M,1]   1 input_projection.bias [C]
+ *   2 mlp.0.weight [4C,C]               3 mlp.0.bias [4C]
+ *   4 mlp.2.weight [C,4C]               5 mlp.2.bias [C]
+ *   6 skip_projection.weight [C,C,1]    7 skip_projection.bias [C]
+ *   8 output_projection.weight [M,C,1]  9 output_projection.bias [M]
+ *   then for each layer i (base = 10 + 8*i), the keys of residual_layers.{i}. in this order:
+ *   +0 dilated_conv.weight [2C,C,3]            +1 dilated_conv.bias [2C]
+ *   +2 diffusion_projection.weight [C,C]       +3 diffusion_projection.bias [C]
+ *   +4 conditioner_projection.weight [2C,H,1]  +5 conditioner_projection.bias [2C]
+ *   +6 output_projection.weight [2C,C,1]       +7 output_projection.bias [2C]
+ * (the reference's state_dict keys) */
+int pd_state_count(const pd_config* cfg);
+
+const char* pd_last_error(void);
+int pd_abi_version(void);
+
+/* Bytes of device memory the packed (16-bit, tile-ordered) weights need. */
+size_t pd_packed_bytes(const pd_config* cfg);
+
+/* Pack the fp32 state into `packed` (device, >= pd_packed_bytes, 1024-byte aligned) on `stream` and build the
+ * model handle.  Replaces: the reference keeping fp32 nn.Parameters and dispatching cuDNN/cuBLAS per op. */
+int pd_model_create(const pd_config* cfg, const float* const* state, int n_state, void* packed,
+                    size_t packed_bytes, void* stream, pd_model** out);
+void pd_model_destroy(pd_model* m);
+
+/* Scratch bytes for B utterances of T frames and up to `max_entries` distinct diffusion steps per call
+ * (K for sampling, B for a per-row-step denoise call). */
+size_t pd_workspace_bytes(const pd_model* m, int B, int T, int max_entries);
+int pd_plan_create(const pd_model* m, int B, int T, int max_entries, void* workspace, size_t workspace_bytes,
+                   pd_plan** out);
+void pd_plan_destroy(pd_plan* p);
+
+/* Hoisted condition projection: all L conditioner_projection 1x1 convs (wavenet.py:62) of cond [B,T,H] fp32
+ * (physically frame-major, i.e. the tensor the reference transposes at prodiff.py:138) in one GEMM, kept in the
+ * plan for every following pd_denoise call.  pd_sample calls it itself. */
+int pd_cond_project(pd_plan* p, const float* cond, void* stream);
+
+/* WaveNet.forward (wavenet.py:100-123): spec [B,1,M,T] fp32, diffusion_step [B] fp32 (device), out [B,1,M,T]
+ * fp32.  Uses the condition projection already in the plan. */
+int pd_denoise(pd_plan* p, const float* spec, const float* diffusion_step, float* out, void* stream);
+
+/* GaussianDiffusion.forward(infer=True) (prodiff.py:145-153): the whole K-step reverse loop.
+ *   cond   [B,T,H] fp32
+ *   x      [B,1,M,T] fp32: in = x_T (the reference draws it with torch.rand, :147), out = x_0
+ *   noise  [K,B,1,M,T] fp32 or NULL: noise[j] is used by the j-th iteration (replaces torch.randn, :118);
+ *          NULL = in-kernel Philox4x32-10 keyed by `seed`
+ *   t_list host int[K]: the step index of each iteration (the reference uses K-1, ..., 0)
+ *   coef1/coef2/logvar host float[n_table]: posterior_mean_coef1/2 and posterior_log_variance_clipped buffers
+ *   x0_trace [K,B,1,M,T] fp32 or NULL: per-step denoiser outputs (for parity checks) */
+int pd_sample(pd_plan* p, const float* cond, float* x, const float* noise, uint64_t seed, int K,
+              const int32_t* t_list, const float* coef1, const float* coef2, const float* logvar, int n_table,
+              float* x0_trace, void* stream);
+
+/* Number of kernels of this library launched by the calling thread since the last reset (bench evidence). */
+long long pd_launch_count(int reset);
+
+/* Introspection for tests: byte offset/size of a named scratch buffer inside the plan's workspace.
+ * Names: "cond16","cp","xin","xa","xb","ybuf","s1","s2","steps","emb","dvec","sb". Returns 0 if found. */
+int pd_plan_buffer(const pd_plan* p, const char* name, size_t* offset, size_t* bytes);
+
+/* Test hook: one implicit-GEMM launch of the production kernel with a plain fp32 store epilogue.
+ *   a [slabs? no: B,T,Cin] 16-bit activations, w [N, taps*Cin] 16-bit weights (K-major, tap-major),
+ *   out [B*T, N] fp32 = conv(a, w) + bias.  N multiple of 256, Cin multiple of 64, taps in {1,3}. */
+int pd_debug_gemm(int dtype, const void* a, int B, int T, int Cin, int taps, int dil, const void* w, int N,
+                  const float* bias, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PRODIFF_B200_H */

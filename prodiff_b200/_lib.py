@@ -1,0 +1,70 @@
+"""ctypes binding of the C-ABI library (include/prodiff_b200.h).
+
+The shared object is built in-tree by ``prodiff_b200/csrc/build.py`` (``__graft_entry__.build()`` calls it).  There is
+no fallback: if the library is missing or a call fails, a ``RuntimeError`` is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libprodiff_b200.so")
+
+PD_BF16, PD_FP16 = 0, 1
+
+# every symbol include/prodiff_b200.h declares (tests/test_abi.py checks the header against this list)
+SYMBOLS = [
+    "pd_state_count", "pd_last_error", "pd_abi_version", "pd_packed_bytes", "pd_model_create", "pd_model_destroy",
+    "pd_workspace_bytes", "pd_plan_create", "pd_plan_destroy", "pd_cond_project", "pd_denoise", "pd_sample",
+    "pd_launch_count", "pd_plan_buffer", "pd_debug_gemm",
+]
+
+
+class pd_config(C.Structure):
+    _fields_ = [("in_dims", C.c_int32), ("hidden_size", C.c_int32), ("residual_layers", C.c_int32),
+                ("residual_channels", C.c_int32), ("dilation_cycle_length", C.c_int32), ("dtype", C.c_int32)]
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the library once; raise loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"prodiff_b200: CUDA library not built ({LIB_PATH} missing). Run `python -c 'import __graft_entry__ as g; "
+            f"g.build()'` or `python prodiff_b200/csrc/build.py`. There is no CPU/PyTorch fallback for this path.")
+    lib = C.CDLL(LIB_PATH)
+    vp, cp, u64, sz = C.c_void_p, C.c_char_p, C.c_uint64, C.c_size_t
+    P = C.POINTER
+    lib.pd_state_count.argtypes = [P(pd_config)]; lib.pd_state_count.restype = C.c_int
+    lib.pd_last_error.argtypes = []; lib.pd_last_error.restype = cp
+    lib.pd_abi_version.argtypes = []; lib.pd_abi_version.restype = C.c_int
+    lib.pd_packed_bytes.argtypes = [P(pd_config)]; lib.pd_packed_bytes.restype = sz
+    lib.pd_model_create.argtypes = [P(pd_config), P(vp), C.c_int, vp, sz, vp, P(vp)]; lib.pd_model_create.restype = C.c_int
+    lib.pd_model_destroy.argtypes = [vp]; lib.pd_model_destroy.restype = None
+    lib.pd_workspace_bytes.argtypes = [vp, C.c_int, C.c_int, C.c_int]; lib.pd_workspace_bytes.restype = sz
+    lib.pd_plan_create.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, sz, P(vp)]; lib.pd_plan_create.restype = C.c_int
+    lib.pd_plan_destroy.argtypes = [vp]; lib.pd_plan_destroy.restype = None
+    lib.pd_cond_project.argtypes = [vp, vp, vp]; lib.pd_cond_project.restype = C.c_int
+    lib.pd_denoise.argtypes = [vp, vp, vp, vp, vp]; lib.pd_denoise.restype = C.c_int
+    lib.pd_sample.argtypes = [vp, vp, vp, vp, u64, C.c_int, P(C.c_int32), P(C.c_float), P(C.c_float), P(C.c_float),
+                              C.c_int, vp, vp]
+    lib.pd_sample.restype = C.c_int
+    lib.pd_launch_count.argtypes = [C.c_int]; lib.pd_launch_count.restype = C.c_longlong
+    lib.pd_plan_buffer.argtypes = [vp, cp, P(sz), P(sz)]; lib.pd_plan_buffer.restype = C.c_int
+    lib.pd_debug_gemm.argtypes = [C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp, vp, vp]
+    lib.pd_debug_gemm.restype = C.c_int
+    if lib.pd_abi_version() != 1:
+        raise RuntimeError(f"prodiff_b200: ABI version mismatch ({lib.pd_abi_version()} != 1); rebuild the library")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise RuntimeError(f"prodiff_b200: {what} failed: {load().pd_last_error().decode()}")

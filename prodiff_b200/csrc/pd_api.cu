@@ -1,0 +1,617 @@
+// C-ABI host side of prodiff_b200 (see include/prodiff_b200.h): weight packing, scratch layout, TMA tensor maps,
+// and the launch sequences behind WaveNet.forward and the K-step GaussianDiffusion reverse loop.
+#include "../../include/prodiff_b200.h"
+#include "pd_aux.cuh"
+
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+using namespace pd;
+
+// ------------------------------------------------------------------ errors / bookkeeping
+static thread_local char g_err[512] = "";
+static thread_local long long g_launches = 0;
+
+static int fail(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return 1;
+}
+#define PD_CUDA(expr)                                                                    \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess) return fail("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+#define PD_LAUNCH_CHECK(name)                                                            \
+  do {                                                                                   \
+    ++g_launches;                                                                        \
+    cudaError_t _e = cudaGetLastError();                                                 \
+    if (_e != cudaSuccess) return fail("launch of %s failed: %s", name, cudaGetErrorString(_e)); \
+  } while (0)
+
+extern "C" const char* pd_last_error(void) { return g_err; }
+extern "C" int pd_abi_version(void) { return PD_ABI_VERSION; }
+extern "C" long long pd_launch_count(int reset) {
+  const long long v = g_launches;
+  if (reset) g_launches = 0;
+  return v;
+}
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ------------------------------------------------------------------ driver entry point for tensor maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+// 16-bit tensor, up to 4 dims (innermost first), box = (64, box1, 1, 1), 128-byte swizzle, zero OOB fill.
+static int make_map(CUtensorMap* m, int dtype, const void* base, int rank, const uint64_t* dims, uint32_t box1) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail("cuTensorMapEncodeTiled entry point unavailable (driver too old?)");
+  cuuint64_t gdim[4] = {1, 1, 1, 1}, gstr[3] = {0, 0, 0};
+  cuuint32_t box[4] = {64, box1, 1, 1}, estr[4] = {1, 1, 1, 1};
+  uint64_t stride = 2;
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    stride *= dims[i];
+    if (i < rank - 1) gstr[i] = stride;
+  }
+  const CUresult r = enc(m, dtype == PD_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                         (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu %llu)", (int)r, rank,
+                                     (unsigned long long)dims[0], (unsigned long long)dims[1]);
+  return 0;
+}
+// activation map: [slabs][B][T][Cin] 16-bit
+static int make_act_map(CUtensorMap* m, int dtype, const void* base, int Cin, int T, int B, int slabs) {
+  const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)T, (uint64_t)B, (uint64_t)slabs};
+  return make_map(m, dtype, base, 4, dims, kBlockM);
+}
+// weight map: [rows][K] 16-bit
+static int make_w_map(CUtensorMap* m, int dtype, const void* base, int K, int rows, int bn) {
+  const uint64_t dims[2] = {(uint64_t)K, (uint64_t)rows};
+  return make_map(m, dtype, base, 2, dims, (uint32_t)bn);
+}
+
+// ------------------------------------------------------------------ packed weight layout
+struct PackedLayout {
+  // 16-bit operands (byte offsets)
+  size_t w_in, w_cond, w_dil, w_res, w_skip, w_sp, w_out;
+  // fp32 biases
+  size_t b_in, b_cp, b_res, b_skipsum, b_sp, b_out;
+  // fp32 copies for the step-embedding chain
+  size_t f_mlp0w, f_mlp0b, f_mlp2w, f_mlp2b, f_dpw, f_dpb, f_dilw;
+  size_t total;
+};
+static PackedLayout packed_layout(const pd_config& c) {
+  const size_t M = c.in_dims, H = c.hidden_size, L = c.residual_layers, C = c.residual_channels;
+  PackedLayout p;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 1024); return r; };
+  p.w_in = take(C * M * 2);
+  p.w_cond = take(L * 2 * C * H * 2);
+  p.w_dil = take(L * 2 * C * 3 * C * 2);
+  p.w_res = take(L * C * C * 2);
+  p.w_skip = take(C * L * C * 2);
+  p.w_sp = take(C * C * 2);
+  p.w_out = take(128 * C * 2);
+  p.b_in = take(C * 4);
+  p.b_cp = take(L * 2 * C * 4);
+  p.b_res = take(L * C * 4);
+  p.b_skipsum = take(C * 4);
+  p.b_sp = take(C * 4);
+  p.b_out = take(128 * 4);
+  p.f_mlp0w = take(4 * C * C * 4);
+  p.f_mlp0b = take(4 * C * 4);
+  p.f_mlp2w = take(4 * C * C * 4);
+  p.f_mlp2b = take(C * 4);
+  p.f_dpw = take(L * C * C * 4);
+  p.f_dpb = take(L * C * 4);
+  p.f_dilw = take(L * 2 * C * C * 3 * 4);
+  p.total = o;
+  return p;
+}
+
+static int check_config(const pd_config* c) {
+  if (!c) return fail("null config");
+  if (c->in_dims != 64 && c->in_dims != 128) return fail("in_dims must be 64 or 128 (got %d)", c->in_dims);
+  if (c->hidden_size <= 0 || c->hidden_size % 64) return fail("hidden_size must be a multiple of 64 (got %d)", c->hidden_size);
+  if (c->residual_channels != 256 && c->residual_channels != 512)
+    return fail("residual_channels must be 256 or 512 (got %d)", c->residual_channels);
+  if (c->residual_layers < 1) return fail("residual_layers must be >= 1");
+  if (c->dilation_cycle_length < 1 || c->dilation_cycle_length > 16) return fail("dilation_cycle_length out of range");
+  if (c->dtype != PD_BF16 && c->dtype != PD_FP16) return fail("dtype must be PD_BF16 or PD_FP16");
+  return 0;
+}
+
+extern "C" int pd_state_count(const pd_config* cfg) { return cfg ? 10 + 8 * cfg->residual_layers : 0; }
+extern "C" size_t pd_packed_bytes(const pd_config* cfg) {
+  if (check_config(cfg)) return 0;
+  return packed_layout(*cfg).total;
+}
+
+struct pd_model {
+  pd_config cfg;
+  PackedLayout lay;
+  uint8_t* packed;
+  int device, sm_count;
+  CUtensorMap tm_w_in, tm_w_cond, tm_w_dil, tm_w_res, tm_w_skip, tm_w_sp, tm_w_out;
+};
+
+static int check_device(int* device, int* sms) {
+  PD_CUDA(cudaGetDevice(device));
+  int major = 0;
+  PD_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, *device));
+  if (major != 10) return fail("prodiff_b200 needs a compute-capability 10.x device (B200); found %d.x -- no fallback path", major);
+  PD_CUDA(cudaDeviceGetAttribute(sms, cudaDevAttrMultiProcessorCount, *device));
+  return 0;
+}
+
+template <typename T>
+static int pack_all(const pd_config& c, const PackedLayout& lay, uint8_t* pk, const float* const* st, cudaStream_t s) {
+  const int M = c.in_dims, H = c.hidden_size, L = c.residual_layers, C = c.residual_channels;
+  const int TB = 256;
+  auto blocks = [&](long long n) { return (int)std::min<long long>((n + TB - 1) / TB, 4096); };
+  // 16-bit operands
+  k_pack_rows<T><<<blocks((long long)C * M), TB, 0, s>>>((T*)(pk + lay.w_in), M, 0, st[0], C, 0, C, M, 0);
+  PD_LAUNCH_CHECK("k_pack_rows(in)");
+  k_pack_rows<T><<<blocks((long long)C * C), TB, 0, s>>>((T*)(pk + lay.w_sp), C, 0, st[6], C, 0, C, C, 0);
+  PD_LAUNCH_CHECK("k_pack_rows(sp)");
+  k_pack_rows<T><<<blocks(128ll * C), TB, 0, s>>>((T*)(pk + lay.w_out), C, 0, st[8], M, 0, 128, C, 0);
+  PD_LAUNCH_CHECK("k_pack_rows(out)");
+  k_pack_bias<<<blocks(C), TB, 0, s>>>((float*)(pk + lay.b_in), st[1], nullptr, 0, C, C, 0, 0);
+  k_pack_bias<<<blocks(C), TB, 0, s>>>((float*)(pk + lay.b_sp), st[7], nullptr, 0, C, C, 0, 0);
+  k_pack_bias<<<1, 128, 0, s>>>((float*)(pk + lay.b_out), st[9], nullptr, 0, M, 128, 0, 0);
+  PD_LAUNCH_CHECK("k_pack_bias");
+  for (int l = 0; l < L; ++l) {
+    const float* const* q = st + 10 + 8 * l;
+    k_pack_dil<T><<<blocks(6ll * C * C), TB, 0, s>>>((T*)(pk + lay.w_dil) + (size_t)l * 2 * C * 3 * C, q[0], C);
+    PD_LAUNCH_CHECK("k_pack_dil");
+    k_pack_rows<T><<<blocks(2ll * C * H), TB, 0, s>>>((T*)(pk + lay.w_cond) + (size_t)l * 2 * C * H, H, 0, q[4], 2 * C, 0, 2 * C, H, C);
+    PD_LAUNCH_CHECK("k_pack_rows(cond)");
+    k_pack_rows<T><<<blocks((long long)C * C), TB, 0, s>>>((T*)(pk + lay.w_res) + (size_t)l * C * C, C, 0, q[6], 2 * C, 0, C, C, 0);
+    PD_LAUNCH_CHECK("k_pack_rows(res)");
+    // skip half of output_projection, K-concatenated over layers: Wskip[r][l*C + c] = W_l[C + r][c]
+    k_pack_rows<T><<<blocks((long long)C * C), TB, 0, s>>>((T*)(pk + lay.w_skip), (long long)L * C, l * C, q[6], 2 * C, C, C, C, 0);
+    PD_LAUNCH_CHECK("k_pack_rows(skip)");
+    // hoisted pre-activation bias: conditioner bias + dilated-conv bias, gate-paired order
+    k_pack_bias<<<blocks(2 * C), TB, 0, s>>>((float*)(pk + lay.b_cp) + (size_t)l * 2 * C, q[5], q[1], 0, 2 * C, 2 * C, C, 0);
+    k_pack_bias<<<blocks(C), TB, 0, s>>>((float*)(pk + lay.b_res) + (size_t)l * C, q[7], nullptr, 0, 2 * C, C, 0, 0);
+    k_pack_bias<<<blocks(C), TB, 0, s>>>((float*)(pk + lay.b_skipsum), q[7], nullptr, C, 2 * C, C, 0, l > 0);
+    PD_LAUNCH_CHECK("k_pack_bias(layer)");
+    PD_CUDA(cudaMemcpyAsync(pk + lay.f_dpw + (size_t)l * C * C * 4, q[2], (size_t)C * C * 4, cudaMemcpyDeviceToDevice, s));
+    PD_CUDA(cudaMemcpyAsync(pk + lay.f_dpb + (size_t)l * C * 4, q[3], (size_t)C * 4, cudaMemcpyDeviceToDevice, s));
+    PD_CUDA(cudaMemcpyAsync(pk + lay.f_dilw + (size_t)l * 2 * C * C * 3 * 4, q[0], (size_t)2 * C * C * 3 * 4, cudaMemcpyDeviceToDevice, s));
+  }
+  PD_CUDA(cudaMemcpyAsync(pk + lay.f_mlp0w, st[2], (size_t)4 * C * C * 4, cudaMemcpyDeviceToDevice, s));
+  PD_CUDA(cudaMemcpyAsync(pk + lay.f_mlp0b, st[3], (size_t)4 * C * 4, cudaMemcpyDeviceToDevice, s));
+  PD_CUDA(cudaMemcpyAsync(pk + lay.f_mlp2w, st[4], (size_t)4 * C * C * 4, cudaMemcpyDeviceToDevice, s));
+  PD_CUDA(cudaMemcpyAsync(pk + lay.f_mlp2b, st[5], (size_t)C * 4, cudaMemcpyDeviceToDevice, s));
+  return 0;
+}
+
+extern "C" int pd_model_create(const pd_config* cfg, const float* const* state, int n_state, void* packed,
+                               size_t packed_bytes, void* stream, pd_model** out) {
+  if (!out) return fail("null out pointer");
+  *out = nullptr;
+  if (check_config(cfg)) return 1;
+  if (!state || n_state != pd_state_count(cfg)) return fail("expected %d state tensors, got %d", pd_state_count(cfg), n_state);
+  for (int i = 0; i < n_state; ++i)
+    if (!state[i]) return fail("state tensor %d is null", i);
+  const PackedLayout lay = packed_layout(*cfg);
+  if (!packed || packed_bytes < lay.total) return fail("packed buffer too small: need %zu bytes, got %zu", lay.total, packed_bytes);
+  if (reinterpret_cast<uintptr_t>(packed) % 1024) return fail("packed buffer must be 1024-byte aligned");
+  int device = 0, sms = 0;
+  if (check_device(&device, &sms)) return 1;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  uint8_t* pk = static_cast<uint8_t*>(packed);
+  const int rc = cfg->dtype == PD_FP16 ? pack_all<__half>(*cfg, lay, pk, state, s) : pack_all<__nv_bfloat16>(*cfg, lay, pk, state, s);
+  if (rc) return rc;
+
+  pd_model* m = new pd_model();
+  m->cfg = *cfg;
+  m->lay = lay;
+  m->packed = pk;
+  m->device = device;
+  m->sm_count = sms;
+  const int M = cfg->in_dims, H = cfg->hidden_size, L = cfg->residual_layers, C = cfg->residual_channels, dt = cfg->dtype;
+  if (make_w_map(&m->tm_w_in, dt, pk + lay.w_in, M, C, 256) || make_w_map(&m->tm_w_cond, dt, pk + lay.w_cond, H, L * 2 * C, 256) ||
+      make_w_map(&m->tm_w_dil, dt, pk + lay.w_dil, 3 * C, L * 2 * C, 256) || make_w_map(&m->tm_w_res, dt, pk + lay.w_res, C, L * C, 256) ||
+      make_w_map(&m->tm_w_skip, dt, pk + lay.w_skip, L * C, C, 256) || make_w_map(&m->tm_w_sp, dt, pk + lay.w_sp, C, C, 256) ||
+      make_w_map(&m->tm_w_out, dt, pk + lay.w_out, C, 128, 128)) {
+    delete m;
+    return 1;
+  }
+  *out = m;
+  return 0;
+}
+extern "C" void pd_model_destroy(pd_model* m) { delete m; }
+
+// ------------------------------------------------------------------ plan (scratch layout + activation maps)
+struct Buf {
+  const char* name;
+  size_t off, bytes;
+};
+struct pd_plan {
+  const pd_model* m;
+  int B, T, E;
+  uint8_t* ws;
+  std::vector<Buf> bufs;
+  CUtensorMap tm_cond, tm_xin, tm_xa, tm_xb, tm_y, tm_s1, tm_s2;
+  size_t off(const char* n) const {
+    for (const Buf& b : bufs)
+      if (!strcmp(b.name, n)) return b.off;
+    return (size_t)-1;
+  }
+  template <typename U> U* ptr(const char* n) const { return reinterpret_cast<U*>(ws + off(n)); }
+};
+
+static size_t plan_layout(const pd_config& c, int B, int T, int E, std::vector<Buf>* bufs) {
+  const size_t N = (size_t)B * T, M = c.in_dims, H = c.hidden_size, L = c.residual_layers, C = c.residual_channels;
+  size_t o = 0;
+  auto take = [&](const char* name, size_t bytes) {
+    if (bufs) bufs->push_back(Buf{name, o, bytes});
+    o = align_up(o + bytes, 1024);
+  };
+  take("cond16", N * H * 2);
+  take("cp", L * N * 2 * C * 2);
+  take("xin", N * M * 2);
+  take("xa", N * C * 2);
+  take("xb", N * C * 2);
+  take("ybuf", L * N * C * 2);
+  take("s1", N * C * 2);
+  take("s2", N * C * 2);
+  take("steps", (size_t)E * 4);
+  take("emb", (size_t)E * C * 4);
+  take("dvec", (size_t)E * L * C * 4);
+  take("sb", (size_t)E * L * 4 * 2 * C * 4);
+  return o;
+}
+
+extern "C" size_t pd_workspace_bytes(const pd_model* m, int B, int T, int max_entries) {
+  if (!m || B < 1 || T < 1 || max_entries < 1) return 0;
+  return plan_layout(m->cfg, B, T, max_entries, nullptr);
+}
+
+extern "C" int pd_plan_create(const pd_model* m, int B, int T, int max_entries, void* workspace, size_t workspace_bytes,
+                              pd_plan** out) {
+  if (!out) return fail("null out pointer");
+  *out = nullptr;
+  if (!m) return fail("null model");
+  if (B < 1 || T < 1 || max_entries < 1) return fail("B, T and max_entries must be >= 1 (got %d, %d, %d)", B, T, max_entries);
+  if ((long long)B * T >= (1ll << 31)) return fail("B*T too large");
+  pd_plan* p = new pd_plan();
+  p->m = m;
+  p->B = B;
+  p->T = T;
+  p->E = max_entries;
+  p->ws = static_cast<uint8_t*>(workspace);
+  const size_t need = plan_layout(m->cfg, B, T, max_entries, &p->bufs);
+  if (!workspace || workspace_bytes < need) {
+    delete p;
+    return fail("workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
+  }
+  if (reinterpret_cast<uintptr_t>(workspace) % 1024) {
+    delete p;
+    return fail("workspace must be 1024-byte aligned");
+  }
+  const pd_config& c = m->cfg;
+  const int dt = c.dtype, C = c.residual_channels;
+  if (make_act_map(&p->tm_cond, dt, p->ptr<void>("cond16"), c.hidden_size, T, B, 1) ||
+      make_act_map(&p->tm_xin, dt, p->ptr<void>("xin"), c.in_dims, T, B, 1) ||
+      make_act_map(&p->tm_xa, dt, p->ptr<void>("xa"), C, T, B, 1) || make_act_map(&p->tm_xb, dt, p->ptr<void>("xb"), C, T, B, 1) ||
+      make_act_map(&p->tm_y, dt, p->ptr<void>("ybuf"), C, T, B, c.residual_layers) ||
+      make_act_map(&p->tm_s1, dt, p->ptr<void>("s1"), C, T, B, 1) || make_act_map(&p->tm_s2, dt, p->ptr<void>("s2"), C, T, B, 1)) {
+    delete p;
+    return 1;
+  }
+  *out = p;
+  return 0;
+}
+extern "C" void pd_plan_destroy(pd_plan* p) { delete p; }
+
+extern "C" int pd_plan_buffer(const pd_plan* p, const char* name, size_t* offset, size_t* bytes) {
+  if (!p || !name) return fail("null argument");
+  for (const Buf& b : p->bufs)
+    if (!strcmp(b.name, name)) {
+      if (offset) *offset = b.off;
+      if (bytes) *bytes = b.bytes;
+      return 0;
+    }
+  return fail("no scratch buffer named '%s'", name);
+}
+
+// ------------------------------------------------------------------ GEMM launch
+static uint32_t make_idesc(int dtype, int bn) {
+  const uint32_t fmt = dtype == PD_FP16 ? 0u : 1u;
+  // c_format = F32 (bit 4), a/b format (bits 7-9 / 10-12), K-major A and B, N >> 3 (bits 17-22), M >> 4 (bits 24-28)
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+}
+
+template <int EPI, int BN, typename T>
+static int launch_gemm_t(const CUtensorMap& a, const CUtensorMap& b, const GemmShape& sh, const EpiArgs& ep, int sms,
+                         cudaStream_t s, const char* name) {
+  auto kern = gemm_kernel<EPI, BN, T>;
+  static bool configured[64] = {false};  // per instantiation, per device
+  int dev = 0;
+  PD_CUDA(cudaGetDevice(&dev));
+  if (!configured[dev & 63]) {
+    PD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GemmCfg<BN>::kSmemBytes));
+    configured[dev & 63] = true;
+  }
+  const int tiles = sh.B * sh.m_tiles_per_row * sh.n_tiles;
+  const int grid = tiles < sms ? tiles : sms;
+  kern<<<grid, kGemmThreads, GemmCfg<BN>::kSmemBytes, s>>>(a, b, sh, ep);
+  PD_LAUNCH_CHECK(name);
+  return 0;
+}
+template <int EPI, int BN>
+static int launch_gemm(int dtype, const CUtensorMap& a, const CUtensorMap& b, GemmShape sh, const EpiArgs& ep, int sms,
+                       cudaStream_t s, const char* name) {
+  sh.idesc = make_idesc(dtype, BN);
+  return dtype == PD_FP16 ? launch_gemm_t<EPI, BN, __half>(a, b, sh, ep, sms, s, name)
+                          : launch_gemm_t<EPI, BN, __nv_bfloat16>(a, b, sh, ep, sms, s, name);
+}
+
+static GemmShape base_shape(int B, int T, int n_tiles, int k_per_tap) {
+  GemmShape sh;
+  memset(&sh, 0, sizeof(sh));
+  sh.B = B;
+  sh.T = T;
+  sh.m_tiles_per_row = (T + kBlockM - 1) / kBlockM;
+  sh.n_tiles = n_tiles;
+  sh.k_per_tap = k_per_tap;
+  sh.taps = 1;
+  sh.tap_mode = 0;
+  sh.dil = 1;
+  return sh;
+}
+static EpiArgs base_epi() {
+  EpiArgs e;
+  memset(&e, 0, sizeof(e));
+  e.scale = 1.f;
+  e.out_type = OUT_T;
+  return e;
+}
+
+// ------------------------------------------------------------------ hot-path sequences
+extern "C" int pd_cond_project(pd_plan* p, const float* cond, void* stream) {
+  if (!p || !cond) return fail("null argument");
+  const pd_model* m = p->m;
+  const pd_config& c = m->cfg;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const long long n4 = (long long)p->B * p->T * c.hidden_size / 4;
+  const int blocks = (int)std::min<long long>((n4 + 255) / 256, 148 * 16);
+  if (c.dtype == PD_FP16) k_cast<__half><<<blocks, 256, 0, s>>>(p->ptr<__half>("cond16"), cond, n4);
+  else k_cast<__nv_bfloat16><<<blocks, 256, 0, s>>>(p->ptr<__nv_bfloat16>("cond16"), cond, n4);
+  PD_LAUNCH_CHECK("k_cast(cond)");
+  const int C2 = 2 * c.residual_channels;
+  GemmShape sh = base_shape(p->B, p->T, c.residual_layers * C2 / 256, c.hidden_size / 64);
+  EpiArgs ep = base_epi();
+  ep.out = p->ptr<void>("cp");
+  ep.bias = reinterpret_cast<const float*>(m->packed + m->lay.b_cp);
+  ep.ld = C2;
+  ep.out_type = OUT_F16;
+  return launch_gemm<EPI_STORE, 256>(c.dtype, p->tm_cond, m->tm_w_cond, sh, ep, m->sm_count, s, "gemm(cond_proj)");
+}
+
+// Step-embedding chain for `E` entries whose step values are already in the plan's "steps" buffer.
+static int run_step_tables(pd_plan* p, int E, cudaStream_t s) {
+  const pd_model* m = p->m;
+  const pd_config& c = m->cfg;
+  const int C = c.residual_channels, L = c.residual_layers;
+  const uint8_t* pk = m->packed;
+  const PackedLayout& lay = m->lay;
+  k_step_embed<<<E, 256, 5 * C * sizeof(float), s>>>(p->ptr<float>("steps"), C, (const float*)(pk + lay.f_mlp0w), (const float*)(pk + lay.f_mlp0b),
+                                                     (const float*)(pk + lay.f_mlp2w), (const float*)(pk + lay.f_mlp2b), p->ptr<float>("emb"));
+  PD_LAUNCH_CHECK("k_step_embed");
+  k_step_proj<<<dim3(L, E), 256, C * sizeof(float), s>>>(p->ptr<float>("emb"), (const float*)(pk + lay.f_dpw), (const float*)(pk + lay.f_dpb),
+                                                         p->ptr<float>("dvec"), L, C);
+  PD_LAUNCH_CHECK("k_step_proj");
+  if (C == 256) k_step_taps<8><<<dim3(2 * C / 8, L), 256, 0, s>>>(p->ptr<float>("dvec"), (const float*)(pk + lay.f_dilw), p->ptr<float>("sb"), E, L);
+  else k_step_taps<16><<<dim3(2 * C / 8, L), 256, 0, s>>>(p->ptr<float>("dvec"), (const float*)(pk + lay.f_dilw), p->ptr<float>("sb"), E, L);
+  PD_LAUNCH_CHECK("k_step_taps");
+  return 0;
+}
+
+struct OutStage {  // what the final GEMM's epilogue does with x0
+  float* x0_out;
+  float* x_state;
+  const float* noise;
+  bool write_xin;
+  float c1, c2, sigma;
+  unsigned long long seed;
+  unsigned int step_id;
+};
+
+// One denoiser evaluation (wavenet.py:100-123) on the operand already in "xin"; entry selection for the step bias is
+// entry = entry_base + b * entry_per_b.
+static int run_denoiser(pd_plan* p, int entry_base, int entry_per_b, const OutStage& os, cudaStream_t s) {
+  const pd_model* m = p->m;
+  const pd_config& c = m->cfg;
+  const int C = c.residual_channels, L = c.residual_layers, M = c.in_dims, B = p->B, T = p->T, dt = c.dtype, sms = m->sm_count;
+  const uint8_t* pk = m->packed;
+  const PackedLayout& lay = m->lay;
+  const size_t N = (size_t)B * T;
+  // input_projection + ReLU (wavenet.py:108-111)
+  {
+    GemmShape sh = base_shape(B, T, C / 256, M / 64);
+    EpiArgs ep = base_epi();
+    ep.out = p->ptr<void>("xa");
+    ep.bias = (const float*)(pk + lay.b_in);
+    ep.ld = C;
+    ep.relu = 1;
+    if (launch_gemm<EPI_STORE, 256>(dt, p->tm_xin, m->tm_w_in, sh, ep, sms, s, "gemm(input_proj)")) return 1;
+  }
+  bool cur_is_a = true;
+  for (int l = 0; l < L; ++l) {
+    const int dil = 1 << (l % c.dilation_cycle_length);
+    const CUtensorMap& tm_cur = cur_is_a ? p->tm_xa : p->tm_xb;
+    uint16_t* x_cur = p->ptr<uint16_t>(cur_is_a ? "xa" : "xb");
+    uint16_t* x_nxt = p->ptr<uint16_t>(cur_is_a ? "xb" : "xa");
+    {  // dilated conv + cond + step bias -> gate (wavenet.py:63-68)
+      GemmShape sh = base_shape(B, T, 2 * C / 256, C / 64);
+      sh.taps = 3;
+      sh.tap_mode = 1;
+      sh.dil = dil;
+      sh.b_row0 = l * 2 * C;
+      EpiArgs ep = base_epi();
+      ep.out = p->ptr<uint16_t>("ybuf") + (size_t)l * N * C;
+      ep.aux = p->ptr<uint16_t>("cp") + (size_t)l * N * 2 * C;
+      ep.sb = p->ptr<float>("sb") + (size_t)l * 4 * 2 * C;
+      ep.sb_entry_stride = (long long)L * 4 * 2 * C;
+      ep.sb_entry_base = entry_base;
+      ep.sb_entry_per_b = entry_per_b;
+      ep.ld = C;
+      if (launch_gemm<EPI_GATE, 256>(dt, tm_cur, m->tm_w_dil, sh, ep, sms, s, "gemm(dilated_conv+gate)")) return 1;
+    }
+    {  // residual half of output_projection + (x + res)/sqrt(2) (wavenet.py:70-72)
+      GemmShape sh = base_shape(B, T, C / 256, C / 64);
+      sh.a_slab0 = l;
+      sh.b_row0 = l * C;
+      EpiArgs ep = base_epi();
+      ep.out = x_nxt;
+      ep.aux = x_cur;
+      ep.bias = (const float*)(pk + lay.b_res) + (size_t)l * C;
+      ep.ld = C;
+      ep.scale = 0.70710678118654752440f;
+      if (launch_gemm<EPI_RES, 256>(dt, p->tm_y, m->tm_w_res, sh, ep, sms, s, "gemm(res_proj)")) return 1;
+    }
+    cur_is_a = !cur_is_a;
+  }
+  {  // sum of the L skip halves as ONE GEMM with K = L*C, then / sqrt(L)  (wavenet.py:119)
+    GemmShape sh = base_shape(B, T, C / 256, C / 64);
+    sh.taps = L;
+    EpiArgs ep = base_epi();
+    ep.out = p->ptr<void>("s1");
+    ep.bias = (const float*)(pk + lay.b_skipsum);
+    ep.ld = C;
+    ep.scale = 1.0f / sqrtf((float)L);
+    if (launch_gemm<EPI_STORE, 256>(dt, p->tm_y, m->tm_w_skip, sh, ep, sms, s, "gemm(skip_sum)")) return 1;
+  }
+  {  // skip_projection + ReLU (wavenet.py:120-121)
+    GemmShape sh = base_shape(B, T, C / 256, C / 64);
+    EpiArgs ep = base_epi();
+    ep.out = p->ptr<void>("s2");
+    ep.bias = (const float*)(pk + lay.b_sp);
+    ep.ld = C;
+    ep.relu = 1;
+    if (launch_gemm<EPI_STORE, 256>(dt, p->tm_s1, m->tm_w_sp, sh, ep, sms, s, "gemm(skip_proj)")) return 1;
+  }
+  {  // output_projection (wavenet.py:122) + q-posterior update (prodiff.py:106-121)
+    GemmShape sh = base_shape(B, T, 1, C / 64);
+    EpiArgs ep = base_epi();
+    ep.bias = (const float*)(pk + lay.b_out);
+    ep.M = M;
+    ep.Mp = M;
+    ep.x0_out = os.x0_out;
+    ep.x_state = os.x_state;
+    ep.noise = os.noise;
+    ep.xin_next = os.write_xin ? p->ptr<void>("xin") : nullptr;
+    ep.c1 = os.c1;
+    ep.c2 = os.c2;
+    ep.sigma = os.sigma;
+    ep.seed = os.seed;
+    ep.step_id = os.step_id;
+    if (launch_gemm<EPI_OUT, 128>(dt, p->tm_s2, m->tm_w_out, sh, ep, sms, s, "gemm(output_proj+posterior)")) return 1;
+  }
+  return 0;
+}
+
+static int spec_to_xin(pd_plan* p, const float* spec, cudaStream_t s) {
+  const pd_config& c = p->m->cfg;
+  const dim3 grid((p->T + 31) / 32, c.in_dims / 32, p->B), block(32, 8);
+  if (c.dtype == PD_FP16) k_spec_to_xin<__half><<<grid, block, 0, s>>>(p->ptr<__half>("xin"), spec, c.in_dims, c.in_dims, p->T);
+  else k_spec_to_xin<__nv_bfloat16><<<grid, block, 0, s>>>(p->ptr<__nv_bfloat16>("xin"), spec, c.in_dims, c.in_dims, p->T);
+  PD_LAUNCH_CHECK("k_spec_to_xin");
+  return 0;
+}
+
+extern "C" int pd_denoise(pd_plan* p, const float* spec, const float* diffusion_step, float* out, void* stream) {
+  if (!p || !spec || !diffusion_step || !out) return fail("null argument");
+  if (p->E < p->B) return fail("plan was created with max_entries=%d < B=%d; per-row steps need one entry per row", p->E, p->B);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  PD_CUDA(cudaMemcpyAsync(p->ptr<float>("steps"), diffusion_step, (size_t)p->B * 4, cudaMemcpyDeviceToDevice, s));
+  if (run_step_tables(p, p->B, s)) return 1;
+  if (spec_to_xin(p, spec, s)) return 1;
+  OutStage os;
+  memset(&os, 0, sizeof(os));
+  os.x0_out = out;
+  return run_denoiser(p, 0, 1, os, s);
+}
+
+extern "C" int pd_sample(pd_plan* p, const float* cond, float* x, const float* noise, uint64_t seed, int K,
+                         const int32_t* t_list, const float* coef1, const float* coef2, const float* logvar, int n_table,
+                         float* x0_trace, void* stream) {
+  if (!p || !cond || !x || !t_list || !coef1 || !coef2 || !logvar) return fail("null argument");
+  if (K < 1 || K > p->E) return fail("K=%d outside [1, max_entries=%d] of this plan", K, p->E);
+  for (int j = 0; j < K; ++j)
+    if (t_list[j] < 0 || t_list[j] >= n_table) return fail("t_list[%d]=%d outside the %d-entry tables", j, t_list[j], n_table);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const pd_config& c = p->m->cfg;
+  const size_t state_elems = (size_t)p->B * c.in_dims * p->T;
+  // step values -> device (by-value kernel arguments: no host memory is read asynchronously)
+  for (int j0 = 0; j0 < K; j0 += 64) {
+    StepVals sv;
+    const int n = K - j0 < 64 ? K - j0 : 64;
+    for (int j = 0; j < n; ++j) sv.v[j] = (float)t_list[j0 + j];
+    k_set_steps<<<1, 64, 0, s>>>(p->ptr<float>("steps") + j0, sv, n);
+    PD_LAUNCH_CHECK("k_set_steps");
+  }
+  if (run_step_tables(p, K, s)) return 1;
+  if (pd_cond_project(p, cond, stream)) return 1;  // once per utterance, reused by all K steps
+  if (spec_to_xin(p, x, s)) return 1;
+  for (int j = 0; j < K; ++j) {
+    const int t = t_list[j];
+    OutStage os;
+    os.x0_out = x0_trace ? x0_trace + (size_t)j * state_elems : nullptr;
+    os.x_state = x;
+    os.noise = noise ? noise + (size_t)j * state_elems : nullptr;
+    os.write_xin = j + 1 < K;
+    os.c1 = coef1[t];
+    os.c2 = coef2[t];
+    os.sigma = t == 0 ? 0.f : expf(0.5f * logvar[t]);  // nonzero_mask * exp(0.5 * log_var), prodiff.py:120-121
+    os.seed = seed;
+    os.step_id = (unsigned int)j;
+    if (run_denoiser(p, j, 0, os, s)) return 1;
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------ test hook
+extern "C" int pd_debug_gemm(int dtype, const void* a, int B, int T, int Cin, int taps, int dil, const void* w, int N,
+                             const float* bias, float* out, void* stream) {
+  if (!a || !w || !bias || !out) return fail("null argument");
+  if (N % 256 || Cin % 64 || (taps != 1 && taps != 3)) return fail("unsupported debug GEMM shape");
+  int device = 0, sms = 0;
+  if (check_device(&device, &sms)) return 1;
+  CUtensorMap ta, tb;
+  if (make_act_map(&ta, dtype, a, Cin, T, B, 1) || make_w_map(&tb, dtype, w, taps * Cin, N, 256)) return 1;
+  GemmShape sh = base_shape(B, T, N / 256, Cin / 64);
+  sh.taps = taps;
+  sh.tap_mode = 1;
+  sh.dil = dil;
+  EpiArgs ep = base_epi();
+  ep.out = out;
+  ep.bias = bias;
+  ep.ld = N;
+  ep.out_type = OUT_F32;
+  return launch_gemm<EPI_STORE, 256>(dtype, ta, tb, sh, ep, sms, static_cast<cudaStream_t>(stream), "gemm(debug)");
+}

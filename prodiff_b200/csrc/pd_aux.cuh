@@ -1,0 +1,199 @@
+// Non-GEMM kernels of the hot path: weight packing (one-time), operand casts / layout changes, and the
+// diffusion-step embedding chain (wavenet.py:26-38 SinusoidalPosEmb, :87-91 mlp, :56,61 diffusion_projection),
+// all fp32 on CUDA cores -- they are O(C^2) per step, not per frame.
+#pragma once
+#include "pd_gemm.cuh"
+
+namespace pd {
+
+// Packed weight rows are ordered so that one 256-wide N tile holds 128 gate rows followed by the 128 filter
+// rows of the SAME channels (torch.chunk pairs channel c with c + C, wavenet.py:67).
+__device__ __host__ __forceinline__ int gate_row_to_orig(int p, int C) {
+  const int j = p >> 8, w = p & 255;
+  return (w >> 7) * C + j * 128 + (w & 127);
+}
+
+template <typename T> __device__ __forceinline__ T from_float(float v);
+template <> __device__ __forceinline__ __nv_bfloat16 from_float<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ __half from_float<__half>(float v) { return __float2half_rn(v); }
+
+// dilated_conv.weight [2C, C, 3] fp32 -> [2C (gate-paired rows), 3 (tap), C] 16-bit: K index = tap * C + c.
+template <typename T>
+__global__ void k_pack_dil(T* __restrict__ dst, const float* __restrict__ src, int C) {
+  const long long total = 2ll * C * 3 * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int p = (int)(i / (3 * C));
+    const int rem = (int)(i - (long long)p * 3 * C);
+    const int tap = rem / C, c = rem - tap * C;
+    const int orig = gate_row_to_orig(p, C);
+    dst[i] = from_float<T>(src[((long long)orig * C + c) * 3 + tap]);
+  }
+}
+
+// Generic row gather: dst[r * dst_ld + dst_col0 + c] = src[(rowmap(r) + src_row0) * cols + c], zero for rows
+// beyond src_rows.  gateC > 0 selects the gate-paired row order.
+template <typename T>
+__global__ void k_pack_rows(T* __restrict__ dst, long long dst_ld, int dst_col0, const float* __restrict__ src,
+                            int src_rows, int src_row0, int rows, int cols, int gateC) {
+  const long long total = (long long)rows * cols;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / cols), c = (int)(i - (long long)r * cols);
+    const int sr = (gateC > 0 ? gate_row_to_orig(r, gateC) : r) + src_row0;
+    const float v = sr < src_rows ? src[(long long)sr * cols + c] : 0.f;
+    dst[(long long)r * dst_ld + dst_col0 + c] = from_float<T>(v);
+  }
+}
+
+// fp32 vector ops used while packing biases: dst[i] = (acc ? dst[i] : 0) + a[map(i) + a0] (+ b[map(i)]), zero padded.
+__global__ void k_pack_bias(float* __restrict__ dst, const float* __restrict__ a, const float* __restrict__ b, int a0,
+                            int a_len, int n, int gateC, int accumulate) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int s = (gateC > 0 ? gate_row_to_orig(i, gateC) : i) + a0;
+    float v = s < a_len ? a[s] : 0.f;
+    if (b != nullptr && s < a_len) v += b[s];
+    dst[i] = (accumulate ? dst[i] : 0.f) + v;
+  }
+}
+
+// fp32 -> 16-bit cast (condition tensor), 4 elements per thread.
+template <typename T>
+__global__ void k_cast(T* __restrict__ dst, const float* __restrict__ src, long long n4) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(src) + i);
+    uint2 o;
+    o.x = Cvt<T>::pack(v.x, v.y);
+    o.y = Cvt<T>::pack(v.z, v.w);
+    reinterpret_cast<uint2*>(dst)[i] = o;
+  }
+}
+
+// spec [B,1,M,T] fp32 (T contiguous) -> xin [B*T, Mp] 16-bit (mel contiguous): the input-projection operand.
+template <typename T>
+__global__ void k_spec_to_xin(T* __restrict__ xin, const float* __restrict__ spec, int M, int Mp, int Tn) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, m0 = blockIdx.y * 32, t0 = blockIdx.x * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+  for (int i = ty; i < 32; i += 8) {
+    const int m = m0 + i, t = t0 + tx;
+    tile[i][tx] = (m < M && t < Tn) ? spec[((long long)b * M + m) * Tn + t] : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int t = t0 + i, m = m0 + tx;
+    if (t < Tn && m < Mp) xin[((long long)b * Tn + t) * Mp + m] = from_float<T>(tile[tx][i]);
+  }
+}
+
+struct StepVals {
+  float v[64];
+};
+__global__ void k_set_steps(float* __restrict__ dst, StepVals vals, int n) {
+  if (threadIdx.x < n) dst[threadIdx.x] = vals.v[threadIdx.x];
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// One block per table entry: e = mlp(SinusoidalPosEmb(step)).  Accurate libm calls (no fast-math): this feeds
+// every layer's pre-activation.
+__global__ void k_step_embed(const float* __restrict__ steps, int C, const float* __restrict__ w0,
+                             const float* __restrict__ b0, const float* __restrict__ w2, const float* __restrict__ b2,
+                             float* __restrict__ emb_out) {
+  extern __shared__ float sm[];  // [C] sinusoid, [4C] hidden
+  float* s_emb = sm;
+  float* s_hid = sm + C;
+  const int e = blockIdx.x;
+  const float step = steps[e];
+  const int half = C / 2;
+  const float neg = -(logf(10000.f) / (float)(half - 1));
+  for (int j = threadIdx.x; j < half; j += blockDim.x) {
+    const float f = expf((float)j * neg);
+    const float a = step * f;
+    s_emb[j] = sinf(a);
+    s_emb[half + j] = cosf(a);
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int o = warp; o < 4 * C; o += nwarps) {
+    float acc = 0.f;
+    for (int c = lane; c < C; c += 32) acc = fmaf(w0[(long long)o * C + c], s_emb[c], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      const float x = acc + b0[o];
+      const float sp = x > 20.f ? x : log1pf(expf(x));  // F.softplus(beta=1, threshold=20)
+      s_hid[o] = x * tanhf(sp);                         // Mish, wavenet.py:22-24
+    }
+  }
+  __syncthreads();
+  for (int o = warp; o < C; o += nwarps) {
+    float acc = 0.f;
+    for (int c = lane; c < 4 * C; c += 32) acc = fmaf(w2[(long long)o * 4 * C + c], s_hid[c], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) emb_out[(long long)e * C + o] = acc + b2[o];
+  }
+}
+
+// d[e][l][:] = diffusion_projection_l(emb[e])   (wavenet.py:61).  grid (L, E).
+__global__ void k_step_proj(const float* __restrict__ emb, const float* __restrict__ dp_w, const float* __restrict__ dp_b,
+                            float* __restrict__ dvec, int L, int C) {
+  extern __shared__ float s_e[];
+  const int l = blockIdx.x, e = blockIdx.y;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) s_e[c] = emb[(long long)e * C + c];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const float* w = dp_w + (long long)l * C * C;
+  for (int o = warp; o < C; o += nwarps) {
+    float acc = 0.f;
+    for (int c = lane; c < C; c += 32) acc = fmaf(w[(long long)o * C + c], s_e[c], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) dvec[((long long)e * L + l) * C + o] = acc + dp_b[(long long)l * C + o];
+  }
+}
+
+// The reference adds d to x BEFORE the zero-padded dilated conv (wavenet.py:63-65), so the step contributes
+// W_k . d through each tap k that lands inside the utterance.  Per (entry, layer) this kernel emits, in packed
+// column order, {sum over the 3 taps, tap 0 alone, tap 2 alone}: interior frames add the first, the first/last
+// `dilation` frames subtract the tap that fell on padding (EPI_GATE).  fp32 weights: this part is exact.
+// grid (2C / 8, L), block 256: one warp per packed output row, looping over all entries with the row in registers.
+template <int CPL>  // C / 32
+__global__ void k_step_taps(const float* __restrict__ dvec, const float* __restrict__ dil_w, float* __restrict__ sb,
+                            int E, int L) {
+  constexpr int C = CPL * 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int p = blockIdx.x * 8 + warp, l = blockIdx.y;
+  const int orig = gate_row_to_orig(p, C);
+  const float* w = dil_w + ((long long)l * 2 * C + orig) * C * 3;
+  float w0[CPL], w1[CPL], w2[CPL];
+#pragma unroll
+  for (int i = 0; i < CPL; ++i) {
+    const int c = lane + 32 * i;
+    w0[i] = w[c * 3 + 0];
+    w1[i] = w[c * 3 + 1];
+    w2[i] = w[c * 3 + 2];
+  }
+  for (int e = 0; e < E; ++e) {
+    const float* d = dvec + ((long long)e * L + l) * C;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) {
+      const float dv = __ldg(d + lane + 32 * i);
+      a0 = fmaf(w0[i], dv, a0);
+      a1 = fmaf(w1[i], dv, a1);
+      a2 = fmaf(w2[i], dv, a2);
+    }
+    a0 = warp_sum(a0);
+    a1 = warp_sum(a1);
+    a2 = warp_sum(a2);
+    if (lane == 0) {
+      float* o = sb + ((long long)e * L + l) * 4 * 2 * C;
+      o[p] = a0 + a1 + a2;
+      o[2 * C + p] = a0;
+      o[4 * C + p] = a2;
+    }
+  }
+}
+
+}  // namespace pd

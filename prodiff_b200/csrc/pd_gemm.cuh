@@ -1,0 +1,433 @@
+// Persistent, warp-specialised implicit-GEMM kernel for sm_100a (tcgen05 + TMEM + TMA).
+//
+// Every dense contraction on the DiffNet hot path is an instance of this one kernel:
+//
+//   D[128 frames, BN channels] = sum over K-blocks of  A_kb[128 frames, 64] * B_kb[BN, 64]^T       (fp32 in TMEM)
+//
+// * A is a channels-last activation tensor [slab][B][T][C] (16-bit) read through a 4-D TMA tensor map with a
+//   (64 ch, 128 frames, 1, 1) box.  For the dilated convolution the K-blocks walk (tap, channel-chunk) and the
+//   frame coordinate of the box is shifted by (tap-1)*dilation; frames before 0 / after T-1 are zero-filled by
+//   TMA, which reproduces the reference's per-utterance zero padding (wavenet.py:55, padding=dilation).
+//   For the deferred skip sum the K-blocks walk (layer slab, channel-chunk) instead.
+// * B is a packed weight matrix [rows][K] (16-bit, K-major) read through a 2-D map with a (64, BN) box.
+// * warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane each), warps 2..9 = epilogue
+//   (TMEM -> registers -> fused epilogue -> global).  Two TMEM accumulator stages let the MMAs of tile i+1 overlap
+//   the epilogue of tile i; a kStages-deep shared-memory ring overlaps TMA with MMA.
+//
+// The epilogues are where the reference's elementwise graph is fused (wavenet.py:60-72,108-122; prodiff.py:106-121):
+//   EPI_STORE : (acc + bias) * scale, optional ReLU             (cond / input / skip projections)
+//   EPI_GATE  : sigmoid(gate) * tanh(filter) with the hoisted condition projection and the edge-aware
+//               diffusion-step bias added first                 (ResidualBlock up to the gate)
+//   EPI_RES   : (x + acc + bias) / sqrt(2)                      (ResidualBlock residual path)
+//   EPI_OUT   : x0 = acc + bias, then the q-posterior update x_{t-1} = c1*x0 + c2*x_t + sigma*noise
+#pragma once
+#include "pd_ptx.cuh"
+
+namespace pd {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;  // 16-bit elements per K-block = one 128-byte swizzle atom
+constexpr int kEpiWarps = 8;
+constexpr int kGemmThreads = 32 * (2 + kEpiWarps);
+constexpr uint32_t kTmemCols = 512;
+
+enum EpiKind { EPI_STORE = 0, EPI_GATE = 1, EPI_RES = 2, EPI_OUT = 3 };
+enum OutType { OUT_T = 0, OUT_F16 = 1, OUT_F32 = 2 };
+
+struct GemmShape {
+  int B, T;             // utterances, frames per utterance
+  int m_tiles_per_row;  // ceil(T / 128)
+  int n_tiles;          // N_total / BN
+  int k_per_tap;        // 64-wide K-blocks per tap (or per slab)
+  int taps;             // conv taps (3), slabs (L) or 1
+  int tap_mode;         // 1: K-block group = conv tap (frame shift); 0: K-block group = A slab
+  int dil;              // dilation
+  int a_slab0;          // base 4th coordinate of A
+  int b_row0;           // first weight row of n-tile 0
+  uint32_t idesc;       // tcgen05 instruction descriptor (M=128, N=BN, operand format)
+};
+
+struct EpiArgs {
+  void* out;
+  const void* aux;    // GATE: hoisted cond projection (fp16) of this layer; RES: x_old (T)
+  const float* bias;  // per output column (fp32)
+  const float* sb;    // GATE: step-bias table of this layer, [entry][4][2C] = {all taps, tap0, tap2, -}
+  long long sb_entry_stride;
+  int sb_entry_base, sb_entry_per_b;
+  int ld;       // STORE: slab width of the output; GATE/RES: C
+  float scale;  // STORE: multiplier after bias; RES: 1/sqrt(2)
+  int relu;
+  int out_type;
+  // EPI_OUT
+  int M, Mp;
+  float* x0_out;       // optional [B,1,M,T]
+  float* x_state;      // optional [B,1,M,T], updated in place
+  const float* noise;  // optional [B,1,M,T]
+  void* xin_next;      // optional [B*T, Mp] 16-bit copy of x_{t-1} (next step's input-projection operand)
+  float c1, c2, sigma;
+  unsigned long long seed;
+  unsigned int step_id;
+};
+
+// ------------------------------------------------------------------ small device helpers
+template <typename T> struct Cvt;
+template <> struct Cvt<__nv_bfloat16> {
+  static __device__ __forceinline__ uint32_t pack(float a, float b) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
+  static __device__ __forceinline__ float2 unpack(uint32_t u) {
+    return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
+  }
+  static constexpr uint32_t kFormat = 1;  // tcgen05 kind::f16 operand format: 1 = BF16
+};
+template <> struct Cvt<__half> {
+  static __device__ __forceinline__ uint32_t pack(float a, float b) {
+    __half2 v = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
+  static __device__ __forceinline__ float2 unpack(uint32_t u) { return __half22float2(*reinterpret_cast<__half2*>(&u)); }
+  static constexpr uint32_t kFormat = 0;  // 0 = F16
+};
+
+// sigmoid(g) * tanh(f) = (e^{2f} - 1) / ((1 + e^{-g}) (e^{2f} + 1)); 2 ex2 + 1 rcp on the MUFU pipe.
+__device__ __forceinline__ float gate_fn(float g, float f) {
+  f = fminf(fmaxf(f, -15.f), 15.f);
+  g = fmaxf(g, -30.f);
+  const float e2f = __expf(2.f * f);
+  const float eg = __expf(-g);
+  return __fdividef(e2f - 1.f, (1.f + eg) * (e2f + 1.f));
+}
+
+// Philox4x32-10 (counter-based RNG) + Box-Muller: 4 standard normals per call.
+__device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += 0x9E3779B9u;
+    key.y += 0xBB67AE85u;
+  }
+  return ctr;
+}
+__device__ __forceinline__ float4 philox_normal4(unsigned long long seed, uint32_t step_id, uint32_t c0, uint32_t c1) {
+  const uint4 r = philox4x32(make_uint4(c0, c1, step_id, 0u), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  const float k = 2.3283064365386963e-10f;  // 2^-32
+  const float u0 = ((float)r.x + 1.0f) * k, u1 = (float)r.y * k;
+  const float u2 = ((float)r.z + 1.0f) * k, u3 = (float)r.w * k;
+  const float r0 = sqrtf(-2.f * __logf(fminf(u0, 1.f))), r1 = sqrtf(-2.f * __logf(fminf(u2, 1.f)));
+  float s0, c0f, s1, c1f;
+  __sincosf(6.283185307179586f * u1, &s0, &c0f);
+  __sincosf(6.283185307179586f * u3, &s1, &c1f);
+  return make_float4(r0 * c0f, r0 * s0, r1 * c1f, r1 * s1);
+}
+
+template <int BN> struct GemmCfg {
+  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr uint32_t kABytes = kBlockM * kBlockK * 2;
+  static constexpr uint32_t kBBytes = BN * kBlockK * 2;
+  static constexpr uint32_t kStageBytes = kABytes + kBBytes;
+  // ring + alignment slack + barriers
+  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 + 256;
+};
+
+// ------------------------------------------------------------------ the kernel
+template <int EPI, int BN, typename T>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmShape sh,
+            const EpiArgs ep) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int kStages = Cfg::kStages;
+  static_assert(BN == 256 || BN == 128, "tile width");
+  static_assert(EPI != EPI_GATE || BN == 256, "gate epilogue pairs 128 gate with 128 filter columns");
+  static_assert(EPI != EPI_OUT || BN == 128, "out epilogue is 128 wide");
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);  // SWIZZLE_128B needs 1024-byte alignment
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  uint64_t* full_bar = bars;                  // [kStages]  TMA -> MMA
+  uint64_t* empty_bar = bars + kStages;       // [kStages]  MMA -> TMA
+  uint64_t* tfull_bar = bars + 2 * kStages;   // [2]        MMA -> epilogue
+  uint64_t* tempty_bar = tfull_bar + 2;       // [2]        epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], kEpiWarps);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_m_tiles = sh.B * sh.m_tiles_per_row;
+  const int num_tiles = num_m_tiles * sh.n_tiles;
+  const int k_blocks = sh.k_per_tap * sh.taps;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int n_tile = tile % sh.n_tiles;
+        const int m_tile = tile / sh.n_tiles;
+        const int b = m_tile / sh.m_tiles_per_row;
+        const int t0 = (m_tile % sh.m_tiles_per_row) * kBlockM;
+        for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+          const uint32_t stage = it % kStages, parity = (it / kStages) & 1u;
+          mbar_wait(&empty_bar[stage], parity ^ 1u, 1);
+          uint8_t* sa = smem + stage * Cfg::kStageBytes;
+          uint8_t* sb = sa + Cfg::kABytes;
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          const int grp = kb / sh.k_per_tap, kc = kb - grp * sh.k_per_tap;
+          const int t = sh.tap_mode ? t0 + (grp - (sh.taps >> 1)) * sh.dil : t0;
+          const int slab = sh.tap_mode ? sh.a_slab0 : sh.a_slab0 + grp;
+          tma_load_4d(sa, &tmA, &full_bar[stage], kc * kBlockK, t, b, slab);
+          tma_load_2d(sb, &tmB, &full_bar[stage], kb * kBlockK, sh.b_row0 + n_tile * BN);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      uint32_t it = 0, ti = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
+        const uint32_t as = ti & 1u, aph = (ti >> 1) & 1u;
+        mbar_wait(&tempty_bar[as], aph ^ 1u, 2);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+          const uint32_t stage = it % kStages, parity = (it / kStages) & 1u;
+          mbar_wait(&full_bar[stage], parity, 3);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint64_t adesc = make_sw128_kmajor_desc(sa);
+          const uint64_t bdesc = make_sw128_kmajor_desc(sa + Cfg::kABytes);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k)
+            umma_f16(d_tmem, desc_advance_k(adesc, k), desc_advance_k(bdesc, k), sh.idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs have read it
+        }
+        umma_commit(&tfull_bar[as]);  // accumulator complete
+      }
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const int q = warp & 3;          // TMEM lane quadrant this warp may access
+    const int h = (warp - 2) >> 2;   // which half of the tile's columns this warp handles
+    const int row = q * 32 + lane;
+    uint32_t ti = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
+      const int n_tile = tile % sh.n_tiles;
+      const int m_tile = tile / sh.n_tiles;
+      const int b = m_tile / sh.m_tiles_per_row;
+      const int t = (m_tile % sh.m_tiles_per_row) * kBlockM + row;
+      const bool valid = t < sh.T;
+      const long long n = (long long)b * sh.T + t;  // global frame index
+      const uint32_t as = ti & 1u, aph = (ti >> 1) & 1u;
+      mbar_wait(&tfull_bar[as], aph, 4);
+      tc_fence_after();
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
+
+      if constexpr (EPI == EPI_STORE) {
+        const long long nfr = (long long)sh.B * sh.T;
+#pragma unroll 1
+        for (int c = h * (BN / 2); c < (h + 1) * (BN / 2); c += 32) {
+          uint32_t r[32];
+          tmem_ld_x32(trow + c, r);
+          tmem_ld_wait();
+          if (valid) {
+            const int g = n_tile * BN + c;
+            const int slab = g / ep.ld, within = g - slab * ep.ld;
+            const long long o = ((long long)slab * nfr + n) * ep.ld + within;
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 bv = __ldg(reinterpret_cast<const float4*>(ep.bias + g + j));
+              v[j + 0] = (__uint_as_float(r[j + 0]) + bv.x) * ep.scale;
+              v[j + 1] = (__uint_as_float(r[j + 1]) + bv.y) * ep.scale;
+              v[j + 2] = (__uint_as_float(r[j + 2]) + bv.z) * ep.scale;
+              v[j + 3] = (__uint_as_float(r[j + 3]) + bv.w) * ep.scale;
+            }
+            if (ep.relu) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+            if (ep.out_type == OUT_F32) {
+              float4* dst = reinterpret_cast<float4*>(static_cast<float*>(ep.out) + o);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            } else {
+              uint4* dst = reinterpret_cast<uint4*>(static_cast<uint16_t*>(ep.out) + o);
+              if (ep.out_type == OUT_F16) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  dst[j] = make_uint4(Cvt<__half>::pack(v[8 * j], v[8 * j + 1]), Cvt<__half>::pack(v[8 * j + 2], v[8 * j + 3]),
+                                      Cvt<__half>::pack(v[8 * j + 4], v[8 * j + 5]), Cvt<__half>::pack(v[8 * j + 6], v[8 * j + 7]));
+              } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  dst[j] = make_uint4(Cvt<T>::pack(v[8 * j], v[8 * j + 1]), Cvt<T>::pack(v[8 * j + 2], v[8 * j + 3]),
+                                      Cvt<T>::pack(v[8 * j + 4], v[8 * j + 5]), Cvt<T>::pack(v[8 * j + 6], v[8 * j + 7]));
+              }
+            }
+          }
+        }
+      } else if constexpr (EPI == EPI_GATE) {
+        const int C = ep.ld, C2 = 2 * ep.ld;
+        const int entry = ep.sb_entry_base + b * ep.sb_entry_per_b;
+        const float* sb_all = ep.sb + (long long)entry * ep.sb_entry_stride + n_tile * 256;
+        const float* sb_t0 = sb_all + C2;
+        const float* sb_t2 = sb_all + 2 * C2;
+        const bool edge_lo = t < sh.dil;            // tap 0 reads x[t - dil] which is padding
+        const bool edge_hi = t + sh.dil >= sh.T;    // tap 2 reads x[t + dil] which is padding
+        const __half* cp_row = static_cast<const __half*>(ep.aux) + n * C2 + n_tile * 256;
+        uint16_t* out_row = static_cast<uint16_t*>(ep.out) + n * C + n_tile * 128;
+#pragma unroll 1
+        for (int i = h * 64; i < h * 64 + 64; i += 16) {
+          uint32_t rg[16], rf[16];
+          tmem_ld_x16(trow + i, rg);
+          tmem_ld_x16(trow + 128 + i, rf);
+          tmem_ld_wait();
+          if (valid) {
+            uint4 cg[2], cf[2];
+            cg[0] = __ldg(reinterpret_cast<const uint4*>(cp_row + i));
+            cg[1] = __ldg(reinterpret_cast<const uint4*>(cp_row + i + 8));
+            cf[0] = __ldg(reinterpret_cast<const uint4*>(cp_row + 128 + i));
+            cf[1] = __ldg(reinterpret_cast<const uint4*>(cp_row + 128 + i + 8));
+            const uint32_t* cgw = reinterpret_cast<const uint32_t*>(cg);
+            const uint32_t* cfw = reinterpret_cast<const uint32_t*>(cf);
+            uint32_t packed[8];
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) {
+              const float2 pg = Cvt<__half>::unpack(cgw[j >> 1]);
+              const float2 pf = Cvt<__half>::unpack(cfw[j >> 1]);
+              float zg0 = __uint_as_float(rg[j]) + pg.x + __ldg(sb_all + i + j);
+              float zg1 = __uint_as_float(rg[j + 1]) + pg.y + __ldg(sb_all + i + j + 1);
+              float zf0 = __uint_as_float(rf[j]) + pf.x + __ldg(sb_all + 128 + i + j);
+              float zf1 = __uint_as_float(rf[j + 1]) + pf.y + __ldg(sb_all + 128 + i + j + 1);
+              if (edge_lo) {
+                zg0 -= __ldg(sb_t0 + i + j);
+                zg1 -= __ldg(sb_t0 + i + j + 1);
+                zf0 -= __ldg(sb_t0 + 128 + i + j);
+                zf1 -= __ldg(sb_t0 + 128 + i + j + 1);
+              }
+              if (edge_hi) {
+                zg0 -= __ldg(sb_t2 + i + j);
+                zg1 -= __ldg(sb_t2 + i + j + 1);
+                zf0 -= __ldg(sb_t2 + 128 + i + j);
+                zf1 -= __ldg(sb_t2 + 128 + i + j + 1);
+              }
+              packed[j >> 1] = Cvt<T>::pack(gate_fn(zg0, zf0), gate_fn(zg1, zf1));
+            }
+            uint4* dst = reinterpret_cast<uint4*>(out_row + i);
+            dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+            dst[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+          }
+        }
+      } else if constexpr (EPI == EPI_RES) {
+        const int C = ep.ld;
+#pragma unroll 1
+        for (int c = h * (BN / 2); c < (h + 1) * (BN / 2); c += 32) {
+          uint32_t r[32];
+          tmem_ld_x32(trow + c, r);
+          tmem_ld_wait();
+          if (valid) {
+            const int g = n_tile * BN + c;
+            const uint4* xo = reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(ep.aux) + n * C + g);
+            uint4* dst = reinterpret_cast<uint4*>(static_cast<uint16_t*>(ep.out) + n * C + g);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 xv = __ldg(xo + j);
+              const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
+              uint32_t ow[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const float2 x2 = Cvt<T>::unpack(xw[u]);
+                const int col = 8 * j + 2 * u;
+                const float a0 = (x2.x + __uint_as_float(r[col]) + __ldg(ep.bias + g + col)) * ep.scale;
+                const float a1 = (x2.y + __uint_as_float(r[col + 1]) + __ldg(ep.bias + g + col + 1)) * ep.scale;
+                ow[u] = Cvt<T>::pack(a0, a1);
+              }
+              dst[j] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+            }
+          }
+        }
+      } else {  // EPI_OUT
+        const int M = ep.M;
+#pragma unroll 1
+        for (int c = h * 64; c < h * 64 + 64; c += 32) {
+          uint32_t r[32];
+          tmem_ld_x32(trow + c, r);
+          tmem_ld_wait();
+          if (valid && c < M) {
+            float xn[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int g = c + j;  // mel bin; M is a multiple of 32 so the whole chunk is valid
+              const long long idx = ((long long)b * M + g) * sh.T + t;
+              const float x0 = __uint_as_float(r[j]) + __ldg(ep.bias + g);
+              if (ep.x0_out) ep.x0_out[idx] = x0;
+              xn[j] = x0;
+            }
+            if (ep.x_state) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                float4 nz = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ep.sigma != 0.f && ep.noise == nullptr)
+                  nz = philox_normal4(ep.seed, ep.step_id, (uint32_t)n, (uint32_t)((c + j) >> 2));
+                const float nzv[4] = {nz.x, nz.y, nz.z, nz.w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  const long long idx = ((long long)b * M + (c + j + u)) * sh.T + t;
+                  float v = ep.c1 * xn[j + u] + ep.c2 * ep.x_state[idx];
+                  if (ep.sigma != 0.f) v += ep.sigma * (ep.noise ? __ldg(ep.noise + idx) : nzv[u]);
+                  ep.x_state[idx] = v;
+                  xn[j + u] = v;
+                }
+              }
+              if (ep.xin_next) {
+                uint4* dst = reinterpret_cast<uint4*>(static_cast<uint16_t*>(ep.xin_next) + n * ep.Mp + c);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  dst[j] = make_uint4(Cvt<T>::pack(xn[8 * j], xn[8 * j + 1]), Cvt<T>::pack(xn[8 * j + 2], xn[8 * j + 3]),
+                                      Cvt<T>::pack(xn[8 * j + 4], xn[8 * j + 5]), Cvt<T>::pack(xn[8 * j + 6], xn[8 * j + 7]));
+              }
+            }
+          }
+        }
+      }
+
+      // this warp has finished reading accumulator stage `as`
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+}  // namespace pd

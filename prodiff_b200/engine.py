@@ -1,0 +1,152 @@
+"""Host-side owner of the C-ABI handles: packed weights (pd_model) and per-shape plans (pd_plan).
+
+PyTorch is plumbing here: it owns device memory (packed-weight block and scratch come from the caching allocator as
+uint8 tensors) and the current stream; every kernel is launched by the C library.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+
+STATE_HEAD = ["input_projection.weight", "input_projection.bias", "mlp.0.weight", "mlp.0.bias", "mlp.2.weight",
+              "mlp.2.bias", "skip_projection.weight", "skip_projection.bias", "output_projection.weight",
+              "output_projection.bias"]
+STATE_LAYER = ["dilated_conv.weight", "dilated_conv.bias", "diffusion_projection.weight", "diffusion_projection.bias",
+               "conditioner_projection.weight", "conditioner_projection.bias", "output_projection.weight",
+               "output_projection.bias"]
+
+
+def state_key_order(residual_layers: int):
+    """The order pd_model_create expects (include/prodiff_b200.h)."""
+    keys = list(STATE_HEAD)
+    for i in range(residual_layers):
+        keys += [f"residual_layers.{i}.{k}" for k in STATE_LAYER]
+    return keys
+
+
+def _require_b200(device: torch.device) -> None:
+    if device.type != "cuda":
+        raise RuntimeError(f"prodiff_b200 runs only on a CUDA sm_100 device (got a tensor on '{device}'); "
+                           "there is no CPU fallback")
+    major, _ = torch.cuda.get_device_capability(device)
+    if major != 10:
+        raise RuntimeError(f"prodiff_b200 needs compute capability 10.x (B200), found {major}.x; no fallback path")
+
+
+def _aligned_bytes(nbytes: int, device) -> torch.Tensor:
+    buf = torch.empty(nbytes + 1024, dtype=torch.uint8, device=device)
+    off = (-buf.data_ptr()) % 1024
+    return buf[off:off + nbytes]
+
+
+class Plan:
+    def __init__(self, engine: "Engine", B: int, T: int, entries: int):
+        lib = engine.lib
+        self.engine, self.B, self.T, self.entries = engine, B, T, entries
+        nbytes = lib.pd_workspace_bytes(engine.handle, B, T, entries)
+        if nbytes == 0:
+            raise RuntimeError(f"prodiff_b200: bad plan shape B={B} T={T} entries={entries}")
+        self.workspace = _aligned_bytes(nbytes, engine.device)
+        h = C.c_void_p()
+        _lib.check(lib.pd_plan_create(engine.handle, B, T, entries, self.workspace.data_ptr(), nbytes, C.byref(h)),
+                   "pd_plan_create")
+        self.handle = h
+
+    def buffer(self, name: str) -> torch.Tensor:
+        """uint8 view of a named scratch buffer (tests only)."""
+        off, n = C.c_size_t(), C.c_size_t()
+        _lib.check(self.engine.lib.pd_plan_buffer(self.handle, name.encode(), C.byref(off), C.byref(n)), "pd_plan_buffer")
+        return self.workspace[off.value:off.value + n.value]
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self.engine.lib.pd_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+class Engine:
+    """Packed weights of one DiffNet on one device + a small cache of plans."""
+
+    MAX_PLANS = 4
+
+    def __init__(self, cfg: dict, state: Dict[str, torch.Tensor], device: torch.device, operand_dtype: str = "bf16"):
+        _require_b200(device)
+        self.lib = _lib.load()
+        self.device = device
+        self.operand_dtype = operand_dtype
+        dt = {"bf16": _lib.PD_BF16, "fp16": _lib.PD_FP16}[operand_dtype]
+        self.cfg = _lib.pd_config(cfg["in_dims"], cfg["hidden_size"], cfg["residual_layers"], cfg["residual_channels"],
+                                  cfg["dilation_cycle_length"], dt)
+        keys = state_key_order(cfg["residual_layers"])
+        with torch.cuda.device(device):
+            tensors = [state[k].detach().to(device=device, dtype=torch.float32).contiguous() for k in keys]
+            nbytes = self.lib.pd_packed_bytes(C.byref(self.cfg))
+            if nbytes == 0:
+                raise RuntimeError(f"prodiff_b200: unsupported DiffNet config: {self.lib.pd_last_error().decode()}")
+            self.packed = _aligned_bytes(nbytes, device)
+            ptrs = (C.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+            h = C.c_void_p()
+            stream = torch.cuda.current_stream(device).cuda_stream
+            _lib.check(self.lib.pd_model_create(C.byref(self.cfg), ptrs, len(tensors), self.packed.data_ptr(), nbytes,
+                                                stream, C.byref(h)), "pd_model_create")
+            # the pack kernels read `tensors` asynchronously: keep them alive until the stream has run them
+            torch.cuda.current_stream(device).synchronize()
+        self.handle = h
+        self.plans: Dict[Tuple[int, int, int], Plan] = {}
+
+    def plan(self, B: int, T: int, entries: int) -> Plan:
+        key = (B, T, entries)
+        p = self.plans.get(key)
+        if p is None:
+            if len(self.plans) >= self.MAX_PLANS:
+                self.plans.pop(next(iter(self.plans)))
+            with torch.cuda.device(self.device):
+                p = Plan(self, B, T, entries)
+            self.plans[key] = p
+        return p
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def denoise(self, spec: torch.Tensor, step: torch.Tensor, cond_bth: torch.Tensor) -> torch.Tensor:
+        """spec [B,1,M,T] fp32, step [B] fp32, cond_bth [B,T,H] fp32 contiguous -> [B,1,M,T] fp32."""
+        B, _, M, T = spec.shape
+        p = self.plan(B, T, B)
+        out = torch.empty_like(spec)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.pd_cond_project(p.handle, cond_bth.data_ptr(), self._stream()), "pd_cond_project")
+            _lib.check(self.lib.pd_denoise(p.handle, spec.data_ptr(), step.data_ptr(), out.data_ptr(), self._stream()),
+                       "pd_denoise")
+        return out
+
+    def sample(self, cond_bth: torch.Tensor, x: torch.Tensor, t_list: Sequence[int], coef1, coef2, logvar,
+               noise: Optional[torch.Tensor] = None, seed: int = 0, x0_trace: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """The whole reverse loop, in place on x [B,1,M,T] (in: x_T, out: x_0)."""
+        B, _, M, T = x.shape
+        K = len(t_list)
+        p = self.plan(B, T, K)
+        tl = (C.c_int32 * K)(*[int(t) for t in t_list])
+        n = len(coef1)
+        fa = lambda a: (C.c_float * n)(*[float(v) for v in a])
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.pd_sample(p.handle, cond_bth.data_ptr(), x.data_ptr(),
+                                          noise.data_ptr() if noise is not None else None, C.c_uint64(seed & (2 ** 64 - 1)),
+                                          K, tl, fa(coef1), fa(coef2), fa(logvar), n,
+                                          x0_trace.data_ptr() if x0_trace is not None else None, self._stream()), "pd_sample")
+        return x
+
+    def __del__(self):
+        try:
+            self.plans.clear()
+            if getattr(self, "handle", None):
+                self.lib.pd_model_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
