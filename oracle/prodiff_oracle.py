@@ -123,7 +123,7 @@ def num_layers(state: State) -> int:
     return n
 
 
-def residual_block(state: State, i: int, dilation: int, x, conditioner, diffusion_step):
+def residual_block(state: State, i: int, dilation: int, x, conditioner, diffusion_step, trace: Optional[dict] = None):
     """wavenet.py:60-72"""
     p = f"residual_layers.{i}."
     d = F.linear(diffusion_step, state[p + "diffusion_projection.weight"],
@@ -134,6 +134,9 @@ def residual_block(state: State, i: int, dilation: int, x, conditioner, diffusio
                  padding=dilation, dilation=dilation) + c
     gate, filt = torch.chunk(y, 2, dim=1)
     y = torch.sigmoid(gate) * torch.tanh(filt)
+    if trace is not None:
+        trace.setdefault("cond_proj", []).append(c)
+        trace.setdefault("gated", []).append(y)
     y = F.conv1d(y, state[p + "output_projection.weight"], state[p + "output_projection.bias"])
     residual, skip = torch.chunk(y, 2, dim=1)
     return (x + residual) / math.sqrt(2.0), skip
@@ -156,7 +159,7 @@ def wavenet_forward(state: State, spec, diffusion_step, cond, dilation_cycle_len
         trace["x_in"] = x
         trace["x"] = []
     for i in range(L):
-        x, s = residual_block(state, i, 2 ** (i % dilation_cycle_length), x, cond, e)
+        x, s = residual_block(state, i, 2 ** (i % dilation_cycle_length), x, cond, e, trace)
         skip.append(s)
         if trace is not None:
             trace["x"].append(x)

@@ -1,0 +1,29 @@
+"""prodiff_b200 -- B200-native implementation of the ProDiff mel sampling hot path.
+
+Public surface (mirrors the reference's module API for this path):
+
+    WaveNet(in_dims, hidden_size, residual_layers, residual_channels, dilation_cycle_length).forward(spec, step, cond)
+    GaussianDiffusion(out_dims, denoise_fn, timesteps, time_scale, betas, schedule_type, max_beta, spec_min, spec_max)
+        .forward(cond, src_spec=None, gt_spec=None, infer_step=4, infer=False)
+
+``install()`` swaps these classes into the reference's own modules so that ``ProDiffTeacher``, the SVS inferer
+(``handler/infer/handler.py``), ``main.py infer`` and the vocoder hand-off run unchanged on top of them.
+"""
+from .wavenet import WaveNet
+from .diffusion import GaussianDiffusion
+from .synth import DiffNetConfig
+
+__version__ = "0.1.0"
+
+
+def install():
+    """Replace the reference classes in-place (call before ``modules.svs.prodiff_teacher`` is imported)."""
+    import importlib
+    wn = importlib.import_module("modules.decoder.wavenet")
+    gd = importlib.import_module("modules.diffusion.prodiff")
+    wn.WaveNet = WaveNet
+    gd.GaussianDiffusion = GaussianDiffusion
+    return wn, gd
+
+
+__all__ = ["WaveNet", "GaussianDiffusion", "DiffNetConfig", "install"]

@@ -36,7 +36,71 @@ def check_gemm(dtype="bf16", B=2, T=300, Cin=256, taps=3, dil=2, N=512):
                 worst_row=int(err.max(dim=1).values.argmax()), worst_col=int(err.max(dim=0).values.argmax()))
 
 
+def check_layers(dtype="bf16", B=2, T=300, L=4, C=256, cycle=2, M=128):
+    """Full denoiser, compared buffer by buffer with the oracle's trace to localise a wrong stage."""
+    import torch
+    import prodiff_b200 as pb
+    from prodiff_b200 import synth
+    from oracle import prodiff_oracle as oracle
+    cfg = synth.DiffNetConfig(M, 256, L, C, cycle)
+    state = synth.make_state(cfg, 7, "kaiming")
+    cond, x_T, _ = synth.make_inputs(cfg, B, T, 1, 8)
+    steps = torch.arange(B, dtype=torch.float32) * 1.5 + 1.0
+    tr = {}
+    with torch.no_grad():
+        ref = oracle.wavenet_forward(state, x_T, steps, cond.transpose(1, 2), cycle, trace=tr)
+    wn = pb.WaveNet(M, 256, L, C, cycle, operand_dtype=dtype)
+    wn.load_state_dict(state)
+    wn = wn.cuda().eval()
+    with torch.no_grad():
+        out = wn(x_T.cuda(), steps.cuda(), cond.cuda().transpose(1, 2))
+    torch.cuda.synchronize()
+    plan = next(iter(wn.engine().plans.values()))
+    tdt = torch.bfloat16 if dtype == "bf16" else torch.float16
+    N = B * T
+    res = {}
+    def unperm(packed):  # packed gate-paired column order -> original channel order
+        idx = torch.tensor([((p & 255) >> 7) * C + (p >> 8) * 128 + (p & 127) for p in range(2 * C)])
+        o = torch.empty_like(packed)
+        o[..., idx] = packed
+        return o
+    cp = plan.buffer("cp").view(torch.float16).view(L, N, 2 * C).float().cpu()
+    sb = plan.buffer("sb").view(torch.float32).view(-1, L, 4, 2 * C).cpu()
+    y = plan.buffer("ybuf").view(tdt).view(L, N, C).float().cpu()
+    for l in range(L):
+        p = f"residual_layers.{l}."
+        c_ref = (tr["cond_proj"][l] + state[p + "dilated_conv.bias"][None, :, None]).transpose(1, 2).reshape(N, 2 * C)
+        res[f"cp{l}"] = float((unperm(cp[l]) - c_ref).abs().max())
+        y_ref = tr["gated"][l].transpose(1, 2).reshape(N, C)
+        res[f"y{l}"] = float((y[l] - y_ref).abs().max())
+    # step-bias table: slot 0 of entry b, layer 0 == W_dil . d summed over taps
+    e = oracle.sinusoidal_pos_emb(steps, C); e = torch.nn.functional.linear(e, state["mlp.0.weight"], state["mlp.0.bias"])
+    e = oracle.mish(e); e = torch.nn.functional.linear(e, state["mlp.2.weight"], state["mlp.2.bias"])
+    d0 = torch.nn.functional.linear(e, state["residual_layers.0.diffusion_projection.weight"], state["residual_layers.0.diffusion_projection.bias"])
+    w = state["residual_layers.0.dilated_conv.weight"]
+    s_all = torch.einsum("ock,bc->bo", w, d0)
+    res["sb_all"] = float((unperm(sb[:B, 0, 0]) - s_all).abs().max())
+    res["sb_tap0"] = float((unperm(sb[:B, 0, 1]) - torch.einsum("oc,bc->bo", w[:, :, 0], d0)).abs().max())
+    xl = plan.buffer("xa" if L % 2 == 0 else "xb").view(tdt).view(N, C).float().cpu()
+    res["x_last"] = float((xl - tr["x"][-1].transpose(1, 2).reshape(N, C)).abs().max())
+    res["out"] = float((out.cpu() - ref).abs().max())
+    res["out_mean"] = float((out.cpu() - ref).abs().mean())
+    res["ref_std"] = float(ref.std())
+    res["nan"] = int(torch.isnan(out).sum())
+    return res
+
+
+def check_pytest(expr):
+    r = subprocess.run([sys.executable, "-m", "pytest", "tests", "-x", "-q", "-m", "gpu", "-k", expr], capture_output=True,
+                       text=True, cwd=ROOT, timeout=900)
+    return dict(rc=r.returncode, tail=(r.stdout + r.stderr)[-1200:])
+
+
 CHECKS = {
+    "layers_bf16": lambda: check_layers("bf16"),
+    "layers_fp16": lambda: check_layers("fp16"),
+    "layers_c512": lambda: check_layers("bf16", B=1, T=200, L=3, C=512, cycle=3),
+    "layers_m64": lambda: check_layers("bf16", B=1, T=100, L=2, C=256, cycle=1, M=64),
     "gemm_k1": lambda: check_gemm(B=1, T=128, Cin=64, taps=1, dil=1, N=256),
     "gemm_k4": lambda: check_gemm(B=1, T=128, Cin=256, taps=1, dil=1, N=256),
     "gemm_multi_tile": lambda: check_gemm(B=3, T=300, Cin=256, taps=1, dil=1, N=512),
