@@ -1,0 +1,333 @@
+"""Benchmark of the ProDiff sampling hot path (BASELINE.json metric: denoised mel frames / second).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+           bench.py --gpus N --steps K --warmup W
+
+One "step" = one full sampling call (cond projection + all reverse steps + posterior updates) over one synthetic batch.
+Workload at every N: BASELINE.json configs[1] per GPU -- DiffNet 20 layers x 256 ch, 4-step ProDiff (vpsde, max_beta 40),
+64 utterances x 1000 frames x 128 mel, random-init weights (seeded, output_projection ~ N(0, 0.02)).  Weak scaling:
+utterances are independent, every rank samples its own 64 x 1000 shard, no collective on the data path.
+
+Printed JSON (rank 0, one line): see the keys below.  `value` is timed with CUDA events with the inputs resident in
+HBM; `e2e` goes through the public module API from pinned HOST buffers with the H2D/D2H copies inside the timed
+region; `roofline` is the dominant kernel (dilated conv + gate GEMM) timed with per-launch CUDA events in a second
+pass over the same steps; `cpu_baseline` is the CPU oracle port (the reference's algorithm in PyTorch fp32) on the host.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.dont_write_bytecode = True
+
+import torch  # noqa: E402
+
+WORKLOAD = dict(name="configs[1]: DiffNet 20x256, 4-step ProDiff, 64 utt x 1000 frames x 128 mel per GPU",
+                in_dims=128, hidden=256, layers=20, channels=256, cycle=1, K=4, timesteps=4, schedule="vpsde",
+                max_beta=40.0, B=64, T=1000)
+FRAME_RATE = 44100.0 / 512.0  # mel frames per second of audio (handler/base_config.yaml:10-11)
+
+
+def flops_per_frame(M, H, L, C, K):
+    """F_frame(K) = K (4MC + 16LC^2 + 2C^2) + 4LHC."""
+    return K * (4 * M * C + 16 * L * C * C + 2 * C * C) + 4 * L * H * C
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(tflops=float(d.get("bf16_tflops_sustained", 1415.4)), hbm=float(d.get("hbm_gbs", 6551.0)), source="measured")
+    return dict(tflops=1400.0, hbm=6650.0, source="fallback")  # B200_PROFILING.md fallback (sustained)
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz, self._halt = index, [], set(), None, threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap", nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake"}
+        while not self._halt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=1.0)
+        s = sorted(self.samples)
+        return dict(sm_mhz=(s[len(s) // 2] if s else None), sm_max_mhz=self.max_mhz, reasons=sorted(self.reasons),
+                    samples=len(s))
+
+
+def build_model(device, operand_dtype="bf16"):
+    import prodiff_b200 as pb
+    from prodiff_b200 import synth
+    w = WORKLOAD
+    cfg = synth.DiffNetConfig(w["in_dims"], w["hidden"], w["layers"], w["channels"], w["cycle"])
+    state = synth.make_state(cfg, 1234, "trained")
+    wn = pb.WaveNet(cfg.in_dims, cfg.hidden_size, cfg.residual_layers, cfg.residual_channels, cfg.dilation_cycle_length,
+                    operand_dtype=operand_dtype)
+    wn.load_state_dict(state)
+    gd = pb.GaussianDiffusion(cfg.in_dims, wn, timesteps=w["timesteps"], time_scale=1000, schedule_type=w["schedule"],
+                              max_beta=w["max_beta"], spec_min=[-12.0], spec_max=[0.0])
+    return gd.to(device).eval(), cfg, state
+
+
+def cpu_baseline(sample_B=8, repeats=3, threads=None):
+    """The reference's algorithm (oracle port, PyTorch fp32 CPU ops) on the host cores, bounded sample."""
+    from oracle import prodiff_oracle as oracle
+    from prodiff_b200 import synth
+    w = WORKLOAD
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    torch.set_flush_denormal(True)
+    cfg = synth.DiffNetConfig(w["in_dims"], w["hidden"], w["layers"], w["channels"], w["cycle"])
+    state = synth.make_state(cfg, 1234, "trained")
+    tables = oracle.diffusion_tables(w["timesteps"], w["schedule"], w["max_beta"])
+    cond, x_T, noise = synth.make_inputs(cfg, sample_B, w["T"], w["K"], 77)
+    oracle.sample(state, tables, cond[:1, :200], x_T[:1, :, :, :200], noise[:, :1, :, :, :200], w["K"], w["timesteps"], w["cycle"])
+    best = float("inf")
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        oracle.sample(state, tables, cond, x_T, noise, w["K"], w["timesteps"], w["cycle"])
+        best = min(best, time.perf_counter() - t0)
+    return dict(value=sample_B * w["T"] / best, unit="mel frames/s", cores=threads, kind="port",
+                sample=f"{sample_B} utt x {w['T']} frames, K={w['K']}, best of {repeats} (full-size DiffNet, fp32, torch CPU ops, "
+                       f"{threads} threads, flush-denormal on)", seconds=best)
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference algorithm on the host CPU (the reference has no GPU-independent install: it is
+    plain Python modules on torch ops, restated in oracle/ and pinned bit-exact against /root/reference here)."""
+    if rank != 0:
+        return
+    w = WORKLOAD
+    from oracle import prodiff_oracle as oracle
+    from prodiff_b200 import synth
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    torch.set_flush_denormal(True)
+    sample_B = 2
+    cfg = synth.DiffNetConfig(w["in_dims"], w["hidden"], w["layers"], w["channels"], w["cycle"])
+    state = synth.make_state(cfg, 1234, "trained")
+    tables = oracle.diffusion_tables(w["timesteps"], w["schedule"], w["max_beta"])
+    cond, x_T, noise = synth.make_inputs(cfg, sample_B, w["T"], w["K"], 77)
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    for _ in range(warmup):
+        oracle.sample(state, tables, cond, x_T, noise, w["K"], w["timesteps"], w["cycle"])
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        oracle.sample(state, tables, cond, x_T, noise, w["K"], w["timesteps"], w["cycle"])
+    dt = (time.perf_counter() - t0) / steps
+    v = sample_B * w["T"] / dt
+    sample = f"each step = {sample_B} utt x {w['T']} frames, K={w['K']} (bounded sample of the 64 x 1000 workload)"
+    print(json.dumps({
+        "impl": "reference", "metric": "denoised mel frames/sec", "value": v, "unit": "mel frames/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": w["name"], "sample": sample},
+        "cpu_baseline": {"value": v, "unit": "mel frames/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "mel frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "rtf_x_realtime": v / FRAME_RATE,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    args.warmup = max(args.warmup, 3)
+    import torch.distributed as dist
+    from prodiff_b200 import _lib
+    device = torch.device("cuda", local_rank)
+    torch.cuda.set_device(device)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    w = WORKLOAD
+    B, T, K, M, H = w["B"], w["T"], w["K"], w["in_dims"], w["hidden"]
+    gd, cfg, _ = build_model(device, args.dtype)
+    from prodiff_b200 import synth
+    cond_h, xT_h, _ = synth.make_inputs(cfg, B, T, 1, 100 + rank)
+    cond_d = cond_h.to(device)
+    lib = _lib.load()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident(i):
+        with torch.no_grad():
+            return gd(cond_d, infer_step=K, infer=True, seed=1000 + i)
+
+    # ---------------- value: inputs resident in HBM
+    for i in range(args.warmup):
+        step_resident(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    lib.pd_launch_count(1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step_resident(i)
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    launches = int(lib.pd_launch_count(1))
+    ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(ms.item()) / args.steps
+    frames_per_step = B * T * world
+    value = frames_per_step / (ms_per_step * 1e-3)
+
+    # ---------------- e2e: host buffers -> public API -> host result, copies inside the timed region
+    cond_pin = cond_h.pin_memory()
+    mel_pin = torch.empty(B, T, M, dtype=torch.float32).pin_memory()
+    # two-deep software pipeline: the H2D of step i+1 and the D2H of step i-1 overlap the sampling of step i
+    copy_s = torch.cuda.Stream(device)
+    comp_s = torch.cuda.current_stream(device)
+    cond_bufs = [torch.empty_like(cond_d), torch.empty_like(cond_d)]
+    mel_bufs = [torch.empty(B, T, M, device=device), torch.empty(B, T, M, device=device)]
+    h2d_done = [torch.cuda.Event(), torch.cuda.Event()]
+    comp_done = [torch.cuda.Event(), torch.cuda.Event()]
+    d2h_done = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def e2e_loop(n):
+        with torch.cuda.stream(copy_s):
+            cond_bufs[0].copy_(cond_pin, non_blocking=True)
+            h2d_done[0].record(copy_s)
+        for i in range(n):
+            cur = i & 1
+            comp_s.wait_event(h2d_done[cur])
+            if i >= 2:
+                comp_s.wait_event(d2h_done[cur])  # mel_bufs[cur] is free again
+            with torch.no_grad():
+                mel = gd(cond_bufs[cur], infer_step=K, infer=True, seed=2000 + i)
+            mel_bufs[cur].copy_(mel)  # [B,T,M]-contiguous result for the host
+            comp_done[cur].record(comp_s)
+            with torch.cuda.stream(copy_s):
+                if i + 1 < n:
+                    if i >= 1:
+                        copy_s.wait_event(comp_done[cur ^ 1])  # cond_bufs[cur^1] no longer read by step i-1
+                    cond_bufs[cur ^ 1].copy_(cond_pin, non_blocking=True)
+                    h2d_done[cur ^ 1].record(copy_s)
+                copy_s.wait_event(comp_done[cur])
+                mel_pin.copy_(mel_bufs[cur], non_blocking=True)
+                d2h_done[cur].record(copy_s)
+        comp_s.wait_stream(copy_s)
+
+    e2e_loop(3)
+    barrier()
+    e0.record()
+    e2e_loop(args.steps)
+    e1.record()
+    barrier()
+    ms2 = torch.tensor([e0.elapsed_time(e1)], device=device)
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    e2e_value = frames_per_step / (float(ms2.item()) / args.steps * 1e-3)
+    h2d_bytes = cond_pin.numel() * 4 * world
+    d2h_bytes = mel_pin.numel() * 4 * world
+
+    # ---------------- roofline of the dominant kernel: per-launch CUDA events, second pass over the same steps
+    peaks = measured_peaks()
+    roofline = None
+    kinds = {}
+    _lib.profile_begin()
+    prof_steps = min(args.steps, 5)
+    for i in range(prof_steps):
+        step_resident(i)
+    torch.cuda.synchronize()
+    kinds = _lib.profile_end()
+    if world > 1:
+        dist.barrier()
+    C, L = w["channels"], w["layers"]
+    if "dilated_conv+gate" in kinds:
+        tot_ms, n = kinds["dilated_conv+gate"]
+        flops_per_launch = 2.0 * (B * T) * (3 * C) * (2 * C)  # 12 C^2 per frame x frames per launch
+        achieved = flops_per_launch / (tot_ms / n * 1e-3) / 1e12
+        all_ms = sum(v[0] for v in kinds.values())
+        roofline = {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
+                    "frac": achieved / peaks["tflops"], "traffic": None, "kernel": "gemm_kernel<EPI_GATE,256> (dilated conv + gate)",
+                    "avg_launch_us": tot_ms / n * 1e3, "launches": n, "share_of_gemm_time": tot_ms / all_ms,
+                    "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']})",
+                    "per_kernel_ms_per_step": {k: v[0] / prof_steps for k, v in kinds.items()}}
+
+    if rank == 0:
+        F = flops_per_frame(M, H, L, C, K)
+        out = {
+            "metric": "denoised mel frames/sec", "value": value, "unit": "mel frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": w["name"], "parallelism": f"batch-sharded x{world}, no data-path collective",
+                       "l2": "per-step working set ~2.1 GB (cond projection 1.3 GB + gated activations 0.66 GB) >> 126 MB L2, no flush needed",
+                       "init": "seeded Kaiming convs, output_projection.weight ~ N(0,0.02)", "noise": "in-kernel Philox4x32-10"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "mel frames/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                    "how": "GaussianDiffusion.forward(infer=True) from pinned host cond to pinned host mel, copies double-buffered on a copy stream"},
+            "gpu_launches": launches,
+            "roofline": roofline,
+            "job_tensor_frac": value / world * F / 1e12 / peaks["tflops"],
+            "flops_per_frame": F,
+            "rtf_x_realtime": value / FRAME_RATE,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            out["cpu_baseline"] = cpu_baseline()
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -102,6 +102,14 @@ int pd_sample(pd_plan* p, const float* cond, float* x, const float* noise, uint6
 /* Number of kernels of this library launched by the calling thread since the last reset (bench evidence). */
 long long pd_launch_count(int reset);
 
+/* Per-kernel timing for bench.py's roofline leg: between begin and end every GEMM launch of the calling thread is
+ * bracketed by a CUDA-event pair on its stream.  pd_profile_end synchronises and returns, per kernel kind, the summed
+ * milliseconds and the launch count.  Kinds: 0 cond_proj, 1 input_proj, 2 dilated_conv+gate, 3 res_proj, 4 skip_sum,
+ * 5 skip_proj, 6 output_proj+posterior, 7 debug. */
+#define PD_N_KINDS 8
+int pd_profile_begin(void);
+int pd_profile_end(float* ms_by_kind, int* count_by_kind, int n_kinds);
+
 /* Introspection for tests: byte offset/size of a named scratch buffer inside the plan's workspace.
  * Names: "cond16","cp","xin","xa","xb","ybuf","s1","s2","steps","emb","dvec","sb". Returns 0 if found. */
 int pd_plan_buffer(const pd_plan* p, const char* name, size_t* offset, size_t* bytes);

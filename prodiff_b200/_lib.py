@@ -17,7 +17,7 @@ PD_BF16, PD_FP16 = 0, 1
 SYMBOLS = [
     "pd_state_count", "pd_last_error", "pd_abi_version", "pd_packed_bytes", "pd_model_create", "pd_model_destroy",
     "pd_workspace_bytes", "pd_plan_create", "pd_plan_destroy", "pd_cond_project", "pd_denoise", "pd_sample",
-    "pd_launch_count", "pd_plan_buffer", "pd_debug_gemm",
+    "pd_launch_count", "pd_plan_buffer", "pd_debug_gemm", "pd_profile_begin", "pd_profile_end",
 ]
 
 
@@ -59,10 +59,28 @@ def load() -> C.CDLL:
     lib.pd_plan_buffer.argtypes = [vp, cp, P(sz), P(sz)]; lib.pd_plan_buffer.restype = C.c_int
     lib.pd_debug_gemm.argtypes = [C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp, vp, vp]
     lib.pd_debug_gemm.restype = C.c_int
+    lib.pd_profile_begin.argtypes = []; lib.pd_profile_begin.restype = C.c_int
+    lib.pd_profile_end.argtypes = [P(C.c_float), P(C.c_int), C.c_int]; lib.pd_profile_end.restype = C.c_int
     if lib.pd_abi_version() != 1:
         raise RuntimeError(f"prodiff_b200: ABI version mismatch ({lib.pd_abi_version()} != 1); rebuild the library")
     _lib = lib
     return lib
+
+
+KIND_NAMES = ["cond_proj", "input_proj", "dilated_conv+gate", "res_proj", "skip_sum", "skip_proj", "output_proj+posterior",
+              "debug"]
+
+
+def profile_begin() -> None:
+    check(load().pd_profile_begin(), "pd_profile_begin")
+
+
+def profile_end() -> dict:
+    """{kind name: (total ms, launches)} for every GEMM launched since profile_begin()."""
+    ms = (C.c_float * 8)()
+    cnt = (C.c_int * 8)()
+    check(load().pd_profile_end(ms, cnt, 8), "pd_profile_end")
+    return {KIND_NAMES[i]: (float(ms[i]), int(cnt[i])) for i in range(8) if cnt[i]}
 
 
 def check(rc: int, what: str) -> None:

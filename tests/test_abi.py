@@ -1,0 +1,88 @@
+"""CPU-only: the C-ABI library builds for sm_100a, loads, and exports every symbol include/prodiff_b200.h declares.
+No compute call is made here (there is no GPU); argument validation that does not touch the device is exercised."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "prodiff_b200.h")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as g
+    g.build()
+    from prodiff_b200 import _lib
+    return _lib.load()
+
+
+def _declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(pd_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_header_symbols_exported(lib):
+    from prodiff_b200 import _lib
+    declared = _declared_symbols()
+    assert len(declared) >= 15
+    for s in declared:
+        assert hasattr(lib, s), f"{s} declared in the header but not exported"
+    assert sorted(_lib.SYMBOLS) == declared, "python binding list and header disagree"
+
+
+def test_no_torch_or_cxx_types_in_header():
+    src = open(HEADER).read()
+    assert 'extern "C"' in src
+    code = re.sub(r"/\*.*?\*/", "", src, flags=re.S)   # declarations only, comments stripped
+    assert "torch" not in code.lower() and "at::" not in code and "std::" not in code and "Tensor" not in code
+
+
+def test_library_is_sm100a_tcgen05_tma():
+    """SASS evidence that the shipped library is the Blackwell-native path (B200_PROFILING.md table)."""
+    from prodiff_b200 import _lib
+    r = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True)
+    if r.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    assert "sm_100a" in r.stdout
+    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM"):
+        assert mnemonic in r.stdout, mnemonic
+    assert "HMMA.16816" not in r.stdout  # no legacy mma.sync path
+
+
+def test_config_validation_and_sizes(lib):
+    from prodiff_b200 import _lib
+    ok = _lib.pd_config(128, 256, 20, 256, 1, 0)
+    assert lib.pd_state_count(C.byref(ok)) == 10 + 8 * 20
+    n = lib.pd_packed_bytes(C.byref(ok))
+    # 16-bit operands: 15.1 M weights + fp32 copies for the step path + biases
+    assert 50e6 < n < 80e6
+    bad = _lib.pd_config(100, 256, 20, 256, 1, 0)
+    assert lib.pd_packed_bytes(C.byref(bad)) == 0
+    assert b"in_dims" in lib.pd_last_error()
+    bad = _lib.pd_config(128, 256, 20, 300, 1, 0)
+    assert lib.pd_packed_bytes(C.byref(bad)) == 0
+    assert b"residual_channels" in lib.pd_last_error()
+    assert lib.pd_workspace_bytes(None, 1, 1, 1) == 0
+    assert lib.pd_abi_version() == 1
+
+
+def test_model_create_rejects_bad_arguments_without_gpu(lib):
+    from prodiff_b200 import _lib
+    cfg = _lib.pd_config(128, 256, 2, 256, 1, 0)
+    h = C.c_void_p()
+    ptrs = (C.c_void_p * 3)()
+    assert lib.pd_model_create(C.byref(cfg), ptrs, 3, None, 0, None, C.byref(h)) != 0
+    assert b"expected 26 state tensors" in lib.pd_last_error()
+    assert not h.value
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    from prodiff_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libprodiff_b200.so")
+    with pytest.raises(RuntimeError, match="no CPU/PyTorch fallback"):
+        _lib.load()

@@ -1,0 +1,132 @@
+"""CPU-only host logic: schedules/tables of the product package vs the oracle, weight-order contract, sharding."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import prodiff_oracle as oracle
+from prodiff_b200 import schedule, sharding, synth
+from prodiff_b200.engine import state_key_order
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("sched,timesteps,max_beta", [("vpsde", 4, 40), ("vpsde", 100, 0.06), ("linear", 8, 0.06),
+                                                      ("cosine", 6, 0.06), ("logsnr", 5, 0.06), ("vpsde", 1000, 0.02)])
+def test_module_buffers_equal_oracle_tables(sched, timesteps, max_beta):
+    import prodiff_b200 as pb
+    gd = pb.GaussianDiffusion(128, pb.WaveNet(128, 256, 1, 256, 1), timesteps=timesteps, schedule_type=sched,
+                              max_beta=max_beta, spec_min=[-12.0], spec_max=[0.0])
+    tb = oracle.diffusion_tables(timesteps, sched, max_beta)
+    for k, v in tb.items():
+        got = getattr(gd, k)
+        assert got.shape == (timesteps + 1,)
+        assert torch.equal(torch.nan_to_num(got), torch.nan_to_num(v)), k
+    assert gd.num_timesteps == timesteps and float(gd.timesteps) == timesteps
+    assert gd.spec_min.shape == (1, 1, 1) and "spec_min" not in gd.state_dict()
+
+
+def test_unknown_schedule_raises():
+    with pytest.raises(NotImplementedError):
+        schedule.get_noise_schedule_list("nope", 4)
+
+
+def test_explicit_betas_tensor():
+    import prodiff_b200 as pb
+    betas = torch.linspace(1e-4, 0.05, 11)
+    gd = pb.GaussianDiffusion(128, pb.WaveNet(128, 256, 1, 256, 1), timesteps=10, betas=betas, spec_min=[-12.0], spec_max=[0.0])
+    assert torch.allclose(gd.betas, betas)
+
+
+def test_state_key_order_matches_reference_state_dict():
+    import prodiff_b200 as pb
+    wn = pb.WaveNet(128, 256, 3, 256, 2)
+    keys = state_key_order(3)
+    assert sorted(keys) == sorted(wn.state_dict().keys()) and len(keys) == 10 + 8 * 3
+    st = synth.make_state(synth.DiffNetConfig(128, 256, 3, 256, 2), 0)
+    assert sorted(st) == sorted(keys)
+    for k in keys:
+        assert st[k].shape == wn.state_dict()[k].shape, k
+    assert [b.dilation for b in wn.residual_layers] == [1, 2, 1]
+
+
+def test_wavenet_from_reference_like_module():
+    import prodiff_b200 as pb
+    src = pb.WaveNet(64, 256, 5, 256, 3)
+    src.load_state_dict(synth.make_state(synth.DiffNetConfig(64, 256, 5, 256, 3), 2))
+    new = pb.WaveNet.from_reference(src, "fp16")
+    assert new.cfg == src.cfg and new.operand_dtype == "fp16"
+    for k, v in src.state_dict().items():
+        assert torch.equal(v, new.state_dict()[k])
+
+
+def test_shard_bounds():
+    assert sharding.shard_bounds(64, 8) == [(8 * i, 8 * i + 8) for i in range(8)]
+    assert sharding.shard_bounds(10, 4) == [(0, 3), (3, 6), (6, 8), (8, 10)]
+    assert sharding.shard_bounds(2, 4) == [(0, 1), (1, 2), (2, 2), (2, 2)]
+    assert sharding.shard_bounds(0, 3) == [(0, 0)] * 3
+    for n, w in [(1, 1), (7, 3), (1024, 8), (5, 8)]:
+        b = sharding.shard_bounds(n, w)
+        assert b[0][0] == 0 and b[-1][1] == n and all(x[1] == y[0] for x, y in zip(b, b[1:]))
+        sizes = [e - s for s, e in b]
+        assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        sharding.shard_bounds(4, 0)
+
+
+def test_sample_sharded_without_process_group_is_identity():
+    cond = torch.randn(3, 5, 4)
+    out = sharding.sample_sharded(lambda c: c[..., :2] * 2, cond, gather=True)
+    assert torch.equal(out, cond[..., :2] * 2)
+
+
+WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from prodiff_b200 import sharding
+rank, world = int(sys.argv[2]), int(sys.argv[3])
+os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=sys.argv[4], RANK=str(rank), WORLD_SIZE=str(world))
+dist.init_process_group("gloo", rank=rank, world_size=world)
+torch.manual_seed(0)
+cond = torch.randn(5, 7, 4)                       # 5 utterances over 2 ranks: ragged shards (3, 2)
+calls = []
+def fake_sampler(c):                               # stands in for gd(cond, infer=True): row-independent
+    calls.append(c.shape[0])
+    return torch.stack([c.sum(-1), c.mean(-1), c.amax(-1)], dim=-1)
+full = sharding.sample_sharded(fake_sampler, cond, gather=True)
+mine = sharding.sample_sharded(fake_sampler, cond, gather=False)
+s, e = sharding.shard_bounds(5, world)[rank]
+assert calls == [e - s, e - s], calls
+assert torch.equal(full, fake_sampler(cond)), "gathered result differs from the unsharded one"
+assert torch.equal(mine, full[s:e])
+dist.barrier(); dist.destroy_process_group()
+print("OK", rank)
+'''
+
+
+def test_sample_sharded_gloo_world2(tmp_path):
+    """N>1 path on CPU: world_size 2, gloo, ragged split, all-gather of the finished shards only."""
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    port = str(29500 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, str(r), "2", port], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=120)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0 and f"OK {r}" in o, o[-2000:]
+
+
+def test_synth_is_deterministic_and_scaled():
+    cfg = synth.DiffNetConfig(128, 256, 2, 256, 1)
+    a, b = synth.make_state(cfg, 9), synth.make_state(cfg, 9)
+    assert synth.digest(a) == synth.digest(b) != synth.digest(synth.make_state(cfg, 10))
+    w = a["residual_layers.0.dilated_conv.weight"]
+    assert abs(float(w.std()) - np.sqrt(2 / (256 * 3))) < 2e-3
+    assert abs(float(a["output_projection.weight"].std()) - 0.02) < 2e-3
+    assert float(synth.make_state(cfg, 9, "zero")["output_projection.weight"].abs().max()) == 0
+    cond, xT, noise = synth.make_inputs(cfg, 2, 10, 3)
+    assert cond.shape == (2, 10, 256) and xT.shape == (2, 1, 128, 10) and noise.shape == (3, 2, 1, 128, 10)
+    assert 0 <= float(xT.min()) and float(xT.max()) < 1
