@@ -120,6 +120,15 @@ int pd_plan_buffer(const pd_plan* p, const char* name, size_t* offset, size_t* b
 int pd_debug_gemm(int dtype, const void* a, int B, int T, int Cin, int taps, int dil, const void* w, int N,
                   const float* bias, float* out, void* stream);
 
+/* Debug: when set to a device buffer of 8 x 1024 int64, CTA 0 of every GEMM launch writes clock64() stamps of its
+ * pipeline events at [kind * 1024 + tile * 16 + slot] (slots: 0/1 first/last TMA issue, 2 accumulator free, 3/4 first/
+ * last operand stage landed, 5/6 epilogue before/after accumulator wait, 7 epilogue done, 14 exit, 15 entry). */
+int pd_debug_set_trace(long long* device_buf);
+
+/* Test hook: D[128,64] = A[shift:shift+128, 0:64] * W[64,64]^T with A read through a row-shifted view of one
+ * 128B-swizzled shared-memory tile (mode 0: descriptor base_offset 0; mode 1: base_offset = (addr >> 7) & 7). */
+int pd_debug_shift(int dtype, const void* a, int R, const void* w, int shift, int mode, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

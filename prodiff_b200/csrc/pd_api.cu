@@ -73,6 +73,12 @@ static void prof_after(cudaStream_t s) {
   cudaEventRecord((*g_prof)[g_prof_used].e1, s);
   ++g_prof_used;
 }
+// debug: device buffer of 8 kinds x 1024 slots; CTA 0 of every GEMM launch records clock64() at pipeline events
+static thread_local long long* g_trace = nullptr;
+extern "C" int pd_debug_set_trace(long long* device_buf) {
+  g_trace = device_buf;
+  return 0;
+}
 extern "C" int pd_profile_begin(void) {
   g_prof_on = true;
   g_prof_used = 0;
@@ -422,6 +428,7 @@ template <int EPI, int BN>
 static int launch_gemm(int dtype, const CUtensorMap& a, const CUtensorMap& b, GemmShape sh, const EpiArgs& ep, int sms,
                        cudaStream_t s, const char* name, int kind) {
   sh.idesc = make_idesc(dtype, BN);
+  sh.trace = g_trace ? g_trace + kind * 1024 : nullptr;
   return dtype == PD_FP16 ? launch_gemm_t<EPI, BN, __half>(a, b, sh, ep, sms, s, name, kind)
                           : launch_gemm_t<EPI, BN, __nv_bfloat16>(a, b, sh, ep, sms, s, name, kind);
 }
@@ -670,4 +677,73 @@ extern "C" int pd_debug_gemm(int dtype, const void* a, int B, int T, int Cin, in
   ep.ld = N;
   ep.out_type = OUT_F32;
   return launch_gemm<EPI_STORE, 256>(dtype, ta, tb, sh, ep, sms, static_cast<cudaStream_t>(stream), "gemm(debug)", 7);
+}
+
+// ------------------------------------------------------------------ experiment: row-shifted SW128 A descriptors
+// One CTA: A tile [R x 64] (16-bit, TMA SWIZZLE_128B, 1024-aligned), B tile [64 x 64]; D[128 x 64] = A[shift : shift+128] * B^T.
+// mode 0: descriptor base_offset = 0; mode 1: base_offset = (start_address >> 7) & 7.  Decides whether the dilated-conv
+// taps can be served as shifted views of ONE resident activation tile.
+__global__ void __launch_bounds__(128, 1)
+k_shift_probe(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int R, int shift, int mode,
+              uint32_t idesc, float* __restrict__ out) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* sA = smem;                 // R * 128 bytes (R <= 256)
+  uint8_t* sB = smem + 256 * 128;     // 64 * 128 bytes
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + 64 * 128);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc<64>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) {
+    mbar_arrive_expect_tx(&bars[0], (uint32_t)(R * 128 + 64 * 128));
+    tma_load_2d(sA, &tmA, &bars[0], 0, 0);
+    tma_load_2d(sB, &tmB, &bars[0], 0, 0);
+    mbar_wait(&bars[0], 0, 10);
+    tc_fence_after();
+    const uint32_t a_addr = smem_u32(sA) + (uint32_t)shift * 128u;
+    uint64_t adesc = make_sw128_kmajor_desc(a_addr);
+    if (mode == 1) adesc |= (uint64_t)((a_addr >> 7) & 7u) << 49;
+    const uint64_t bdesc = make_sw128_kmajor_desc(smem_u32(sB));
+    for (int k = 0; k < 4; ++k) umma_f16(tmem_base, desc_advance_k(adesc, k), desc_advance_k(bdesc, k), idesc, k != 0);
+    umma_commit(&bars[1]);
+  }
+  mbar_wait(&bars[1], 0, 11);
+  tc_fence_after();
+  const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+  uint32_t r[32];
+  for (int c = 0; c < 64; c += 32) {
+    tmem_ld_x32(trow + c, r);
+    tmem_ld_wait();
+    for (int j = 0; j < 32; ++j) out[(warp * 32 + lane) * 64 + c + j] = __uint_as_float(r[j]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<64>(tmem_base);
+}
+
+extern "C" int pd_debug_shift(int dtype, const void* a, int R, const void* w, int shift, int mode, float* out, void* stream) {
+  if (!a || !w || !out) return fail("null argument");
+  if (R < 128 || R > 256 || shift < 0 || shift + 128 > R) return fail("bad R/shift");
+  int device = 0, sms = 0;
+  if (check_device(&device, &sms)) return 1;
+  CUtensorMap ta, tb;
+  const uint64_t da[2] = {64, (uint64_t)R}, db[2] = {64, 64};
+  if (make_map(&ta, dtype, a, 2, da, (uint32_t)R) || make_map(&tb, dtype, w, 2, db, 64)) return 1;
+  const uint32_t fmt = dtype == PD_FP16 ? 0u : 1u;
+  const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  const int smem = 256 * 128 + 64 * 128 + 1024 + 64;
+  PD_CUDA(cudaFuncSetAttribute(k_shift_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  k_shift_probe<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(ta, tb, R, shift, mode, idesc, out);
+  PD_LAUNCH_CHECK("k_shift_probe");
+  return 0;
 }

@@ -45,6 +45,7 @@ struct GemmShape {
   int a_slab0;          // base 4th coordinate of A
   int b_row0;           // first weight row of n-tile 0
   uint32_t idesc;       // tcgen05 instruction descriptor (M=128, N=BN, operand format)
+  long long* trace;     // debug: CTA 0 records clock64() at pipeline events (nullptr in production)
 };
 
 struct EpiArgs {
@@ -155,6 +156,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if (sh.trace && blockIdx.x == 0 && threadIdx.x == 0) sh.trace[15] = clock64();  // kernel entry
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -193,6 +195,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         for (int kb = 0; kb < k_blocks; ++kb, ++it) {
           const uint32_t stage = it % kStages, parity = (it / kStages) & 1u;
           mbar_wait(&empty_bar[stage], parity ^ 1u, 1);
+          if (sh.trace && blockIdx.x == 0 && (kb == 0 || kb == k_blocks - 1)) sh.trace[(tile / gridDim.x) * 16 + (kb == 0 ? 0 : 1)] = clock64();
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
@@ -212,11 +215,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const uint32_t as = ti & 1u, aph = (ti >> 1) & 1u;
         mbar_wait(&tempty_bar[as], aph ^ 1u, 2);
         tc_fence_after();
+        if (sh.trace && blockIdx.x == 0) sh.trace[ti * 16 + 2] = clock64();
         const uint32_t d_tmem = tmem_base + as * BN;
         for (int kb = 0; kb < k_blocks; ++kb, ++it) {
           const uint32_t stage = it % kStages, parity = (it / kStages) & 1u;
           mbar_wait(&full_bar[stage], parity, 3);
           tc_fence_after();
+          if (sh.trace && blockIdx.x == 0 && (kb == 0 || kb == k_blocks - 1)) sh.trace[ti * 16 + (kb == 0 ? 3 : 4)] = clock64();
           const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
           const uint64_t adesc = make_sw128_kmajor_desc(sa);
           const uint64_t bdesc = make_sw128_kmajor_desc(sa + Cfg::kABytes);
@@ -242,9 +247,38 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const bool valid = t < sh.T;
       const long long n = (long long)b * sh.T + t;  // global frame index
       const uint32_t as = ti & 1u, aph = (ti >> 1) & 1u;
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
+      // Global operands of the epilogue do not depend on the accumulator: issue their loads BEFORE waiting for the
+      // MMAs of this tile, so HBM latency hides under the tensor work instead of serialising after it.
+      uint4 pre[16];
+      if constexpr (EPI == EPI_GATE) {
+        const __half* cp_row = static_cast<const __half*>(ep.aux) + n * (2 * ep.ld) + n_tile * 256 + h * 64;
+        if (valid) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            pre[u] = __ldg(reinterpret_cast<const uint4*>(cp_row) + u);            // 64 gate pre-activations
+            pre[8 + u] = __ldg(reinterpret_cast<const uint4*>(cp_row + 128) + u);  // 64 filter pre-activations
+          }
+        }
+      }
+      if constexpr (EPI == EPI_RES) {
+        const uint16_t* xo = static_cast<const uint16_t*>(ep.aux) + n * ep.ld + n_tile * BN + h * (BN / 2);
+        if (valid) {
+#pragma unroll
+          for (int u = 0; u < 16; ++u) pre[u] = __ldg(reinterpret_cast<const uint4*>(xo) + u);
+        }
+      }
+      if constexpr (EPI == EPI_OUT) {
+        if (valid && ep.x_state != nullptr && h * 64 < ep.M) {
+          float* pfw = reinterpret_cast<float*>(pre);
+#pragma unroll
+          for (int j = 0; j < 64; ++j) pfw[j] = ep.x_state[((long long)b * ep.M + (h * 64 + j)) * sh.T + t];
+        }
+      }
+      if (sh.trace && blockIdx.x == 0 && warp == 2 && lane == 0) sh.trace[ti * 16 + 5] = clock64();
       mbar_wait(&tfull_bar[as], aph, 4);
       tc_fence_after();
-      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
+      if (sh.trace && blockIdx.x == 0 && warp == 2 && lane == 0) sh.trace[ti * 16 + 6] = clock64();
 
       if constexpr (EPI == EPI_STORE) {
         const long long nfr = (long long)sh.B * sh.T;
@@ -298,44 +332,46 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const float* sb_t2 = sb_all + 2 * C2;
         const bool edge_lo = t < sh.dil;            // tap 0 reads x[t - dil] which is padding
         const bool edge_hi = t + sh.dil >= sh.T;    // tap 2 reads x[t + dil] which is padding
-        const __half* cp_row = static_cast<const __half*>(ep.aux) + n * C2 + n_tile * 256;
         uint16_t* out_row = static_cast<uint16_t*>(ep.out) + n * C + n_tile * 128;
-#pragma unroll 1
-        for (int i = h * 64; i < h * 64 + 64; i += 16) {
+        const uint32_t* prew = reinterpret_cast<const uint32_t*>(pre);
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci) {
+          const int i = h * 64 + ci * 16;
           uint32_t rg[16], rf[16];
           tmem_ld_x16(trow + i, rg);
           tmem_ld_x16(trow + 128 + i, rf);
           tmem_ld_wait();
           if (valid) {
-            uint4 cg[2], cf[2];
-            cg[0] = __ldg(reinterpret_cast<const uint4*>(cp_row + i));
-            cg[1] = __ldg(reinterpret_cast<const uint4*>(cp_row + i + 8));
-            cf[0] = __ldg(reinterpret_cast<const uint4*>(cp_row + 128 + i));
-            cf[1] = __ldg(reinterpret_cast<const uint4*>(cp_row + 128 + i + 8));
-            const uint32_t* cgw = reinterpret_cast<const uint32_t*>(cg);
-            const uint32_t* cfw = reinterpret_cast<const uint32_t*>(cf);
             uint32_t packed[8];
 #pragma unroll
-            for (int j = 0; j < 16; j += 2) {
-              const float2 pg = Cvt<__half>::unpack(cgw[j >> 1]);
-              const float2 pf = Cvt<__half>::unpack(cfw[j >> 1]);
-              float zg0 = __uint_as_float(rg[j]) + pg.x + __ldg(sb_all + i + j);
-              float zg1 = __uint_as_float(rg[j + 1]) + pg.y + __ldg(sb_all + i + j + 1);
-              float zf0 = __uint_as_float(rf[j]) + pf.x + __ldg(sb_all + 128 + i + j);
-              float zf1 = __uint_as_float(rf[j + 1]) + pf.y + __ldg(sb_all + 128 + i + j + 1);
+            for (int j = 0; j < 16; j += 4) {
+              const float4 bg = __ldg(reinterpret_cast<const float4*>(sb_all + i + j));
+              const float4 bf = __ldg(reinterpret_cast<const float4*>(sb_all + 128 + i + j));
+              float zg[4] = {bg.x, bg.y, bg.z, bg.w}, zf[4] = {bf.x, bf.y, bf.z, bf.w};
               if (edge_lo) {
-                zg0 -= __ldg(sb_t0 + i + j);
-                zg1 -= __ldg(sb_t0 + i + j + 1);
-                zf0 -= __ldg(sb_t0 + 128 + i + j);
-                zf1 -= __ldg(sb_t0 + 128 + i + j + 1);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  zg[u] -= __ldg(sb_t0 + i + j + u);
+                  zf[u] -= __ldg(sb_t0 + 128 + i + j + u);
+                }
               }
               if (edge_hi) {
-                zg0 -= __ldg(sb_t2 + i + j);
-                zg1 -= __ldg(sb_t2 + i + j + 1);
-                zf0 -= __ldg(sb_t2 + 128 + i + j);
-                zf1 -= __ldg(sb_t2 + 128 + i + j + 1);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  zg[u] -= __ldg(sb_t2 + i + j + u);
+                  zf[u] -= __ldg(sb_t2 + 128 + i + j + u);
+                }
               }
-              packed[j >> 1] = Cvt<T>::pack(gate_fn(zg0, zf0), gate_fn(zg1, zf1));
+#pragma unroll
+              for (int u = 0; u < 4; u += 2) {
+                const float2 pg = Cvt<__half>::unpack(prew[(ci * 16 + j + u) >> 1]);
+                const float2 pf = Cvt<__half>::unpack(prew[32 + ((ci * 16 + j + u) >> 1)]);
+                const float g0 = __uint_as_float(rg[j + u]) + pg.x + zg[u];
+                const float g1 = __uint_as_float(rg[j + u + 1]) + pg.y + zg[u + 1];
+                const float f0 = __uint_as_float(rf[j + u]) + pf.x + zf[u];
+                const float f1 = __uint_as_float(rf[j + u + 1]) + pf.y + zf[u + 1];
+                packed[(j + u) >> 1] = Cvt<T>::pack(gate_fn(g0, f0), gate_fn(g1, f1));
+              }
             }
             uint4* dst = reinterpret_cast<uint4*>(out_row + i);
             dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
@@ -344,27 +380,29 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       } else if constexpr (EPI == EPI_RES) {
         const int C = ep.ld;
-#pragma unroll 1
-        for (int c = h * (BN / 2); c < (h + 1) * (BN / 2); c += 32) {
+        const uint32_t* prew = reinterpret_cast<const uint32_t*>(pre);
+#pragma unroll
+        for (int ci = 0; ci < (BN / 2) / 32; ++ci) {
+          const int c = h * (BN / 2) + ci * 32;
           uint32_t r[32];
           tmem_ld_x32(trow + c, r);
           tmem_ld_wait();
           if (valid) {
             const int g = n_tile * BN + c;
-            const uint4* xo = reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(ep.aux) + n * C + g);
             uint4* dst = reinterpret_cast<uint4*>(static_cast<uint16_t*>(ep.out) + n * C + g);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const uint4 xv = __ldg(xo + j);
-              const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
               uint32_t ow[4];
 #pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const float2 x2 = Cvt<T>::unpack(xw[u]);
+              for (int u = 0; u < 4; u += 2) {
+                const float4 bv = __ldg(reinterpret_cast<const float4*>(ep.bias + g + 8 * j + 2 * u));
+                const float2 xa = Cvt<T>::unpack(prew[ci * 16 + 4 * j + u]);
+                const float2 xb = Cvt<T>::unpack(prew[ci * 16 + 4 * j + u + 1]);
                 const int col = 8 * j + 2 * u;
-                const float a0 = (x2.x + __uint_as_float(r[col]) + __ldg(ep.bias + g + col)) * ep.scale;
-                const float a1 = (x2.y + __uint_as_float(r[col + 1]) + __ldg(ep.bias + g + col + 1)) * ep.scale;
-                ow[u] = Cvt<T>::pack(a0, a1);
+                ow[u] = Cvt<T>::pack((xa.x + __uint_as_float(r[col]) + bv.x) * ep.scale,
+                                     (xa.y + __uint_as_float(r[col + 1]) + bv.y) * ep.scale);
+                ow[u + 1] = Cvt<T>::pack((xb.x + __uint_as_float(r[col + 2]) + bv.z) * ep.scale,
+                                         (xb.y + __uint_as_float(r[col + 3]) + bv.w) * ep.scale);
               }
               dst[j] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
             }
@@ -372,8 +410,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       } else {  // EPI_OUT
         const int M = ep.M;
-#pragma unroll 1
-        for (int c = h * 64; c < h * 64 + 64; c += 32) {
+        const float* pf = reinterpret_cast<const float*>(pre);
+#pragma unroll
+        for (int ci = 0; ci < 2; ++ci) {
+          const int c = h * 64 + ci * 32;
           uint32_t r[32];
           tmem_ld_x32(trow + c, r);
           tmem_ld_wait();
@@ -397,7 +437,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                   const long long idx = ((long long)b * M + (c + j + u)) * sh.T + t;
-                  float v = ep.c1 * xn[j + u] + ep.c2 * ep.x_state[idx];
+                  float v = ep.c1 * xn[j + u] + ep.c2 * pf[ci * 32 + j + u];
                   if (ep.sigma != 0.f) v += ep.sigma * (ep.noise ? __ldg(ep.noise + idx) : nzv[u]);
                   ep.x_state[idx] = v;
                   xn[j + u] = v;
@@ -416,6 +456,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
 
       // this warp has finished reading accumulator stage `as`
+      if (sh.trace && blockIdx.x == 0 && warp == 2 && lane == 0) sh.trace[ti * 16 + 7] = clock64();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[as]);
@@ -424,6 +465,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   tc_fence_before();
   __syncthreads();
+  if (sh.trace && blockIdx.x == 0 && threadIdx.x == 0) sh.trace[14] = clock64();  // all roles done
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc<kTmemCols>(tmem_base);

@@ -90,6 +90,60 @@ def check_layers(dtype="bf16", B=2, T=300, L=4, C=256, cycle=2, M=128):
     return res
 
 
+def check_shift():
+    """Row-shifted views of one SW128 tile as UMMA A operand: which base_offset convention is right?"""
+    import torch
+    from prodiff_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(1)
+    R = 160
+    a = torch.randn(R, 64, generator=g).to(torch.bfloat16).cuda()
+    w = torch.randn(64, 64, generator=g).to(torch.bfloat16).cuda()
+    res = {}
+    for mode in (0, 1):
+        errs = []
+        for shift in range(0, 33):
+            out = torch.full((128, 64), float("nan"), device="cuda")
+            _lib.check(lib.pd_debug_shift(0, a.data_ptr(), R, w.data_ptr(), shift, mode, out.data_ptr(),
+                                          torch.cuda.current_stream().cuda_stream), "pd_debug_shift")
+            torch.cuda.synchronize()
+            ref = a[shift:shift + 128].float() @ w.float().t()
+            errs.append(round(float((out - ref).abs().max()), 4))
+        res[f"mode{mode}"] = errs
+    return res
+
+
+def check_trace():
+    """Pipeline timeline of CTA 0 for the conv+gate (kind 2) and res (kind 3) kernels at the bench shape."""
+    import torch
+    sys.argv = ["bench"]
+    import bench
+    from prodiff_b200 import _lib
+    lib = _lib.load()
+    gd, cfg, _ = bench.build_model(torch.device("cuda"))
+    from prodiff_b200 import synth
+    cond, _, _ = synth.make_inputs(cfg, 64, 1000, 1, 5)
+    cond = cond.cuda()
+    with torch.no_grad():
+        gd(cond, infer_step=4, infer=True, seed=1)
+        buf = torch.zeros(8 * 1024, dtype=torch.int64, device="cuda")
+        lib.pd_debug_set_trace(buf.data_ptr())
+        gd(cond, infer_step=4, infer=True, seed=1)
+        torch.cuda.synchronize()
+        lib.pd_debug_set_trace(None)
+    out = {}
+    for kind, name in ((2, "gate"), (3, "res"), (0, "cond"), (6, "out")):
+        t = buf[kind * 1024:(kind + 1) * 1024].cpu().view(64, 16)
+        t0 = int(t[0, 15])
+        rows = []
+        for i in range(8):
+            if int(t[i, 7]) == 0:
+                break
+            rows.append([int(v) - t0 if int(v) else -1 for v in t[i, :8]])
+        out[name] = dict(exit=int(t[0, 14]) - t0, tiles=rows)
+    return out
+
+
 def check_pytest(expr):
     r = subprocess.run([sys.executable, "-m", "pytest", "tests", "-x", "-q", "-m", "gpu", "-k", expr], capture_output=True,
                        text=True, cwd=ROOT, timeout=900)
@@ -97,6 +151,8 @@ def check_pytest(expr):
 
 
 CHECKS = {
+    "shift": check_shift,
+    "trace": check_trace,
     "layers_bf16": lambda: check_layers("bf16"),
     "layers_fp16": lambda: check_layers("fp16"),
     "layers_c512": lambda: check_layers("bf16", B=1, T=200, L=3, C=512, cycle=3),
