@@ -331,7 +331,8 @@ static size_t plan_layout(const pd_config& c, int B, int T, int E, std::vector<B
     o = align_up(o + bytes, 1024);
   };
   take("cond16", N * H * 2);
-  take("cp", L * N * 2 * C * 2);
+  const size_t mtiles = (size_t)B * ((T + kBlockM - 1) / kBlockM);
+  take("cp", L * mtiles * kBlockM * 2 * C * 2);  // tile-blocked layout, tiles padded to 128 frames
   take("xin", N * M * 2);
   take("xa", N * C * 2);
   take("xb", N * C * 2);
@@ -406,31 +407,34 @@ static uint32_t make_idesc(int dtype, int bn) {
 }
 
 template <int EPI, int BN, typename T>
-static int launch_gemm_t(const CUtensorMap& a, const CUtensorMap& b, const GemmShape& sh, const EpiArgs& ep, int sms,
-                         cudaStream_t s, const char* name, int kind) {
+static int launch_gemm_t(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, const CUtensorMap& x,
+                         const GemmShape& sh, const EpiArgs& ep, int sms, cudaStream_t s, const char* name, int kind) {
   auto kern = gemm_kernel<EPI, BN, T>;
   static bool configured[64] = {false};  // per instantiation, per device
   int dev = 0;
   PD_CUDA(cudaGetDevice(&dev));
   if (!configured[dev & 63]) {
-    PD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GemmCfg<BN>::kSmemBytes));
+    PD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GemmCfg<EPI, BN>::kSmemBytes));
     configured[dev & 63] = true;
   }
   const int tiles = sh.B * sh.m_tiles_per_row * sh.n_tiles;
   const int grid = tiles < sms ? tiles : sms;
   prof_before(kind, s);
-  kern<<<grid, kGemmThreads, GemmCfg<BN>::kSmemBytes, s>>>(a, b, sh, ep);
+  kern<<<grid, kGemmThreads, GemmCfg<EPI, BN>::kSmemBytes, s>>>(a, b, o, x, sh, ep);
   prof_after(s);
   PD_LAUNCH_CHECK(name);
   return 0;
 }
 template <int EPI, int BN>
 static int launch_gemm(int dtype, const CUtensorMap& a, const CUtensorMap& b, GemmShape sh, const EpiArgs& ep, int sms,
-                       cudaStream_t s, const char* name, int kind) {
+                       cudaStream_t s, const char* name, int kind, const CUtensorMap* o = nullptr,
+                       const CUtensorMap* x = nullptr) {
   sh.idesc = make_idesc(dtype, BN);
   sh.trace = g_trace ? g_trace + kind * 1024 : nullptr;
-  return dtype == PD_FP16 ? launch_gemm_t<EPI, BN, __half>(a, b, sh, ep, sms, s, name, kind)
-                          : launch_gemm_t<EPI, BN, __nv_bfloat16>(a, b, sh, ep, sms, s, name, kind);
+  const CUtensorMap& om = o ? *o : a;  // unused maps alias the A map
+  const CUtensorMap& xm = x ? *x : a;
+  return dtype == PD_FP16 ? launch_gemm_t<EPI, BN, __half>(a, b, om, xm, sh, ep, sms, s, name, kind)
+                          : launch_gemm_t<EPI, BN, __nv_bfloat16>(a, b, om, xm, sh, ep, sms, s, name, kind);
 }
 
 static GemmShape base_shape(int B, int T, int n_tiles, int k_per_tap) {
@@ -472,6 +476,7 @@ extern "C" int pd_cond_project(pd_plan* p, const float* cond, void* stream) {
   ep.bias = reinterpret_cast<const float*>(m->packed + m->lay.b_cp);
   ep.ld = C2;
   ep.out_type = OUT_F16;
+  ep.out_blocked = 1;
   return launch_gemm<EPI_STORE, 256>(c.dtype, p->tm_cond, m->tm_w_cond, sh, ep, m->sm_count, s, "gemm(cond_proj)", 0);
 }
 
@@ -527,8 +532,7 @@ static int run_denoiser(pd_plan* p, int entry_base, int entry_per_b, const OutSt
   for (int l = 0; l < L; ++l) {
     const int dil = 1 << (l % c.dilation_cycle_length);
     const CUtensorMap& tm_cur = cur_is_a ? p->tm_xa : p->tm_xb;
-    uint16_t* x_cur = p->ptr<uint16_t>(cur_is_a ? "xa" : "xb");
-    uint16_t* x_nxt = p->ptr<uint16_t>(cur_is_a ? "xb" : "xa");
+    const CUtensorMap& tm_nxt = cur_is_a ? p->tm_xb : p->tm_xa;
     {  // dilated conv + cond + step bias -> gate (wavenet.py:63-68)
       GemmShape sh = base_shape(B, T, 2 * C / 256, C / 64);
       sh.taps = 3;
@@ -536,26 +540,25 @@ static int run_denoiser(pd_plan* p, int entry_base, int entry_per_b, const OutSt
       sh.dil = dil;
       sh.b_row0 = l * 2 * C;
       EpiArgs ep = base_epi();
-      ep.out = p->ptr<uint16_t>("ybuf") + (size_t)l * N * C;
-      ep.aux = p->ptr<uint16_t>("cp") + (size_t)l * N * 2 * C;
+      const size_t mtiles = (size_t)B * ((T + kBlockM - 1) / kBlockM);
+      ep.out_slab = l;  // gated activations leave through a TMA store into ybuf[l]
+      ep.aux = p->ptr<uint16_t>("cp") + (size_t)l * mtiles * kBlockM * 2 * C;
       ep.sb = p->ptr<float>("sb") + (size_t)l * 4 * 2 * C;
       ep.sb_entry_stride = (long long)L * 4 * 2 * C;
       ep.sb_entry_base = entry_base;
       ep.sb_entry_per_b = entry_per_b;
       ep.ld = C;
-      if (launch_gemm<EPI_GATE, 256>(dt, tm_cur, m->tm_w_dil, sh, ep, sms, s, "gemm(dilated_conv+gate)", 2)) return 1;
+      if (launch_gemm<EPI_GATE, 256>(dt, tm_cur, m->tm_w_dil, sh, ep, sms, s, "gemm(dilated_conv+gate)", 2, &p->tm_y)) return 1;
     }
     {  // residual half of output_projection + (x + res)/sqrt(2) (wavenet.py:70-72)
       GemmShape sh = base_shape(B, T, C / 256, C / 64);
       sh.a_slab0 = l;
       sh.b_row0 = l * C;
       EpiArgs ep = base_epi();
-      ep.out = x_nxt;
-      ep.aux = x_cur;
       ep.bias = (const float*)(pk + lay.b_res) + (size_t)l * C;
       ep.ld = C;
       ep.scale = 0.70710678118654752440f;
-      if (launch_gemm<EPI_RES, 256>(dt, p->tm_y, m->tm_w_res, sh, ep, sms, s, "gemm(res_proj)", 3)) return 1;
+      if (launch_gemm<EPI_RES, 256>(dt, p->tm_y, m->tm_w_res, sh, ep, sms, s, "gemm(res_proj)", 3, &tm_nxt, &tm_cur)) return 1;
     }
     cur_is_a = !cur_is_a;
   }

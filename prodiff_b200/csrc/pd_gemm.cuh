@@ -56,6 +56,8 @@ struct EpiArgs {
   long long sb_entry_stride;
   int sb_entry_base, sb_entry_per_b;
   int ld;       // STORE: slab width of the output; GATE/RES: C
+  int out_blocked;  // STORE: write the tile-blocked layout (see blocked_off) instead of row-major
+  int out_slab;     // GATE: 4th TMA coordinate (layer) of the gated-activation store
   float scale;  // STORE: multiplier after bias; RES: 1/sqrt(2)
   int relu;
   int out_type;
@@ -91,13 +93,28 @@ template <> struct Cvt<__half> {
   static constexpr uint32_t kFormat = 0;  // 0 = F16
 };
 
-// sigmoid(g) * tanh(f) = (e^{2f} - 1) / ((1 + e^{-g}) (e^{2f} + 1)); 2 ex2 + 1 rcp on the MUFU pipe.
+// sigmoid(g) * tanh(f).
+//  * fp16 operands (strict-parity mode): (e^{2f} - 1) / ((1 + e^{-g}) (e^{2f} + 1)), 2 ex2 + 1 rcp, ~1e-6 accurate.
+//  * bf16 operands: MUFU.TANH twice (sigmoid(g) = 0.5 tanh(g/2) + 0.5).  tanh.approx has ~2^-11 max error, below the
+//    2^-9 rounding of the bf16 value the result is stored as, and it is 5 issue slots instead of 14.
+template <typename T>
 __device__ __forceinline__ float gate_fn(float g, float f) {
-  f = fminf(fmaxf(f, -15.f), 15.f);
-  g = fmaxf(g, -30.f);
-  const float e2f = __expf(2.f * f);
-  const float eg = __expf(-g);
-  return __fdividef(e2f - 1.f, (1.f + eg) * (e2f + 1.f));
+  if constexpr (sizeof(T) == 2 && Cvt<T>::kFormat == 1) {
+    return fmaf(0.5f, tanh_approx(0.5f * g), 0.5f) * tanh_approx(f);
+  } else {
+    f = fminf(fmaxf(f, -15.f), 15.f);
+    g = fmaxf(g, -30.f);
+    const float e2f = __expf(2.f * f);
+    const float eg = __expf(-g);
+    return __fdividef(e2f - 1.f, (1.f + eg) * (e2f + 1.f));
+  }
+}
+
+// Tile-blocked layout for tensors that only epilogues touch (the hoisted condition projection): within one 128-frame
+// tile the 16-byte chunks of a row are strided by 128 rows, i.e. [tile][chunk][row][8 x 16-bit].  With one thread per
+// row, a warp's 16-byte accesses to one chunk are 512 contiguous bytes (4 wavefronts) instead of 32 scattered lines.
+__device__ __forceinline__ long long blocked_off(long long tile, int chunks_per_row, int chunk, int row) {
+  return ((tile * chunks_per_row + chunk) * 128 + row) * 8;  // in 16-bit elements
 }
 
 // Philox4x32-10 (counter-based RNG) + Box-Muller: 4 standard normals per call.
@@ -124,35 +141,48 @@ __device__ __forceinline__ float4 philox_normal4(unsigned long long seed, uint32
   return make_float4(r0 * c0f, r0 * s0, r1 * c1f, r1 * s1);
 }
 
-template <int BN> struct GemmCfg {
-  static constexpr int kStages = (BN == 256) ? 4 : 6;
+template <int EPI, int BN> struct GemmCfg {
+  // smem ring depth; the gate / residual epilogues also keep an operand-or-output tile in shared memory
+  static constexpr int kStages = (EPI == EPI_RES) ? 3 : (BN == 256 ? 4 : 6);
   static constexpr uint32_t kABytes = kBlockM * kBlockK * 2;
   static constexpr uint32_t kBBytes = BN * kBlockK * 2;
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;
-  // ring + alignment slack + barriers
-  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 + 256;
+  static constexpr uint32_t kExtraBytes = (EPI == EPI_GATE) ? 2 * 16384 : (EPI == EPI_RES ? 4 * 16384 : 0);
+  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kExtraBytes + 1024 + 256;  // + alignment slack + barriers
 };
 
+// address of the 16-byte chunk `c` (0..7) of row `r` in a [128 x 64] 16-bit tile laid out with the 128-byte swizzle
+__device__ __forceinline__ uint4* sw128_chunk(uint8_t* tile, int r, int c) {
+  return reinterpret_cast<uint4*>(tile + r * 128 + ((c ^ (r & 7)) << 4));
+}
+
 // ------------------------------------------------------------------ the kernel
+// tmA: A operand (activations); tmB: B operand (weights); tmO: TMA-store target (GATE: gated activations, RES: x_next);
+// tmX: RES only, x_cur tile load.  Unused maps are passed as copies of tmA.
 template <int EPI, int BN, typename T>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmShape sh,
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmX, const GemmShape sh,
             const EpiArgs ep) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<EPI, BN>;
   constexpr int kStages = Cfg::kStages;
   static_assert(BN == 256 || BN == 128, "tile width");
   static_assert(EPI != EPI_GATE || BN == 256, "gate epilogue pairs 128 gate with 128 filter columns");
+  static_assert(EPI != EPI_RES || BN == 256, "residual epilogue is 256 wide");
   static_assert(EPI != EPI_OUT || BN == 128, "out epilogue is 128 wide");
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);  // SWIZZLE_128B needs 1024-byte alignment
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  uint8_t* extra = smem + kStages * Cfg::kStageBytes;                   // GATE: y staging, RES: x tile
+  uint64_t* bars = reinterpret_cast<uint64_t*>(extra + Cfg::kExtraBytes);
   uint64_t* full_bar = bars;                  // [kStages]  TMA -> MMA
   uint64_t* empty_bar = bars + kStages;       // [kStages]  MMA -> TMA
   uint64_t* tfull_bar = bars + 2 * kStages;   // [2]        MMA -> epilogue
   uint64_t* tempty_bar = tfull_bar + 2;       // [2]        epilogue -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* xfull_bar = tempty_bar + 2;       // RES: x tile landed
+  uint64_t* xempty_bar = xfull_bar + 1;       // RES: x tile stored, buffer reusable
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xempty_bar + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -161,6 +191,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if constexpr (EPI == EPI_GATE || EPI == EPI_RES) tma_prefetch_desc(&tmO);
+    if constexpr (EPI == EPI_RES) tma_prefetch_desc(&tmX);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kStages; ++i) {
@@ -171,6 +203,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], kEpiWarps);
     }
+    mbar_init(xfull_bar, 1);
+    mbar_init(xempty_bar, 1);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc<kTmemCols>(tmem_slot);
@@ -186,16 +220,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      uint32_t it = 0, ti = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
         const int n_tile = tile % sh.n_tiles;
         const int m_tile = tile / sh.n_tiles;
         const int b = m_tile / sh.m_tiles_per_row;
         const int t0 = (m_tile % sh.m_tiles_per_row) * kBlockM;
+        if constexpr (EPI == EPI_RES) {
+          // x_cur tile for the residual add: [128 frames x 256 ch] as four swizzled [128 x 64] sub-tiles
+          mbar_wait(xempty_bar, (ti & 1u) ^ 1u, 5);
+          mbar_arrive_expect_tx(xfull_bar, 4 * 16384);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) tma_load_4d(extra + j * 16384, &tmX, xfull_bar, n_tile * BN + j * 64, t0, b, 0);
+        }
         for (int kb = 0; kb < k_blocks; ++kb, ++it) {
           const uint32_t stage = it % kStages, parity = (it / kStages) & 1u;
           mbar_wait(&empty_bar[stage], parity ^ 1u, 1);
-          if (sh.trace && blockIdx.x == 0 && (kb == 0 || kb == k_blocks - 1)) sh.trace[(tile / gridDim.x) * 16 + (kb == 0 ? 0 : 1)] = clock64();
+          if (sh.trace && blockIdx.x == 0 && (kb == 0 || kb == k_blocks - 1)) sh.trace[ti * 16 + (kb == 0 ? 0 : 1)] = clock64();
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
@@ -238,12 +279,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int q = warp & 3;          // TMEM lane quadrant this warp may access
     const int h = (warp - 2) >> 2;   // which half of the tile's columns this warp handles
     const int row = q * 32 + lane;
+    const bool issuer = (warp == 2 && lane == 0);  // the one thread that issues TMA stores
     uint32_t ti = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
       const int n_tile = tile % sh.n_tiles;
       const int m_tile = tile / sh.n_tiles;
       const int b = m_tile / sh.m_tiles_per_row;
-      const int t = (m_tile % sh.m_tiles_per_row) * kBlockM + row;
+      const int t0 = (m_tile % sh.m_tiles_per_row) * kBlockM;
+      const int t = t0 + row;
       const bool valid = t < sh.T;
       const long long n = (long long)b * sh.T + t;  // global frame index
       const uint32_t as = ti & 1u, aph = (ti >> 1) & 1u;
@@ -252,20 +295,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       // MMAs of this tile, so HBM latency hides under the tensor work instead of serialising after it.
       uint4 pre[16];
       if constexpr (EPI == EPI_GATE) {
-        const __half* cp_row = static_cast<const __half*>(ep.aux) + n * (2 * ep.ld) + n_tile * 256 + h * 64;
         if (valid) {
+          const uint16_t* cpb = static_cast<const uint16_t*>(ep.aux);
+          const int cpr = (2 * ep.ld) >> 3;             // 16-byte chunks per row of the cond projection
+          const int cg = n_tile * 32 + h * 8;           // first gate chunk of this warp's 64 columns
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
-            pre[u] = __ldg(reinterpret_cast<const uint4*>(cp_row) + u);            // 64 gate pre-activations
-            pre[8 + u] = __ldg(reinterpret_cast<const uint4*>(cp_row + 128) + u);  // 64 filter pre-activations
+            pre[u] = __ldg(reinterpret_cast<const uint4*>(cpb + blocked_off(m_tile, cpr, cg + u, row)));
+            pre[8 + u] = __ldg(reinterpret_cast<const uint4*>(cpb + blocked_off(m_tile, cpr, cg + 16 + u, row)));
           }
-        }
-      }
-      if constexpr (EPI == EPI_RES) {
-        const uint16_t* xo = static_cast<const uint16_t*>(ep.aux) + n * ep.ld + n_tile * BN + h * (BN / 2);
-        if (valid) {
-#pragma unroll
-          for (int u = 0; u < 16; ++u) pre[u] = __ldg(reinterpret_cast<const uint4*>(xo) + u);
         }
       }
       if constexpr (EPI == EPI_OUT) {
@@ -276,6 +314,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       }
       if (sh.trace && blockIdx.x == 0 && warp == 2 && lane == 0) sh.trace[ti * 16 + 5] = clock64();
+      if constexpr (EPI == EPI_RES) mbar_wait(xfull_bar, ti & 1u, 6);
       mbar_wait(&tfull_bar[as], aph, 4);
       tc_fence_after();
       if (sh.trace && blockIdx.x == 0 && warp == 2 && lane == 0) sh.trace[ti * 16 + 6] = clock64();
@@ -290,7 +329,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (valid) {
             const int g = n_tile * BN + c;
             const int slab = g / ep.ld, within = g - slab * ep.ld;
-            const long long o = ((long long)slab * nfr + n) * ep.ld + within;
             float v[32];
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
@@ -305,35 +343,51 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
             }
             if (ep.out_type == OUT_F32) {
-              float4* dst = reinterpret_cast<float4*>(static_cast<float*>(ep.out) + o);
+              float4* dst = reinterpret_cast<float4*>(static_cast<float*>(ep.out) + ((long long)slab * nfr + n) * ep.ld + within);
 #pragma unroll
               for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
             } else {
-              uint4* dst = reinterpret_cast<uint4*>(static_cast<uint16_t*>(ep.out) + o);
+              uint4 o[4];
               if (ep.out_type == OUT_F16) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
-                  dst[j] = make_uint4(Cvt<__half>::pack(v[8 * j], v[8 * j + 1]), Cvt<__half>::pack(v[8 * j + 2], v[8 * j + 3]),
-                                      Cvt<__half>::pack(v[8 * j + 4], v[8 * j + 5]), Cvt<__half>::pack(v[8 * j + 6], v[8 * j + 7]));
+                  o[j] = make_uint4(Cvt<__half>::pack(v[8 * j], v[8 * j + 1]), Cvt<__half>::pack(v[8 * j + 2], v[8 * j + 3]),
+                                    Cvt<__half>::pack(v[8 * j + 4], v[8 * j + 5]), Cvt<__half>::pack(v[8 * j + 6], v[8 * j + 7]));
               } else {
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
-                  dst[j] = make_uint4(Cvt<T>::pack(v[8 * j], v[8 * j + 1]), Cvt<T>::pack(v[8 * j + 2], v[8 * j + 3]),
-                                      Cvt<T>::pack(v[8 * j + 4], v[8 * j + 5]), Cvt<T>::pack(v[8 * j + 6], v[8 * j + 7]));
+                  o[j] = make_uint4(Cvt<T>::pack(v[8 * j], v[8 * j + 1]), Cvt<T>::pack(v[8 * j + 2], v[8 * j + 3]),
+                                    Cvt<T>::pack(v[8 * j + 4], v[8 * j + 5]), Cvt<T>::pack(v[8 * j + 6], v[8 * j + 7]));
+              }
+              uint16_t* ob = static_cast<uint16_t*>(ep.out);
+              if (ep.out_blocked) {
+                const int cpr = ep.ld >> 3;
+                const long long tile_b = (long long)slab * num_m_tiles + m_tile;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  *reinterpret_cast<uint4*>(ob + blocked_off(tile_b, cpr, (within >> 3) + j, row)) = o[j];
+              } else {
+                uint4* dst = reinterpret_cast<uint4*>(ob + ((long long)slab * nfr + n) * ep.ld + within);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dst[j] = o[j];
               }
             }
           }
         }
       } else if constexpr (EPI == EPI_GATE) {
-        const int C = ep.ld, C2 = 2 * ep.ld;
+        const int C2 = 2 * ep.ld;
         const int entry = ep.sb_entry_base + b * ep.sb_entry_per_b;
         const float* sb_all = ep.sb + (long long)entry * ep.sb_entry_stride + n_tile * 256;
         const float* sb_t0 = sb_all + C2;
         const float* sb_t2 = sb_all + 2 * C2;
         const bool edge_lo = t < sh.dil;            // tap 0 reads x[t - dil] which is padding
         const bool edge_hi = t + sh.dil >= sh.T;    // tap 2 reads x[t + dil] which is padding
-        uint16_t* out_row = static_cast<uint16_t*>(ep.out) + n * C + n_tile * 128;
+        const bool warp_edge = __any_sync(0xffffffffu, valid && (edge_lo || edge_hi));  // rare: first/last frames only
         const uint32_t* prew = reinterpret_cast<const uint32_t*>(pre);
+        uint8_t* ytile = extra + h * 16384;  // [128 frames x 64 ch] staging tile of this column half
+        // the TMA store of the previous tile must have finished reading the staging tiles
+        if (issuer) tma_store_wait_read<0>();
+        named_bar_sync(1, kEpiWarps * 32);
 #pragma unroll
         for (int ci = 0; ci < 4; ++ci) {
           const int i = h * 64 + ci * 16;
@@ -341,71 +395,68 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           tmem_ld_x16(trow + i, rg);
           tmem_ld_x16(trow + 128 + i, rf);
           tmem_ld_wait();
-          if (valid) {
-            uint32_t packed[8];
+          uint32_t packed[8];
 #pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-              const float4 bg = __ldg(reinterpret_cast<const float4*>(sb_all + i + j));
-              const float4 bf = __ldg(reinterpret_cast<const float4*>(sb_all + 128 + i + j));
-              float zg[4] = {bg.x, bg.y, bg.z, bg.w}, zf[4] = {bf.x, bf.y, bf.z, bf.w};
-              if (edge_lo) {
+          for (int j = 0; j < 16; j += 4) {
+            const float4 bg = __ldg(reinterpret_cast<const float4*>(sb_all + i + j));
+            const float4 bf = __ldg(reinterpret_cast<const float4*>(sb_all + 128 + i + j));
+            float zg[4] = {bg.x, bg.y, bg.z, bg.w}, zf[4] = {bf.x, bf.y, bf.z, bf.w};
+            if (warp_edge) {
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+              for (int u = 0; u < 4; ++u) {
+                if (edge_lo) {
                   zg[u] -= __ldg(sb_t0 + i + j + u);
                   zf[u] -= __ldg(sb_t0 + 128 + i + j + u);
                 }
-              }
-              if (edge_hi) {
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                if (edge_hi) {
                   zg[u] -= __ldg(sb_t2 + i + j + u);
                   zf[u] -= __ldg(sb_t2 + 128 + i + j + u);
                 }
               }
-#pragma unroll
-              for (int u = 0; u < 4; u += 2) {
-                const float2 pg = Cvt<__half>::unpack(prew[(ci * 16 + j + u) >> 1]);
-                const float2 pf = Cvt<__half>::unpack(prew[32 + ((ci * 16 + j + u) >> 1)]);
-                const float g0 = __uint_as_float(rg[j + u]) + pg.x + zg[u];
-                const float g1 = __uint_as_float(rg[j + u + 1]) + pg.y + zg[u + 1];
-                const float f0 = __uint_as_float(rf[j + u]) + pf.x + zf[u];
-                const float f1 = __uint_as_float(rf[j + u + 1]) + pf.y + zf[u + 1];
-                packed[(j + u) >> 1] = Cvt<T>::pack(gate_fn(g0, f0), gate_fn(g1, f1));
-              }
             }
-            uint4* dst = reinterpret_cast<uint4*>(out_row + i);
-            dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-            dst[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+#pragma unroll
+            for (int u = 0; u < 4; u += 2) {
+              const float2 pg = Cvt<__half>::unpack(prew[(ci * 16 + j + u) >> 1]);
+              const float2 pf = Cvt<__half>::unpack(prew[32 + ((ci * 16 + j + u) >> 1)]);
+              const float g0 = __uint_as_float(rg[j + u]) + pg.x + zg[u];
+              const float g1 = __uint_as_float(rg[j + u + 1]) + pg.y + zg[u + 1];
+              const float f0 = __uint_as_float(rf[j + u]) + pf.x + zf[u];
+              const float f1 = __uint_as_float(rf[j + u + 1]) + pf.y + zf[u + 1];
+              packed[(j + u) >> 1] = Cvt<T>::pack(gate_fn<T>(g0, f0), gate_fn<T>(g1, f1));
+            }
           }
+          // rows past T hold junk here; the TMA store clips them
+          *sw128_chunk(ytile, row, 2 * ci) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+          *sw128_chunk(ytile, row, 2 * ci + 1) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
         }
       } else if constexpr (EPI == EPI_RES) {
-        const int C = ep.ld;
-        const uint32_t* prew = reinterpret_cast<const uint32_t*>(pre);
 #pragma unroll
-        for (int ci = 0; ci < (BN / 2) / 32; ++ci) {
-          const int c = h * (BN / 2) + ci * 32;
+        for (int ci = 0; ci < 4; ++ci) {
+          const int c = h * 128 + ci * 32;
+          uint8_t* xt = extra + (c >> 6) * 16384;  // sub-tile holding channels [c, c + 32)
+          const int ch0 = (c & 63) >> 3;           // first 16-byte chunk inside the sub-tile
           uint32_t r[32];
           tmem_ld_x32(trow + c, r);
           tmem_ld_wait();
-          if (valid) {
-            const int g = n_tile * BN + c;
-            uint4* dst = reinterpret_cast<uint4*>(static_cast<uint16_t*>(ep.out) + n * C + g);
+          const int g = n_tile * BN + c;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint32_t ow[4];
+          for (int j = 0; j < 4; ++j) {
+            uint4* px = sw128_chunk(xt, row, ch0 + j);
+            const uint4 xv = *px;
+            const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
+            uint32_t ow[4];
 #pragma unroll
-              for (int u = 0; u < 4; u += 2) {
-                const float4 bv = __ldg(reinterpret_cast<const float4*>(ep.bias + g + 8 * j + 2 * u));
-                const float2 xa = Cvt<T>::unpack(prew[ci * 16 + 4 * j + u]);
-                const float2 xb = Cvt<T>::unpack(prew[ci * 16 + 4 * j + u + 1]);
-                const int col = 8 * j + 2 * u;
-                ow[u] = Cvt<T>::pack((xa.x + __uint_as_float(r[col]) + bv.x) * ep.scale,
-                                     (xa.y + __uint_as_float(r[col + 1]) + bv.y) * ep.scale);
-                ow[u + 1] = Cvt<T>::pack((xb.x + __uint_as_float(r[col + 2]) + bv.z) * ep.scale,
-                                         (xb.y + __uint_as_float(r[col + 3]) + bv.w) * ep.scale);
-              }
-              dst[j] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+            for (int u = 0; u < 4; u += 2) {
+              const float4 bv = __ldg(reinterpret_cast<const float4*>(ep.bias + g + 8 * j + 2 * u));
+              const float2 xa = Cvt<T>::unpack(xw[u]);
+              const float2 xb = Cvt<T>::unpack(xw[u + 1]);
+              const int col = 8 * j + 2 * u;
+              ow[u] = Cvt<T>::pack((xa.x + __uint_as_float(r[col]) + bv.x) * ep.scale,
+                                   (xa.y + __uint_as_float(r[col + 1]) + bv.y) * ep.scale);
+              ow[u + 1] = Cvt<T>::pack((xb.x + __uint_as_float(r[col + 2]) + bv.z) * ep.scale,
+                                       (xb.y + __uint_as_float(r[col + 3]) + bv.w) * ep.scale);
             }
+            *px = make_uint4(ow[0], ow[1], ow[2], ow[3]);  // in place: x_next overwrites x_cur
           }
         }
       } else {  // EPI_OUT
@@ -460,6 +511,28 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[as]);
+
+      if constexpr (EPI == EPI_GATE || EPI == EPI_RES) {
+        // publish the shared-memory tile to the async proxy, then one thread hands it to the TMA store engine
+        fence_proxy_async_smem();
+        named_bar_sync(2, kEpiWarps * 32);
+        if (issuer) {
+          if constexpr (EPI == EPI_GATE) {
+            tma_store_4d(&tmO, extra, n_tile * 128, t0, b, ep.out_slab);
+            tma_store_4d(&tmO, extra + 16384, n_tile * 128 + 64, t0, b, ep.out_slab);
+            tma_store_commit();
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) tma_store_4d(&tmO, extra + j * 16384, n_tile * BN + j * 64, t0, b, 0);
+            tma_store_commit();
+            tma_store_wait_read<0>();   // the x tile may be overwritten by the next TMA load after this
+            mbar_arrive(xempty_bar);
+          }
+        }
+      }
+    }
+    if constexpr (EPI == EPI_GATE || EPI == EPI_RES) {
+      if (issuer) tma_store_wait_all();  // all bulk stores complete before the CTA retires
     }
   }
 

@@ -64,7 +64,9 @@ def check_layers(dtype="bf16", B=2, T=300, L=4, C=256, cycle=2, M=128):
         o = torch.empty_like(packed)
         o[..., idx] = packed
         return o
-    cp = plan.buffer("cp").view(torch.float16).view(L, N, 2 * C).float().cpu()
+    mtr = (T + 127) // 128
+    cpb = plan.buffer("cp").view(torch.float16).view(L, B, mtr, 2 * C // 8, 128, 8)   # [layer][utt][tile][chunk][row][8]
+    cp = cpb.permute(0, 1, 2, 4, 3, 5).reshape(L, B, mtr * 128, 2 * C)[:, :, :T].reshape(L, N, 2 * C).float().cpu()
     sb = plan.buffer("sb").view(torch.float32).view(-1, L, 4, 2 * C).cpu()
     y = plan.buffer("ybuf").view(tdt).view(L, N, C).float().cpu()
     for l in range(L):
