@@ -292,13 +292,20 @@ def main():
     if world > 1:
         dist.barrier()
     C, L = w["channels"], w["layers"]
-    if "dilated_conv+gate" in kinds:
-        tot_ms, n = kinds["dilated_conv+gate"]
-        flops_per_launch = 2.0 * (B * T) * (3 * C) * (2 * C)  # 12 C^2 per frame x frames per launch
+    dom = "residual_layer(fused)" if "residual_layer(fused)" in kinds else "dilated_conv+gate"
+    if dom in kinds:
+        tot_ms, n = kinds[dom]
+        # algorithmic FLOPs per frame per launch: dilated conv 12 C^2 (+ residual half of the 1x1
+        # output projection, 2 C^2, when the fused ResidualBlock kernel is the one running)
+        per_frame = 12 * C * C + (2 * C * C if dom.startswith("residual_layer") else 0)
+        flops_per_launch = float(per_frame) * (B * T)
         achieved = flops_per_launch / (tot_ms / n * 1e-3) / 1e12
         all_ms = sum(v[0] for v in kinds.values())
+        name = ("layer_kernel (fused ResidualBlock: dilated conv + gate + residual 1x1, cta_group::2)" if dom.startswith("residual_layer")
+                else "gemm_kernel<EPI_GATE,256> (dilated conv + gate)")
         roofline = {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
-                    "frac": achieved / peaks["tflops"], "traffic": None, "kernel": "gemm_kernel<EPI_GATE,256> (dilated conv + gate)",
+                    "frac": achieved / peaks["tflops"], "traffic": None, "kernel": name,
+                    "flops_per_frame_per_launch": per_frame,
                     "avg_launch_us": tot_ms / n * 1e3, "launches": n, "share_of_gemm_time": tot_ms / all_ms,
                     "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']})",
                     "per_kernel_ms_per_step": {k: v[0] / prof_steps for k, v in kinds.items()}}

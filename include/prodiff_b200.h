@@ -106,7 +106,7 @@ long long pd_launch_count(int reset);
  * bracketed by a CUDA-event pair on its stream.  pd_profile_end synchronises and returns, per kernel kind, the summed
  * milliseconds and the launch count.  Kinds: 0 cond_proj, 1 input_proj, 2 dilated_conv+gate, 3 res_proj, 4 skip_sum,
  * 5 skip_proj, 6 output_proj+posterior, 7 debug. */
-#define PD_N_KINDS 8
+#define PD_N_KINDS 9   /* kind 8 = fused ResidualBlock layer kernel (2-CTA) */
 int pd_profile_begin(void);
 int pd_profile_end(float* ms_by_kind, int* count_by_kind, int n_kinds);
 
@@ -120,7 +120,11 @@ int pd_plan_buffer(const pd_plan* p, const char* name, size_t* offset, size_t* b
 int pd_debug_gemm(int dtype, const void* a, int B, int T, int Cin, int taps, int dil, const void* w, int N,
                   const float* bias, float* out, void* stream);
 
-/* Debug: when set to a device buffer of 8 x 1024 int64, CTA 0 of every GEMM launch writes clock64() stamps of its
+/* Select the fused 2-CTA ResidualBlock kernel (1, default; env PD_FUSED=0 also disables) or the unfused
+ * conv+gate / res_proj pair (0).  Returns the previous setting (-1 = not yet decided). */
+int pd_set_fused(int on);
+
+/* Debug: when set to a device buffer of 9 x 1024 int64, CTA 0 of every GEMM launch writes clock64() stamps of its
  * pipeline events at [kind * 1024 + tile * 16 + slot] (slots: 0/1 first/last TMA issue, 2 accumulator free, 3/4 first/
  * last operand stage landed, 5/6 epilogue before/after accumulator wait, 7 epilogue done, 14 exit, 15 entry). */
 int pd_debug_set_trace(long long* device_buf);

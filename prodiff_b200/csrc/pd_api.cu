@@ -2,6 +2,7 @@
 // and the launch sequences behind WaveNet.forward and the K-step GaussianDiffusion reverse loop.
 #include "../../include/prodiff_b200.h"
 #include "pd_aux.cuh"
+#include "pd_layer.cuh"
 
 #include <math.h>
 #include <stdarg.h>
@@ -74,7 +75,7 @@ static void prof_after(cudaStream_t s) {
   ++g_prof_used;
 }
 // debug: device buffer of 8 kinds x 1024 slots; CTA 0 of every GEMM launch records clock64() at pipeline events
-static thread_local long long* g_trace = nullptr;
+static thread_local long long* g_trace = nullptr;  // 9 kinds x 1024 slots
 extern "C" int pd_debug_set_trace(long long* device_buf) {
   g_trace = device_buf;
   return 0;
@@ -140,9 +141,9 @@ static int make_map(CUtensorMap* m, int dtype, const void* base, int rank, const
   return 0;
 }
 // activation map: [slabs][B][T][Cin] 16-bit
-static int make_act_map(CUtensorMap* m, int dtype, const void* base, int Cin, int T, int B, int slabs) {
+static int make_act_map(CUtensorMap* m, int dtype, const void* base, int Cin, int T, int B, int slabs, int box_rows = kBlockM) {
   const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)T, (uint64_t)B, (uint64_t)slabs};
-  return make_map(m, dtype, base, 4, dims, kBlockM);
+  return make_map(m, dtype, base, 4, dims, (uint32_t)box_rows);
 }
 // weight map: [rows][K] 16-bit
 static int make_w_map(CUtensorMap* m, int dtype, const void* base, int K, int rows, int bn) {
@@ -168,7 +169,7 @@ static PackedLayout packed_layout(const pd_config& c) {
   p.w_in = take(C * M * 2);
   p.w_cond = take(L * 2 * C * H * 2);
   p.w_dil = take(L * 2 * C * 3 * C * 2);
-  p.w_res = take(L * C * C * 2);
+  p.w_res = take((L + 1) * C * C * 2);  // + one [C x C] identity block (fused layer kernel: residual add on the tensor core)
   p.w_skip = take(C * L * C * 2);
   p.w_sp = take(C * C * 2);
   p.w_out = take(128 * C * 2);
@@ -213,6 +214,7 @@ struct pd_model {
   uint8_t* packed;
   int device, sm_count;
   CUtensorMap tm_w_in, tm_w_cond, tm_w_dil, tm_w_res, tm_w_skip, tm_w_sp, tm_w_out;
+  CUtensorMap tm_w_dil128, tm_w_res128;  // 128-row boxes: one CTA's half of a cta_group::2 weight block
 };
 
 static int check_device(int* device, int* sms) {
@@ -236,6 +238,8 @@ static int pack_all(const pd_config& c, const PackedLayout& lay, uint8_t* pk, co
   PD_LAUNCH_CHECK("k_pack_rows(sp)");
   k_pack_rows<T><<<blocks(128ll * C), TB, 0, s>>>((T*)(pk + lay.w_out), C, 0, st[8], M, 0, 128, C, 0);
   PD_LAUNCH_CHECK("k_pack_rows(out)");
+  k_identity<T><<<blocks((long long)C * C), TB, 0, s>>>((T*)(pk + lay.w_res) + (size_t)L * C * C, C);
+  PD_LAUNCH_CHECK("k_identity");
   k_pack_bias<<<blocks(C), TB, 0, s>>>((float*)(pk + lay.b_in), st[1], nullptr, 0, C, C, 0, 0);
   k_pack_bias<<<blocks(C), TB, 0, s>>>((float*)(pk + lay.b_sp), st[7], nullptr, 0, C, C, 0, 0);
   k_pack_bias<<<1, 128, 0, s>>>((float*)(pk + lay.b_out), st[9], nullptr, 0, M, 128, 0, 0);
@@ -295,7 +299,8 @@ extern "C" int pd_model_create(const pd_config* cfg, const float* const* state, 
   if (make_w_map(&m->tm_w_in, dt, pk + lay.w_in, M, C, 256) || make_w_map(&m->tm_w_cond, dt, pk + lay.w_cond, H, L * 2 * C, 256) ||
       make_w_map(&m->tm_w_dil, dt, pk + lay.w_dil, 3 * C, L * 2 * C, 256) || make_w_map(&m->tm_w_res, dt, pk + lay.w_res, C, L * C, 256) ||
       make_w_map(&m->tm_w_skip, dt, pk + lay.w_skip, L * C, C, 256) || make_w_map(&m->tm_w_sp, dt, pk + lay.w_sp, C, C, 256) ||
-      make_w_map(&m->tm_w_out, dt, pk + lay.w_out, C, 128, 128)) {
+      make_w_map(&m->tm_w_out, dt, pk + lay.w_out, C, 128, 128) ||
+      make_w_map(&m->tm_w_dil128, dt, pk + lay.w_dil, 3 * C, L * 2 * C, 128) || make_w_map(&m->tm_w_res128, dt, pk + lay.w_res, C, (L + 1) * C, 128)) {
     delete m;
     return 1;
   }
@@ -315,6 +320,9 @@ struct pd_plan {
   uint8_t* ws;
   std::vector<Buf> bufs;
   CUtensorMap tm_cond, tm_xin, tm_xa, tm_xb, tm_y, tm_s1, tm_s2;
+  CUtensorMap tm_xa_halo[5], tm_xb_halo[5];   // box (64, 128 + 2*2^i): haloed tile loads of the fused layer kernel
+  CUtensorMap tm_xa_st, tm_xb_st, tm_y_st;    // box (64, 32): per-warp TMA stores
+  bool fused_ok;
   size_t off(const char* n) const {
     for (const Buf& b : bufs)
       if (!strcmp(b.name, n)) return b.off;
@@ -382,6 +390,21 @@ extern "C" int pd_plan_create(const pd_model* m, int B, int T, int max_entries, 
       make_act_map(&p->tm_s1, dt, p->ptr<void>("s1"), C, T, B, 1) || make_act_map(&p->tm_s2, dt, p->ptr<void>("s2"), C, T, B, 1)) {
     delete p;
     return 1;
+  }
+  // fused layer kernel (C = 256, dilations <= 16): haloed loads and 32-row store boxes
+  p->fused_ok = (C == kLayerC) && (1 << (c.dilation_cycle_length - 1)) <= kLayerMaxDil;
+  if (p->fused_ok) {
+    for (int i = 0; i < 5 && i < c.dilation_cycle_length; ++i)
+      if (make_act_map(&p->tm_xa_halo[i], dt, p->ptr<void>("xa"), C, T, B, 1, kBlockM + 2 * (1 << i)) ||
+          make_act_map(&p->tm_xb_halo[i], dt, p->ptr<void>("xb"), C, T, B, 1, kBlockM + 2 * (1 << i))) {
+        delete p;
+        return 1;
+      }
+    if (make_act_map(&p->tm_xa_st, dt, p->ptr<void>("xa"), C, T, B, 1, 32) || make_act_map(&p->tm_xb_st, dt, p->ptr<void>("xb"), C, T, B, 1, 32) ||
+        make_act_map(&p->tm_y_st, dt, p->ptr<void>("ybuf"), C, T, B, c.residual_layers, 32)) {
+      delete p;
+      return 1;
+    }
   }
   *out = p;
   return 0;
@@ -458,6 +481,54 @@ static EpiArgs base_epi() {
   return e;
 }
 
+// ------------------------------------------------------------------ fused layer kernel launch (2-CTA clusters)
+static int g_fused = -1;  // -1: read PD_FUSED from the environment on first use
+extern "C" int pd_set_fused(int on) {
+  const int prev = g_fused;
+  g_fused = on ? 1 : 0;
+  return prev;
+}
+static bool fused_enabled() {
+  if (g_fused < 0) {
+    const char* e = getenv("PD_FUSED");
+    g_fused = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_fused == 1;
+}
+
+template <typename T>
+static int launch_layer_t(const CUtensorMap& x, const CUtensorMap& wd, const CUtensorMap& wr, const CUtensorMap& ys,
+                          const CUtensorMap& xs, const LayerParams& lp, int sms, cudaStream_t s) {
+  auto kern = layer_kernel<T>;
+  static bool configured[64] = {false};
+  int dev = 0;
+  PD_CUDA(cudaGetDevice(&dev));
+  if (!configured[dev & 63]) {
+    PD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLayerSmemBytes));
+    configured[dev & 63] = true;
+  }
+  const int num_pairs = (lp.B * lp.m_tiles_per_row + 1) / 2;
+  const int clusters = num_pairs < sms / 2 ? num_pairs : sms / 2;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(2 * clusters);
+  cfg.blockDim = dim3(kLayerThreads);
+  cfg.dynamicSmemBytes = kLayerSmemBytes;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  prof_before(8, s);
+  PD_CUDA(cudaLaunchKernelEx(&cfg, kern, x, wd, wr, ys, xs, lp));
+  prof_after(s);
+  PD_LAUNCH_CHECK("layer_kernel");
+  return 0;
+}
+
 // ------------------------------------------------------------------ hot-path sequences
 extern "C" int pd_cond_project(pd_plan* p, const float* cond, void* stream) {
   if (!p || !cond) return fail("null argument");
@@ -529,8 +600,37 @@ static int run_denoiser(pd_plan* p, int entry_base, int entry_per_b, const OutSt
     if (launch_gemm<EPI_STORE, 256>(dt, p->tm_xin, m->tm_w_in, sh, ep, sms, s, "gemm(input_proj)", 1)) return 1;
   }
   bool cur_is_a = true;
+  const bool fused = p->fused_ok && fused_enabled();
   for (int l = 0; l < L; ++l) {
     const int dil = 1 << (l % c.dilation_cycle_length);
+    if (fused) {  // whole ResidualBlock in one 2-CTA kernel
+      const size_t mtiles = (size_t)B * ((T + kBlockM - 1) / kBlockM);
+      LayerParams lp;
+      memset(&lp, 0, sizeof(lp));
+      lp.B = B;
+      lp.T = T;
+      lp.m_tiles_per_row = (T + kBlockM - 1) / kBlockM;
+      lp.dil = dil;
+      lp.layer = l;
+      lp.ident_row0 = L * C;
+      lp.idesc = (1u << 4) | ((dt == PD_FP16 ? 0u : 1u) << 7) | ((dt == PD_FP16 ? 0u : 1u) << 10) | ((256u >> 3) << 17) | ((256u >> 4) << 24);
+      lp.cp = p->ptr<uint16_t>("cp") + (size_t)l * mtiles * kBlockM * 2 * C;
+      lp.sb = p->ptr<float>("sb") + (size_t)l * 4 * 2 * C;
+      lp.sb_entry_stride = (long long)L * 4 * 2 * C;
+      lp.sb_entry_base = entry_base;
+      lp.sb_entry_per_b = entry_per_b;
+      lp.b_res = (const float*)(pk + lay.b_res) + (size_t)l * C;
+      lp.scale = 0.70710678118654752440f;
+      lp.trace = g_trace ? g_trace + 8 * 1024 : nullptr;
+      const int di = l % c.dilation_cycle_length;
+      const CUtensorMap& xh = cur_is_a ? p->tm_xa_halo[di] : p->tm_xb_halo[di];
+      const CUtensorMap& xs = cur_is_a ? p->tm_xb_st : p->tm_xa_st;
+      const int rc = dt == PD_FP16 ? launch_layer_t<__half>(xh, m->tm_w_dil128, m->tm_w_res128, p->tm_y_st, xs, lp, sms, s)
+                                   : launch_layer_t<__nv_bfloat16>(xh, m->tm_w_dil128, m->tm_w_res128, p->tm_y_st, xs, lp, sms, s);
+      if (rc) return rc;
+      cur_is_a = !cur_is_a;
+      continue;
+    }
     const CUtensorMap& tm_cur = cur_is_a ? p->tm_xa : p->tm_xb;
     const CUtensorMap& tm_nxt = cur_is_a ? p->tm_xb : p->tm_xa;
     {  // dilated conv + cond + step bias -> gate (wavenet.py:63-68)

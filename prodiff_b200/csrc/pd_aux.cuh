@@ -44,6 +44,13 @@ __global__ void k_pack_rows(T* __restrict__ dst, long long dst_ld, int dst_col0,
   }
 }
 
+template <typename T>
+__global__ void k_identity(T* __restrict__ dst, int C) {
+  const long long total = (long long)C * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+    dst[i] = from_float<T>((i / C) == (i % C) ? 1.f : 0.f);
+}
+
 // fp32 vector ops used while packing biases: dst[i] = (acc ? dst[i] : 0) + a[map(i) + a0] (+ b[map(i)]), zero padded.
 __global__ void k_pack_bias(float* __restrict__ dst, const float* __restrict__ a, const float* __restrict__ b, int a0,
                             int a_len, int n, int gateC, int accumulate) {

@@ -95,8 +95,9 @@ template <> struct Cvt<__half> {
 
 // sigmoid(g) * tanh(f).
 //  * fp16 operands (strict-parity mode): (e^{2f} - 1) / ((1 + e^{-g}) (e^{2f} + 1)), 2 ex2 + 1 rcp, ~1e-6 accurate.
-//  * bf16 operands: MUFU.TANH twice (sigmoid(g) = 0.5 tanh(g/2) + 0.5).  tanh.approx has ~2^-11 max error, below the
-//    2^-9 rounding of the bf16 value the result is stored as, and it is 5 issue slots instead of 14.
+//  * bf16 operands: MUFU.TANH twice (sigmoid(g) = 0.5 tanh(g/2) + 0.5): 5 issue slots instead of 14.  tanh.approx has
+//    ~2^-11 max error, below the 2^-9 rounding of the bf16 value the result is stored as.  (tanh.approx.f16x2 was
+//    tried: ptxas splits it into two scalar MUFU.TANH.F16, so it saves nothing.)
 template <typename T>
 __device__ __forceinline__ float gate_fn(float g, float f) {
   if constexpr (sizeof(T) == 2 && Cvt<T>::kFormat == 1) {
@@ -139,6 +140,45 @@ __device__ __forceinline__ float4 philox_normal4(unsigned long long seed, uint32
   __sincosf(6.283185307179586f * u1, &s0, &c0f);
   __sincosf(6.283185307179586f * u3, &s1, &c1f);
   return make_float4(r0 * c0f, r0 * s0, r1 * c1f, r1 * s1);
+}
+
+// One 16-channel step of the gate epilogue: z = acc + cond_proj + step bias (minus the taps that fell on padding when
+// kEdge), y = sigmoid(z_gate) * tanh(z_filter), packed to 16-bit.  rg/rf: accumulator columns of the 16 gate / filter
+// channels; cpg/cpf: 8 packed fp16 pairs each; sb: step-bias row positioned at the first gate channel (filter at
+// +128, tap-0 table at +t0_off, tap-2 table at +t2_off).  kEdge is warp-uniform so the hot path has no predication.
+template <typename T, bool kEdge>
+__device__ __forceinline__ void gate_chunk16(const uint32_t (&rg)[16], const uint32_t (&rf)[16], const uint32_t* cpg,
+                                             const uint32_t* cpf, const float* sb, int t0_off, int t2_off, bool edge_lo,
+                                             bool edge_hi, uint32_t (&packed)[8]) {
+#pragma unroll
+  for (int j = 0; j < 16; j += 4) {
+    const float4 bg = __ldg(reinterpret_cast<const float4*>(sb + j));
+    const float4 bf = __ldg(reinterpret_cast<const float4*>(sb + 128 + j));
+    float zg[4] = {bg.x, bg.y, bg.z, bg.w}, zf[4] = {bf.x, bf.y, bf.z, bf.w};
+    if constexpr (kEdge) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (edge_lo) {
+          zg[u] -= __ldg(sb + t0_off + j + u);
+          zf[u] -= __ldg(sb + t0_off + 128 + j + u);
+        }
+        if (edge_hi) {
+          zg[u] -= __ldg(sb + t2_off + j + u);
+          zf[u] -= __ldg(sb + t2_off + 128 + j + u);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u += 2) {
+      const float2 pg = Cvt<__half>::unpack(cpg[(j + u) >> 1]);
+      const float2 pf = Cvt<__half>::unpack(cpf[(j + u) >> 1]);
+      const float g0 = __uint_as_float(rg[j + u]) + (pg.x + zg[u]);
+      const float g1 = __uint_as_float(rg[j + u + 1]) + (pg.y + zg[u + 1]);
+      const float f0 = __uint_as_float(rf[j + u]) + (pf.x + zf[u]);
+      const float f1 = __uint_as_float(rf[j + u + 1]) + (pf.y + zf[u + 1]);
+      packed[(j + u) >> 1] = Cvt<T>::pack(gate_fn<T>(g0, f0), gate_fn<T>(g1, f1));
+    }
+  }
 }
 
 template <int EPI, int BN> struct GemmCfg {
@@ -378,8 +418,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int C2 = 2 * ep.ld;
         const int entry = ep.sb_entry_base + b * ep.sb_entry_per_b;
         const float* sb_all = ep.sb + (long long)entry * ep.sb_entry_stride + n_tile * 256;
-        const float* sb_t0 = sb_all + C2;
-        const float* sb_t2 = sb_all + 2 * C2;
         const bool edge_lo = t < sh.dil;            // tap 0 reads x[t - dil] which is padding
         const bool edge_hi = t + sh.dil >= sh.T;    // tap 2 reads x[t + dil] which is padding
         const bool warp_edge = __any_sync(0xffffffffu, valid && (edge_lo || edge_hi));  // rare: first/last frames only
@@ -396,35 +434,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           tmem_ld_x16(trow + 128 + i, rf);
           tmem_ld_wait();
           uint32_t packed[8];
-#pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            const float4 bg = __ldg(reinterpret_cast<const float4*>(sb_all + i + j));
-            const float4 bf = __ldg(reinterpret_cast<const float4*>(sb_all + 128 + i + j));
-            float zg[4] = {bg.x, bg.y, bg.z, bg.w}, zf[4] = {bf.x, bf.y, bf.z, bf.w};
-            if (warp_edge) {
-#pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                if (edge_lo) {
-                  zg[u] -= __ldg(sb_t0 + i + j + u);
-                  zf[u] -= __ldg(sb_t0 + 128 + i + j + u);
-                }
-                if (edge_hi) {
-                  zg[u] -= __ldg(sb_t2 + i + j + u);
-                  zf[u] -= __ldg(sb_t2 + 128 + i + j + u);
-                }
-              }
-            }
-#pragma unroll
-            for (int u = 0; u < 4; u += 2) {
-              const float2 pg = Cvt<__half>::unpack(prew[(ci * 16 + j + u) >> 1]);
-              const float2 pf = Cvt<__half>::unpack(prew[32 + ((ci * 16 + j + u) >> 1)]);
-              const float g0 = __uint_as_float(rg[j + u]) + pg.x + zg[u];
-              const float g1 = __uint_as_float(rg[j + u + 1]) + pg.y + zg[u + 1];
-              const float f0 = __uint_as_float(rf[j + u]) + pf.x + zf[u];
-              const float f1 = __uint_as_float(rf[j + u + 1]) + pf.y + zf[u + 1];
-              packed[(j + u) >> 1] = Cvt<T>::pack(gate_fn<T>(g0, f0), gate_fn<T>(g1, f1));
-            }
-          }
+          if (warp_edge) gate_chunk16<T, true>(rg, rf, prew + ci * 8, prew + 32 + ci * 8, sb_all + i, C2, 2 * C2, edge_lo, edge_hi, packed);
+          else gate_chunk16<T, false>(rg, rf, prew + ci * 8, prew + 32 + ci * 8, sb_all + i, C2, 2 * C2, false, false, packed);
           // rows past T hold junk here; the TMA store clips them
           *sw128_chunk(ytile, row, 2 * ci) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
           *sw128_chunk(ytile, row, 2 * ci + 1) = make_uint4(packed[4], packed[5], packed[6], packed[7]);

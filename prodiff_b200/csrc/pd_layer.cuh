@@ -1,0 +1,423 @@
+// Fused ResidualBlock kernel for sm_100a: one launch per layer does what wavenet.py:60-72 does for a whole batch,
+//
+//   y      = sigmoid(gate) * tanh(filter),  [gate|filter] = DilConv3(x + d) + cond_proj        (MMA1 + epilogue 1)
+//   x_next = (x + W_res y + b_res) / sqrt(2)                                                    (MMA2 + epilogue 2)
+//            where "x +" is itself part of MMA2: an identity weight block over the centre view of the resident x tile
+//            initialises the accumulator (exact: bf16 x times 1.0 in fp32).  That work runs on the tensor pipe while
+//            the epilogue drains the last gate chunk (when the pipe would otherwise idle), and it lets the x tile be
+//            released -- and the next one prefetched -- before the epilogue has finished.
+//
+// and leaves y in HBM for the deferred skip GEMM.  C = 256 residual channels.
+//
+// B200 mapping
+// * A thread-block CLUSTER of 2 CTAs (one SM pair) works on two 128-frame tiles at once with `tcgen05.mma.cta_group::2`
+//   (M = 256, N = 256, K = 16): each CTA stages only HALF of every weight block (128 of 256 rows), so weight traffic
+//   from L2 and shared-memory operand bandwidth per SM are halved -- the single-CTA kernel was bound by L2->SM feed.
+// * The activation tile is loaded ONCE per layer with a halo (128 + 2*dilation frames, TMA zero-fills frames outside
+//   the utterance = the conv's padding) and the three taps are row-shifted views of that resident tile (legal with
+//   descriptor base_offset 0: the 128B swizzle is a function of absolute smem address bits; profiles/r01_probe_shift.json).
+// * The gated activations are written by the epilogue straight into a swizzled K-major shared-memory tile, which is
+//   both the A operand of MMA2 and the source of the TMA store to HBM; x_next is staged in the same tile afterwards.
+// * TMEM (512 columns) is two 256-column regions; per tile they hold D1[gate/filter chunk 0], D1[chunk 1] and then D2,
+//   rotating so that the MMAs of one region overlap the epilogue draining the other.
+//
+// Roles per CTA: warp 0 = weight-block TMA producer, warp 1 = MMA issuer (leader CTA only), warps 2..9 = epilogue,
+// warp 10 = x-tile TMA producer.
+// Warp (q = warp & 3, h = (warp - 2) >> 2) owns rows 32q..32q+31 of Y sub-tiles h and 2 + h for the whole tile
+// (channels [64h, 64h+64) and [128+64h, 128+64h+64)), so every shared-memory hazard on Y is warp-local.
+#pragma once
+#include "pd_gemm.cuh"
+
+namespace pd {
+
+constexpr int kLayerC = 256;
+constexpr int kLayerStages = 5;                  // 16 KB weight blocks in flight per CTA
+constexpr int kXSubStride = 160 * 128;           // bytes reserved per 64-channel X sub-tile (up to 128 + 2*16 frames)
+constexpr int kLayerMaxDil = 16;
+constexpr int kLayerThreads = kGemmThreads + 32;  // + warp 10: dedicated X-tile producer (never queued behind weight blocks)
+constexpr int kLayerBlocks = 32;                 // weight blocks per tile: 2 x 12 dilated-conv, 4 identity, 4 residual 1x1
+constexpr uint32_t kLayerSmemBytes = 4 * kXSubStride + 4 * 16384 + kLayerStages * 16384 + 1024 + 512;
+constexpr uint32_t kPeerMask = 0xFEFFFFFFu;      // clears the CTA-rank bit of a shared::cluster address -> leader CTA
+
+struct LayerParams {
+  int B, T, m_tiles_per_row;
+  int dil;
+  int layer;              // weight row block / y slab
+  int ident_row0;         // first row of the [C x C] identity block appended to the W_res matrix
+  uint32_t idesc;         // cta_group::2 instruction descriptor (M = 256, N = 256)
+  const void* cp;         // this layer's hoisted cond projection, tile-blocked fp16
+  const float* sb;        // this layer's step-bias table
+  long long sb_entry_stride;
+  int sb_entry_base, sb_entry_per_b;
+  const float* b_res;     // residual-half bias of output_projection [C]
+  float scale;            // 1/sqrt(2)
+  long long* trace;
+};
+
+// ---- cluster / 2-CTA PTX
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same offset in the LEADER CTA (rank 0) of the pair
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerMask) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_2sm(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_dst) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "n"(kCols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
+}
+__device__ __forceinline__ void umma_f16_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive (once all prior MMAs of this thread completed) on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kLayerThreads, 1)
+layer_kernel(const __grid_constant__ CUtensorMap tmX,     // x_cur  [1][B][T][C], box (64, 128 + 2*dil)
+             const __grid_constant__ CUtensorMap tmWd,    // W_dil  [L*2C][3C],   box (64, 128)
+             const __grid_constant__ CUtensorMap tmWr,    // W_res  [L*C][C],     box (64, 128)
+             const __grid_constant__ CUtensorMap tmYs,    // ybuf   [L][B][T][C], box (64, 32)  (store)
+             const __grid_constant__ CUtensorMap tmXs,    // x_next [1][B][T][C], box (64, 32)  (store)
+             const LayerParams lp) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* sX = smem;                                  // 4 x [<=160 frames x 64 ch]   haloed activation tile
+  uint8_t* sY = sX + 4 * kXSubStride;                  // 4 x [128 frames x 64 ch]     gated y, later x_next
+  uint8_t* sW = sY + 4 * 16384;                        // kLayerStages x [128 rows x 64 k] weight blocks (this CTA's half)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sW + kLayerStages * 16384);
+  uint64_t* full_bar = bars;                           // [S] leader: weight block landed in both CTAs
+  uint64_t* empty_bar = full_bar + kLayerStages;       // [S] local : MMAs finished reading the block
+  uint64_t* xfull_bar = empty_bar + kLayerStages;      // leader: X landed in both CTAs
+  uint64_t* xempty_bar = xfull_bar + 1;                // local : X reusable (all tensor-core reads of it completed)
+  uint64_t* rfull_bar = xempty_bar + 1;                // [2] local : accumulator region complete
+  uint64_t* rfree_bar = rfull_bar + 2;                 // [2] leader: region drained by all 16 epilogue warps
+  uint64_t* yready_bar = rfree_bar + 2;                // [2] leader: y channels [128j, 128j+128) written in both CTAs
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(yready_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const bool tr = lp.trace != nullptr && blockIdx.x == 0;
+  if (tr && threadIdx.x == 0) lp.trace[15] = clock64();
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmWd);
+    tma_prefetch_desc(&tmWr);
+    tma_prefetch_desc(&tmYs);
+    tma_prefetch_desc(&tmXs);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kLayerStages; ++i) {
+      mbar_init(&full_bar[i], 2);
+      mbar_init(&empty_bar[i], 1);
+    }
+    mbar_init(xfull_bar, 2);
+    mbar_init(xempty_bar, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&rfull_bar[i], 1);
+      mbar_init(&rfree_bar[i], 2 * kEpiWarps);
+      mbar_init(&yready_bar[i], 2 * kEpiWarps);
+    }
+    fence_mbar_init();
+  }
+  cluster_sync_all();                      // both CTAs alive + barriers initialised before any remote arrive / alloc
+  if (warp == 2) tmem_alloc_2sm<kTmemCols>(tmem_slot);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_m_tiles = lp.B * lp.m_tiles_per_row;
+  const int num_pairs = (num_m_tiles + 1) >> 1;
+  const int num_clusters = gridDim.x >> 1;
+  const int cluster_id = blockIdx.x >> 1;
+  // Every cluster walks the same weight blocks; starting each one at a different K block spreads the simultaneous
+  // requests over different L2 lines instead of hammering one hot block (fp32 accumulation order differs per
+  // cluster but is fixed for a given launch geometry, so results stay deterministic).
+  const int rot12 = cluster_id % 12, rot4 = cluster_id & 3;
+  const int xrows = kBlockM + 2 * lp.dil;
+  const uint32_t xbytes = 4u * (uint32_t)xrows * 128u;     // per CTA
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      uint32_t it = 0, ti = 0;
+      for (int pair = cluster_id; pair < num_pairs; pair += num_clusters, ++ti) {
+        const int m_tile = 2 * pair + (int)rank;
+        const int b = m_tile / lp.m_tiles_per_row;           // == B for the dummy tile of an odd count: fully OOB
+        const int t0 = (m_tile - b * lp.m_tiles_per_row) * kBlockM;
+        auto load_block = [&](int blk) {
+          const uint32_t stage = it % kLayerStages, parity = (it / kLayerStages) & 1u;
+          mbar_wait(&empty_bar[stage], parity ^ 1u, 1);
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * 16384);
+          else mbar_arrive_leader(&full_bar[stage]);
+          if (blk < 24) {
+            const int j = blk / 12;                           // gate/filter chunk
+            const int kb = (blk - j * 12 + rot12) % 12;       // (tap, channel-chunk) K block, start rotated per cluster
+            tma_load_2d_2sm(sW + stage * 16384, &tmWd, &full_bar[stage], kb * kBlockK,
+                            lp.layer * 2 * kLayerC + j * 256 + (int)rank * 128);
+          } else if (blk < 28) {                             // identity block: D2 starts as the x tile itself
+            tma_load_2d_2sm(sW + stage * 16384, &tmWr, &full_bar[stage], ((blk - 24 + rot4) & 3) * kBlockK,
+                            lp.ident_row0 + (int)rank * 128);
+          } else {
+            tma_load_2d_2sm(sW + stage * 16384, &tmWr, &full_bar[stage], (blk - 28) * kBlockK,
+                            lp.layer * kLayerC + (int)rank * 128);
+          }
+          ++it;
+        };
+        for (int blk = 0; blk < kLayerBlocks; ++blk) load_block(blk);
+        if (tr) lp.trace[ti * 16 + 1] = clock64();
+      }
+    }
+  } else if (warp == 10) {
+    // ===================== x-tile producer (both CTAs) =====================
+    if (lane == 0) {
+      uint32_t ti = 0;
+      for (int pair = cluster_id; pair < num_pairs; pair += num_clusters, ++ti) {
+        const int m_tile = 2 * pair + (int)rank;
+        const int b = m_tile / lp.m_tiles_per_row;           // == B for the dummy tile of an odd count: fully OOB
+        const int t0 = (m_tile - b * lp.m_tiles_per_row) * kBlockM;
+        mbar_wait(xempty_bar, (ti & 1u) ^ 1u, 5);
+        if (tr) lp.trace[ti * 16 + 0] = clock64();
+        if (leader) mbar_arrive_expect_tx(xfull_bar, 2 * xbytes);
+        else mbar_arrive_leader(xfull_bar);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tma_load_4d_2sm(sX + c * kXSubStride, &tmX, xfull_bar, c * 64, t0 - lp.dil, b, 0);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (leader && lane == 0) {
+      uint32_t it = 0, ti = 0;
+      uint32_t wcount[2] = {0u, 0u};   // writes issued to each TMEM region
+      const uint32_t sXa = smem_u32(sX), sYa = smem_u32(sY), sWa = smem_u32(sW);
+      for (int pair = cluster_id; pair < num_pairs; pair += num_clusters, ++ti) {
+        const uint32_t p = ti & 1u;
+        mbar_wait(xfull_bar, ti & 1u, 2);
+        tc_fence_after();
+        if (tr) lp.trace[ti * 16 + 2] = clock64();
+        // ---- MMA1: D1[j] = sum over taps / channel chunks of X(tap view) * W_dil^T
+        for (int j = 0; j < 2; ++j) {
+          const uint32_t reg = p ^ (uint32_t)j;
+          mbar_wait(&rfree_bar[reg], (wcount[reg] & 1u) ^ 1u, 3);
+          ++wcount[reg];
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + reg * 256u;
+          for (int kk = 0; kk < 12; ++kk, ++it) {
+            const int kb = (kk + rot12) % 12;
+            const uint32_t stage = it % kLayerStages, parity = (it / kLayerStages) & 1u;
+            mbar_wait(&full_bar[stage], parity, 4);
+            tc_fence_after();
+            const int tap = kb >> 2, cc = kb & 3;
+            const uint64_t adesc = make_sw128_kmajor_desc(sXa + cc * kXSubStride + (uint32_t)(tap * lp.dil) * 128u);
+            const uint64_t bdesc = make_sw128_kmajor_desc(sWa + stage * 16384);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_f16_2sm(d_tmem, desc_advance_k(adesc, k), desc_advance_k(bdesc, k), lp.idesc, (kk | k) != 0 ? 1u : 0u);
+            umma_commit_2sm(&empty_bar[stage]);
+          }
+          umma_commit_2sm(&rfull_bar[reg]);
+          if (tr) lp.trace[ti * 16 + 3 + j] = clock64();
+        }
+        // ---- MMA2: D2 = x_centre * I  +  Y * W_res^T, into the region epilogue-1(j=0) has drained
+        {
+          const uint32_t reg = p;
+          mbar_wait(&rfree_bar[reg], (wcount[reg] & 1u) ^ 1u, 6);
+          ++wcount[reg];
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + reg * 256u;
+          for (int kb = 0; kb < 8; ++kb, ++it) {
+            if (kb == 4) {
+              umma_commit_2sm(xempty_bar);   // tensor side is done with X: the next tile's X may be prefetched now
+              mbar_wait(&yready_bar[0], ti & 1u, 7);
+            }
+            if (kb == 6) mbar_wait(&yready_bar[1], ti & 1u, 8);
+            const uint32_t stage = it % kLayerStages, parity = (it / kLayerStages) & 1u;
+            mbar_wait(&full_bar[stage], parity, 9);
+            tc_fence_after();
+            const uint64_t adesc = kb < 4 ? make_sw128_kmajor_desc(sXa + ((kb + rot4) & 3) * kXSubStride + (uint32_t)lp.dil * 128u)   // centre rows
+                                          : make_sw128_kmajor_desc(sYa + (kb - 4) * 16384);
+            const uint64_t bdesc = make_sw128_kmajor_desc(sWa + stage * 16384);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_f16_2sm(d_tmem, desc_advance_k(adesc, k), desc_advance_k(bdesc, k), lp.idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_commit_2sm(&empty_bar[stage]);
+          }
+          umma_commit_2sm(&rfull_bar[reg]);
+          if (tr) lp.trace[ti * 16 + 5] = clock64();
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue warps (both CTAs) =====================
+    const int q = warp & 3, h = (warp - 2) >> 2;
+    const int row = q * 32 + lane;
+    uint32_t ti = 0;
+    uint32_t dcount[2] = {0u, 0u};   // drains performed on each TMEM region
+    const uint16_t* cpb = static_cast<const uint16_t*>(lp.cp);
+    for (int pair = cluster_id; pair < num_pairs; pair += num_clusters, ++ti) {
+      const uint32_t p = ti & 1u;
+      const int m_tile = 2 * pair + (int)rank;
+      const int b = m_tile / lp.m_tiles_per_row;
+      const int t0 = (m_tile - b * lp.m_tiles_per_row) * kBlockM;
+      const int t = t0 + row;
+      const bool valid = (m_tile < num_m_tiles) && (t < lp.T);
+      const int entry = lp.sb_entry_base + (b < lp.B ? b : 0) * lp.sb_entry_per_b;
+      const bool edge_lo = t < lp.dil, edge_hi = t + lp.dil >= lp.T;
+      const bool warp_edge = __any_sync(0xffffffffu, valid && (edge_lo || edge_hi));
+
+      // ---------------- epilogue 1: gate, for the two 128-channel chunks
+#pragma unroll 1
+      for (int j = 0; j < 2; ++j) {
+        const uint32_t reg = p ^ (uint32_t)j;
+        uint4 pre[16];
+        if (valid) {   // hoisted cond projection of this warp's 64 gate + 64 filter columns (coalesced, blocked layout)
+          const int cg = j * 32 + h * 8;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            pre[u] = __ldg(reinterpret_cast<const uint4*>(cpb + blocked_off(m_tile, 64, cg + u, row)));
+            pre[8 + u] = __ldg(reinterpret_cast<const uint4*>(cpb + blocked_off(m_tile, 64, cg + 16 + u, row)));
+          }
+        }
+        const float* sb_all = lp.sb + (long long)entry * lp.sb_entry_stride + j * 256;
+        const uint32_t* prew = reinterpret_cast<const uint32_t*>(pre);
+        uint8_t* ytile = sY + (2 * j + h) * 16384;
+        // Y rows of this warp may still be the source of its own earlier TMA stores (x_next of the previous tile)
+        if (tr && warp == 2 && lane == 0 && j == 0) lp.trace[ti * 16 + 10] = clock64();
+        // sub-tile h (j = 0) was last read by the x_next store of the previous tile (this warp's newest bulk group);
+        // sub-tile 2+h (j = 1) by the same store, which is now one group older than the y store just issued
+        if (lane == 0) {
+          if (j == 0) tma_store_wait_read<0>();
+          else tma_store_wait_read<1>();
+        }
+        __syncwarp();
+        if (tr && warp == 2 && lane == 0 && j == 0) lp.trace[ti * 16 + 11] = clock64();
+        mbar_wait(&rfull_bar[reg], dcount[reg] & 1u, 10);
+        ++dcount[reg];
+        tc_fence_after();
+        if (tr && warp == 2 && lane == 0) lp.trace[ti * 16 + 6 + j] = clock64();
+        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + reg * 256u;
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci) {
+          const int i = h * 64 + ci * 16;
+          uint32_t rg[16], rf[16];
+          tmem_ld_x16(trow + i, rg);
+          tmem_ld_x16(trow + 128 + i, rf);
+          tmem_ld_wait();
+          uint32_t packed[8];
+          if (warp_edge) gate_chunk16<T, true>(rg, rf, prew + ci * 8, prew + 32 + ci * 8, sb_all + i, 2 * kLayerC, 4 * kLayerC, edge_lo, edge_hi, packed);
+          else gate_chunk16<T, false>(rg, rf, prew + ci * 8, prew + 32 + ci * 8, sb_all + i, 2 * kLayerC, 4 * kLayerC, false, false, packed);
+          if (!valid) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) packed[u] = 0u;   // keep junk (NaN) out of MMA2's operand rows
+          }
+          *sw128_chunk(ytile, row, 2 * ci) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+          *sw128_chunk(ytile, row, 2 * ci + 1) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+        }
+        tc_fence_before();          // TMEM reads of this region are done
+        fence_proxy_async_smem();   // Y rows visible to the tensor core (MMA2) and the TMA store engine
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive_leader(&rfree_bar[reg]);
+          mbar_arrive_leader(&yready_bar[j]);
+          tma_store_4d(&tmYs, ytile + q * 4096, (2 * j + h) * 64, t0 + q * 32, b, lp.layer);   // 32 frames x 64 ch
+          tma_store_commit();
+        }
+        if (tr && warp == 2 && lane == 0) lp.trace[ti * 16 + 12 + j] = clock64();
+      }
+
+      // ---------------- epilogue 2: x_next = (D2 + b) / sqrt(2) (D2 already contains x), staged in Y, stored by TMA
+      {
+        const uint32_t reg = p;
+        if (lane == 0) tma_store_wait_read<0>();   // y stores of this tile have read their Y rows
+        __syncwarp();
+        mbar_wait(&rfull_bar[reg], dcount[reg] & 1u, 11);
+        ++dcount[reg];
+        tc_fence_after();
+        if (tr && warp == 2 && lane == 0) lp.trace[ti * 16 + 8] = clock64();
+        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + reg * 256u;
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+          uint8_t* ytile = sY + (2 * jj + h) * 16384;
+#pragma unroll
+          for (int ci = 0; ci < 2; ++ci) {
+            const int c = (2 * jj + h) * 64 + ci * 32;   // first channel of this 32-column group
+            uint32_t r[32];
+            tmem_ld_x32(trow + c, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int u4 = 0; u4 < 4; ++u4) {
+              uint32_t ow[4];
+#pragma unroll
+              for (int u = 0; u < 4; u += 2) {
+                const float4 bv = __ldg(reinterpret_cast<const float4*>(lp.b_res + c + 8 * u4 + 2 * u));
+                const int col = 8 * u4 + 2 * u;
+                ow[u] = Cvt<T>::pack((__uint_as_float(r[col]) + bv.x) * lp.scale, (__uint_as_float(r[col + 1]) + bv.y) * lp.scale);
+                ow[u + 1] = Cvt<T>::pack((__uint_as_float(r[col + 2]) + bv.z) * lp.scale, (__uint_as_float(r[col + 3]) + bv.w) * lp.scale);
+              }
+              *sw128_chunk(ytile, row, ci * 4 + u4) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+            }
+          }
+        }
+        tc_fence_before();
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive_leader(&rfree_bar[reg]);
+          tma_store_4d(&tmXs, sY + h * 16384 + q * 4096, h * 64, t0 + q * 32, b, 0);
+          tma_store_4d(&tmXs, sY + (2 + h) * 16384 + q * 4096, (2 + h) * 64, t0 + q * 32, b, 0);
+          tma_store_commit();
+        }
+        if (tr && warp == 2 && lane == 0) lp.trace[ti * 16 + 9] = clock64();
+      }
+    }
+    if (lane == 0) tma_store_wait_all();
+  }
+
+  // both CTAs must be completely done (the leader's MMAs read the peer's shared memory and write its TMEM)
+  tc_fence_before();
+  cluster_sync_all();
+  if (tr && threadIdx.x == 0) lp.trace[14] = clock64();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2sm<kTmemCols>(tmem_base);
+  }
+}
+
+}  // namespace pd

@@ -128,20 +128,20 @@ def check_trace():
     cond = cond.cuda()
     with torch.no_grad():
         gd(cond, infer_step=4, infer=True, seed=1)
-        buf = torch.zeros(8 * 1024, dtype=torch.int64, device="cuda")
+        buf = torch.zeros(9 * 1024, dtype=torch.int64, device="cuda")
         lib.pd_debug_set_trace(buf.data_ptr())
         gd(cond, infer_step=4, infer=True, seed=1)
         torch.cuda.synchronize()
         lib.pd_debug_set_trace(None)
     out = {}
-    for kind, name in ((2, "gate"), (3, "res"), (0, "cond"), (6, "out")):
+    for kind, name in ((8, "layer"), (2, "gate"), (3, "res"), (0, "cond"), (6, "out")):
         t = buf[kind * 1024:(kind + 1) * 1024].cpu().view(64, 16)
         t0 = int(t[0, 15])
         rows = []
         for i in range(8):
-            if int(t[i, 7]) == 0:
+            if int(t[i, 6]) == 0:
                 break
-            rows.append([int(v) - t0 if int(v) else -1 for v in t[i, :8]])
+            rows.append([int(v) - t0 if int(v) else -1 for v in t[i, :14]])
         out[name] = dict(exit=int(t[0, 14]) - t0, tiles=rows)
     return out
 
