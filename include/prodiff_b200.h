@@ -111,7 +111,7 @@ int pd_profile_begin(void);
 int pd_profile_end(float* ms_by_kind, int* count_by_kind, int n_kinds);
 
 /* Introspection for tests: byte offset/size of a named scratch buffer inside the plan's workspace.
- * Names: "cond16","cp","xin","xa","xb","ybuf","s1","s2","steps","emb","dvec","sb". Returns 0 if found. */
+ * Names: "cond16","cp","xin","xa","xb","ybuf","s1","s2","steps","emb0","hid","emb","dvec","sb". Returns 0 if found. */
 int pd_plan_buffer(const pd_plan* p, const char* name, size_t* offset, size_t* bytes);
 
 /* Test hook: one implicit-GEMM launch of the production kernel with a plain fp32 store epilogue.

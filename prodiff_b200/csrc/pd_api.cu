@@ -348,6 +348,8 @@ static size_t plan_layout(const pd_config& c, int B, int T, int E, std::vector<B
   take("s1", N * C * 2);
   take("s2", N * C * 2);
   take("steps", (size_t)E * 4);
+  take("emb0", (size_t)E * C * 4);
+  take("hid", (size_t)E * 4 * C * 4);
   take("emb", (size_t)E * C * 4);
   take("dvec", (size_t)E * L * C * 4);
   take("sb", (size_t)E * L * 4 * 2 * C * 4);
@@ -558,12 +560,19 @@ static int run_step_tables(pd_plan* p, int E, cudaStream_t s) {
   const int C = c.residual_channels, L = c.residual_layers;
   const uint8_t* pk = m->packed;
   const PackedLayout& lay = m->lay;
-  k_step_embed<<<E, 256, 5 * C * sizeof(float), s>>>(p->ptr<float>("steps"), C, (const float*)(pk + lay.f_mlp0w), (const float*)(pk + lay.f_mlp0b),
-                                                     (const float*)(pk + lay.f_mlp2w), (const float*)(pk + lay.f_mlp2b), p->ptr<float>("emb"));
-  PD_LAUNCH_CHECK("k_step_embed");
-  k_step_proj<<<dim3(L, E), 256, C * sizeof(float), s>>>(p->ptr<float>("emb"), (const float*)(pk + lay.f_dpw), (const float*)(pk + lay.f_dpb),
-                                                         p->ptr<float>("dvec"), L, C);
-  PD_LAUNCH_CHECK("k_step_proj");
+  // sinusoid -> Linear(C,4C) + Mish -> Linear(4C,C) -> L x diffusion_projection (wavenet.py:112-113, :61)
+  float* hid = p->ptr<float>("hid");
+  k_step_sinusoid<<<E, 128, 0, s>>>(p->ptr<float>("steps"), C, p->ptr<float>("emb0"));
+  PD_LAUNCH_CHECK("k_step_sinusoid");
+  k_step_matvec<<<dim3(4 * C / 32, E, 1), 256, C * sizeof(float), s>>>((const float*)(pk + lay.f_mlp0w), (const float*)(pk + lay.f_mlp0b),
+                                                                      p->ptr<float>("emb0"), hid, 4 * C, C, 1, 1);
+  PD_LAUNCH_CHECK("k_step_matvec(mlp0)");
+  k_step_matvec<<<dim3(C / 32, E, 1), 256, 4 * C * sizeof(float), s>>>((const float*)(pk + lay.f_mlp2w), (const float*)(pk + lay.f_mlp2b), hid,
+                                                                      p->ptr<float>("emb"), C, 4 * C, 1, 0);
+  PD_LAUNCH_CHECK("k_step_matvec(mlp2)");
+  k_step_matvec<<<dim3(C / 32, E, L), 256, C * sizeof(float), s>>>((const float*)(pk + lay.f_dpw), (const float*)(pk + lay.f_dpb),
+                                                                  p->ptr<float>("emb"), p->ptr<float>("dvec"), C, C, L, 0);
+  PD_LAUNCH_CHECK("k_step_matvec(diffusion_projection)");
   if (C == 256) k_step_taps<8><<<dim3(2 * C / 8, L), 256, 0, s>>>(p->ptr<float>("dvec"), (const float*)(pk + lay.f_dilw), p->ptr<float>("sb"), E, L);
   else k_step_taps<16><<<dim3(2 * C / 8, L), 256, 0, s>>>(p->ptr<float>("dvec"), (const float*)(pk + lay.f_dilw), p->ptr<float>("sb"), E, L);
   PD_LAUNCH_CHECK("k_step_taps");

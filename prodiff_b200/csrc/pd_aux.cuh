@@ -104,59 +104,46 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// One block per table entry: e = mlp(SinusoidalPosEmb(step)).  Accurate libm calls (no fast-math): this feeds
-// every layer's pre-activation.
-__global__ void k_step_embed(const float* __restrict__ steps, int C, const float* __restrict__ w0,
-                             const float* __restrict__ b0, const float* __restrict__ w2, const float* __restrict__ b2,
-                             float* __restrict__ emb_out) {
-  extern __shared__ float sm[];  // [C] sinusoid, [4C] hidden
-  float* s_emb = sm;
-  float* s_hid = sm + C;
+// SinusoidalPosEmb (wavenet.py:31-38): emb[e] = [sin(step * f_j), cos(step * f_j)], f_j = exp(-j ln(1e4) / (C/2 - 1)).
+// Accurate libm calls (no fast-math): this feeds every layer's pre-activation.
+__global__ void k_step_sinusoid(const float* __restrict__ steps, int C, float* __restrict__ emb0) {
   const int e = blockIdx.x;
   const float step = steps[e];
   const int half = C / 2;
   const float neg = -(logf(10000.f) / (float)(half - 1));
   for (int j = threadIdx.x; j < half; j += blockDim.x) {
-    const float f = expf((float)j * neg);
-    const float a = step * f;
-    s_emb[j] = sinf(a);
-    s_emb[half + j] = cosf(a);
-  }
-  __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  for (int o = warp; o < 4 * C; o += nwarps) {
-    float acc = 0.f;
-    for (int c = lane; c < C; c += 32) acc = fmaf(w0[(long long)o * C + c], s_emb[c], acc);
-    acc = warp_sum(acc);
-    if (lane == 0) {
-      const float x = acc + b0[o];
-      const float sp = x > 20.f ? x : log1pf(expf(x));  // F.softplus(beta=1, threshold=20)
-      s_hid[o] = x * tanhf(sp);                         // Mish, wavenet.py:22-24
-    }
-  }
-  __syncthreads();
-  for (int o = warp; o < C; o += nwarps) {
-    float acc = 0.f;
-    for (int c = lane; c < 4 * C; c += 32) acc = fmaf(w2[(long long)o * 4 * C + c], s_hid[c], acc);
-    acc = warp_sum(acc);
-    if (lane == 0) emb_out[(long long)e * C + o] = acc + b2[o];
+    const float a = step * expf((float)j * neg);
+    emb0[(long long)e * C + j] = sinf(a);
+    emb0[(long long)e * C + half + j] = cosf(a);
   }
 }
 
-// d[e][l][:] = diffusion_projection_l(emb[e])   (wavenet.py:61).  grid (L, E).
-__global__ void k_step_proj(const float* __restrict__ emb, const float* __restrict__ dp_w, const float* __restrict__ dp_b,
-                            float* __restrict__ dvec, int L, int C) {
-  extern __shared__ float s_e[];
-  const int l = blockIdx.x, e = blockIdx.y;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) s_e[c] = emb[(long long)e * C + c];
+// Batched fp32 mat-vec for the step chain: y[e][l][o] = act(W_l[o][:] . x[e][:] + b_l[o]).
+// grid (ceil(O / 32), E, L), block 256: 8 warps x 4 outputs, the input vector staged in shared memory.
+// act 0 = identity, 1 = Mish (x * tanh(softplus(x)), wavenet.py:22-24; softplus threshold 20).
+__global__ void k_step_matvec(const float* __restrict__ W, const float* __restrict__ bias, const float* __restrict__ x,
+                              float* __restrict__ y, int O, int I, int L, int act) {
+  extern __shared__ float s_x[];
+  const int e = blockIdx.y, l = blockIdx.z;
+  for (int c = threadIdx.x; c < I; c += blockDim.x) s_x[c] = x[(long long)e * I + c];
   __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  const float* w = dp_w + (long long)l * C * C;
-  for (int o = warp; o < C; o += nwarps) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* w = W + (long long)l * O * I;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int o = blockIdx.x * 32 + warp * 4 + r;
+    if (o >= O) break;
     float acc = 0.f;
-    for (int c = lane; c < C; c += 32) acc = fmaf(w[(long long)o * C + c], s_e[c], acc);
+    for (int c = lane; c < I; c += 32) acc = fmaf(__ldg(w + (long long)o * I + c), s_x[c], acc);
     acc = warp_sum(acc);
-    if (lane == 0) dvec[((long long)e * L + l) * C + o] = acc + dp_b[(long long)l * C + o];
+    if (lane == 0) {
+      float v = acc + bias[(long long)l * O + o];
+      if (act == 1) {
+        const float sp = v > 20.f ? v : log1pf(expf(v));
+        v = v * tanhf(sp);
+      }
+      y[((long long)e * L + l) * O + o] = v;
+    }
   }
 }
 
