@@ -190,6 +190,8 @@ def main():
     device = torch.device("cuda", local_rank)
     torch.cuda.set_device(device)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
         dist.init_process_group("nccl", device_id=device)
     w = WORKLOAD
     B, T, K, M, H = w["B"], w["T"], w["K"], w["in_dims"], w["hidden"]

@@ -154,7 +154,7 @@ static int make_w_map(CUtensorMap* m, int dtype, const void* base, int K, int ro
 // ------------------------------------------------------------------ packed weight layout
 struct PackedLayout {
   // 16-bit operands (byte offsets)
-  size_t w_in, w_cond, w_dil, w_res, w_skip, w_sp, w_out;
+  size_t w_in, w_cond, w_dil, w_dil64, w_res, w_skip, w_sp, w_out;
   // fp32 biases
   size_t b_in, b_cp, b_res, b_skipsum, b_sp, b_out;
   // fp32 copies for the step-embedding chain
@@ -169,6 +169,7 @@ static PackedLayout packed_layout(const pd_config& c) {
   p.w_in = take(C * M * 2);
   p.w_cond = take(L * 2 * C * H * 2);
   p.w_dil = take(L * 2 * C * 3 * C * 2);
+  p.w_dil64 = take(L * 2 * C * 3 * C * 2);  // 64-channel gate/filter pairing (fused layer kernel)
   p.w_res = take((L + 1) * C * C * 2);  // + one [C x C] identity block (fused layer kernel: residual add on the tensor core)
   p.w_skip = take(C * L * C * 2);
   p.w_sp = take(C * C * 2);
@@ -215,6 +216,7 @@ struct pd_model {
   int device, sm_count;
   CUtensorMap tm_w_in, tm_w_cond, tm_w_dil, tm_w_res, tm_w_skip, tm_w_sp, tm_w_out;
   CUtensorMap tm_w_dil128, tm_w_res128;  // 128-row boxes: one CTA's half of a cta_group::2 weight block
+  CUtensorMap tm_w_dil64;                // 64-row boxes over the 64-channel-paired packing
 };
 
 static int check_device(int* device, int* sms) {
@@ -248,6 +250,8 @@ static int pack_all(const pd_config& c, const PackedLayout& lay, uint8_t* pk, co
     const float* const* q = st + 10 + 8 * l;
     k_pack_dil<T><<<blocks(6ll * C * C), TB, 0, s>>>((T*)(pk + lay.w_dil) + (size_t)l * 2 * C * 3 * C, q[0], C);
     PD_LAUNCH_CHECK("k_pack_dil");
+    k_pack_dil64<T><<<blocks(6ll * C * C), TB, 0, s>>>((T*)(pk + lay.w_dil64) + (size_t)l * 2 * C * 3 * C, q[0], C);
+    PD_LAUNCH_CHECK("k_pack_dil64");
     k_pack_rows<T><<<blocks(2ll * C * H), TB, 0, s>>>((T*)(pk + lay.w_cond) + (size_t)l * 2 * C * H, H, 0, q[4], 2 * C, 0, 2 * C, H, C);
     PD_LAUNCH_CHECK("k_pack_rows(cond)");
     k_pack_rows<T><<<blocks((long long)C * C), TB, 0, s>>>((T*)(pk + lay.w_res) + (size_t)l * C * C, C, 0, q[6], 2 * C, 0, C, C, 0);
@@ -300,7 +304,8 @@ extern "C" int pd_model_create(const pd_config* cfg, const float* const* state, 
       make_w_map(&m->tm_w_dil, dt, pk + lay.w_dil, 3 * C, L * 2 * C, 256) || make_w_map(&m->tm_w_res, dt, pk + lay.w_res, C, L * C, 256) ||
       make_w_map(&m->tm_w_skip, dt, pk + lay.w_skip, L * C, C, 256) || make_w_map(&m->tm_w_sp, dt, pk + lay.w_sp, C, C, 256) ||
       make_w_map(&m->tm_w_out, dt, pk + lay.w_out, C, 128, 128) ||
-      make_w_map(&m->tm_w_dil128, dt, pk + lay.w_dil, 3 * C, L * 2 * C, 128) || make_w_map(&m->tm_w_res128, dt, pk + lay.w_res, C, (L + 1) * C, 128)) {
+      make_w_map(&m->tm_w_dil128, dt, pk + lay.w_dil, 3 * C, L * 2 * C, 128) || make_w_map(&m->tm_w_res128, dt, pk + lay.w_res, C, (L + 1) * C, 128) ||
+      make_w_map(&m->tm_w_dil64, dt, pk + lay.w_dil64, 3 * C, L * 2 * C, 64)) {
     delete m;
     return 1;
   }
@@ -499,8 +504,8 @@ static bool fused_enabled() {
 }
 
 template <typename T>
-static int launch_layer_t(const CUtensorMap& x, const CUtensorMap& wd, const CUtensorMap& wr, const CUtensorMap& ys,
-                          const CUtensorMap& xs, const LayerParams& lp, int sms, cudaStream_t s) {
+static int launch_layer_t(const CUtensorMap& x, const CUtensorMap& wd, const CUtensorMap& wq, const CUtensorMap& wr,
+                          const CUtensorMap& ys, const CUtensorMap& xs, const LayerParams& lp, int sms, cudaStream_t s) {
   auto kern = layer_kernel<T>;
   static bool configured[64] = {false};
   int dev = 0;
@@ -525,7 +530,7 @@ static int launch_layer_t(const CUtensorMap& x, const CUtensorMap& wd, const CUt
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   prof_before(8, s);
-  PD_CUDA(cudaLaunchKernelEx(&cfg, kern, x, wd, wr, ys, xs, lp));
+  PD_CUDA(cudaLaunchKernelEx(&cfg, kern, x, wd, wq, wr, ys, xs, lp));
   prof_after(s);
   PD_LAUNCH_CHECK("layer_kernel");
   return 0;
@@ -623,6 +628,7 @@ static int run_denoiser(pd_plan* p, int entry_base, int entry_per_b, const OutSt
       lp.layer = l;
       lp.ident_row0 = L * C;
       lp.idesc = (1u << 4) | ((dt == PD_FP16 ? 0u : 1u) << 7) | ((dt == PD_FP16 ? 0u : 1u) << 10) | ((256u >> 3) << 17) | ((256u >> 4) << 24);
+      lp.idesc128 = (lp.idesc & ~(0x3Fu << 17)) | ((128u >> 3) << 17);
       lp.cp = p->ptr<uint16_t>("cp") + (size_t)l * mtiles * kBlockM * 2 * C;
       lp.sb = p->ptr<float>("sb") + (size_t)l * 4 * 2 * C;
       lp.sb_entry_stride = (long long)L * 4 * 2 * C;
@@ -630,12 +636,17 @@ static int run_denoiser(pd_plan* p, int entry_base, int entry_per_b, const OutSt
       lp.sb_entry_per_b = entry_per_b;
       lp.b_res = (const float*)(pk + lay.b_res) + (size_t)l * C;
       lp.scale = 0.70710678118654752440f;
+      {
+        static int fl = -1;
+        if (fl < 0) { const char* e = getenv("PD_LAYER_FLAGS"); fl = e ? atoi(e) : 0; }
+        lp.flags = fl;
+      }
       lp.trace = g_trace ? g_trace + 8 * 1024 : nullptr;
       const int di = l % c.dilation_cycle_length;
       const CUtensorMap& xh = cur_is_a ? p->tm_xa_halo[di] : p->tm_xb_halo[di];
       const CUtensorMap& xs = cur_is_a ? p->tm_xb_st : p->tm_xa_st;
-      const int rc = dt == PD_FP16 ? launch_layer_t<__half>(xh, m->tm_w_dil128, m->tm_w_res128, p->tm_y_st, xs, lp, sms, s)
-                                   : launch_layer_t<__nv_bfloat16>(xh, m->tm_w_dil128, m->tm_w_res128, p->tm_y_st, xs, lp, sms, s);
+      const int rc = dt == PD_FP16 ? launch_layer_t<__half>(xh, m->tm_w_dil128, m->tm_w_dil64, m->tm_w_res128, p->tm_y_st, xs, lp, sms, s)
+                                   : launch_layer_t<__nv_bfloat16>(xh, m->tm_w_dil128, m->tm_w_dil64, m->tm_w_res128, p->tm_y_st, xs, lp, sms, s);
       if (rc) return rc;
       cur_is_a = !cur_is_a;
       continue;

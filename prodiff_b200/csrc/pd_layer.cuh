@@ -18,11 +18,15 @@
 //   descriptor base_offset 0: the 128B swizzle is a function of absolute smem address bits; profiles/r01_probe_shift.json).
 // * The gated activations are written by the epilogue straight into a swizzled K-major shared-memory tile, which is
 //   both the A operand of MMA2 and the source of the TMA store to HBM; x_next is staged in the same tile afterwards.
-// * TMEM (512 columns) is two 256-column regions; per tile they hold D1[gate/filter chunk 0], D1[chunk 1] and then D2,
-//   rotating so that the MMAs of one region overlap the epilogue draining the other.
+// * TMEM (512 columns) holds three accumulators per tile: channels 0..127 as one N = 256 chunk ("c01", 128 gate +
+//   128 filter columns), channels 128..191 and 192..255 as two N = 128 chunks ("c2", "c3"), and later D2 in c01's
+//   columns.  The column assignment mirrors every tile (c01 lands where the previous tile's c2+c3 were), and only the
+//   LAST QUARTER of the gate epilogue is not hidden behind dilated-conv MMAs -- that quarter overlaps the identity and
+//   first residual K-blocks of MMA2, so the tensor pipe has no structural bubble.
 //
 // Roles per CTA: warp 0 = weight-block TMA producer, warp 1 = MMA issuer (leader CTA only), warps 2..9 = epilogue,
-// warp 10 = x-tile TMA producer.
+// warp 10 = x-tile TMA producer.  (Giving the control warps the highest warp ids -- the sub-partition arbiter favours
+// high ids -- was measured: MMA issue got faster but the epilogue chain, which is the longer one, got slower; net -4%.)
 // Warp (q = warp & 3, h = (warp - 2) >> 2) owns rows 32q..32q+31 of Y sub-tiles h and 2 + h for the whole tile
 // (channels [64h, 64h+64) and [128+64h, 128+64h+64)), so every shared-memory hazard on Y is warp-local.
 #pragma once
@@ -45,15 +49,22 @@ struct LayerParams {
   int layer;              // weight row block / y slab
   int ident_row0;         // first row of the [C x C] identity block appended to the W_res matrix
   uint32_t idesc;         // cta_group::2 instruction descriptor (M = 256, N = 256)
+  uint32_t idesc128;      // same with N = 128 (the two 64-channel chunks)
   const void* cp;         // this layer's hoisted cond projection, tile-blocked fp16
   const float* sb;        // this layer's step-bias table
   long long sb_entry_stride;
   int sb_entry_base, sb_entry_per_b;
   const float* b_res;     // residual-half bias of output_projection [C]
   float scale;            // 1/sqrt(2)
+  int flags;              // bit 0: L2-prefetch the next tile's x and cond projection
   long long* trace;
 };
 
+__device__ __forceinline__ long long global_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 // ---- cluster / 2-CTA PTX
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -109,6 +120,7 @@ template <typename T>
 __global__ void __launch_bounds__(kLayerThreads, 1)
 layer_kernel(const __grid_constant__ CUtensorMap tmX,     // x_cur  [1][B][T][C], box (64, 128 + 2*dil)
              const __grid_constant__ CUtensorMap tmWd,    // W_dil  [L*2C][3C],   box (64, 128)
+             const __grid_constant__ CUtensorMap tmWq,    // W_dil, 64-channel pairing [L*2C][3C], box (64, 64)
              const __grid_constant__ CUtensorMap tmWr,    // W_res  [L*C][C],     box (64, 128)
              const __grid_constant__ CUtensorMap tmYs,    // ybuf   [L][B][T][C], box (64, 32)  (store)
              const __grid_constant__ CUtensorMap tmXs,    // x_next [1][B][T][C], box (64, 32)  (store)
@@ -124,10 +136,11 @@ layer_kernel(const __grid_constant__ CUtensorMap tmX,     // x_cur  [1][B][T][C]
   uint64_t* empty_bar = full_bar + kLayerStages;       // [S] local : MMAs finished reading the block
   uint64_t* xfull_bar = empty_bar + kLayerStages;      // leader: X landed in both CTAs
   uint64_t* xempty_bar = xfull_bar + 1;                // local : X reusable (all tensor-core reads of it completed)
-  uint64_t* rfull_bar = xempty_bar + 1;                // [2] local : accumulator region complete
-  uint64_t* rfree_bar = rfull_bar + 2;                 // [2] leader: region drained by all 16 epilogue warps
-  uint64_t* yready_bar = rfree_bar + 2;                // [2] leader: y channels [128j, 128j+128) written in both CTAs
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(yready_bar + 2);
+  // accumulators, indexed by kind: 0 = c01 (channels 0..127), 1 = c2 (128..191), 2 = c3 (192..255), 3 = D2
+  uint64_t* afull_bar = xempty_bar + 1;                // [4] local : accumulator complete (MMA commit, both CTAs)
+  uint64_t* afree_bar = afull_bar + 4;                 // [4] leader: accumulator drained by all 16 epilogue warps
+  uint64_t* yready_bar = afree_bar + 4;                // [3] leader: y of chunk c01 / c2 / c3 written in both CTAs
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(yready_bar + 3);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -138,6 +151,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tmX,     // x_cur  [1][B][T][C]
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmWd);
+    tma_prefetch_desc(&tmWq);
     tma_prefetch_desc(&tmWr);
     tma_prefetch_desc(&tmYs);
     tma_prefetch_desc(&tmXs);
@@ -149,11 +163,11 @@ layer_kernel(const __grid_constant__ CUtensorMap tmX,     // x_cur  [1][B][T][C]
     }
     mbar_init(xfull_bar, 2);
     mbar_init(xempty_bar, 1);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&rfull_bar[i], 1);
-      mbar_init(&rfree_bar[i], 2 * kEpiWarps);
-      mbar_init(&yready_bar[i], 2 * kEpiWarps);
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&afull_bar[i], 1);
+      mbar_init(&afree_bar[i], 2 * kEpiWarps);
     }
+    for (int i = 0; i < 3; ++i) mbar_init(&yready_bar[i], 2 * kEpiWarps);
     fence_mbar_init();
   }
   cluster_sync_all();                      // both CTAs alive + barriers initialised before any remote arrive / alloc
@@ -170,7 +184,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tmX,     // x_cur  [1][B][T][C]
   // Every cluster walks the same weight blocks; starting each one at a different K block spreads the simultaneous
   // requests over different L2 lines instead of hammering one hot block (fp32 accumulation order differs per
   // cluster but is fixed for a given launch geometry, so results stay deterministic).
-  const int rot12 = cluster_id % 12, rot4 = cluster_id & 3;
+  const int rot12 = cluster_id % 12, rot6 = cluster_id % 6, rot4 = cluster_id & 3;
   const int xrows = kBlockM + 2 * lp.dil;
   const uint32_t xbytes = 4u * (uint32_t)xrows * 128u;     // per CTA
 
@@ -187,17 +201,20 @@ layer_kernel(const __grid_constant__ CUtensorMap tmX,     // x_cur  [1][B][T][C]
           mbar_wait(&empty_bar[stage], parity ^ 1u, 1);
           if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * 16384);
           else mbar_arrive_leader(&full_bar[stage]);
-          if (blk < 24) {
-            const int j = blk / 12;                           // gate/filter chunk
-            const int kb = (blk - j * 12 + rot12) % 12;       // (tap, channel-chunk) K block, start rotated per cluster
-            tma_load_2d_2sm(sW + stage * 16384, &tmWd, &full_bar[stage], kb * kBlockK,
-                            lp.layer * 2 * kLayerC + j * 256 + (int)rank * 128);
-          } else if (blk < 28) {                             // identity block: D2 starts as the x tile itself
-            tma_load_2d_2sm(sW + stage * 16384, &tmWr, &full_bar[stage], ((blk - 24 + rot4) & 3) * kBlockK,
-                            lp.ident_row0 + (int)rank * 128);
+          uint8_t* dst = sW + stage * 16384;
+          if (blk < 12) {          // c01: [128 rows = this CTA's gate (rank 0) or filter (rank 1) half] x 64 K
+            const int kb = (blk + rot12) % 12;
+            tma_load_2d_2sm(dst, &tmWd, &full_bar[stage], kb * kBlockK, lp.layer * 2 * kLayerC + (int)rank * 128);
+          } else if (blk < 24) {   // c2 / c3: two [64 rows x 64 K] sub-blocks (K blocks 2*kq, 2*kq + 1) per stage
+            const int c = 2 + (blk - 12) / 6;
+            const int kq = ((blk - 12) % 6 + rot6) % 6;
+            const int row0 = lp.layer * 2 * kLayerC + c * 128 + (int)rank * 64;
+            tma_load_2d_2sm(dst, &tmWq, &full_bar[stage], (2 * kq) * kBlockK, row0);
+            tma_load_2d_2sm(dst + 8192, &tmWq, &full_bar[stage], (2 * kq + 1) * kBlockK, row0);
+          } else if (blk < 28) {   // identity block: D2 starts as the x tile itself
+            tma_load_2d_2sm(dst, &tmWr, &full_bar[stage], ((blk - 24 + rot4) & 3) * kBlockK, lp.ident_row0 + (int)rank * 128);
           } else {
-            tma_load_2d_2sm(sW + stage * 16384, &tmWr, &full_bar[stage], (blk - 28) * kBlockK,
-                            lp.layer * kLayerC + (int)rank * 128);
+            tma_load_2d_2sm(dst, &tmWr, &full_bar[stage], (blk - 28) * kBlockK, lp.layer * kLayerC + (int)rank * 128);
           }
           ++it;
         };
@@ -209,6 +226,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tmX,     // x_cur  [1][B][T][C]
     // ===================== x-tile producer (both CTAs) =====================
     if (lane == 0) {
       uint32_t ti = 0;
+      const uint8_t* cpb8 = static_cast<const uint8_t*>(lp.cp);
       for (int pair = cluster_id; pair < num_pairs; pair += num_clusters, ++ti) {
         const int m_tile = 2 * pair + (int)rank;
         const int b = m_tile / lp.m_tiles_per_row;           // == B for the dummy tile of an odd count: fully OOB
@@ -219,69 +237,105 @@ layer_kernel(const __grid_constant__ CUtensorMap tmX,     // x_cur  [1][B][T][C]
         else mbar_arrive_leader(xfull_bar);
 #pragma unroll
         for (int c = 0; c < 4; ++c) tma_load_4d_2sm(sX + c * kXSubStride, &tmX, xfull_bar, c * 64, t0 - lp.dil, b, 0);
+        // Pull the NEXT tile's activations and cond projection into L2 now, a whole tile ahead of their use: the x
+        // tile can only be requested once this tile's MMAs have released the buffer, and by then HBM latency would be
+        // fully exposed on the tensor pipe; the epilogue's cond-projection loads are likewise latency-critical.
+        const int pair_n = pair + num_clusters;
+        if ((lp.flags & 1) && pair_n < num_pairs) {
+          const int m_n = 2 * pair_n + (int)rank;
+          if (m_n < num_m_tiles) {
+            const int b_n = m_n / lp.m_tiles_per_row;
+            const int t0_n = (m_n - b_n * lp.m_tiles_per_row) * kBlockM;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) tma_prefetch_4d(&tmX, c * 64, t0_n - lp.dil, b_n, 0);
+            const uint8_t* cpt = cpb8 + (size_t)m_n * (kBlockM * 2 * kLayerC * 2);   // one tile of the blocked layout is contiguous
+#pragma unroll
+            for (int u = 0; u < 8; ++u) bulk_prefetch_l2(cpt + u * 16384, 16384);
+          }
+        }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
     if (leader && lane == 0) {
       uint32_t it = 0, ti = 0;
-      uint32_t wcount[2] = {0u, 0u};   // writes issued to each TMEM region
       const uint32_t sXa = smem_u32(sX), sYa = smem_u32(sY), sWa = smem_u32(sW);
       for (int pair = cluster_id; pair < num_pairs; pair += num_clusters, ++ti) {
-        const uint32_t p = ti & 1u;
-        mbar_wait(xfull_bar, ti & 1u, 2);
+        const uint32_t par = ti & 1u;                       // this tile's barrier phase parity and column layout
+        const uint32_t colA = par ? 256u : 0u;              // c01, later D2
+        const uint32_t colB1 = par ? 0u : 256u;             // c2
+        const uint32_t colB2 = colB1 + 128u;                // c3
+        mbar_wait(xfull_bar, par, 2);
         tc_fence_after();
         if (tr) lp.trace[ti * 16 + 2] = clock64();
-        // ---- MMA1: D1[j] = sum over taps / channel chunks of X(tap view) * W_dil^T
-        for (int j = 0; j < 2; ++j) {
-          const uint32_t reg = p ^ (uint32_t)j;
-          mbar_wait(&rfree_bar[reg], (wcount[reg] & 1u) ^ 1u, 3);
-          ++wcount[reg];
+        // ---- MMA1, channels 0..127 (N = 256).  Its columns were the previous tile's c2 and c3.
+        mbar_wait(&afree_bar[1], par ^ 1u, 3);
+        mbar_wait(&afree_bar[2], par ^ 1u, 3);
+        tc_fence_after();
+        for (int kk = 0; kk < 12; ++kk, ++it) {
+          const int kb = (kk + rot12) % 12;
+          const uint32_t stage = it % kLayerStages, parity = (it / kLayerStages) & 1u;
+          mbar_wait(&full_bar[stage], parity, 4);
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + reg * 256u;
-          for (int kk = 0; kk < 12; ++kk, ++it) {
-            const int kb = (kk + rot12) % 12;
-            const uint32_t stage = it % kLayerStages, parity = (it / kLayerStages) & 1u;
-            mbar_wait(&full_bar[stage], parity, 4);
-            tc_fence_after();
-            const int tap = kb >> 2, cc = kb & 3;
-            const uint64_t adesc = make_sw128_kmajor_desc(sXa + cc * kXSubStride + (uint32_t)(tap * lp.dil) * 128u);
-            const uint64_t bdesc = make_sw128_kmajor_desc(sWa + stage * 16384);
+          const uint64_t adesc = make_sw128_kmajor_desc(sXa + (kb & 3) * kXSubStride + (uint32_t)((kb >> 2) * lp.dil) * 128u);
+          const uint64_t bdesc = make_sw128_kmajor_desc(sWa + stage * 16384);
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_f16_2sm(d_tmem, desc_advance_k(adesc, k), desc_advance_k(bdesc, k), lp.idesc, (kk | k) != 0 ? 1u : 0u);
-            umma_commit_2sm(&empty_bar[stage]);
-          }
-          umma_commit_2sm(&rfull_bar[reg]);
-          if (tr) lp.trace[ti * 16 + 3 + j] = clock64();
+          for (int k = 0; k < 4; ++k)
+            umma_f16_2sm(tmem_base + colA, desc_advance_k(adesc, k), desc_advance_k(bdesc, k), lp.idesc, (kk | k) != 0 ? 1u : 0u);
+          umma_commit_2sm(&empty_bar[stage]);
         }
-        // ---- MMA2: D2 = x_centre * I  +  Y * W_res^T, into the region epilogue-1(j=0) has drained
-        {
-          const uint32_t reg = p;
-          mbar_wait(&rfree_bar[reg], (wcount[reg] & 1u) ^ 1u, 6);
-          ++wcount[reg];
-          tc_fence_after();
-          const uint32_t d_tmem = tmem_base + reg * 256u;
-          for (int kb = 0; kb < 8; ++kb, ++it) {
-            if (kb == 4) {
-              umma_commit_2sm(xempty_bar);   // tensor side is done with X: the next tile's X may be prefetched now
-              mbar_wait(&yready_bar[0], ti & 1u, 7);
+        umma_commit_2sm(&afull_bar[0]);
+        if (tr) lp.trace[ti * 16 + 3] = clock64();
+        // ---- MMA1, channels 128..191 and 192..255 (N = 128 each).  Their columns held the previous tile's D2.
+        mbar_wait(&afree_bar[3], par ^ 1u, 5);
+        tc_fence_after();
+        for (int c = 0; c < 2; ++c) {
+          const uint32_t d_tmem = tmem_base + (c ? colB2 : colB1);
+          for (int kk = 0; kk < 6; ++kk, ++it) {
+            const int kq = (kk + rot6) % 6;
+            const uint32_t stage = it % kLayerStages, parity = (it / kLayerStages) & 1u;
+            mbar_wait(&full_bar[stage], parity, 6);
+            tc_fence_after();
+#pragma unroll
+            for (int sub = 0; sub < 2; ++sub) {
+              const int kb = 2 * kq + sub;
+              const uint64_t adesc = make_sw128_kmajor_desc(sXa + (kb & 3) * kXSubStride + (uint32_t)((kb >> 2) * lp.dil) * 128u);
+              const uint64_t bdesc = make_sw128_kmajor_desc(sWa + stage * 16384 + sub * 8192);
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_f16_2sm(d_tmem, desc_advance_k(adesc, k), desc_advance_k(bdesc, k), lp.idesc128, (kk | sub | k) != 0 ? 1u : 0u);
             }
-            if (kb == 6) mbar_wait(&yready_bar[1], ti & 1u, 8);
-            const uint32_t stage = it % kLayerStages, parity = (it / kLayerStages) & 1u;
-            mbar_wait(&full_bar[stage], parity, 9);
-            tc_fence_after();
-            const uint64_t adesc = kb < 4 ? make_sw128_kmajor_desc(sXa + ((kb + rot4) & 3) * kXSubStride + (uint32_t)lp.dil * 128u)   // centre rows
-                                          : make_sw128_kmajor_desc(sYa + (kb - 4) * 16384);
-            const uint64_t bdesc = make_sw128_kmajor_desc(sWa + stage * 16384);
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_f16_2sm(d_tmem, desc_advance_k(adesc, k), desc_advance_k(bdesc, k), lp.idesc, (kb | k) != 0 ? 1u : 0u);
             umma_commit_2sm(&empty_bar[stage]);
           }
-          umma_commit_2sm(&rfull_bar[reg]);
-          if (tr) lp.trace[ti * 16 + 5] = clock64();
+          umma_commit_2sm(&afull_bar[1 + c]);
+          if (tr) lp.trace[ti * 16 + 4 + c] = clock64();
         }
+        // ---- MMA2: D2 = x_centre * I  +  Y * W_res^T, in c01's columns once epilogue(c01) has drained them
+        mbar_wait(&afree_bar[0], par, 7);
+        tc_fence_after();
+        if (tr) lp.trace[512 + ti * 16 + 12] = clock64();
+        for (int kb = 0; kb < 8; ++kb, ++it) {
+          if (kb == 4) {
+            umma_commit_2sm(xempty_bar);   // tensor side is done with X: the next tile's X may be prefetched now
+            mbar_wait(&yready_bar[0], par, 8);
+          }
+          if (kb == 6) mbar_wait(&yready_bar[1], par, 8);
+          if (kb == 7) mbar_wait(&yready_bar[2], par, 8);
+          if (tr) lp.trace[512 + ti * 16 + 8 + (kb >> 1)] = clock64();
+          const uint32_t stage = it % kLayerStages, parity = (it / kLayerStages) & 1u;
+          mbar_wait(&full_bar[stage], parity, 9);
+          tc_fence_after();
+          if (tr) lp.trace[512 + ti * 16 + kb] = clock64();
+          const uint64_t adesc = kb < 4 ? make_sw128_kmajor_desc(sXa + ((kb + rot4) & 3) * kXSubStride + (uint32_t)lp.dil * 128u)   // centre rows
+                                        : make_sw128_kmajor_desc(sYa + (kb - 4) * 16384);
+          const uint64_t bdesc = make_sw128_kmajor_desc(sWa + stage * 16384);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_f16_2sm(tmem_base + colA, desc_advance_k(adesc, k), desc_advance_k(bdesc, k), lp.idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit_2sm(&empty_bar[stage]);
+        }
+        umma_commit_2sm(&afull_bar[3]);
+        if (tr) lp.trace[ti * 16 + 6] = clock64();
       }
     }
   } else {
@@ -289,10 +343,10 @@ layer_kernel(const __grid_constant__ CUtensorMap tmX,     // x_cur  [1][B][T][C]
     const int q = warp & 3, h = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     uint32_t ti = 0;
-    uint32_t dcount[2] = {0u, 0u};   // drains performed on each TMEM region
     const uint16_t* cpb = static_cast<const uint16_t*>(lp.cp);
     for (int pair = cluster_id; pair < num_pairs; pair += num_clusters, ++ti) {
-      const uint32_t p = ti & 1u;
+      const uint32_t par = ti & 1u;
+      const uint32_t colA = par ? 256u : 0u, colB1 = par ? 0u : 256u;
       const int m_tile = 2 * pair + (int)rank;
       const int b = m_tile / lp.m_tiles_per_row;
       const int t0 = (m_tile - b * lp.m_tiles_per_row) * kBlockM;
@@ -301,38 +355,28 @@ layer_kernel(const __grid_constant__ CUtensorMap tmX,     // x_cur  [1][B][T][C]
       const int entry = lp.sb_entry_base + (b < lp.B ? b : 0) * lp.sb_entry_per_b;
       const bool edge_lo = t < lp.dil, edge_hi = t + lp.dil >= lp.T;
       const bool warp_edge = __any_sync(0xffffffffu, valid && (edge_lo || edge_hi));
+      const float* sb_row = lp.sb + (long long)entry * lp.sb_entry_stride;
+      const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
 
-      // ---------------- epilogue 1: gate, for the two 128-channel chunks
-#pragma unroll 1
-      for (int j = 0; j < 2; ++j) {
-        const uint32_t reg = p ^ (uint32_t)j;
+      // ---------------- gate epilogue, channels 0..127: this warp does channels [64h, 64h + 64) -> Y sub-tile h
+      {
         uint4 pre[16];
-        if (valid) {   // hoisted cond projection of this warp's 64 gate + 64 filter columns (coalesced, blocked layout)
-          const int cg = j * 32 + h * 8;
+        if (valid) {   // hoisted cond projection: 64 gate + 64 filter pre-activations (coalesced, blocked layout)
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
-            pre[u] = __ldg(reinterpret_cast<const uint4*>(cpb + blocked_off(m_tile, 64, cg + u, row)));
-            pre[8 + u] = __ldg(reinterpret_cast<const uint4*>(cpb + blocked_off(m_tile, 64, cg + 16 + u, row)));
+            pre[u] = __ldg(reinterpret_cast<const uint4*>(cpb + blocked_off(m_tile, 64, h * 8 + u, row)));
+            pre[8 + u] = __ldg(reinterpret_cast<const uint4*>(cpb + blocked_off(m_tile, 64, 16 + h * 8 + u, row)));
           }
         }
-        const float* sb_all = lp.sb + (long long)entry * lp.sb_entry_stride + j * 256;
         const uint32_t* prew = reinterpret_cast<const uint32_t*>(pre);
-        uint8_t* ytile = sY + (2 * j + h) * 16384;
-        // Y rows of this warp may still be the source of its own earlier TMA stores (x_next of the previous tile)
-        if (tr && warp == 2 && lane == 0 && j == 0) lp.trace[ti * 16 + 10] = clock64();
-        // sub-tile h (j = 0) was last read by the x_next store of the previous tile (this warp's newest bulk group);
-        // sub-tile 2+h (j = 1) by the same store, which is now one group older than the y store just issued
-        if (lane == 0) {
-          if (j == 0) tma_store_wait_read<0>();
-          else tma_store_wait_read<1>();
-        }
+        uint8_t* ytile = sY + h * 16384;
+        // sub-tile h rows of this warp were last read by its own x_next store of the previous tile (newest group)
+        if (lane == 0) tma_store_wait_read<0>();
         __syncwarp();
-        if (tr && warp == 2 && lane == 0 && j == 0) lp.trace[ti * 16 + 11] = clock64();
-        mbar_wait(&rfull_bar[reg], dcount[reg] & 1u, 10);
-        ++dcount[reg];
+        mbar_wait(&afull_bar[0], par, 10);
         tc_fence_after();
-        if (tr && warp == 2 && lane == 0) lp.trace[ti * 16 + 6 + j] = clock64();
-        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + reg * 256u;
+        if (tr && warp == 2 && lane == 0) lp.trace[ti * 16 + 7] = clock64();
+        const uint32_t trow = lane_base + colA;
 #pragma unroll
         for (int ci = 0; ci < 4; ++ci) {
           const int i = h * 64 + ci * 16;
@@ -341,8 +385,8 @@ layer_kernel(const __grid_constant__ CUtensorMap tmX,     // x_cur  [1][B][T][C]
           tmem_ld_x16(trow + 128 + i, rf);
           tmem_ld_wait();
           uint32_t packed[8];
-          if (warp_edge) gate_chunk16<T, true>(rg, rf, prew + ci * 8, prew + 32 + ci * 8, sb_all + i, 2 * kLayerC, 4 * kLayerC, edge_lo, edge_hi, packed);
-          else gate_chunk16<T, false>(rg, rf, prew + ci * 8, prew + 32 + ci * 8, sb_all + i, 2 * kLayerC, 4 * kLayerC, false, false, packed);
+          if (warp_edge) gate_chunk16<T, true>(rg, rf, prew + ci * 8, prew + 32 + ci * 8, sb_row + i, 2 * kLayerC, 4 * kLayerC, edge_lo, edge_hi, packed);
+          else gate_chunk16<T, false>(rg, rf, prew + ci * 8, prew + 32 + ci * 8, sb_row + i, 2 * kLayerC, 4 * kLayerC, false, false, packed);
           if (!valid) {
 #pragma unroll
             for (int u = 0; u < 8; ++u) packed[u] = 0u;   // keep junk (NaN) out of MMA2's operand rows
@@ -350,28 +394,78 @@ layer_kernel(const __grid_constant__ CUtensorMap tmX,     // x_cur  [1][B][T][C]
           *sw128_chunk(ytile, row, 2 * ci) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
           *sw128_chunk(ytile, row, 2 * ci + 1) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
         }
-        tc_fence_before();          // TMEM reads of this region are done
+        tc_fence_before();          // TMEM reads of this accumulator are done
         fence_proxy_async_smem();   // Y rows visible to the tensor core (MMA2) and the TMA store engine
         __syncwarp();
         if (lane == 0) {
-          mbar_arrive_leader(&rfree_bar[reg]);
-          mbar_arrive_leader(&yready_bar[j]);
-          tma_store_4d(&tmYs, ytile + q * 4096, (2 * j + h) * 64, t0 + q * 32, b, lp.layer);   // 32 frames x 64 ch
+          mbar_arrive_leader(&afree_bar[0]);
+          mbar_arrive_leader(&yready_bar[0]);
+          tma_store_4d(&tmYs, ytile + q * 4096, h * 64, t0 + q * 32, b, lp.layer);   // 32 frames x 64 channels
           tma_store_commit();
         }
-        if (tr && warp == 2 && lane == 0) lp.trace[ti * 16 + 12 + j] = clock64();
       }
 
-      // ---------------- epilogue 2: x_next = (D2 + b) / sqrt(2) (D2 already contains x), staged in Y, stored by TMA
-      {
-        const uint32_t reg = p;
-        if (lane == 0) tma_store_wait_read<0>();   // y stores of this tile have read their Y rows
-        __syncwarp();
-        mbar_wait(&rfull_bar[reg], dcount[reg] & 1u, 11);
-        ++dcount[reg];
+      // ---------------- gate epilogue, channels 128..191 (c = 0 -> Y sub-tile 2) and 192..255 (c = 1 -> sub-tile 3):
+      // the two warps of a lane quadrant split the 64 channels (32 each) and share the sub-tile's 32 rows
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        uint4 pre[8];
+        if (valid) {
+          const int cg = 32 + c * 8 + h * 4;   // 16-byte chunk of gate channel 128 + 64c + 32h in the 256-paired layout
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            pre[u] = __ldg(reinterpret_cast<const uint4*>(cpb + blocked_off(m_tile, 64, cg + u, row)));
+            pre[4 + u] = __ldg(reinterpret_cast<const uint4*>(cpb + blocked_off(m_tile, 64, cg + 16 + u, row)));
+          }
+        }
+        const uint32_t* prew = reinterpret_cast<const uint32_t*>(pre);
+        uint8_t* ytile = sY + (2 + c) * 16384;
+        // sub-tile 2 + c rows were last read by the x_next store issued by warp (q, h = c); its y(c01) store is newer
+        if (h == c && lane == 0) tma_store_wait_read<1>();
+        named_bar_sync(1 + q, 64);
+        mbar_wait(&afull_bar[1 + c], par, 11);
         tc_fence_after();
-        if (tr && warp == 2 && lane == 0) lp.trace[ti * 16 + 8] = clock64();
-        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + reg * 256u;
+        if (tr && warp == 2 && lane == 0) lp.trace[ti * 16 + 8 + c] = clock64();
+        const uint32_t trow = lane_base + colB1 + (uint32_t)c * 128u;
+        const float* sbp = sb_row + 256 + c * 64 + h * 32;
+#pragma unroll
+        for (int ci = 0; ci < 2; ++ci) {
+          uint32_t rg[16], rf[16];
+          tmem_ld_x16(trow + h * 32 + ci * 16, rg);
+          tmem_ld_x16(trow + 64 + h * 32 + ci * 16, rf);
+          tmem_ld_wait();
+          uint32_t packed[8];
+          if (warp_edge) gate_chunk16<T, true>(rg, rf, prew + ci * 8, prew + 16 + ci * 8, sbp + ci * 16, 2 * kLayerC, 4 * kLayerC, edge_lo, edge_hi, packed);
+          else gate_chunk16<T, false>(rg, rf, prew + ci * 8, prew + 16 + ci * 8, sbp + ci * 16, 2 * kLayerC, 4 * kLayerC, false, false, packed);
+          if (!valid) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) packed[u] = 0u;
+          }
+          *sw128_chunk(ytile, row, h * 4 + 2 * ci) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+          *sw128_chunk(ytile, row, h * 4 + 2 * ci + 1) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+        }
+        tc_fence_before();
+        fence_proxy_async_smem();
+        named_bar_sync(1 + q, 64);   // both halves of the 32 x 64 slab are written
+        if (lane == 0) {
+          mbar_arrive_leader(&afree_bar[1 + c]);
+          mbar_arrive_leader(&yready_bar[1 + c]);
+          if (h == c) {
+            tma_store_4d(&tmYs, ytile + q * 4096, (2 + c) * 64, t0 + q * 32, b, lp.layer);
+            tma_store_commit();
+          }
+        }
+      }
+
+      // ---------------- epilogue 2: x_next = (D2 + b) / sqrt(2) (D2 already contains x), staged in Y, stored by TMA.
+      // Warp (q, h) handles channels of sub-tiles h and 2 + h, whose earlier TMA stores it issued itself.
+      {
+        if (lane == 0) tma_store_wait_read<0>();
+        __syncwarp();
+        mbar_wait(&afull_bar[3], par, 12);
+        tc_fence_after();
+        if (tr && warp == 2 && lane == 0) lp.trace[ti * 16 + 10] = clock64();
+        const uint32_t trow = lane_base + colA;
 #pragma unroll
         for (int jj = 0; jj < 2; ++jj) {
           uint8_t* ytile = sY + (2 * jj + h) * 16384;
@@ -399,12 +493,12 @@ layer_kernel(const __grid_constant__ CUtensorMap tmX,     // x_cur  [1][B][T][C]
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-          mbar_arrive_leader(&rfree_bar[reg]);
+          mbar_arrive_leader(&afree_bar[3]);
           tma_store_4d(&tmXs, sY + h * 16384 + q * 4096, h * 64, t0 + q * 32, b, 0);
           tma_store_4d(&tmXs, sY + (2 + h) * 16384 + q * 4096, (2 + h) * 64, t0 + q * 32, b, 0);
           tma_store_commit();
         }
-        if (tr && warp == 2 && lane == 0) lp.trace[ti * 16 + 9] = clock64();
+        if (tr && warp == 2 && lane == 0) lp.trace[ti * 16 + 11] = clock64();
       }
     }
     if (lane == 0) tma_store_wait_all();

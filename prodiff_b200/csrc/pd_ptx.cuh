@@ -40,24 +40,30 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
 }
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+// try_wait with a suspend-time hint: the thread sleeps IN HARDWARE until the phase completes (wake-up is prompt) or
+// ~hint_ns pass, instead of spinning.  Spinning waiters were measured to starve the epilogue warps that share their
+// SM sub-partition (the leader CTA's gate epilogue ran 2-3x slower than its peer's).
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity, uint32_t hint_ns = 2000u) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
       : "memory");
   return ok != 0;
 }
 // Wait for the phase with the given parity to complete.  `tag` identifies the call site in the trap message.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag) {
+// A waiter that is not ready backs off with nanosleep so it does not burn issue slots of the warps sharing its SM
+// sub-partition (the waiting control warps have the highest arbiter priority).
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag, uint32_t sleep_ns = 40u) {
   if (mbar_try_wait(bar, parity)) return;
 #if PD_WATCHDOG_CYCLES > 0
   const long long t0 = clock64();
 #endif
   while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(sleep_ns);
 #if PD_WATCHDOG_CYCLES > 0
     if (clock64() - t0 > PD_WATCHDOG_CYCLES) {
       printf("[prodiff_b200] mbarrier watchdog: block %d thread %d tag %d parity %u\n", (int)blockIdx.x,
@@ -88,6 +94,15 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* m, uin
       "[%2];" ::"r"(smem_u32(dst)),
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
+}
+// L2 prefetch of a tensor box / of a contiguous range: no shared memory, no completion to wait for.
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* m, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(reinterpret_cast<uint64_t>(m)),
+               "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gptr, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
 }
 // 2-D tiled store shared -> global (bulk async group).
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* src, int c0, int c1) {

@@ -143,6 +143,9 @@ def check_trace():
                 break
             rows.append([int(v) - t0 if int(v) else -1 for v in t[i, :14]])
         out[name] = dict(exit=int(t[0, 14]) - t0, tiles=rows)
+        if kind == 8:
+            out["layer_mma2"] = [[int(v) - t0 if int(v) else -1 for v in t[32 + i, :13]] for i in range(4)]
+
     return out
 
 
