@@ -305,8 +305,13 @@ def main():
         all_ms = sum(v[0] for v in kinds.values())
         name = ("layer_kernel (fused ResidualBlock: dilated conv + gate + residual 1x1, cta_group::2)" if dom.startswith("residual_layer")
                 else "gemm_kernel<EPI_GATE,256> (dilated conv + gate)")
+        # DRAM traffic of one launch of the dominant kernel at THIS workload, from the committed `ncu --set full`
+        # capture (profiles/r01p_ncu_layer_summary.txt: dram__bytes_read.sum 99.49 MB + dram__bytes_write.sum 27.40 MB)
+        traffic = 126.9e6 if (dom.startswith("residual_layer") and (B, T, C) == (64, 1000, 256)) else None
         roofline = {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
-                    "frac": achieved / peaks["tflops"], "traffic": None, "kernel": name,
+                    "frac": achieved / peaks["tflops"], "traffic": traffic,
+                    "traffic_source": "profiles/r01p_ncu_layer_summary.txt (bytes per launch; algorithmic bytes per launch = frames x 2560 B = 163.8 MB)" if traffic else None,
+                    "kernel": name,
                     "flops_per_frame_per_launch": per_frame,
                     "avg_launch_us": tot_ms / n * 1e3, "launches": n, "share_of_gemm_time": tot_ms / all_ms,
                     "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']})",
@@ -319,7 +324,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": w["name"], "parallelism": f"batch-sharded x{world}, no data-path collective",
-                       "l2": "per-step working set ~2.1 GB (cond projection 1.3 GB + gated activations 0.66 GB) >> 126 MB L2, no flush needed",
+                       "l2": "per-step working set ~2.2 GB (cond projection 1.34 GB + gated activations 0.66 GB + streams) >> 126 MB L2, no flush needed",
                        "init": "seeded Kaiming convs, output_projection.weight ~ N(0,0.02)", "noise": "in-kernel Philox4x32-10"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "mel frames/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,

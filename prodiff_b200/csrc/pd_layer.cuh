@@ -262,15 +262,21 @@ layer_kernel(const __grid_constant__ CUtensorMap tmX,     // x_cur  [1][B][T][C]
       const uint32_t sXa = smem_u32(sX), sYa = smem_u32(sY), sWa = smem_u32(sW);
       for (int pair = cluster_id; pair < num_pairs; pair += num_clusters, ++ti) {
         const uint32_t par = ti & 1u;                       // this tile's barrier phase parity and column layout
-        const uint32_t colA = par ? 256u : 0u;              // c01, later D2
-        const uint32_t colB1 = par ? 0u : 256u;             // c2
+        const uint32_t lay = (lp.flags & 2) ? 1u : ((lp.flags & 4) ? 0u : par);   // fixed or alternating column layout
+        const uint32_t colA = lay ? 256u : 0u;              // c01, later D2
+        const uint32_t colB1 = lay ? 0u : 256u;             // c2
         const uint32_t colB2 = colB1 + 128u;                // c3
+        const bool fixed_layout = (lp.flags & 6) != 0;
         mbar_wait(xfull_bar, par, 2);
         tc_fence_after();
         if (tr) lp.trace[ti * 16 + 2] = clock64();
         // ---- MMA1, channels 0..127 (N = 256).  Its columns were the previous tile's c2 and c3.
-        mbar_wait(&afree_bar[1], par ^ 1u, 3);
-        mbar_wait(&afree_bar[2], par ^ 1u, 3);
+        if (fixed_layout) {
+          mbar_wait(&afree_bar[3], par ^ 1u, 3);   // same columns as the previous tile's D2
+        } else {
+          mbar_wait(&afree_bar[1], par ^ 1u, 3);
+          mbar_wait(&afree_bar[2], par ^ 1u, 3);
+        }
         tc_fence_after();
         for (int kk = 0; kk < 12; ++kk, ++it) {
           const int kb = (kk + rot12) % 12;
@@ -287,9 +293,13 @@ layer_kernel(const __grid_constant__ CUtensorMap tmX,     // x_cur  [1][B][T][C]
         umma_commit_2sm(&afull_bar[0]);
         if (tr) lp.trace[ti * 16 + 3] = clock64();
         // ---- MMA1, channels 128..191 and 192..255 (N = 128 each).  Their columns held the previous tile's D2.
-        mbar_wait(&afree_bar[3], par ^ 1u, 5);
+        if (!fixed_layout) mbar_wait(&afree_bar[3], par ^ 1u, 5);
         tc_fence_after();
         for (int c = 0; c < 2; ++c) {
+          if (fixed_layout) {
+            mbar_wait(&afree_bar[1 + c], par ^ 1u, 5);   // same columns as the previous tile's chunk
+            tc_fence_after();
+          }
           const uint32_t d_tmem = tmem_base + (c ? colB2 : colB1);
           for (int kk = 0; kk < 6; ++kk, ++it) {
             const int kq = (kk + rot6) % 6;
@@ -346,7 +356,8 @@ layer_kernel(const __grid_constant__ CUtensorMap tmX,     // x_cur  [1][B][T][C]
     const uint16_t* cpb = static_cast<const uint16_t*>(lp.cp);
     for (int pair = cluster_id; pair < num_pairs; pair += num_clusters, ++ti) {
       const uint32_t par = ti & 1u;
-      const uint32_t colA = par ? 256u : 0u, colB1 = par ? 0u : 256u;
+      const uint32_t lay = (lp.flags & 2) ? 1u : ((lp.flags & 4) ? 0u : par);
+      const uint32_t colA = lay ? 256u : 0u, colB1 = lay ? 0u : 256u;
       const int m_tile = 2 * pair + (int)rank;
       const int b = m_tile / lp.m_tiles_per_row;
       const int t0 = (m_tile - b * lp.m_tiles_per_row) * kBlockM;

@@ -156,3 +156,58 @@ def test_dropin_contract():
     with torch.no_grad():
         o2 = gd(torch.zeros(1, 8, 256, device="cuda"), infer=True, x_T=torch.zeros(1, 1, 128, 8), seed=1)
     assert float((o2 - out).abs().max()) > 1e-3
+
+
+def test_fused_layer_kernel_equals_unfused_pair():
+    """The fused 2-CTA ResidualBlock kernel against the conv+gate / res_proj kernel pair on the same inputs.
+    Same operands, same fp32 accumulation per output, so the two paths must agree to bf16 rounding of one layer
+    (they differ only in accumulation order across K blocks: the fused kernel staggers its weight walk per cluster)."""
+    from prodiff_b200 import _lib, synth
+    lib = _lib.load()
+    cfg = synth.DiffNetConfig(128, 256, 6, 256, 3)
+    state = synth.make_state(cfg, 17, "trained")
+    cond, x_T, _ = synth.make_inputs(cfg, 5, 333, 1, 18)     # 5 x 3 = 15 tiles: odd count -> dummy peer tile path
+    steps = torch.tensor([0.0, 1.0, 2.0, 3.0, 4.0])
+    outs = []
+    for fused in (1, 0):
+        prev = lib.pd_set_fused(fused)
+        try:
+            wn = _build(cfg, state)
+            with torch.no_grad():
+                outs.append(wn(x_T.cuda(), steps.cuda(), cond.cuda().transpose(1, 2)).cpu())
+        finally:
+            lib.pd_set_fused(1 if prev != 0 else 0)
+    with torch.no_grad():
+        ref = oracle.wavenet_forward(state, x_T, steps, cond.transpose(1, 2), cfg.dilation_cycle_length)
+    assert float((outs[0] - outs[1]).abs().max()) <= 4e-3
+    assert float((outs[0] - ref).abs().max()) <= STEP_TOL and float((outs[1] - ref).abs().max()) <= STEP_TOL
+
+
+def test_full_size_roundtrip_properties():
+    """BASELINE config-2 size (64 x 1000, K = 4), properties that need no oracle run:
+    determinism per seed, batch-row independence (a row sampled alone equals the same row inside the batch, which is
+    what makes batch sharding across GPUs exact), finiteness, and linear response of the posterior step to noise."""
+    from prodiff_b200 import synth
+    cfg = synth.DiffNetConfig(128, 256, 20, 256, 1)
+    state = synth.make_state(cfg, 1234, "trained")
+    case = dict(timesteps=4, schedule_type="vpsde", max_beta=40)
+    gd = _build(cfg, state, case)
+    B, T, K = 64, 1000, 4
+    cond, x_T, _ = synth.make_inputs(cfg, B, T, 1, 31)
+    cond, x_T = cond.cuda(), x_T.cuda()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    noise = torch.randn(K, B, 1, 128, T, device="cuda", generator=g)
+    with torch.no_grad():
+        a = gd(cond, infer_step=K, infer=True, x_T=x_T, noise=noise).clone()
+        b = gd(cond, infer_step=K, infer=True, x_T=x_T, noise=noise).clone()
+        assert torch.equal(a, b) and torch.isfinite(a).all() and a.shape == (B, T, 128)
+        rows = [0, 37, 63]
+        sub = gd(cond[rows], infer_step=K, infer=True, x_T=x_T[rows], noise=noise[:, rows].contiguous())
+        # tiles pair up differently when the batch changes, so accumulation order (not operands) may differ
+        assert float((sub - a[rows]).abs().max()) <= 5e-3
+        # x_{t-1} is affine in the injected noise of that step: check on the last noisy step (t = 1)
+        n2 = noise.clone()
+        n2[K - 2] += 1.0
+        c = gd(cond[:2], infer_step=K, infer=True, x_T=x_T[:2], noise=noise[:, :2].contiguous())
+        d = gd(cond[:2], infer_step=K, infer=True, x_T=x_T[:2], noise=n2[:, :2].contiguous())
+    assert float((c - d).abs().mean()) > 1e-3
