@@ -300,17 +300,19 @@ def main():
         # algorithmic FLOPs per frame per launch: dilated conv 12 C^2 (+ residual half of the 1x1
         # output projection, 2 C^2, when the fused ResidualBlock kernel is the one running)
         per_frame = 12 * C * C + (2 * C * C if dom.startswith("residual_layer") else 0)
-        flops_per_launch = float(per_frame) * (B * T)
+        layers_per_launch = max(1, round(K * L * prof_steps / n))   # L when the whole stack runs as one persistent launch
+        flops_per_launch = float(per_frame) * (B * T) * layers_per_launch
         achieved = flops_per_launch / (tot_ms / n * 1e-3) / 1e12
         all_ms = sum(v[0] for v in kinds.values())
-        name = ("layer_kernel (fused ResidualBlock: dilated conv + gate + residual 1x1, cta_group::2)" if dom.startswith("residual_layer")
+        name = (f"layer_kernel (fused ResidualBlock: dilated conv + gate + residual 1x1, cta_group::2; {layers_per_launch} layer(s) per persistent launch)" if dom.startswith("residual_layer")
                 else "gemm_kernel<EPI_GATE,256> (dilated conv + gate)")
         # DRAM traffic of one launch of the dominant kernel at THIS workload, from the committed `ncu --set full`
         # capture (profiles/r01p_ncu_layer_summary.txt: dram__bytes_read.sum 99.49 MB + dram__bytes_write.sum 27.40 MB)
-        traffic = 126.9e6 if (dom.startswith("residual_layer") and (B, T, C) == (64, 1000, 256)) else None
+        traffic = 126.9e6 * layers_per_launch if (dom.startswith("residual_layer") and (B, T, C) == (64, 1000, 256)) else None
         roofline = {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
                     "frac": achieved / peaks["tflops"], "traffic": traffic,
-                    "traffic_source": "profiles/r01p_ncu_layer_summary.txt (bytes per launch; algorithmic bytes per launch = frames x 2560 B = 163.8 MB)" if traffic else None,
+                    "traffic_source": "profiles/r01p_ncu_layer_summary.txt: 126.9 MB DRAM per layer (one-layer launch captured under ncu), x layers per launch; algorithmic = frames x 2560 B = 163.8 MB per layer" if traffic else None,
+                    "flops_per_launch": flops_per_launch,
                     "kernel": name,
                     "flops_per_frame_per_launch": per_frame,
                     "avg_launch_us": tot_ms / n * 1e3, "launches": n, "share_of_gemm_time": tot_ms / all_ms,

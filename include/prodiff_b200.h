@@ -111,7 +111,7 @@ int pd_profile_begin(void);
 int pd_profile_end(float* ms_by_kind, int* count_by_kind, int n_kinds);
 
 /* Introspection for tests: byte offset/size of a named scratch buffer inside the plan's workspace.
- * Names: "cond16","cp","xin","xa","xb","ybuf","s1","s2","steps","emb0","hid","emb","dvec","sb". Returns 0 if found. */
+ * Names: "cond16","cp","xin","xa","xb","ybuf","s1","s2","steps","emb0","hid","emb","dvec","sb","flags". Returns 0 if found. */
 int pd_plan_buffer(const pd_plan* p, const char* name, size_t* offset, size_t* bytes);
 
 /* Test hook: one implicit-GEMM launch of the production kernel with a plain fp32 store epilogue.
@@ -123,6 +123,9 @@ int pd_debug_gemm(int dtype, const void* a, int B, int T, int Cin, int taps, int
 /* Select the fused 2-CTA ResidualBlock kernel (1, default; env PD_FUSED=0 also disables) or the unfused
  * conv+gate / res_proj pair (0).  Returns the previous setting (-1 = not yet decided). */
 int pd_set_fused(int on);
+/* With the fused kernel: run all layers of a denoiser call in ONE persistent launch whose tiles synchronise through
+ * per-tile flags (1, default; env PD_STACK=0 also disables) or launch one kernel per layer (0). Returns the previous value. */
+int pd_set_stack(int on);
 
 /* Debug: when set to a device buffer of 9 x 1024 int64, CTA 0 of every GEMM launch writes clock64() stamps of its
  * pipeline events at [kind * 1024 + tile * 16 + slot] (slots: 0/1 first/last TMA issue, 2 accumulator free, 3/4 first/

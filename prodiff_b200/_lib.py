@@ -17,7 +17,7 @@ PD_BF16, PD_FP16 = 0, 1
 SYMBOLS = [
     "pd_state_count", "pd_last_error", "pd_abi_version", "pd_packed_bytes", "pd_model_create", "pd_model_destroy",
     "pd_workspace_bytes", "pd_plan_create", "pd_plan_destroy", "pd_cond_project", "pd_denoise", "pd_sample",
-    "pd_launch_count", "pd_plan_buffer", "pd_debug_gemm", "pd_profile_begin", "pd_profile_end", "pd_debug_shift", "pd_debug_set_trace", "pd_set_fused",
+    "pd_launch_count", "pd_plan_buffer", "pd_debug_gemm", "pd_profile_begin", "pd_profile_end", "pd_debug_shift", "pd_debug_set_trace", "pd_set_fused", "pd_set_stack",
 ]
 
 
@@ -62,6 +62,7 @@ def load() -> C.CDLL:
     lib.pd_debug_shift.argtypes = [C.c_int, vp, C.c_int, vp, C.c_int, C.c_int, vp, vp]; lib.pd_debug_shift.restype = C.c_int
     lib.pd_debug_set_trace.argtypes = [vp]; lib.pd_debug_set_trace.restype = C.c_int
     lib.pd_set_fused.argtypes = [C.c_int]; lib.pd_set_fused.restype = C.c_int
+    lib.pd_set_stack.argtypes = [C.c_int]; lib.pd_set_stack.restype = C.c_int
     lib.pd_profile_begin.argtypes = []; lib.pd_profile_begin.restype = C.c_int
     lib.pd_profile_end.argtypes = [P(C.c_float), P(C.c_int), C.c_int]; lib.pd_profile_end.restype = C.c_int
     if lib.pd_abi_version() != 1:

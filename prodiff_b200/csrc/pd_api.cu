@@ -358,6 +358,7 @@ static size_t plan_layout(const pd_config& c, int B, int T, int E, std::vector<B
   take("emb", (size_t)E * C * 4);
   take("dvec", (size_t)E * L * C * 4);
   take("sb", (size_t)E * L * 4 * 2 * C * 4);
+  take("flags", L * mtiles * 4);  // multi-layer kernel: per (layer, tile) completion counters
   return o;
 }
 
@@ -503,9 +504,25 @@ static bool fused_enabled() {
   return g_fused == 1;
 }
 
+static int g_stack = -1;  // -1: read PD_STACK from the environment on first use
+extern "C" int pd_set_stack(int on) {
+  const int prev = g_stack;
+  g_stack = on ? 1 : 0;
+  return prev;
+}
+static bool stack_enabled() {
+  if (g_stack < 0) {
+    const char* e = getenv("PD_STACK");
+    g_stack = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_stack == 1;
+}
+
+// Launch the fused ResidualBlock kernel for layers [lp.layer0, lp.layer0 + lp.n_layers).  n_layers > 1 is the persistent
+// multi-layer form: its clusters wait on one another through global flags, so every cluster must be co-resident --
+// `*ok_multi` reports whether the occupancy query allows that (the caller falls back to one launch per layer).
 template <typename T>
-static int launch_layer_t(const CUtensorMap& x, const CUtensorMap& wd, const CUtensorMap& wq, const CUtensorMap& wr,
-                          const CUtensorMap& ys, const CUtensorMap& xs, const LayerParams& lp, int sms, cudaStream_t s) {
+static int launch_layer_t(const LayerMaps& mp, const LayerParams& lp, int sms, cudaStream_t s, bool* ok_multi) {
   auto kern = layer_kernel<T>;
   static bool configured[64] = {false};
   int dev = 0;
@@ -529,8 +546,15 @@ static int launch_layer_t(const CUtensorMap& x, const CUtensorMap& wd, const CUt
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  if (ok_multi) {
+    int max_clusters = 0;
+    const cudaError_t e = cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg);
+    *ok_multi = (e == cudaSuccess) && max_clusters >= clusters;
+    if (e != cudaSuccess) cudaGetLastError();
+    if (!*ok_multi) return 0;
+  }
   prof_before(8, s);
-  PD_CUDA(cudaLaunchKernelEx(&cfg, kern, x, wd, wq, wr, ys, xs, lp));
+  PD_CUDA(cudaLaunchKernelEx(&cfg, kern, mp, lp));
   prof_after(s);
   PD_LAUNCH_CHECK("layer_kernel");
   return 0;
@@ -617,39 +641,68 @@ static int run_denoiser(pd_plan* p, int entry_base, int entry_per_b, const OutSt
   const bool fused = p->fused_ok && fused_enabled();
   for (int l = 0; l < L; ++l) {
     const int dil = 1 << (l % c.dilation_cycle_length);
-    if (fused) {  // whole ResidualBlock in one 2-CTA kernel
+    if (fused) {  // ResidualBlocks as the fused 2-CTA kernel: all layers in one persistent launch, or one launch per layer
       const size_t mtiles = (size_t)B * ((T + kBlockM - 1) / kBlockM);
+      LayerMaps mp;
+      for (int i = 0; i < 5; ++i) {
+        const int j = i < c.dilation_cycle_length ? i : 0;
+        mp.xh[0][i] = p->tm_xa_halo[j];
+        mp.xh[1][i] = p->tm_xb_halo[j];
+      }
+      mp.xs[0] = p->tm_xa_st;
+      mp.xs[1] = p->tm_xb_st;
+      mp.wd = m->tm_w_dil128;
+      mp.wq = m->tm_w_dil64;
+      mp.wr = m->tm_w_res128;
+      mp.ys = p->tm_y_st;
       LayerParams lp;
       memset(&lp, 0, sizeof(lp));
       lp.B = B;
       lp.T = T;
       lp.m_tiles_per_row = (T + kBlockM - 1) / kBlockM;
-      lp.dil = dil;
-      lp.layer = l;
+      lp.cycle = c.dilation_cycle_length;
       lp.ident_row0 = L * C;
       lp.idesc = (1u << 4) | ((dt == PD_FP16 ? 0u : 1u) << 7) | ((dt == PD_FP16 ? 0u : 1u) << 10) | ((256u >> 3) << 17) | ((256u >> 4) << 24);
       lp.idesc128 = (lp.idesc & ~(0x3Fu << 17)) | ((128u >> 3) << 17);
-      lp.cp = p->ptr<uint16_t>("cp") + (size_t)l * mtiles * kBlockM * 2 * C;
-      lp.sb = p->ptr<float>("sb") + (size_t)l * 4 * 2 * C;
+      lp.cp = p->ptr<uint16_t>("cp");
+      lp.cp_layer_stride = (long long)mtiles * kBlockM * 2 * C;
+      lp.sb = p->ptr<float>("sb");
       lp.sb_entry_stride = (long long)L * 4 * 2 * C;
       lp.sb_entry_base = entry_base;
       lp.sb_entry_per_b = entry_per_b;
-      lp.b_res = (const float*)(pk + lay.b_res) + (size_t)l * C;
+      lp.b_res = (const float*)(pk + lay.b_res);
       lp.scale = 0.70710678118654752440f;
       {
         static int fl = -1;
         if (fl < 0) { const char* e = getenv("PD_LAYER_FLAGS"); fl = e ? atoi(e) : 0; }
-        lp.flags = fl;
+        lp.flags_opt = fl;
       }
       lp.trace = g_trace ? g_trace + 8 * 1024 : nullptr;
-      const int di = l % c.dilation_cycle_length;
-      const CUtensorMap& xh = cur_is_a ? p->tm_xa_halo[di] : p->tm_xb_halo[di];
-      const CUtensorMap& xs = cur_is_a ? p->tm_xb_st : p->tm_xa_st;
-      const int rc = dt == PD_FP16 ? launch_layer_t<__half>(xh, m->tm_w_dil128, m->tm_w_dil64, m->tm_w_res128, p->tm_y_st, xs, lp, sms, s)
-                                   : launch_layer_t<__nv_bfloat16>(xh, m->tm_w_dil128, m->tm_w_dil64, m->tm_w_res128, p->tm_y_st, xs, lp, sms, s);
-      if (rc) return rc;
-      cur_is_a = !cur_is_a;
-      continue;
+      bool done = false;
+      if (stack_enabled() && L > 1) {
+        // one persistent launch for the whole stack; tiles of consecutive layers synchronise through per-tile flags
+        lp.layer0 = 0;
+        lp.n_layers = L;
+        lp.rot = 29;
+        lp.flags = p->ptr<unsigned int>("flags");
+        PD_CUDA(cudaMemsetAsync(lp.flags, 0, (size_t)L * mtiles * 4, s));
+        bool ok = false;
+        const int rc = dt == PD_FP16 ? launch_layer_t<__half>(mp, lp, sms, s, &ok) : launch_layer_t<__nv_bfloat16>(mp, lp, sms, s, &ok);
+        if (rc) return rc;
+        done = ok;
+      }
+      if (!done) {
+        lp.flags = nullptr;
+        lp.rot = 0;
+        lp.n_layers = 1;
+        for (int ll = 0; ll < L; ++ll) {
+          lp.layer0 = ll;
+          const int rc = dt == PD_FP16 ? launch_layer_t<__half>(mp, lp, sms, s, nullptr) : launch_layer_t<__nv_bfloat16>(mp, lp, sms, s, nullptr);
+          if (rc) return rc;
+        }
+      }
+      cur_is_a = (L % 2 == 0);
+      break;
     }
     const CUtensorMap& tm_cur = cur_is_a ? p->tm_xa : p->tm_xb;
     const CUtensorMap& tm_nxt = cur_is_a ? p->tm_xb : p->tm_xa;

