@@ -164,8 +164,9 @@ __global__ void k_step_matvec(const float* __restrict__ W, const float* __restri
 
 // The reference adds d to x BEFORE the zero-padded dilated conv (wavenet.py:63-65), so the step contributes
 // W_k . d through each tap k that lands inside the utterance.  Per (entry, layer) this kernel emits, in packed
-// column order, {sum over the 3 taps, tap 0 alone, tap 2 alone}: interior frames add the first, the first/last
-// `dilation` frames subtract the tap that fell on padding (EPI_GATE).  fp32 weights: this part is exact.
+// column order, the four sums a frame can need: slot 0 = all three taps (interior frames), slot 1 = taps 1+2 (the first
+// `dilation` frames: tap 0 fell on padding), slot 2 = taps 0+1 (the last `dilation` frames), slot 3 = tap 1 only
+// (utterances shorter than the dilation).  The gate epilogue just picks a slot per frame.  fp32 weights: exact.
 // grid (2C / 8, L), block 256: one warp per packed output row, looping over all entries with the row in registers.
 template <int CPL>  // C / 32
 __global__ void k_step_taps(const float* __restrict__ dvec, const float* __restrict__ dil_w, float* __restrict__ sb,
@@ -199,8 +200,9 @@ __global__ void k_step_taps(const float* __restrict__ dvec, const float* __restr
     if (lane == 0) {
       float* o = sb + ((long long)e * L + l) * 4 * 2 * C;
       o[p] = a0 + a1 + a2;
-      o[2 * C + p] = a0;
-      o[4 * C + p] = a2;
+      o[2 * C + p] = a1 + a2;
+      o[4 * C + p] = a0 + a1;
+      o[6 * C + p] = a1;
     }
   }
 }

@@ -52,7 +52,7 @@ struct EpiArgs {
   void* out;
   const void* aux;    // GATE: hoisted cond projection (fp16) of this layer; RES: x_old (T)
   const float* bias;  // per output column (fp32)
-  const float* sb;    // GATE: step-bias table of this layer, [entry][4][2C] = {all taps, tap0, tap2, -}
+  const float* sb;    // GATE: step-bias table of this layer, [entry][4][2C] = {all taps, no tap 0, no tap 2, tap 1 only}
   long long sb_entry_stride;
   int sb_entry_base, sb_entry_per_b;
   int ld;       // STORE: slab width of the output; GATE/RES: C
@@ -142,32 +142,18 @@ __device__ __forceinline__ float4 philox_normal4(unsigned long long seed, uint32
   return make_float4(r0 * c0f, r0 * s0, r1 * c1f, r1 * s1);
 }
 
-// One 16-channel step of the gate epilogue: z = acc + cond_proj + step bias (minus the taps that fell on padding when
-// kEdge), y = sigmoid(z_gate) * tanh(z_filter), packed to 16-bit.  rg/rf: accumulator columns of the 16 gate / filter
-// channels; cpg/cpf: 8 packed fp16 pairs each; sb: step-bias row positioned at the first gate channel (filter at
-// +128, tap-0 table at +t0_off, tap-2 table at +t2_off).  kEdge is warp-uniform so the hot path has no predication.
-template <typename T, bool kEdge>
+// One 16-channel step of the gate epilogue: z = acc + cond_proj + step bias, y = sigmoid(z_gate) * tanh(z_filter), packed
+// to 16-bit.  rg/rf: accumulator columns of the 16 gate / filter channels; cpg/cpf: 8 packed fp16 pairs each; sb: THIS
+// FRAME's step-bias row (the slot for interior / first / last frames is chosen per lane by the caller) positioned at
+// the first gate channel, filter at +128.  One code path for every frame: no edge branch, no predication.
+template <typename T>
 __device__ __forceinline__ void gate_chunk16(const uint32_t (&rg)[16], const uint32_t (&rf)[16], const uint32_t* cpg,
-                                             const uint32_t* cpf, const float* sb, int t0_off, int t2_off, bool edge_lo,
-                                             bool edge_hi, uint32_t (&packed)[8]) {
+                                             const uint32_t* cpf, const float* sb, uint32_t (&packed)[8]) {
 #pragma unroll
   for (int j = 0; j < 16; j += 4) {
     const float4 bg = __ldg(reinterpret_cast<const float4*>(sb + j));
     const float4 bf = __ldg(reinterpret_cast<const float4*>(sb + 128 + j));
-    float zg[4] = {bg.x, bg.y, bg.z, bg.w}, zf[4] = {bf.x, bf.y, bf.z, bf.w};
-    if constexpr (kEdge) {
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (edge_lo) {
-          zg[u] -= __ldg(sb + t0_off + j + u);
-          zf[u] -= __ldg(sb + t0_off + 128 + j + u);
-        }
-        if (edge_hi) {
-          zg[u] -= __ldg(sb + t2_off + j + u);
-          zf[u] -= __ldg(sb + t2_off + 128 + j + u);
-        }
-      }
-    }
+    const float zg[4] = {bg.x, bg.y, bg.z, bg.w}, zf[4] = {bf.x, bf.y, bf.z, bf.w};
 #pragma unroll
     for (int u = 0; u < 4; u += 2) {
       const float2 pg = Cvt<__half>::unpack(cpg[(j + u) >> 1]);
@@ -418,9 +404,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int C2 = 2 * ep.ld;
         const int entry = ep.sb_entry_base + b * ep.sb_entry_per_b;
         const float* sb_all = ep.sb + (long long)entry * ep.sb_entry_stride + n_tile * 256;
-        const bool edge_lo = t < sh.dil;            // tap 0 reads x[t - dil] which is padding
-        const bool edge_hi = t + sh.dil >= sh.T;    // tap 2 reads x[t + dil] which is padding
-        const bool warp_edge = __any_sync(0xffffffffu, valid && (edge_lo || edge_hi));  // rare: first/last frames only
+        // step-bias slot of this frame: tap 0 reads x[t - dil], tap 2 reads x[t + dil]; taps on padding contribute nothing
+        const int slot = (t < sh.dil ? 1 : 0) + (t + sh.dil >= sh.T ? 2 : 0);
+        const float* sb_lane = sb_all + slot * C2;
         const uint32_t* prew = reinterpret_cast<const uint32_t*>(pre);
         uint8_t* ytile = extra + h * 16384;  // [128 frames x 64 ch] staging tile of this column half
         // the TMA store of the previous tile must have finished reading the staging tiles
@@ -434,8 +420,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           tmem_ld_x16(trow + 128 + i, rf);
           tmem_ld_wait();
           uint32_t packed[8];
-          if (warp_edge) gate_chunk16<T, true>(rg, rf, prew + ci * 8, prew + 32 + ci * 8, sb_all + i, C2, 2 * C2, edge_lo, edge_hi, packed);
-          else gate_chunk16<T, false>(rg, rf, prew + ci * 8, prew + 32 + ci * 8, sb_all + i, C2, 2 * C2, false, false, packed);
+          gate_chunk16<T>(rg, rf, prew + ci * 8, prew + 32 + ci * 8, sb_lane + i, packed);
           // rows past T hold junk here; the TMA store clips them
           *sw128_chunk(ytile, row, 2 * ci) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
           *sw128_chunk(ytile, row, 2 * ci + 1) = make_uint4(packed[4], packed[5], packed[6], packed[7]);

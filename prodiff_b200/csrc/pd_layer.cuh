@@ -370,6 +370,7 @@ layer_kernel(const __grid_constant__ LayerMaps mp,
     const int q = warp & 3, h = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     uint32_t ti = 0;
+    unsigned int* pending_flag = nullptr;   // completion counter of the x_next slab this warp stored last (lane 0 only)
     for (int l = lp.layer0; l < l_end; ++l)
     for (int pair = first_pair(l); pair < num_pairs; pair += num_clusters, ++ti) {
       const int dil = 1 << (l % lp.cycle);
@@ -385,9 +386,9 @@ layer_kernel(const __grid_constant__ LayerMaps mp,
       const int t = t0 + row;
       const bool valid = (m_tile < num_m_tiles) && (t < lp.T);
       const int entry = lp.sb_entry_base + (b < lp.B ? b : 0) * lp.sb_entry_per_b;
-      const bool edge_lo = t < dil, edge_hi = t + dil >= lp.T;
-      const bool warp_edge = __any_sync(0xffffffffu, valid && (edge_lo || edge_hi));
-      const float* sb_row = lp.sb + (long long)entry * lp.sb_entry_stride + (long long)l * (4 * 2 * kLayerC);
+      // step-bias slot of this frame (all taps / no tap 0 / no tap 2 / centre tap only), see k_step_taps
+      const int slot = (t < dil ? 1 : 0) + (t + dil >= lp.T ? 2 : 0);
+      const float* sb_row = lp.sb + (long long)entry * lp.sb_entry_stride + (long long)l * (4 * 2 * kLayerC) + slot * (2 * kLayerC);
       const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
 
       // ---------------- gate epilogue, channels 0..127: this warp does channels [64h, 64h + 64) -> Y sub-tile h
@@ -402,8 +403,19 @@ layer_kernel(const __grid_constant__ LayerMaps mp,
         }
         const uint32_t* prew = reinterpret_cast<const uint32_t*>(pre);
         uint8_t* ytile = sY + h * 16384;
-        // sub-tile h rows of this warp were last read by its own x_next store of the previous tile (newest group)
-        if (lane == 0) tma_store_wait_read<0>();
+        // sub-tile h rows of this warp were last read by its own x_next store of the previous tile (newest group).
+        // Multi-layer launches publish that store here, one tile late: waiting for its COMPLETION right after issuing it
+        // would put the store latency on the epilogue chain, whereas here the warp is about to wait for MMAs anyway.
+        if (lane == 0) {
+          if (pending_flag != nullptr) {
+            tma_store_wait_all();
+            fence_proxy_async_all();
+            red_release_add_u32(pending_flag, 1u);
+            pending_flag = nullptr;
+          } else {
+            tma_store_wait_read<0>();
+          }
+        }
         __syncwarp();
         mbar_wait(&afull_bar[0], par, 10);
         tc_fence_after();
@@ -417,8 +429,7 @@ layer_kernel(const __grid_constant__ LayerMaps mp,
           tmem_ld_x16(trow + 128 + i, rf);
           tmem_ld_wait();
           uint32_t packed[8];
-          if (warp_edge) gate_chunk16<T, true>(rg, rf, prew + ci * 8, prew + 32 + ci * 8, sb_row + i, 2 * kLayerC, 4 * kLayerC, edge_lo, edge_hi, packed);
-          else gate_chunk16<T, false>(rg, rf, prew + ci * 8, prew + 32 + ci * 8, sb_row + i, 2 * kLayerC, 4 * kLayerC, false, false, packed);
+          gate_chunk16<T>(rg, rf, prew + ci * 8, prew + 32 + ci * 8, sb_row + i, packed);
           if (!valid) {
 #pragma unroll
             for (int u = 0; u < 8; ++u) packed[u] = 0u;   // keep junk (NaN) out of MMA2's operand rows
@@ -467,8 +478,7 @@ layer_kernel(const __grid_constant__ LayerMaps mp,
           tmem_ld_x16(trow + 64 + h * 32 + ci * 16, rf);
           tmem_ld_wait();
           uint32_t packed[8];
-          if (warp_edge) gate_chunk16<T, true>(rg, rf, prew + ci * 8, prew + 16 + ci * 8, sbp + ci * 16, 2 * kLayerC, 4 * kLayerC, edge_lo, edge_hi, packed);
-          else gate_chunk16<T, false>(rg, rf, prew + ci * 8, prew + 16 + ci * 8, sbp + ci * 16, 2 * kLayerC, 4 * kLayerC, false, false, packed);
+          gate_chunk16<T>(rg, rf, prew + ci * 8, prew + 16 + ci * 8, sbp + ci * 16, packed);
           if (!valid) {
 #pragma unroll
             for (int u = 0; u < 8; ++u) packed[u] = 0u;
@@ -529,17 +539,18 @@ layer_kernel(const __grid_constant__ LayerMaps mp,
           tma_store_4d(tmXs, sY + h * 16384 + q * 4096, h * 64, t0 + q * 32, b, 0);
           tma_store_4d(tmXs, sY + (2 + h) * 16384 + q * 4096, (2 + h) * 64, t0 + q * 32, b, 0);
           tma_store_commit();
-          if (lp.flags != nullptr && m_tile < num_m_tiles) {
-            // publish: this warp's slab of x_next (and everything it wrote before) is complete in global memory
-            tma_store_wait_all();
-            fence_proxy_async_all();
-            red_release_add_u32(lp.flags + (size_t)l * num_m_tiles + m_tile, 1u);
-          }
+          if (lp.flags != nullptr && m_tile < num_m_tiles) pending_flag = lp.flags + (size_t)l * num_m_tiles + m_tile;
         }
         if (tr && warp == 2 && lane == 0) lp.trace[(ti & 31) * 16 + 11] = clock64();
       }
     }
-    if (lane == 0) tma_store_wait_all();
+    if (lane == 0) {
+      tma_store_wait_all();
+      if (pending_flag != nullptr) {
+        fence_proxy_async_all();
+        red_release_add_u32(pending_flag, 1u);
+      }
+    }
   }
 
   // both CTAs must be completely done (the leader's MMAs read the peer's shared memory and write its TMEM)

@@ -82,7 +82,7 @@ def check_layers(dtype="bf16", B=2, T=300, L=4, C=256, cycle=2, M=128):
     w = state["residual_layers.0.dilated_conv.weight"]
     s_all = torch.einsum("ock,bc->bo", w, d0)
     res["sb_all"] = float((unperm(sb[:B, 0, 0]) - s_all).abs().max())
-    res["sb_tap0"] = float((unperm(sb[:B, 0, 1]) - torch.einsum("oc,bc->bo", w[:, :, 0], d0)).abs().max())
+    res["sb_tap0"] = float((unperm(sb[:B, 0, 1]) - torch.einsum("ock,bc->bo", w[:, :, 1:], d0)).abs().max())   # slot 1 = taps 1 + 2
     xl = plan.buffer("xa" if L % 2 == 0 else "xb").view(tdt).view(N, C).float().cpu()
     res["x_last"] = float((xl - tr["x"][-1].transpose(1, 2).reshape(N, C)).abs().max())
     res["out"] = float((out.cpu() - ref).abs().max())
