@@ -217,6 +217,7 @@ struct pd_model {
   CUtensorMap tm_w_in, tm_w_cond, tm_w_dil, tm_w_res, tm_w_skip, tm_w_sp, tm_w_out;
   CUtensorMap tm_w_dil128, tm_w_res128;  // 128-row boxes: one CTA's half of a cta_group::2 weight block
   CUtensorMap tm_w_dil64;                // 64-row boxes over the 64-channel-paired packing
+  CUtensorMap tm_w_in_h, tm_w_cond_h, tm_w_skip_h, tm_w_sp_h, tm_w_out_h;  // half-height boxes for the cta_group::2 GEMMs
 };
 
 static int check_device(int* device, int* sms) {
@@ -305,7 +306,10 @@ extern "C" int pd_model_create(const pd_config* cfg, const float* const* state, 
       make_w_map(&m->tm_w_skip, dt, pk + lay.w_skip, L * C, C, 256) || make_w_map(&m->tm_w_sp, dt, pk + lay.w_sp, C, C, 256) ||
       make_w_map(&m->tm_w_out, dt, pk + lay.w_out, C, 128, 128) ||
       make_w_map(&m->tm_w_dil128, dt, pk + lay.w_dil, 3 * C, L * 2 * C, 128) || make_w_map(&m->tm_w_res128, dt, pk + lay.w_res, C, (L + 1) * C, 128) ||
-      make_w_map(&m->tm_w_dil64, dt, pk + lay.w_dil64, 3 * C, L * 2 * C, 64)) {
+      make_w_map(&m->tm_w_dil64, dt, pk + lay.w_dil64, 3 * C, L * 2 * C, 64) ||
+      make_w_map(&m->tm_w_in_h, dt, pk + lay.w_in, M, C, 128) || make_w_map(&m->tm_w_cond_h, dt, pk + lay.w_cond, H, L * 2 * C, 128) ||
+      make_w_map(&m->tm_w_skip_h, dt, pk + lay.w_skip, L * C, C, 128) || make_w_map(&m->tm_w_sp_h, dt, pk + lay.w_sp, C, C, 128) ||
+      make_w_map(&m->tm_w_out_h, dt, pk + lay.w_out, C, 128, 64)) {
     delete m;
     return 1;
   }
@@ -431,41 +435,72 @@ extern "C" int pd_plan_buffer(const pd_plan* p, const char* name, size_t* offset
 }
 
 // ------------------------------------------------------------------ GEMM launch
-static uint32_t make_idesc(int dtype, int bn) {
+static uint32_t make_idesc(int dtype, int bn, int m = kBlockM) {
   const uint32_t fmt = dtype == PD_FP16 ? 0u : 1u;
   // c_format = F32 (bit 4), a/b format (bits 7-9 / 10-12), K-major A and B, N >> 3 (bits 17-22), M >> 4 (bits 24-28)
-  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
-template <int EPI, int BN, typename T>
+static int g_pair = -1;  // -1: read PD_PAIR from the environment on first use
+static bool pair_enabled() {
+  if (g_pair < 0) {
+    const char* e = getenv("PD_PAIR");
+    g_pair = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_pair == 1;
+}
+
+template <int EPI, int BN, typename T, bool kPair>
 static int launch_gemm_t(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, const CUtensorMap& x,
                          const GemmShape& sh, const EpiArgs& ep, int sms, cudaStream_t s, const char* name, int kind) {
-  auto kern = gemm_kernel<EPI, BN, T>;
+  auto kern = gemm_kernel<EPI, BN, T, kPair>;
+  using Cfg = GemmCfg<EPI, BN, kPair>;
   static bool configured[64] = {false};  // per instantiation, per device
   int dev = 0;
   PD_CUDA(cudaGetDevice(&dev));
   if (!configured[dev & 63]) {
-    PD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GemmCfg<EPI, BN>::kSmemBytes));
+    PD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes));
     configured[dev & 63] = true;
   }
-  const int tiles = sh.B * sh.m_tiles_per_row * sh.n_tiles;
-  const int grid = tiles < sms ? tiles : sms;
+  const int m_tiles = sh.B * sh.m_tiles_per_row;
+  const int items = (kPair ? (m_tiles + 1) / 2 : m_tiles) * sh.n_tiles;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  const int ctas = kPair ? 2 * (items < sms / 2 ? items : sms / 2) : (items < sms ? items : sms);
+  cfg.gridDim = dim3(ctas);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kPair ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
   prof_before(kind, s);
-  kern<<<grid, kGemmThreads, GemmCfg<EPI, BN>::kSmemBytes, s>>>(a, b, o, x, sh, ep);
+  PD_CUDA(cudaLaunchKernelEx(&cfg, kern, a, b, o, x, sh, ep));
   prof_after(s);
   PD_LAUNCH_CHECK(name);
   return 0;
 }
+// `bh`: the weight map with half-height boxes; when given (and the problem has at least two frame tiles) the GEMM runs as
+// cta_group::2 pairs.
 template <int EPI, int BN>
 static int launch_gemm(int dtype, const CUtensorMap& a, const CUtensorMap& b, GemmShape sh, const EpiArgs& ep, int sms,
                        cudaStream_t s, const char* name, int kind, const CUtensorMap* o = nullptr,
-                       const CUtensorMap* x = nullptr) {
-  sh.idesc = make_idesc(dtype, BN);
+                       const CUtensorMap* x = nullptr, const CUtensorMap* bh = nullptr) {
   sh.trace = g_trace ? g_trace + kind * 1024 : nullptr;
   const CUtensorMap& om = o ? *o : a;  // unused maps alias the A map
   const CUtensorMap& xm = x ? *x : a;
-  return dtype == PD_FP16 ? launch_gemm_t<EPI, BN, __half>(a, b, om, xm, sh, ep, sms, s, name, kind)
-                          : launch_gemm_t<EPI, BN, __nv_bfloat16>(a, b, om, xm, sh, ep, sms, s, name, kind);
+  if (bh != nullptr && pair_enabled() && sh.B * sh.m_tiles_per_row >= 2) {
+    sh.idesc = make_idesc(dtype, BN, 256);
+    return dtype == PD_FP16 ? launch_gemm_t<EPI, BN, __half, true>(a, *bh, om, xm, sh, ep, sms, s, name, kind)
+                            : launch_gemm_t<EPI, BN, __nv_bfloat16, true>(a, *bh, om, xm, sh, ep, sms, s, name, kind);
+  }
+  sh.idesc = make_idesc(dtype, BN);
+  return dtype == PD_FP16 ? launch_gemm_t<EPI, BN, __half, false>(a, b, om, xm, sh, ep, sms, s, name, kind)
+                          : launch_gemm_t<EPI, BN, __nv_bfloat16, false>(a, b, om, xm, sh, ep, sms, s, name, kind);
 }
 
 static GemmShape base_shape(int B, int T, int n_tiles, int k_per_tap) {
@@ -579,7 +614,7 @@ extern "C" int pd_cond_project(pd_plan* p, const float* cond, void* stream) {
   ep.ld = C2;
   ep.out_type = OUT_F16;
   ep.out_blocked = 1;
-  return launch_gemm<EPI_STORE, 256>(c.dtype, p->tm_cond, m->tm_w_cond, sh, ep, m->sm_count, s, "gemm(cond_proj)", 0);
+  return launch_gemm<EPI_STORE, 256>(c.dtype, p->tm_cond, m->tm_w_cond, sh, ep, m->sm_count, s, "gemm(cond_proj)", 0);  // epilogue-store bound: pairing measured neutral
 }
 
 // Step-embedding chain for `E` entries whose step values are already in the plan's "steps" buffer.
@@ -721,7 +756,7 @@ static int run_denoiser(pd_plan* p, int entry_base, int entry_per_b, const OutSt
       ep.sb_entry_base = entry_base;
       ep.sb_entry_per_b = entry_per_b;
       ep.ld = C;
-      if (launch_gemm<EPI_GATE, 256>(dt, tm_cur, m->tm_w_dil, sh, ep, sms, s, "gemm(dilated_conv+gate)", 2, &p->tm_y)) return 1;
+      if (launch_gemm<EPI_GATE, 256>(dt, tm_cur, m->tm_w_dil, sh, ep, sms, s, "gemm(dilated_conv+gate)", 2, &p->tm_y, nullptr, &m->tm_w_dil128)) return 1;
     }
     {  // residual half of output_projection + (x + res)/sqrt(2) (wavenet.py:70-72)
       GemmShape sh = base_shape(B, T, C / 256, C / 64);
@@ -731,7 +766,7 @@ static int run_denoiser(pd_plan* p, int entry_base, int entry_per_b, const OutSt
       ep.bias = (const float*)(pk + lay.b_res) + (size_t)l * C;
       ep.ld = C;
       ep.scale = 0.70710678118654752440f;
-      if (launch_gemm<EPI_RES, 256>(dt, p->tm_y, m->tm_w_res, sh, ep, sms, s, "gemm(res_proj)", 3, &tm_nxt, &tm_cur)) return 1;
+      if (launch_gemm<EPI_RES, 256>(dt, p->tm_y, m->tm_w_res, sh, ep, sms, s, "gemm(res_proj)", 3, &tm_nxt, &tm_cur, &m->tm_w_res128)) return 1;
     }
     cur_is_a = !cur_is_a;
   }
@@ -743,7 +778,7 @@ static int run_denoiser(pd_plan* p, int entry_base, int entry_per_b, const OutSt
     ep.bias = (const float*)(pk + lay.b_skipsum);
     ep.ld = C;
     ep.scale = 1.0f / sqrtf((float)L);
-    if (launch_gemm<EPI_STORE, 256>(dt, p->tm_y, m->tm_w_skip, sh, ep, sms, s, "gemm(skip_sum)", 4)) return 1;
+    if (launch_gemm<EPI_STORE, 256>(dt, p->tm_y, m->tm_w_skip, sh, ep, sms, s, "gemm(skip_sum)", 4, nullptr, nullptr, &m->tm_w_skip_h)) return 1;
   }
   {  // skip_projection + ReLU (wavenet.py:120-121)
     GemmShape sh = base_shape(B, T, C / 256, C / 64);

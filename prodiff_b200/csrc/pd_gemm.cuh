@@ -167,13 +167,17 @@ __device__ __forceinline__ void gate_chunk16(const uint32_t (&rg)[16], const uin
   }
 }
 
-template <int EPI, int BN> struct GemmCfg {
-  // smem ring depth; the gate / residual epilogues also keep an operand-or-output tile in shared memory
-  static constexpr int kStages = (EPI == EPI_RES) ? 3 : (BN == 256 ? 4 : 6);
+// kPair: two CTAs of a cluster compute two adjacent 128-frame tiles with tcgen05.mma.cta_group::2 (M = 256); each CTA
+// stages its own A tile and only HALF of the weight block, which halves L2 -> SM weight traffic (the single-CTA form of
+// cond_proj / skip_sum re-streams the weights per 128-row tile and sits at the L2 throughput cap).
+template <int EPI, int BN, bool kPair = false> struct GemmCfg {
   static constexpr uint32_t kABytes = kBlockM * kBlockK * 2;
-  static constexpr uint32_t kBBytes = BN * kBlockK * 2;
+  static constexpr uint32_t kBBytes = (kPair ? BN / 2 : BN) * kBlockK * 2;
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;
   static constexpr uint32_t kExtraBytes = (EPI == EPI_GATE) ? 2 * 16384 : (EPI == EPI_RES ? 4 * 16384 : 0);
+  // smem ring depth: as many stages as fit next to the epilogue's operand/output tile (cap 8)
+  static constexpr int kStagesFit = (int)((227u * 1024u - 1024u - 256u - kExtraBytes) / kStageBytes);
+  static constexpr int kStages = kPair ? (kStagesFit > 8 ? 8 : kStagesFit) : ((EPI == EPI_RES) ? 3 : (BN == 256 ? 4 : 6));
   static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kExtraBytes + 1024 + 256;  // + alignment slack + barriers
 };
 
@@ -185,12 +189,12 @@ __device__ __forceinline__ uint4* sw128_chunk(uint8_t* tile, int r, int c) {
 // ------------------------------------------------------------------ the kernel
 // tmA: A operand (activations); tmB: B operand (weights); tmO: TMA-store target (GATE: gated activations, RES: x_next);
 // tmX: RES only, x_cur tile load.  Unused maps are passed as copies of tmA.
-template <int EPI, int BN, typename T>
+template <int EPI, int BN, typename T, bool kPair = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmX, const GemmShape sh,
             const EpiArgs ep) {
-  using Cfg = GemmCfg<EPI, BN>;
+  using Cfg = GemmCfg<EPI, BN, kPair>;
   constexpr int kStages = Cfg::kStages;
   static_assert(BN == 256 || BN == 128, "tile width");
   static_assert(EPI != EPI_GATE || BN == 256, "gate epilogue pairs 128 gate with 128 filter columns");
@@ -212,6 +216,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = kPair ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
   if (sh.trace && blockIdx.x == 0 && threadIdx.x == 0) sh.trace[15] = clock64();  // kernel entry
 
   if (warp == 0 && lane == 0) {
@@ -222,34 +228,44 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kStages; ++i) {
-      mbar_init(&full_bar[i], 1);
+      mbar_init(&full_bar[i], kPair ? 2 : 1);
       mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], kEpiWarps);
+      mbar_init(&tempty_bar[i], kPair ? 2 * kEpiWarps : kEpiWarps);
     }
     mbar_init(xfull_bar, 1);
     mbar_init(xempty_bar, 1);
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc<kTmemCols>(tmem_slot);
-  tc_fence_before();
-  __syncthreads();
+  if constexpr (kPair) {
+    cluster_sync_all();  // both CTAs alive + barriers initialised before any remote arrive / paired allocation
+    if (warp == 2) tmem_alloc_2sm<kTmemCols>(tmem_slot);
+    tc_fence_before();
+    cluster_sync_all();
+  } else {
+    if (warp == 2) tmem_alloc<kTmemCols>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+  }
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   const int num_m_tiles = sh.B * sh.m_tiles_per_row;
-  const int num_tiles = num_m_tiles * sh.n_tiles;
+  // work items: (m-tile, n-tile), or (pair of adjacent m-tiles, n-tile) with this CTA taking m-tile 2 * pair + rank
+  const int num_tiles = (kPair ? (num_m_tiles + 1) / 2 : num_m_tiles) * sh.n_tiles;
+  const int tile_first = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_step = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const int k_blocks = sh.k_per_tap * sh.taps;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       uint32_t it = 0, ti = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
+      for (int tile = tile_first; tile < num_tiles; tile += tile_step, ++ti) {
         const int n_tile = tile % sh.n_tiles;
-        const int m_tile = tile / sh.n_tiles;
+        const int m_tile = kPair ? 2 * (tile / sh.n_tiles) + (int)rank : tile / sh.n_tiles;
         const int b = m_tile / sh.m_tiles_per_row;
         const int t0 = (m_tile % sh.m_tiles_per_row) * kBlockM;
         if constexpr (EPI == EPI_RES) {
@@ -265,20 +281,27 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (sh.trace && blockIdx.x == 0 && (kb == 0 || kb == k_blocks - 1)) sh.trace[ti * 16 + (kb == 0 ? 0 : 1)] = clock64();
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
           const int grp = kb / sh.k_per_tap, kc = kb - grp * sh.k_per_tap;
           const int t = sh.tap_mode ? t0 + (grp - (sh.taps >> 1)) * sh.dil : t0;
           const int slab = sh.tap_mode ? sh.a_slab0 : sh.a_slab0 + grp;
-          tma_load_4d(sa, &tmA, &full_bar[stage], kc * kBlockK, t, b, slab);
-          tma_load_2d(sb, &tmB, &full_bar[stage], kb * kBlockK, sh.b_row0 + n_tile * BN);
+          if constexpr (kPair) {
+            if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+            else mbar_arrive_leader(&full_bar[stage]);
+            tma_load_4d_2sm(sa, &tmA, &full_bar[stage], kc * kBlockK, t, b, slab);
+            tma_load_2d_2sm(sb, &tmB, &full_bar[stage], kb * kBlockK, sh.b_row0 + n_tile * BN + (int)rank * (BN / 2));
+          } else {
+            mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+            tma_load_4d(sa, &tmA, &full_bar[stage], kc * kBlockK, t, b, slab);
+            tma_load_2d(sb, &tmB, &full_bar[stage], kb * kBlockK, sh.b_row0 + n_tile * BN);
+          }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (pair mode: leader CTA only) =====================
+    if (lane == 0 && leader) {
       uint32_t it = 0, ti = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
+      for (int tile = tile_first; tile < num_tiles; tile += tile_step, ++ti) {
         const uint32_t as = ti & 1u, aph = (ti >> 1) & 1u;
         mbar_wait(&tempty_bar[as], aph ^ 1u, 2);
         tc_fence_after();
@@ -293,11 +316,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           const uint64_t adesc = make_sw128_kmajor_desc(sa);
           const uint64_t bdesc = make_sw128_kmajor_desc(sa + Cfg::kABytes);
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k)
-            umma_f16(d_tmem, desc_advance_k(adesc, k), desc_advance_k(bdesc, k), sh.idesc, (kb | k) != 0 ? 1u : 0u);
-          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs have read it
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            if constexpr (kPair) umma_f16_2sm(d_tmem, desc_advance_k(adesc, k), desc_advance_k(bdesc, k), sh.idesc, (kb | k) != 0 ? 1u : 0u);
+            else umma_f16(d_tmem, desc_advance_k(adesc, k), desc_advance_k(bdesc, k), sh.idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          // smem slot reusable once these MMAs have read it (pair mode: in both CTAs)
+          if constexpr (kPair) umma_commit_2sm(&empty_bar[stage]);
+          else umma_commit(&empty_bar[stage]);
         }
-        umma_commit(&tfull_bar[as]);  // accumulator complete
+        // accumulator complete
+        if constexpr (kPair) umma_commit_2sm(&tfull_bar[as]);
+        else umma_commit(&tfull_bar[as]);
       }
     }
   } else {
@@ -307,13 +336,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int row = q * 32 + lane;
     const bool issuer = (warp == 2 && lane == 0);  // the one thread that issues TMA stores
     uint32_t ti = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
+    for (int tile = tile_first; tile < num_tiles; tile += tile_step, ++ti) {
       const int n_tile = tile % sh.n_tiles;
-      const int m_tile = tile / sh.n_tiles;
+      const int m_tile = kPair ? 2 * (tile / sh.n_tiles) + (int)rank : tile / sh.n_tiles;
       const int b = m_tile / sh.m_tiles_per_row;
       const int t0 = (m_tile % sh.m_tiles_per_row) * kBlockM;
       const int t = t0 + row;
-      const bool valid = t < sh.T;
+      const bool valid = (t < sh.T) && (m_tile < num_m_tiles);   // pair mode: an odd tile count leaves one dummy tile
       const long long n = (long long)b * sh.T + t;  // global frame index
       const uint32_t as = ti & 1u, aph = (ti >> 1) & 1u;
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
@@ -506,7 +535,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       if (sh.trace && blockIdx.x == 0 && warp == 2 && lane == 0) sh.trace[ti * 16 + 7] = clock64();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      if (lane == 0) {
+        if constexpr (kPair) mbar_arrive_leader(&tempty_bar[as]);
+        else mbar_arrive(&tempty_bar[as]);
+      }
 
       if constexpr (EPI == EPI_GATE || EPI == EPI_RES) {
         // publish the shared-memory tile to the async proxy, then one thread hands it to the TMA store engine
@@ -533,11 +565,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (kPair) cluster_sync_all();  // the leader's MMAs read the peer's shared memory and write its TMEM
+  else __syncthreads();
   if (sh.trace && blockIdx.x == 0 && threadIdx.x == 0) sh.trace[14] = clock64();  // all roles done
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc<kTmemCols>(tmem_base);
+    if constexpr (kPair) tmem_dealloc_2sm<kTmemCols>(tmem_base);
+    else tmem_dealloc<kTmemCols>(tmem_base);
   }
 }
 

@@ -138,10 +138,12 @@ def check_trace():
         t = buf[kind * 1024:(kind + 1) * 1024].cpu().view(64, 16)
         t0 = int(t[0, 15])
         rows = []
-        for i in range(8):
+        for i in range(32 if kind == 8 else 8):
             if int(t[i, 6]) == 0:
                 break
             rows.append([int(v) - t0 if int(v) else -1 for v in t[i, :14]])
+        if kind == 8:
+            rows.sort(key=lambda r: r[2])
         out[name] = dict(exit=int(t[0, 14]) - t0, tiles=rows)
         if kind == 8:
             out["layer_mma2"] = [[int(v) - t0 if int(v) else -1 for v in t[32 + i, :13]] for i in range(4)]
