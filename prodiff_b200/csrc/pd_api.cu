@@ -563,7 +563,7 @@ static int launch_layer_t(const LayerMaps& mp, const LayerParams& lp, int sms, c
   int dev = 0;
   PD_CUDA(cudaGetDevice(&dev));
   if (!configured[dev & 63]) {
-    PD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLayerSmemBytes));
+    PD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLayerSmemMax));
     configured[dev & 63] = true;
   }
   const int num_pairs = (lp.B * lp.m_tiles_per_row + 1) / 2;
@@ -572,7 +572,7 @@ static int launch_layer_t(const LayerMaps& mp, const LayerParams& lp, int sms, c
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(2 * clusters);
   cfg.blockDim = dim3(kLayerThreads);
-  cfg.dynamicSmemBytes = kLayerSmemBytes;
+  cfg.dynamicSmemBytes = layer_smem_bytes(lp.xsub, lp.ident_resident);
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -697,8 +697,16 @@ static int run_denoiser(pd_plan* p, int entry_base, int entry_per_b, const OutSt
       lp.m_tiles_per_row = (T + kBlockM - 1) / kBlockM;
       lp.cycle = c.dilation_cycle_length;
       lp.ident_row0 = L * C;
+      {
+        const int max_dil = 1 << (c.dilation_cycle_length - 1);
+        lp.xsub = (int)align_up((size_t)(kBlockM + 2 * max_dil) * 128, 1024);
+        static int res_opt = -1;
+        if (res_opt < 0) { const char* e = getenv("PD_IDENT_RESIDENT"); res_opt = (e && e[0] == '0') ? 0 : 1; }
+        lp.ident_resident = (res_opt && layer_smem_bytes(lp.xsub, 1) <= kLayerSmemMax) ? 1 : 0;
+      }
       lp.idesc = (1u << 4) | ((dt == PD_FP16 ? 0u : 1u) << 7) | ((dt == PD_FP16 ? 0u : 1u) << 10) | ((256u >> 3) << 17) | ((256u >> 4) << 24);
       lp.idesc128 = (lp.idesc & ~(0x3Fu << 17)) | ((128u >> 3) << 17);
+      lp.idesc64 = (lp.idesc & ~(0x3Fu << 17)) | ((64u >> 3) << 17);
       lp.cp = p->ptr<uint16_t>("cp");
       lp.cp_layer_stride = (long long)mtiles * kBlockM * 2 * C;
       lp.sb = p->ptr<float>("sb");

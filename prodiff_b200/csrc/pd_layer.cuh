@@ -36,11 +36,13 @@ namespace pd {
 
 constexpr int kLayerC = 256;
 constexpr int kLayerStages = 5;                  // 16 KB weight blocks in flight per CTA
-constexpr int kXSubStride = 160 * 128;           // bytes reserved per 64-channel X sub-tile (up to 128 + 2*16 frames)
 constexpr int kLayerMaxDil = 16;
 constexpr int kLayerThreads = kGemmThreads + 32;  // + warp 10: dedicated X-tile producer (never queued behind weight blocks)
-constexpr int kLayerBlocks = 32;                 // weight blocks per tile: 2 x 12 dilated-conv, 4 identity, 4 residual 1x1
-constexpr uint32_t kLayerSmemBytes = 4 * kXSubStride + 4 * 16384 + kLayerStages * 16384 + 1024 + 512;
+constexpr uint32_t kLayerSmemMax = 227u * 1024u;  // opt-in limit per CTA
+// dynamic shared memory of one CTA: haloed x tile (4 sub-tiles of `xsub` bytes) + Y + weight ring (+ resident identity) + barriers + slack
+__host__ __device__ inline uint32_t layer_smem_bytes(int xsub, int ident_resident) {
+  return 4u * (uint32_t)xsub + 4u * 16384u + kLayerStages * 16384u + (ident_resident ? 4096u : 0u) + 512u + 1024u;
+}
 
 // All tensor maps of the kernel, passed by value in parameter space.
 struct LayerMaps {
@@ -59,6 +61,10 @@ struct LayerParams {
   int rot;                // per-layer rotation of the tile-pair -> cluster assignment (multi-layer launches)
   unsigned int* flags;    // multi-layer launches: [L][num_m_tiles] completion counters (8 = x_next of that tile written)
   int ident_row0;         // first row of the [C x C] identity block appended to the W_res matrix
+  int xsub;               // bytes reserved per 64-channel sub-tile of the haloed x tile: align_up((128 + 2*max_dil) * 128, 1024)
+  int ident_resident;     // 1: the residual add uses a 4 KB identity block kept in shared memory (N = 64 MMAs, no weight
+                          //    traffic); 0: identity blocks are streamed through the weight ring like W_res (N = 256)
+  uint32_t idesc64;       // N = 64 instruction descriptor for the resident-identity MMAs
   uint32_t idesc;         // cta_group::2 instruction descriptor (M = 256, N = 256)
   uint32_t idesc128;      // same with N = 128 (the two 64-channel chunks)
   const void* cp;         // hoisted cond projection of layer 0, tile-blocked fp16
@@ -85,9 +91,11 @@ layer_kernel(const __grid_constant__ LayerMaps mp,
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   uint8_t* sX = smem;                                  // 4 x [<=160 frames x 64 ch]   haloed activation tile
-  uint8_t* sY = sX + 4 * kXSubStride;                  // 4 x [128 frames x 64 ch]     gated y, later x_next
+  const uint32_t xsub = (uint32_t)lp.xsub;
+  uint8_t* sY = sX + 4 * xsub;                         // 4 x [128 frames x 64 ch]     gated y, later x_next
   uint8_t* sW = sY + 4 * 16384;                        // kLayerStages x [128 rows x 64 k] weight blocks (this CTA's half)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sW + kLayerStages * 16384);
+  uint8_t* sI = sW + kLayerStages * 16384;             // [32 rows x 64 k] this CTA's half of a 64 x 64 identity (optional)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sI + (lp.ident_resident ? 4096 : 0));
   uint64_t* full_bar = bars;                           // [S] leader: weight block landed in both CTAs
   uint64_t* empty_bar = full_bar + kLayerStages;       // [S] local : MMAs finished reading the block
   uint64_t* xfull_bar = empty_bar + kLayerStages;      // leader: X landed in both CTAs
@@ -126,6 +134,16 @@ layer_kernel(const __grid_constant__ LayerMaps mp,
   }
   cluster_sync_all();                      // both CTAs alive + barriers initialised before any remote arrive / alloc
   if (warp == 2) tmem_alloc_2sm<kTmemCols>(tmem_slot);
+  if (lp.ident_resident && threadIdx.x < 256) {
+    // B operand of the residual-add MMAs: rows n = 32 * rank + r of the 64 x 64 identity, K-major, 128B-swizzled
+    const int r = threadIdx.x >> 3, c = threadIdx.x & 7;
+    const int n = (int)rank * 32 + r;
+    uint32_t w[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) w[u] = Cvt<T>::pack(n == 8 * c + 2 * u ? 1.f : 0.f, n == 8 * c + 2 * u + 1 ? 1.f : 0.f);
+    *sw128_chunk(sI, r, c) = make_uint4(w[0], w[1], w[2], w[3]);
+    fence_proxy_async_smem();
+  }
   tc_fence_before();
   cluster_sync_all();
   tc_fence_after();
@@ -172,7 +190,9 @@ layer_kernel(const __grid_constant__ LayerMaps mp,
           }
           ++it;
         };
-        for (int blk = 0; blk < kLayerBlocks; ++blk) load_block(blk);
+        // weight blocks per tile: 12 (c01) + 6 + 6 (c2, c3) [+ 4 streamed identity] + 4 residual 1x1
+        for (int blk = 0; blk < 32; ++blk)
+          if (!(lp.ident_resident && blk >= 24 && blk < 28)) load_block(blk);
         if (tr) lp.trace[(ti & 31) * 16 + 1] = clock64();
       }
     }
@@ -214,7 +234,7 @@ layer_kernel(const __grid_constant__ LayerMaps mp,
           if (leader) mbar_arrive_expect_tx(xfull_bar, 2 * xbytes);
           else mbar_arrive_leader(xfull_bar);
 #pragma unroll
-          for (int c = 0; c < 4; ++c) tma_load_4d_2sm(sX + c * kXSubStride, tmX, xfull_bar, c * 64, t0 - dil, b, 0);
+          for (int c = 0; c < 4; ++c) tma_load_4d_2sm(sX + c * xsub, tmX, xfull_bar, c * 64, t0 - dil, b, 0);
         }
       }
     }
@@ -248,7 +268,7 @@ layer_kernel(const __grid_constant__ LayerMaps mp,
           const uint32_t stage = it % kLayerStages, parity = (it / kLayerStages) & 1u;
           mbar_wait(&full_bar[stage], parity, 4);
           tc_fence_after();
-          const uint64_t adesc = make_sw128_kmajor_desc(sXa + (kb & 3) * kXSubStride + (uint32_t)((kb >> 2) * dil) * 128u);
+          const uint64_t adesc = make_sw128_kmajor_desc(sXa + (kb & 3) * xsub + (uint32_t)((kb >> 2) * dil) * 128u);
           const uint64_t bdesc = make_sw128_kmajor_desc(sWa + stage * 16384);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
@@ -274,7 +294,7 @@ layer_kernel(const __grid_constant__ LayerMaps mp,
 #pragma unroll
             for (int sub = 0; sub < 2; ++sub) {
               const int kb = 2 * kq + sub;
-              const uint64_t adesc = make_sw128_kmajor_desc(sXa + (kb & 3) * kXSubStride + (uint32_t)((kb >> 2) * dil) * 128u);
+              const uint64_t adesc = make_sw128_kmajor_desc(sXa + (kb & 3) * xsub + (uint32_t)((kb >> 2) * dil) * 128u);
               const uint64_t bdesc = make_sw128_kmajor_desc(sWa + stage * 16384 + sub * 8192);
 #pragma unroll
               for (int k = 0; k < 4; ++k)
@@ -289,7 +309,18 @@ layer_kernel(const __grid_constant__ LayerMaps mp,
         mbar_wait(&afree_bar[0], par, 7);
         tc_fence_after();
         if (tr) lp.trace[512 + (ti & 15) * 16 + 12] = clock64();
-        for (int kb = 0; kb < 8; ++kb, ++it) {
+        if (lp.ident_resident) {
+          // x_centre * I with the resident 64 x 64 identity: four N = 64 column slices, no weight traffic
+          const uint64_t bdesc = make_sw128_kmajor_desc(smem_u32(sI));
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) {
+            const uint64_t adesc = make_sw128_kmajor_desc(sXa + cc * xsub + (uint32_t)dil * 128u);   // centre rows
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_f16_2sm(tmem_base + colA + cc * 64, desc_advance_k(adesc, k), desc_advance_k(bdesc, k), lp.idesc64, k != 0 ? 1u : 0u);
+          }
+        }
+        for (int kb = lp.ident_resident ? 4 : 0; kb < 8; ++kb) {
           if (kb == 4) {
             umma_commit_2sm(xempty_bar);   // tensor side is done with X: the next tile's X may be prefetched now
             mbar_wait(&yready_bar[0], par, 8);
@@ -301,13 +332,15 @@ layer_kernel(const __grid_constant__ LayerMaps mp,
           mbar_wait(&full_bar[stage], parity, 9);
           tc_fence_after();
           if (tr) lp.trace[512 + (ti & 15) * 16 + kb] = clock64();
-          const uint64_t adesc = kb < 4 ? make_sw128_kmajor_desc(sXa + ((kb + rot4) & 3) * kXSubStride + (uint32_t)dil * 128u)   // centre rows
+          const uint64_t adesc = kb < 4 ? make_sw128_kmajor_desc(sXa + ((kb + rot4) & 3) * xsub + (uint32_t)dil * 128u)   // centre rows
                                         : make_sw128_kmajor_desc(sYa + (kb - 4) * 16384);
           const uint64_t bdesc = make_sw128_kmajor_desc(sWa + stage * 16384);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_f16_2sm(tmem_base + colA, desc_advance_k(adesc, k), desc_advance_k(bdesc, k), lp.idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_f16_2sm(tmem_base + colA, desc_advance_k(adesc, k), desc_advance_k(bdesc, k), lp.idesc,
+                         (lp.ident_resident || (kb | k) != 0) ? 1u : 0u);
           umma_commit_2sm(&empty_bar[stage]);
+          ++it;
         }
         umma_commit_2sm(&afull_bar[3]);
         if (tr) lp.trace[(ti & 31) * 16 + 6] = clock64();
