@@ -362,10 +362,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       }
       if constexpr (EPI == EPI_OUT) {
+        // x_t of the first 16 mel bins this warp handles (the other chunks are fetched one chunk ahead, below)
         if (valid && ep.x_state != nullptr && h * 64 < ep.M) {
           float* pfw = reinterpret_cast<float*>(pre);
+          const float* xs = ep.x_state + ((long long)b * ep.M + h * 64) * sh.T + t;
 #pragma unroll
-          for (int j = 0; j < 64; ++j) pfw[j] = ep.x_state[((long long)b * ep.M + (h * 64 + j)) * sh.T + t];
+          for (int j = 0; j < 16; ++j) pfw[j] = xs[(long long)j * sh.T];
         }
       }
       if (sh.trace && blockIdx.x == 0 && warp == 2 && lane == 0) sh.trace[ti * 16 + 5] = clock64();
@@ -376,11 +378,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
       if constexpr (EPI == EPI_STORE) {
         const long long nfr = (long long)sh.B * sh.T;
-#pragma unroll 1
-        for (int c = h * (BN / 2); c < (h + 1) * (BN / 2); c += 32) {
-          uint32_t r[32];
-          tmem_ld_x32(trow + c, r);
+        // two register buffers: the TMEM load of chunk i+1 is in flight while chunk i is converted and stored
+        uint32_t rr[2][32];
+        tmem_ld_x32(trow + h * (BN / 2), rr[0]);
+#pragma unroll
+        for (int ci = 0; ci < (BN / 2) / 32; ++ci) {
+          const int c = h * (BN / 2) + ci * 32;
           tmem_ld_wait();
+          if (ci + 1 < (BN / 2) / 32) tmem_ld_x32(trow + c + 32, rr[(ci + 1) & 1]);
+          const uint32_t (&r)[32] = rr[ci & 1];
           if (valid) {
             const int g = n_tile * BN + c;
             const int slab = g / ep.ld, within = g - slab * ep.ld;
@@ -486,45 +492,65 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       } else {  // EPI_OUT
         const int M = ep.M;
-        const float* pf = reinterpret_cast<const float*>(pre);
+        const bool act = valid && (h * 64 < M);               // M is 64 or 128: a warp's 64 mel bins are all in or all out
+        const long long col0 = ((long long)b * M + h * 64) * sh.T + t;   // element (b, mel = 64h, t) of a [B,1,M,T] tensor
+        const long long Tn = sh.T;
+        float xv[2][16];                                        // x_t of the current / next 16-bin chunk
+        {
+          const float* pf = reinterpret_cast<const float*>(pre);
 #pragma unroll
-        for (int ci = 0; ci < 2; ++ci) {
-          const int c = h * 64 + ci * 32;
-          uint32_t r[32];
-          tmem_ld_x32(trow + c, r);
+          for (int j = 0; j < 16; ++j) xv[0][j] = pf[j];
+        }
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci) {
+          const int c = h * 64 + ci * 16;
+          uint32_t r[16];
+          tmem_ld_x16(trow + c, r);
+          if (act && ep.x_state != nullptr && ci < 3) {        // fetch the next chunk's x_t while this one is processed
+            const float* xs = ep.x_state + col0 + (long long)(ci + 1) * 16 * Tn;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) xv[(ci + 1) & 1][j] = xs[(long long)j * Tn];
+          }
           tmem_ld_wait();
-          if (valid && c < M) {
-            float xn[32];
+          if (act) {
+            const long long cbase = col0 + (long long)ci * 16 * Tn;
+            float xn[16];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int g = c + j;  // mel bin; M is a multiple of 32 so the whole chunk is valid
-              const long long idx = ((long long)b * M + g) * sh.T + t;
-              const float x0 = __uint_as_float(r[j]) + __ldg(ep.bias + g);
-              if (ep.x0_out) ep.x0_out[idx] = x0;
-              xn[j] = x0;
+            for (int j = 0; j < 16; j += 4) {
+              const float4 bv = __ldg(reinterpret_cast<const float4*>(ep.bias + c + j));
+              xn[j] = __uint_as_float(r[j]) + bv.x;
+              xn[j + 1] = __uint_as_float(r[j + 1]) + bv.y;
+              xn[j + 2] = __uint_as_float(r[j + 2]) + bv.z;
+              xn[j + 3] = __uint_as_float(r[j + 3]) + bv.w;
+            }
+            if (ep.x0_out) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) ep.x0_out[cbase + (long long)j * Tn] = xn[j];
             }
             if (ep.x_state) {
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                float4 nz = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (ep.sigma != 0.f && ep.noise == nullptr)
-                  nz = philox_normal4(ep.seed, ep.step_id, (uint32_t)n, (uint32_t)((c + j) >> 2));
-                const float nzv[4] = {nz.x, nz.y, nz.z, nz.w};
+              for (int j = 0; j < 16; j += 4) {
+                float nzv[4] = {0.f, 0.f, 0.f, 0.f};
+                if (ep.sigma != 0.f) {
+                  if (ep.noise == nullptr) {
+                    const float4 nz = philox_normal4(ep.seed, ep.step_id, (uint32_t)n, (uint32_t)((c + j) >> 2));
+                    nzv[0] = nz.x; nzv[1] = nz.y; nzv[2] = nz.z; nzv[3] = nz.w;
+                  } else {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) nzv[u] = __ldg(ep.noise + cbase + (long long)(j + u) * Tn);
+                  }
+                }
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                  const long long idx = ((long long)b * M + (c + j + u)) * sh.T + t;
-                  float v = ep.c1 * xn[j + u] + ep.c2 * pf[ci * 32 + j + u];
-                  if (ep.sigma != 0.f) v += ep.sigma * (ep.noise ? __ldg(ep.noise + idx) : nzv[u]);
-                  ep.x_state[idx] = v;
+                  const float v = fmaf(ep.sigma, nzv[u], fmaf(ep.c1, xn[j + u], ep.c2 * xv[ci & 1][j + u]));
+                  ep.x_state[cbase + (long long)(j + u) * Tn] = v;
                   xn[j + u] = v;
                 }
               }
               if (ep.xin_next) {
                 uint4* dst = reinterpret_cast<uint4*>(static_cast<uint16_t*>(ep.xin_next) + n * ep.Mp + c);
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                  dst[j] = make_uint4(Cvt<T>::pack(xn[8 * j], xn[8 * j + 1]), Cvt<T>::pack(xn[8 * j + 2], xn[8 * j + 3]),
-                                      Cvt<T>::pack(xn[8 * j + 4], xn[8 * j + 5]), Cvt<T>::pack(xn[8 * j + 6], xn[8 * j + 7]));
+                dst[0] = make_uint4(Cvt<T>::pack(xn[0], xn[1]), Cvt<T>::pack(xn[2], xn[3]), Cvt<T>::pack(xn[4], xn[5]), Cvt<T>::pack(xn[6], xn[7]));
+                dst[1] = make_uint4(Cvt<T>::pack(xn[8], xn[9]), Cvt<T>::pack(xn[10], xn[11]), Cvt<T>::pack(xn[12], xn[13]), Cvt<T>::pack(xn[14], xn[15]));
               }
             }
           }
