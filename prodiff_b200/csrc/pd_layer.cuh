@@ -74,7 +74,6 @@ struct LayerParams {
   int sb_entry_base, sb_entry_per_b;
   const float* b_res;     // residual-half bias of output_projection, [L][C]
   float scale;            // 1/sqrt(2)
-  int flags_opt;          // experiment switches: bit 1 / bit 2 = fixed (non-mirrored) TMEM column layouts
   long long* trace;
 };
 
@@ -247,21 +246,15 @@ layer_kernel(const __grid_constant__ LayerMaps mp,
       for (int pair = first_pair(l); pair < num_pairs; pair += num_clusters, ++ti) {
         const int dil = 1 << (l % lp.cycle);
         const uint32_t par = ti & 1u;                       // this tile's barrier phase parity and column layout
-        const uint32_t lay = (lp.flags_opt & 2) ? 1u : ((lp.flags_opt & 4) ? 0u : par);   // fixed or alternating column layout
-        const uint32_t colA = lay ? 256u : 0u;              // c01, later D2
-        const uint32_t colB1 = lay ? 0u : 256u;             // c2
+        const uint32_t colA = par ? 256u : 0u;              // c01, later D2 (the layout mirrors every tile)
+        const uint32_t colB1 = par ? 0u : 256u;             // c2
         const uint32_t colB2 = colB1 + 128u;                // c3
-        const bool fixed_layout = (lp.flags_opt & 6) != 0;
         mbar_wait(xfull_bar, par, 2);
         tc_fence_after();
         if (tr) lp.trace[(ti & 31) * 16 + 2] = clock64();
         // ---- MMA1, channels 0..127 (N = 256).  Its columns were the previous tile's c2 and c3.
-        if (fixed_layout) {
-          mbar_wait(&afree_bar[3], par ^ 1u, 3);   // same columns as the previous tile's D2
-        } else {
-          mbar_wait(&afree_bar[1], par ^ 1u, 3);
-          mbar_wait(&afree_bar[2], par ^ 1u, 3);
-        }
+        mbar_wait(&afree_bar[1], par ^ 1u, 3);
+        mbar_wait(&afree_bar[2], par ^ 1u, 3);
         tc_fence_after();
         for (int kk = 0; kk < 12; ++kk, ++it) {
           const int kb = (kk + rot12) % 12;
@@ -278,13 +271,9 @@ layer_kernel(const __grid_constant__ LayerMaps mp,
         umma_commit_2sm(&afull_bar[0]);
         if (tr) lp.trace[(ti & 31) * 16 + 3] = clock64();
         // ---- MMA1, channels 128..191 and 192..255 (N = 128 each).  Their columns held the previous tile's D2.
-        if (!fixed_layout) mbar_wait(&afree_bar[3], par ^ 1u, 5);
+        mbar_wait(&afree_bar[3], par ^ 1u, 5);
         tc_fence_after();
         for (int c = 0; c < 2; ++c) {
-          if (fixed_layout) {
-            mbar_wait(&afree_bar[1 + c], par ^ 1u, 5);   // same columns as the previous tile's chunk
-            tc_fence_after();
-          }
           const uint32_t d_tmem = tmem_base + (c ? colB2 : colB1);
           for (int kk = 0; kk < 6; ++kk, ++it) {
             const int kq = (kk + rot6) % 6;
@@ -359,8 +348,7 @@ layer_kernel(const __grid_constant__ LayerMaps mp,
       const float* b_res = lp.b_res + l * kLayerC;
       const CUtensorMap* tmXs = &mp.xs[(l + 1) & 1];
       const uint32_t par = ti & 1u;
-      const uint32_t lay = (lp.flags_opt & 2) ? 1u : ((lp.flags_opt & 4) ? 0u : par);
-      const uint32_t colA = lay ? 256u : 0u, colB1 = lay ? 0u : 256u;
+      const uint32_t colA = par ? 256u : 0u, colB1 = par ? 0u : 256u;
       const int m_tile = 2 * pair + (int)rank;
       const int b = m_tile / lp.m_tiles_per_row;
       const int t0 = (m_tile - b * lp.m_tiles_per_row) * kBlockM;
