@@ -241,6 +241,7 @@ layer_kernel(const __grid_constant__ LayerMaps mp,
     // ===================== MMA issuer (leader CTA only) =====================
     if (leader && lane == 0) {
       uint32_t it = 0, ti = 0;
+      long long wfull = 0;   // trace only: cycles this thread spent waiting for weight blocks in the current tile
       const uint32_t sXa = smem_u32(sX), sYa = smem_u32(sY), sWa = smem_u32(sW);
       for (int l = lp.layer0; l < l_end; ++l)
       for (int pair = first_pair(l); pair < num_pairs; pair += num_clusters, ++ti) {
@@ -259,7 +260,7 @@ layer_kernel(const __grid_constant__ LayerMaps mp,
         for (int kk = 0; kk < 12; ++kk, ++it) {
           const int kb = (kk + rot12) % 12;
           const uint32_t stage = it % kLayerStages, parity = (it / kLayerStages) & 1u;
-          mbar_wait(&full_bar[stage], parity, 4);
+          { const long long w0 = tr ? clock64() : 0; mbar_wait(&full_bar[stage], parity, 4); if (tr) wfull += clock64() - w0; }
           tc_fence_after();
           const uint64_t adesc = make_sw128_kmajor_desc(sXa + (kb & 3) * xsub + (uint32_t)((kb >> 2) * dil) * 128u);
           const uint64_t bdesc = make_sw128_kmajor_desc(sWa + stage * 16384);
@@ -278,7 +279,7 @@ layer_kernel(const __grid_constant__ LayerMaps mp,
           for (int kk = 0; kk < 6; ++kk, ++it) {
             const int kq = (kk + rot6) % 6;
             const uint32_t stage = it % kLayerStages, parity = (it / kLayerStages) & 1u;
-            mbar_wait(&full_bar[stage], parity, 6);
+            { const long long w0 = tr ? clock64() : 0; mbar_wait(&full_bar[stage], parity, 6); if (tr) wfull += clock64() - w0; }
             tc_fence_after();
 #pragma unroll
             for (int sub = 0; sub < 2; ++sub) {
@@ -318,7 +319,7 @@ layer_kernel(const __grid_constant__ LayerMaps mp,
           if (kb == 7) mbar_wait(&yready_bar[2], par, 8);
           if (tr) lp.trace[512 + (ti & 15) * 16 + 8 + (kb >> 1)] = clock64();
           const uint32_t stage = it % kLayerStages, parity = (it / kLayerStages) & 1u;
-          mbar_wait(&full_bar[stage], parity, 9);
+          { const long long w0 = tr ? clock64() : 0; mbar_wait(&full_bar[stage], parity, 9); if (tr) wfull += clock64() - w0; }
           tc_fence_after();
           if (tr) lp.trace[512 + (ti & 15) * 16 + kb] = clock64();
           const uint64_t adesc = kb < 4 ? make_sw128_kmajor_desc(sXa + ((kb + rot4) & 3) * xsub + (uint32_t)dil * 128u)   // centre rows
@@ -332,7 +333,7 @@ layer_kernel(const __grid_constant__ LayerMaps mp,
           ++it;
         }
         umma_commit_2sm(&afull_bar[3]);
-        if (tr) lp.trace[(ti & 31) * 16 + 6] = clock64();
+        if (tr) { lp.trace[(ti & 31) * 16 + 6] = clock64(); lp.trace[(ti & 31) * 16 + 12] = wfull; wfull = 0; }
       }
     }
   } else {
@@ -368,6 +369,13 @@ layer_kernel(const __grid_constant__ LayerMaps mp,
           for (int u = 0; u < 8; ++u) {
             pre[u] = __ldg(reinterpret_cast<const uint4*>(cpb + blocked_off(m_tile, 64, h * 8 + u, row)));
             pre[8 + u] = __ldg(reinterpret_cast<const uint4*>(cpb + blocked_off(m_tile, 64, 16 + h * 8 + u, row)));
+          }
+        }
+        if (valid) {   // bring the cond-projection lines of the two later sections into L2 now; they are loaded ~6-10k cycles later
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            prefetch_l2(cpb + blocked_off(m_tile, 64, 32 + h * 4 + (u & 3) + (u >> 2) * 8, row));        // gate chunks of c2, c3
+            prefetch_l2(cpb + blocked_off(m_tile, 64, 48 + h * 4 + (u & 3) + (u >> 2) * 8, row));        // filter chunks
           }
         }
         const uint32_t* prew = reinterpret_cast<const uint32_t*>(pre);
@@ -477,15 +485,18 @@ layer_kernel(const __grid_constant__ LayerMaps mp,
         tc_fence_after();
         if (tr && warp == 2 && lane == 0) lp.trace[(ti & 31) * 16 + 10] = clock64();
         const uint32_t trow = lane_base + colA;
+        uint32_t rr[2][32];   // the TMEM load of group i+1 is in flight while group i is converted and stored
+        tmem_ld_x32(trow + h * 64, rr[0]);
 #pragma unroll
         for (int jj = 0; jj < 2; ++jj) {
           uint8_t* ytile = sY + (2 * jj + h) * 16384;
 #pragma unroll
           for (int ci = 0; ci < 2; ++ci) {
+            const int gi = jj * 2 + ci;
             const int c = (2 * jj + h) * 64 + ci * 32;   // first channel of this 32-column group
-            uint32_t r[32];
-            tmem_ld_x32(trow + c, r);
             tmem_ld_wait();
+            if (gi < 3) tmem_ld_x32(trow + (2 * ((gi + 1) >> 1) + h) * 64 + ((gi + 1) & 1) * 32, rr[(gi + 1) & 1]);
+            const uint32_t (&r)[32] = rr[gi & 1];
 #pragma unroll
             for (int u4 = 0; u4 < 4; ++u4) {
               uint32_t ow[4];

@@ -104,6 +104,7 @@ __device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* m, int c0, in
 __device__ __forceinline__ void bulk_prefetch_l2(const void* gptr, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void prefetch_l2(const void* gptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(gptr) : "memory"); }
 // 2-D tiled store shared -> global (bulk async group).
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
