@@ -127,7 +127,7 @@ int pd_set_fused(int on);
  * per-tile flags (1, default; env PD_STACK=0 also disables) or launch one kernel per layer (0). Returns the previous value. */
 int pd_set_stack(int on);
 
-/* Debug: when set to a device buffer of 9 x 1024 int64, CTA 0 of every GEMM launch writes clock64() stamps of its
+/* Debug: when set to a device buffer of 12 x 1024 int64, CTA 0 of every GEMM launch writes clock64() stamps of its
  * pipeline events at [kind * 1024 + tile * 16 + slot] (slots: 0/1 first/last TMA issue, 2 accumulator free, 3/4 first/
  * last operand stage landed, 5/6 epilogue before/after accumulator wait, 7 epilogue done, 14 exit, 15 entry). */
 int pd_debug_set_trace(long long* device_buf);

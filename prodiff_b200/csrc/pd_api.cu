@@ -556,9 +556,9 @@ static bool stack_enabled() {
 // Launch the fused ResidualBlock kernel for layers [lp.layer0, lp.layer0 + lp.n_layers).  n_layers > 1 is the persistent
 // multi-layer form: its clusters wait on one another through global flags, so every cluster must be co-resident --
 // `*ok_multi` reports whether the occupancy query allows that (the caller falls back to one launch per layer).
-template <typename T>
+template <typename T, bool kHybrid>
 static int launch_layer_t(const LayerMaps& mp, const LayerParams& lp, int sms, cudaStream_t s, bool* ok_multi) {
-  auto kern = layer_kernel<T>;
+  auto kern = layer_kernel<T, kHybrid>;
   static bool configured[64] = {false};
   int dev = 0;
   PD_CUDA(cudaGetDevice(&dev));
@@ -593,6 +593,11 @@ static int launch_layer_t(const LayerMaps& mp, const LayerParams& lp, int sms, c
   prof_after(s);
   PD_LAUNCH_CHECK("layer_kernel");
   return 0;
+}
+
+static int launch_layer(int dt, bool hybrid, const LayerMaps& mp, const LayerParams& lp, int sms, cudaStream_t s, bool* ok_multi) {
+  if (dt == PD_FP16) return hybrid ? launch_layer_t<__half, true>(mp, lp, sms, s, ok_multi) : launch_layer_t<__half, false>(mp, lp, sms, s, ok_multi);
+  return hybrid ? launch_layer_t<__nv_bfloat16, true>(mp, lp, sms, s, ok_multi) : launch_layer_t<__nv_bfloat16, false>(mp, lp, sms, s, ok_multi);
 }
 
 // ------------------------------------------------------------------ hot-path sequences
@@ -727,6 +732,9 @@ static int run_denoiser(pd_plan* p, int entry_base, int entry_per_b, const OutSt
       lp.b_res = (const float*)(pk + lay.b_res);
       lp.scale = 0.70710678118654752440f;
       lp.trace = g_trace ? g_trace + 8 * 1024 : nullptr;
+      static int hyb = -1;
+      if (hyb < 0) { const char* e = getenv("PD_HYBRID"); hyb = (e && e[0] == '1') ? 1 : 0; }
+      const bool hybrid = hyb == 1;
       bool done = false;
       if (stack_enabled() && L > 1) {
         // one persistent launch for the whole stack; tiles of consecutive layers synchronise through per-tile flags
@@ -736,7 +744,7 @@ static int run_denoiser(pd_plan* p, int entry_base, int entry_per_b, const OutSt
         lp.flags = p->ptr<unsigned int>("flags");
         PD_CUDA(cudaMemsetAsync(lp.flags, 0, (size_t)L * mtiles * 4, s));
         bool ok = false;
-        const int rc = dt == PD_FP16 ? launch_layer_t<__half>(mp, lp, sms, s, &ok) : launch_layer_t<__nv_bfloat16>(mp, lp, sms, s, &ok);
+        const int rc = launch_layer(dt, hybrid, mp, lp, sms, s, &ok);
         if (rc) return rc;
         done = ok;
       }
@@ -746,7 +754,7 @@ static int run_denoiser(pd_plan* p, int entry_base, int entry_per_b, const OutSt
         lp.n_layers = 1;
         for (int ll = 0; ll < L; ++ll) {
           lp.layer0 = ll;
-          const int rc = dt == PD_FP16 ? launch_layer_t<__half>(mp, lp, sms, s, nullptr) : launch_layer_t<__nv_bfloat16>(mp, lp, sms, s, nullptr);
+          const int rc = launch_layer(dt, hybrid, mp, lp, sms, s, nullptr);
           if (rc) return rc;
         }
       }

@@ -82,7 +82,10 @@ __device__ __forceinline__ long long global_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-template <typename T>
+// kHybrid: accumulator schedule, see the header comment.  true = 256 + 128 + 128 columns (c01, c2, c3); false = two
+// 256-column chunks (c01, c23): every dilated-conv MMA is a full-rate N = 256 instruction, but the whole second half of
+// the gate epilogue is exposed (only MMA2's identity + first residual K-blocks overlap it).
+template <typename T, bool kHybrid>
 __global__ void __launch_bounds__(kLayerThreads, 1)
 layer_kernel(const __grid_constant__ LayerMaps mp,
              const LayerParams lp) {
@@ -109,7 +112,7 @@ layer_kernel(const __grid_constant__ LayerMaps mp,
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   const bool tr = lp.trace != nullptr && blockIdx.x == 0;
-  if (tr && threadIdx.x == 0) lp.trace[15] = clock64();
+  if (tr && threadIdx.x == 0) { lp.trace[15] = clock64(); lp.trace[1008] = global_ns(); }
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mp.wd);
@@ -176,6 +179,9 @@ layer_kernel(const __grid_constant__ LayerMaps mp,
           if (blk < 12) {          // c01: [128 rows = this CTA's gate (rank 0) or filter (rank 1) half] x 64 K
             const int kb = (blk + rot12) % 12;
             tma_load_2d_2sm(dst, &mp.wd, &full_bar[stage], kb * kBlockK, l * 2 * kLayerC + (int)rank * 128);
+          } else if (blk < 24 && !kHybrid) {   // c23: channels 128..255 as a second N = 256 chunk
+            const int kb = (blk - 12 + rot12) % 12;
+            tma_load_2d_2sm(dst, &mp.wd, &full_bar[stage], kb * kBlockK, l * 2 * kLayerC + 256 + (int)rank * 128);
           } else if (blk < 24) {   // c2 / c3: two [64 rows x 64 K] sub-blocks (K blocks 2*kq, 2*kq + 1) per stage
             const int c = 2 + (blk - 12) / 6;
             const int kq = ((blk - 12) % 6 + rot6) % 6;
@@ -187,6 +193,7 @@ layer_kernel(const __grid_constant__ LayerMaps mp,
           } else {
             tma_load_2d_2sm(dst, &mp.wr, &full_bar[stage], (blk - 28) * kBlockK, l * kLayerC + (int)rank * 128);
           }
+          if (tr) lp.trace[1024 + (ti & 7) * 128 + blk] = clock64();   // weight-load latency trace: issue time
           ++it;
         };
         // weight blocks per tile: 12 (c01) + 6 + 6 (c2, c3) [+ 4 streamed identity] + 4 residual 1x1
@@ -255,12 +262,12 @@ layer_kernel(const __grid_constant__ LayerMaps mp,
         if (tr) lp.trace[(ti & 31) * 16 + 2] = clock64();
         // ---- MMA1, channels 0..127 (N = 256).  Its columns were the previous tile's c2 and c3.
         mbar_wait(&afree_bar[1], par ^ 1u, 3);
-        mbar_wait(&afree_bar[2], par ^ 1u, 3);
+        if constexpr (kHybrid) mbar_wait(&afree_bar[2], par ^ 1u, 3);
         tc_fence_after();
         for (int kk = 0; kk < 12; ++kk, ++it) {
           const int kb = (kk + rot12) % 12;
           const uint32_t stage = it % kLayerStages, parity = (it / kLayerStages) & 1u;
-          { const long long w0 = tr ? clock64() : 0; mbar_wait(&full_bar[stage], parity, 4); if (tr) wfull += clock64() - w0; }
+          { const long long w0 = tr ? clock64() : 0; mbar_wait(&full_bar[stage], parity, 4); if (tr) { const long long w1 = clock64(); wfull += w1 - w0; lp.trace[1024 + (ti & 7) * 128 + 32 + kk] = w1; lp.trace[1024 + (ti & 7) * 128 + 64 + kk] = w1 - w0; } }
           tc_fence_after();
           const uint64_t adesc = make_sw128_kmajor_desc(sXa + (kb & 3) * xsub + (uint32_t)((kb >> 2) * dil) * 128u);
           const uint64_t bdesc = make_sw128_kmajor_desc(sWa + stage * 16384);
@@ -274,7 +281,23 @@ layer_kernel(const __grid_constant__ LayerMaps mp,
         // ---- MMA1, channels 128..191 and 192..255 (N = 128 each).  Their columns held the previous tile's D2.
         mbar_wait(&afree_bar[3], par ^ 1u, 5);
         tc_fence_after();
-        for (int c = 0; c < 2; ++c) {
+        if constexpr (!kHybrid) {
+          for (int kk = 0; kk < 12; ++kk, ++it) {
+            const int kb = (kk + rot12) % 12;
+            const uint32_t stage = it % kLayerStages, parity = (it / kLayerStages) & 1u;
+            { const long long w0 = tr ? clock64() : 0; mbar_wait(&full_bar[stage], parity, 6); if (tr) { const long long w1 = clock64(); wfull += w1 - w0; lp.trace[1024 + (ti & 7) * 128 + 32 + 12 + kk] = w1; lp.trace[1024 + (ti & 7) * 128 + 64 + 12 + kk] = w1 - w0; } }
+            tc_fence_after();
+            const uint64_t adesc = make_sw128_kmajor_desc(sXa + (kb & 3) * xsub + (uint32_t)((kb >> 2) * dil) * 128u);
+            const uint64_t bdesc = make_sw128_kmajor_desc(sWa + stage * 16384);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_f16_2sm(tmem_base + colB1, desc_advance_k(adesc, k), desc_advance_k(bdesc, k), lp.idesc, (kk | k) != 0 ? 1u : 0u);
+            umma_commit_2sm(&empty_bar[stage]);
+          }
+          umma_commit_2sm(&afull_bar[1]);
+          if (tr) lp.trace[(ti & 31) * 16 + 4] = lp.trace[(ti & 31) * 16 + 5] = clock64();
+        }
+        for (int c = 0; c < (kHybrid ? 2 : 0); ++c) {
           const uint32_t d_tmem = tmem_base + (c ? colB2 : colB1);
           for (int kk = 0; kk < 6; ++kk, ++it) {
             const int kq = (kk + rot6) % 6;
@@ -316,10 +339,10 @@ layer_kernel(const __grid_constant__ LayerMaps mp,
             mbar_wait(&yready_bar[0], par, 8);
           }
           if (kb == 6) mbar_wait(&yready_bar[1], par, 8);
-          if (kb == 7) mbar_wait(&yready_bar[2], par, 8);
+          if (kHybrid && kb == 7) mbar_wait(&yready_bar[2], par, 8);
           if (tr) lp.trace[512 + (ti & 15) * 16 + 8 + (kb >> 1)] = clock64();
           const uint32_t stage = it % kLayerStages, parity = (it / kLayerStages) & 1u;
-          { const long long w0 = tr ? clock64() : 0; mbar_wait(&full_bar[stage], parity, 9); if (tr) wfull += clock64() - w0; }
+          { const long long w0 = tr ? clock64() : 0; mbar_wait(&full_bar[stage], parity, 9); if (tr) { const long long w1 = clock64(); wfull += w1 - w0; lp.trace[1024 + (ti & 7) * 128 + 32 + 24 + kb] = w1; lp.trace[1024 + (ti & 7) * 128 + 64 + 24 + kb] = w1 - w0; } }
           tc_fence_after();
           if (tr) lp.trace[512 + (ti & 15) * 16 + kb] = clock64();
           const uint64_t adesc = kb < 4 ? make_sw128_kmajor_desc(sXa + ((kb + rot4) & 3) * xsub + (uint32_t)dil * 128u)   // centre rows
@@ -361,30 +384,39 @@ layer_kernel(const __grid_constant__ LayerMaps mp,
       const float* sb_row = lp.sb + (long long)entry * lp.sb_entry_stride + (long long)l * (4 * 2 * kLayerC) + slot * (2 * kLayerC);
       const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
 
-      // ---------------- gate epilogue, channels 0..127: this warp does channels [64h, 64h + 64) -> Y sub-tile h
-      {
+      // ---------------- gate epilogue of a 128-channel chunk (j = 0: channels 0..127; j = 1, two-chunk schedule only:
+      // channels 128..255): this warp does channels [128j + 64h, +64) -> Y sub-tile 2j + h
+#pragma unroll 1
+      for (int j = 0; j < (kHybrid ? 1 : 2); ++j) {
         uint4 pre[16];
         if (valid) {   // hoisted cond projection: 64 gate + 64 filter pre-activations (coalesced, blocked layout)
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
-            pre[u] = __ldg(reinterpret_cast<const uint4*>(cpb + blocked_off(m_tile, 64, h * 8 + u, row)));
-            pre[8 + u] = __ldg(reinterpret_cast<const uint4*>(cpb + blocked_off(m_tile, 64, 16 + h * 8 + u, row)));
+            pre[u] = __ldg(reinterpret_cast<const uint4*>(cpb + blocked_off(m_tile, 64, j * 32 + h * 8 + u, row)));
+            pre[8 + u] = __ldg(reinterpret_cast<const uint4*>(cpb + blocked_off(m_tile, 64, j * 32 + 16 + h * 8 + u, row)));
           }
         }
-        if (valid) {   // bring the cond-projection lines of the two later sections into L2 now; they are loaded ~6-10k cycles later
+        if (valid && j == 0) {   // bring the cond-projection lines of the later sections into L2 now; they are loaded ~6-10k cycles later
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
-            prefetch_l2(cpb + blocked_off(m_tile, 64, 32 + h * 4 + (u & 3) + (u >> 2) * 8, row));        // gate chunks of c2, c3
-            prefetch_l2(cpb + blocked_off(m_tile, 64, 48 + h * 4 + (u & 3) + (u >> 2) * 8, row));        // filter chunks
+            if constexpr (kHybrid) {
+              prefetch_l2(cpb + blocked_off(m_tile, 64, 32 + h * 4 + (u & 3) + (u >> 2) * 8, row));      // gate chunks of c2, c3
+              prefetch_l2(cpb + blocked_off(m_tile, 64, 48 + h * 4 + (u & 3) + (u >> 2) * 8, row));      // filter chunks
+            } else {
+              prefetch_l2(cpb + blocked_off(m_tile, 64, 32 + h * 8 + u, row));
+              prefetch_l2(cpb + blocked_off(m_tile, 64, 48 + h * 8 + u, row));
+            }
           }
         }
         const uint32_t* prew = reinterpret_cast<const uint32_t*>(pre);
-        uint8_t* ytile = sY + h * 16384;
+        uint8_t* ytile = sY + (2 * j + h) * 16384;
         // sub-tile h rows of this warp were last read by its own x_next store of the previous tile (newest group).
         // Multi-layer launches publish that store here, one tile late: waiting for its COMPLETION right after issuing it
         // would put the store latency on the epilogue chain, whereas here the warp is about to wait for MMAs anyway.
         if (lane == 0) {
-          if (pending_flag != nullptr) {
+          if (j == 1) {
+            tma_store_wait_read<1>();   // sub-tile 2 + h: last read by the same x_next store, now one group older than y(c01)
+          } else if (pending_flag != nullptr) {
             tma_store_wait_all();
             fence_proxy_async_all();
             red_release_add_u32(pending_flag, 1u);
@@ -394,10 +426,11 @@ layer_kernel(const __grid_constant__ LayerMaps mp,
           }
         }
         __syncwarp();
-        mbar_wait(&afull_bar[0], par, 10);
+        mbar_wait(&afull_bar[j], par, 10);
         tc_fence_after();
-        if (tr && warp == 2 && lane == 0) lp.trace[(ti & 31) * 16 + 7] = clock64();
-        const uint32_t trow = lane_base + colA;
+        if (tr && warp == 2 && lane == 0) lp.trace[(ti & 31) * 16 + 7 + j] = clock64();
+        const uint32_t trow = lane_base + (j ? colB1 : colA);
+        const float* sbj = sb_row + j * 256;
 #pragma unroll
         for (int ci = 0; ci < 4; ++ci) {
           const int i = h * 64 + ci * 16;
@@ -406,7 +439,7 @@ layer_kernel(const __grid_constant__ LayerMaps mp,
           tmem_ld_x16(trow + 128 + i, rf);
           tmem_ld_wait();
           uint32_t packed[8];
-          gate_chunk16<T>(rg, rf, prew + ci * 8, prew + 32 + ci * 8, sb_row + i, packed);
+          gate_chunk16<T>(rg, rf, prew + ci * 8, prew + 32 + ci * 8, sbj + i, packed);
           if (!valid) {
 #pragma unroll
             for (int u = 0; u < 8; ++u) packed[u] = 0u;   // keep junk (NaN) out of MMA2's operand rows
@@ -418,9 +451,9 @@ layer_kernel(const __grid_constant__ LayerMaps mp,
         fence_proxy_async_smem();   // Y rows visible to the tensor core (MMA2) and the TMA store engine
         __syncwarp();
         if (lane == 0) {
-          mbar_arrive_leader(&afree_bar[0]);
-          mbar_arrive_leader(&yready_bar[0]);
-          tma_store_4d(&mp.ys, ytile + q * 4096, h * 64, t0 + q * 32, b, l);   // 32 frames x 64 channels
+          mbar_arrive_leader(&afree_bar[j]);
+          mbar_arrive_leader(&yready_bar[j]);
+          tma_store_4d(&mp.ys, ytile + q * 4096, (2 * j + h) * 64, t0 + q * 32, b, l);   // 32 frames x 64 channels
           tma_store_commit();
         }
       }
@@ -428,7 +461,7 @@ layer_kernel(const __grid_constant__ LayerMaps mp,
       // ---------------- gate epilogue, channels 128..191 (c = 0 -> Y sub-tile 2) and 192..255 (c = 1 -> sub-tile 3):
       // the two warps of a lane quadrant split the 64 channels (32 each) and share the sub-tile's 32 rows
 #pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
+      for (int c = 0; c < (kHybrid ? 2 : 0); ++c) {
         uint4 pre[8];
         if (valid) {
           const int cg = 32 + c * 8 + h * 4;   // 16-byte chunk of gate channel 128 + 64c + 32h in the 256-paired layout
@@ -536,7 +569,7 @@ layer_kernel(const __grid_constant__ LayerMaps mp,
   // both CTAs must be completely done (the leader's MMAs read the peer's shared memory and write its TMEM)
   tc_fence_before();
   cluster_sync_all();
-  if (tr && threadIdx.x == 0) lp.trace[14] = clock64();
+  if (tr && threadIdx.x == 0) { lp.trace[14] = clock64(); lp.trace[1009] = global_ns(); }
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc_2sm<kTmemCols>(tmem_base);

@@ -128,7 +128,7 @@ def check_trace():
     cond = cond.cuda()
     with torch.no_grad():
         gd(cond, infer_step=4, infer=True, seed=1)
-        buf = torch.zeros(9 * 1024, dtype=torch.int64, device="cuda")
+        buf = torch.zeros(12 * 1024, dtype=torch.int64, device="cuda")
         lib.pd_debug_set_trace(buf.data_ptr())
         gd(cond, infer_step=4, infer=True, seed=1)
         torch.cuda.synchronize()
@@ -147,6 +147,12 @@ def check_trace():
         out[name] = dict(exit=int(t[0, 14]) - t0, tiles=rows)
         if kind == 8:
             out["layer_mma2"] = [[int(v) - t0 if int(v) else -1 for v in t[32 + i, :13]] for i in range(4)]
+            w = buf[9 * 1024:10 * 1024].cpu().view(8, 128)
+            out["weight_loads"] = [dict(issue=[int(v) - t0 for v in w[i, 0:32]], landed=[int(v) - t0 for v in w[i, 32:64]],
+                                        waited=[int(v) for v in w[i, 64:96]]) for i in range(8)]
+            ns = int(t[63, 1]) - int(t[63, 0])
+            out["layer_wall_ns"] = ns
+            out["layer_sm_mhz_effective"] = round((int(t[0, 14]) - t0) / max(ns, 1) * 1e3, 1)
 
     return out
 
