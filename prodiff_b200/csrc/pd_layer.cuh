@@ -364,6 +364,7 @@ layer_kernel(const __grid_constant__ LayerMaps mp,
     const int q = warp & 3, h = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     uint32_t ti = 0;
+    const uint64_t pol_stream = l2_policy_evict_first();   // cond projection (read once) and gated y (read by a later kernel)
     unsigned int* pending_flag = nullptr;   // completion counter of the x_next slab this warp stored last (lane 0 only)
     for (int l = lp.layer0; l < l_end; ++l)
     for (int pair = first_pair(l); pair < num_pairs; pair += num_clusters, ++ti) {
@@ -392,8 +393,8 @@ layer_kernel(const __grid_constant__ LayerMaps mp,
         if (valid) {   // hoisted cond projection: 64 gate + 64 filter pre-activations (coalesced, blocked layout)
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
-            pre[u] = __ldg(reinterpret_cast<const uint4*>(cpb + blocked_off(m_tile, 64, j * 32 + h * 8 + u, row)));
-            pre[8 + u] = __ldg(reinterpret_cast<const uint4*>(cpb + blocked_off(m_tile, 64, j * 32 + 16 + h * 8 + u, row)));
+            pre[u] = ldg_stream_v4(cpb + blocked_off(m_tile, 64, j * 32 + h * 8 + u, row), pol_stream);
+            pre[8 + u] = ldg_stream_v4(cpb + blocked_off(m_tile, 64, j * 32 + 16 + h * 8 + u, row), pol_stream);
           }
         }
         if (valid && j == 0) {   // bring the cond-projection lines of the later sections into L2 now; they are loaded ~6-10k cycles later
@@ -431,13 +432,19 @@ layer_kernel(const __grid_constant__ LayerMaps mp,
         if (tr && warp == 2 && lane == 0) lp.trace[(ti & 31) * 16 + 7 + j] = clock64();
         const uint32_t trow = lane_base + (j ? colB1 : colA);
         const float* sbj = sb_row + j * 256;
+        uint32_t rgf[2][2][16];   // the TMEM loads of group ci + 1 are in flight while group ci is gated
+        tmem_ld_x16(trow + h * 64, rgf[0][0]);
+        tmem_ld_x16(trow + 128 + h * 64, rgf[0][1]);
 #pragma unroll
         for (int ci = 0; ci < 4; ++ci) {
           const int i = h * 64 + ci * 16;
-          uint32_t rg[16], rf[16];
-          tmem_ld_x16(trow + i, rg);
-          tmem_ld_x16(trow + 128 + i, rf);
           tmem_ld_wait();
+          if (ci < 3) {
+            tmem_ld_x16(trow + i + 16, rgf[(ci + 1) & 1][0]);
+            tmem_ld_x16(trow + 128 + i + 16, rgf[(ci + 1) & 1][1]);
+          }
+          const uint32_t (&rg)[16] = rgf[ci & 1][0];
+          const uint32_t (&rf)[16] = rgf[ci & 1][1];
           uint32_t packed[8];
           gate_chunk16<T>(rg, rf, prew + ci * 8, prew + 32 + ci * 8, sbj + i, packed);
           if (!valid) {
@@ -450,10 +457,11 @@ layer_kernel(const __grid_constant__ LayerMaps mp,
         tc_fence_before();          // TMEM reads of this accumulator are done
         fence_proxy_async_smem();   // Y rows visible to the tensor core (MMA2) and the TMA store engine
         __syncwarp();
+        if (tr && warp == 2 && lane == 0) lp.trace[(ti & 31) * 16 + (j ? 13 : 9)] = clock64();   // section end
         if (lane == 0) {
           mbar_arrive_leader(&afree_bar[j]);
           mbar_arrive_leader(&yready_bar[j]);
-          tma_store_4d(&mp.ys, ytile + q * 4096, (2 * j + h) * 64, t0 + q * 32, b, l);   // 32 frames x 64 channels
+          tma_store_4d_hint(&mp.ys, ytile + q * 4096, (2 * j + h) * 64, t0 + q * 32, b, l, pol_stream);   // 32 frames x 64 channels
           tma_store_commit();
         }
       }

@@ -141,7 +141,7 @@ def check_trace():
         for i in range(32 if kind == 8 else 8):
             if int(t[i, 6]) == 0:
                 break
-            rows.append([int(v) - t0 if int(v) else -1 for v in t[i, :12]] + [int(t[i, 12]), int(t[i, 13])])
+            rows.append([int(v) - t0 if int(v) else -1 for v in t[i, :12]] + [int(t[i, 12]), int(t[i, 13]) - t0 if int(t[i, 13]) else 0])
         if kind == 8:
             rows.sort(key=lambda r: r[2])
         out[name] = dict(exit=int(t[0, 14]) - t0, tiles=rows)
