@@ -106,7 +106,8 @@ long long pd_launch_count(int reset);
  * bracketed by a CUDA-event pair on its stream.  pd_profile_end synchronises and returns, per kernel kind, the summed
  * milliseconds and the launch count.  Kinds: 0 cond_proj, 1 input_proj, 2 dilated_conv+gate, 3 res_proj, 4 skip_sum,
  * 5 skip_proj, 6 output_proj+posterior, 7 debug. */
-#define PD_N_KINDS 9   /* kind 8 = fused ResidualBlock layer kernel (2-CTA) */
+#define PD_N_KINDS 10  /* kind 8 = fused ResidualBlock layer kernel (2-CTA); kind 9 = fused sampler tail (skip_projection +
+                          output_projection + q-posterior + next step's input_projection, pd_sample only) */
 int pd_profile_begin(void);
 int pd_profile_end(float* ms_by_kind, int* count_by_kind, int n_kinds);
 
@@ -126,6 +127,12 @@ int pd_set_fused(int on);
 /* With the fused kernel: run all layers of a denoiser call in ONE persistent launch whose tiles synchronise through
  * per-tile flags (1, default; env PD_STACK=0 also disables) or launch one kernel per layer (0). Returns the previous value. */
 int pd_set_stack(int on);
+
+/* pd_sample only: run skip_projection (wavenet.py:120-121), output_projection (:122), the q-posterior update
+ * (prodiff.py:106-121) and the NEXT step's input_projection (wavenet.py:108-111) as one kernel whose intermediates stay in
+ * shared memory (1, default when C = 256 and M = 128; env PD_TAIL=0 also disables) or as separate GEMM launches (0).
+ * Returns the previous value. */
+int pd_set_tail(int on);
 
 /* Debug: when set to a device buffer of 12 x 1024 int64, CTA 0 of every GEMM launch writes clock64() stamps of its
  * pipeline events at [kind * 1024 + tile * 16 + slot] (slots: 0/1 first/last TMA issue, 2 accumulator free, 3/4 first/

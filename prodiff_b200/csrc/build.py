@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 OUT = os.path.join(HERE, "libprodiff_b200.so")
 SRCS = ["pd_api.cu"]
-DEPS = SRCS + ["pd_ptx.cuh", "pd_gemm.cuh", "pd_aux.cuh", "pd_layer.cuh", os.path.join("..", "..", "include", "prodiff_b200.h")]
+DEPS = SRCS + sorted(f for f in os.listdir(HERE) if f.endswith(".cuh")) + [os.path.join("..", "..", "include", "prodiff_b200.h")]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared", "-Xcompiler", "-fPIC"]
 
 

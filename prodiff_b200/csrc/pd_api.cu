@@ -3,6 +3,7 @@
 #include "../../include/prodiff_b200.h"
 #include "pd_aux.cuh"
 #include "pd_layer.cuh"
+#include "pd_tail.cuh"
 
 #include <math.h>
 #include <stdarg.h>
@@ -332,6 +333,7 @@ struct pd_plan {
   CUtensorMap tm_xa_halo[5], tm_xb_halo[5];   // box (64, 128 + 2*2^i): haloed tile loads of the fused layer kernel
   CUtensorMap tm_xa_st, tm_xb_st, tm_y_st;    // box (64, 32): per-warp TMA stores
   bool fused_ok;
+  bool tail_ok;
   size_t off(const char* n) const {
     for (const Buf& b : bufs)
       if (!strcmp(b.name, n)) return b.off;
@@ -405,6 +407,7 @@ extern "C" int pd_plan_create(const pd_model* m, int B, int T, int max_entries, 
   }
   // fused layer kernel (C = 256, dilations <= 16): haloed loads and 32-row store boxes
   p->fused_ok = (C == kLayerC) && (1 << (c.dilation_cycle_length - 1)) <= kLayerMaxDil;
+  p->tail_ok = p->fused_ok && c.in_dims == 128;   // fused sampler tail (pd_tail.cuh) is specialised for C = 256, M = 128
   if (p->fused_ok) {
     for (int i = 0; i < 5 && i < c.dilation_cycle_length; ++i)
       if (make_act_map(&p->tm_xa_halo[i], dt, p->ptr<void>("xa"), C, T, B, 1, kBlockM + 2 * (1 << i)) ||
@@ -600,6 +603,39 @@ static int launch_layer(int dt, bool hybrid, const LayerMaps& mp, const LayerPar
   return hybrid ? launch_layer_t<__nv_bfloat16, true>(mp, lp, sms, s, ok_multi) : launch_layer_t<__nv_bfloat16, false>(mp, lp, sms, s, ok_multi);
 }
 
+// ------------------------------------------------------------------ fused sampler tail launch
+static int g_tail = -1;  // -1: read PD_TAIL from the environment on first use
+extern "C" int pd_set_tail(int on) {
+  const int prev = g_tail;
+  g_tail = on ? 1 : 0;
+  return prev;
+}
+static bool tail_enabled() {
+  if (g_tail < 0) {
+    const char* e = getenv("PD_TAIL");
+    g_tail = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_tail == 1;
+}
+template <typename T>
+static int launch_tail_t(const CUtensorMap& s1, const CUtensorMap& wsp, const CUtensorMap& wout, const CUtensorMap& win,
+                         const CUtensorMap& xst, const TailParams& tp, int sms, cudaStream_t s) {
+  auto kern = tail_kernel<T>;
+  static bool configured[64] = {false};
+  int dev = 0;
+  PD_CUDA(cudaGetDevice(&dev));
+  if (!configured[dev & 63]) {
+    PD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTailSmemBytes));
+    configured[dev & 63] = true;
+  }
+  const int tiles = tp.B * tp.m_tiles_per_row;
+  prof_before(9, s);
+  kern<<<tiles < sms ? tiles : sms, kGemmThreads, kTailSmemBytes, s>>>(s1, wsp, wout, win, xst, tp);
+  prof_after(s);
+  PD_LAUNCH_CHECK("tail_kernel");
+  return 0;
+}
+
 // ------------------------------------------------------------------ hot-path sequences
 extern "C" int pd_cond_project(pd_plan* p, const float* cond, void* stream) {
   if (!p || !cond) return fail("null argument");
@@ -664,6 +700,7 @@ struct OutStage {  // what the final GEMM's epilogue does with x0
   float* x_state;
   const float* noise;
   bool write_xin;
+  bool have_xa;    // layer-0 input already produced by the previous step's fused tail: skip input_projection
   float c1, c2, sigma;
   unsigned long long seed;
   unsigned int step_id;
@@ -679,7 +716,7 @@ static int run_denoiser(pd_plan* p, int entry_base, int entry_per_b, const OutSt
   const PackedLayout& lay = m->lay;
   const size_t N = (size_t)B * T;
   // input_projection + ReLU (wavenet.py:108-111)
-  {
+  if (!os.have_xa) {
     GemmShape sh = base_shape(B, T, C / 256, M / 64);
     EpiArgs ep = base_epi();
     ep.out = p->ptr<void>("xa");
@@ -802,6 +839,33 @@ static int run_denoiser(pd_plan* p, int entry_base, int entry_per_b, const OutSt
     ep.scale = 1.0f / sqrtf((float)L);
     if (launch_gemm<EPI_STORE, 256>(dt, p->tm_y, m->tm_w_skip, sh, ep, sms, s, "gemm(skip_sum)", 4, nullptr, nullptr, &m->tm_w_skip_h)) return 1;
   }
+  if (os.x_state != nullptr && p->tail_ok && tail_enabled()) {
+    // sampling loop: skip_projection, output_projection, the q-posterior update and the next step's input_projection as
+    // one kernel (pd_tail.cuh)
+    TailParams tp;
+    memset(&tp, 0, sizeof(tp));
+    tp.B = B;
+    tp.T = T;
+    tp.m_tiles_per_row = (T + kBlockM - 1) / kBlockM;
+    tp.do_in = os.write_xin ? 1 : 0;
+    tp.idesc256 = make_idesc(dt, 256);
+    tp.idesc128 = make_idesc(dt, 128);
+    tp.b_sp = (const float*)(pk + lay.b_sp);
+    tp.b_out = (const float*)(pk + lay.b_out);
+    tp.b_in = (const float*)(pk + lay.b_in);
+    tp.M = M;
+    tp.x0_out = os.x0_out;
+    tp.x_state = os.x_state;
+    tp.noise = os.noise;
+    tp.c1 = os.c1;
+    tp.c2 = os.c2;
+    tp.sigma = os.sigma;
+    tp.seed = os.seed;
+    tp.step_id = os.step_id;
+    tp.trace = g_trace ? g_trace + 10 * 1024 : nullptr;
+    return dt == PD_FP16 ? launch_tail_t<__half>(p->tm_s1, m->tm_w_sp, m->tm_w_out, m->tm_w_in, p->tm_xa_st, tp, sms, s)
+                         : launch_tail_t<__nv_bfloat16>(p->tm_s1, m->tm_w_sp, m->tm_w_out, m->tm_w_in, p->tm_xa_st, tp, sms, s);
+  }
   {  // skip_projection + ReLU (wavenet.py:120-121)
     GemmShape sh = base_shape(B, T, C / 256, C / 64);
     EpiArgs ep = base_epi();
@@ -881,6 +945,7 @@ extern "C" int pd_sample(pd_plan* p, const float* cond, float* x, const float* n
     os.x_state = x;
     os.noise = noise ? noise + (size_t)j * state_elems : nullptr;
     os.write_xin = j + 1 < K;
+    os.have_xa = j > 0 && p->tail_ok && tail_enabled();
     os.c1 = coef1[t];
     os.c2 = coef2[t];
     os.sigma = t == 0 ? 0.f : expf(0.5f * logvar[t]);  // nonzero_mask * exp(0.5 * log_var), prodiff.py:120-121

@@ -122,8 +122,10 @@ __device__ __forceinline__ long long blocked_off(long long tile, int chunks_per_
 __device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
 #pragma unroll
   for (int r = 0; r < 10; ++r) {
-    const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
-    const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+    const unsigned long long p0 = (unsigned long long)0xD2511F53u * ctr.x;   // one IMAD.WIDE each instead of mul.hi + mul.lo
+    const unsigned long long p1 = (unsigned long long)0xCD9E8D57u * ctr.z;
+    const uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0;
+    const uint32_t hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
     ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
     key.x += 0x9E3779B9u;
     key.y += 0xBB67AE85u;
@@ -587,7 +589,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 }
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                  const float v = fmaf(ep.sigma, nzv[u], fmaf(ep.c1, xn[j + u], ep.c2 * xv[ci & 1][j + u]));
+                  const float v = fmaf(ep.c1, xn[j + u], fmaf(ep.sigma, nzv[u], ep.c2 * xv[ci & 1][j + u]));   // same order as pd_tail.cuh
                   ep.x_state[cbase + (long long)(j + u) * Tn] = v;
                   xn[j + u] = v;
                 }

@@ -183,6 +183,37 @@ def test_fused_layer_kernel_equals_unfused_pair():
     assert float((outs[0] - ref).abs().max()) <= STEP_TOL and float((outs[1] - ref).abs().max()) <= STEP_TOL
 
 
+def test_fused_sampler_tail_equals_separate_kernels():
+    """pd_sample with the fused tail kernel (skip_projection -> output_projection -> q-posterior -> next step's
+    input_projection, intermediates in shared memory) against the same loop running those as separate GEMM launches.
+    Identical operands, identical K order and identical 16-bit rounding points, so the mel must agree exactly; both
+    injected noise and the in-kernel Philox stream are covered, and the per-step x0 trace as well."""
+    from prodiff_b200 import _lib, synth
+    lib = _lib.load()
+    cfg = synth.DiffNetConfig(128, 256, 4, 256, 2)
+    state = synth.make_state(cfg, 23, "trained")
+    case = dict(timesteps=4, schedule_type="vpsde", max_beta=40)
+    B, T, K = 3, 333, 4                                     # ragged last tile per utterance
+    cond, x_T, noise = synth.make_inputs(cfg, B, T, K, 24)
+    res = []
+    for tail in (1, 0):
+        prev = lib.pd_set_tail(tail)
+        try:
+            gd = _build(cfg, state, case)
+            with torch.no_grad():
+                tr = torch.empty(K, B, 1, 128, T, device="cuda")
+                a = gd(cond.cuda(), infer_step=K, infer=True, x_T=x_T.cuda(), noise=noise.cuda(), x0_trace=tr).cpu()
+                b = gd(cond.cuda(), infer_step=K, infer=True, x_T=x_T.cuda(), seed=77).cpu()
+                res.append((a, b, tr.cpu()))
+        finally:
+            lib.pd_set_tail(1 if prev != 0 else 0)
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+    assert torch.equal(res[0][2], res[1][2])
+    mel_ref, x0s = helpers.oracle_sample(dict(case, infer_step=K), cfg, state, cond, x_T, noise)
+    assert float((res[0][0] - mel_ref).abs().mean()) <= MEL_L1_TOL
+    assert float((res[0][2][K - 1] - x0s[K - 1]).abs().max()) <= STEP_TOL * 4   # last step: errors of K - 1 updates ride along
+
+
 def test_full_size_roundtrip_properties():
     """BASELINE config-2 size (64 x 1000, K = 4), properties that need no oracle run:
     determinism per seed, batch-row independence (a row sampled alone equals the same row inside the batch, which is

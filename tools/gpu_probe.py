@@ -154,6 +154,9 @@ def check_trace():
             out["layer_wall_ns"] = ns
             out["layer_sm_mhz_effective"] = round((int(t[0, 14]) - t0) / max(ns, 1) * 1e3, 1)
 
+    t = buf[10 * 1024:11 * 1024].cpu().view(64, 16)
+    t0 = int(t[0, 15])
+    out["tail"] = dict(exit=int(t[0, 14]) - t0, tiles=[[int(v) - t0 if int(v) else -1 for v in t[i, :11]] for i in range(8)])
     return out
 
 
