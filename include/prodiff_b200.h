@@ -99,6 +99,21 @@ int pd_sample(pd_plan* p, const float* cond, float* x, const float* noise, uint6
               const int32_t* t_list, const float* coef1, const float* coef2, const float* logvar, int n_table,
               float* x0_trace, void* stream);
 
+/* RectifiedFlow.forward(infer=True) (/root/reference/modules/diffusion/reflow.py:32-46, 86-107): the rectified-flow ODE
+ * x' = v(x, time_scale * t) integrated from t = 0 to 1 in n_steps steps of dt = 1 / n_steps with sample_euler (:48-52),
+ * sample_rk2 (:54-60), sample_rk4 (:62-70) or sample_rk5 (:72-84), the velocity being the same DiffNet denoiser
+ * (WaveNet.forward with a float diffusion step shared by the batch), followed by denorm_spec (:106-107).
+ *   cond      [B,T,H] fp32 device; projected once and reused by every evaluation.
+ *   x         [B,1,M,T] fp32 device, in place: in = the N(0,1) start the reference draws at :88, out = denormalised result
+ *             (the caller returns the [B,T,M] view x[:,0].transpose(1,2) like :100).
+ *   algorithm 0 euler, 1 rk2, 2 rk4, 3 rk5 (the caller maps unknown names to euler as the reference's dict.get does, :95).
+ *   k_scratch fp32 device scratch for the stage velocities: stages * B*M*T floats (stages = 1, 2, 4, 6).
+ *   spec_min / spec_max  device fp32, n_spec = 1 or >= M entries; both NULL skips denorm_spec.
+ *   v_trace   optional [n_steps * stages, B,1,M,T] fp32: every velocity in call order (then k_scratch is unused).
+ * The plan needs max_entries >= stages. */
+int pd_reflow_sample(pd_plan* p, const float* cond, float* x, int algorithm, int n_steps, float time_scale,
+                     float* k_scratch, const float* spec_min, const float* spec_max, int n_spec, float* v_trace, void* stream);
+
 /* Number of kernels of this library launched by the calling thread since the last reset (bench evidence). */
 long long pd_launch_count(int reset);
 

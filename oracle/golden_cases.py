@@ -38,3 +38,29 @@ DENOISE_CASES = {
     "fwd_in64": dict(cfg=DiffNetConfig(64, 256, 2, 256, 1), B=1, T=100, steps=[2], out_init="trained",
                      wseed=81, iseed=82),
 }
+
+# Rectified-flow sampler over the same denoiser (reflow.py:48-107).  x_start ~ N(0,1) is injected in place
+# of the torch.randn at reflow.py:88.  spec_min / spec_max: "bins" = a per-bin ramp, else the one-element lists the configs use.
+REFLOW_CASES = {
+    "euler": dict(cfg=DiffNetConfig(128, 256, 4, 256, 2), algorithm="euler", infer_step=4, time_scale=1000, B=2, T=150,
+                  spec="bins", out_init="trained", wseed=91, iseed=92),
+    "rk2": dict(cfg=DiffNetConfig(128, 256, 3, 256, 1), algorithm="rk2", infer_step=3, time_scale=1000, B=1, T=129,
+                spec="scalar", out_init="trained", wseed=93, iseed=94),
+    "rk4": dict(cfg=DiffNetConfig(128, 256, 3, 256, 3), algorithm="rk4", infer_step=2, time_scale=1000, B=2, T=77,
+                spec="scalar", out_init="kaiming", wseed=95, iseed=96),
+    "rk5": dict(cfg=DiffNetConfig(128, 256, 2, 256, 1), algorithm="rk5", infer_step=2, time_scale=1000, B=1, T=64,
+                spec="bins", out_init="trained", wseed=97, iseed=98),
+    # PitchRectifiedFlow shape: 64 repeat bins, denorm = mean over bins + clamp (reflow.py:110-143), default euler
+    "pitch64": dict(cfg=DiffNetConfig(64, 256, 2, 256, 1), algorithm="euler", infer_step=5, time_scale=1000, B=2, T=100,
+                    spec="pitch", out_init="trained", wseed=99, iseed=100),
+}
+
+
+def reflow_spec_range(case):
+    """(spec_min, spec_max) lists for a REFLOW case."""
+    M = case["cfg"].in_dims
+    if case["spec"] == "bins":
+        return [-12.0 + 0.03 * i for i in range(M)], [0.0 + 0.01 * i for i in range(M)]
+    if case["spec"] == "pitch":
+        return [-8.0], [8.0]
+    return [-12.0], [0.0]

@@ -95,8 +95,44 @@ def run_reference_denoise(case):
     return dict(out=out.numpy(), digest=np.array(synth.digest(state, cond, x_T)))
 
 
+def run_reference_reflow(case):
+    """RectifiedFlow / PitchRectifiedFlow .forward(infer=True) of the unmodified reference on injected start noise."""
+    from prodiff_b200 import synth
+    from oracle.golden_cases import reflow_spec_range
+    WaveNet, _ = load_reference()
+    from modules.diffusion.reflow import RectifiedFlow, PitchRectifiedFlow  # noqa
+    cfg = case["cfg"]
+    state = synth.make_state(cfg, case["wseed"], case["out_init"])
+    cond, _, noise = synth.make_inputs(cfg, case["B"], case["T"], 1, case["iseed"])
+    wn = WaveNet(cfg.in_dims, cfg.hidden_size, cfg.residual_layers, cfg.residual_channels, cfg.dilation_cycle_length)
+    wn.load_state_dict(state, strict=True)
+    smin, smax = reflow_spec_range(case)
+    if case["spec"] == "pitch":
+        rf = PitchRectifiedFlow(cfg.in_dims, wn, time_scale=case["time_scale"], sampling_algorithm=case["algorithm"],
+                                spec_min=smin[0], spec_max=smax[0]).eval()
+    else:
+        rf = RectifiedFlow(cfg.in_dims, wn, time_scale=case["time_scale"], num_features=1,
+                           sampling_algorithm=case["algorithm"], spec_min=smin, spec_max=smax).eval()
+    vs = []
+    h = wn.register_forward_hook(lambda m, i, o: vs.append(o.detach().clone()))
+    real_randn = torch.randn
+
+    def randn(*shape, **kw):
+        assert tuple(shape) == tuple(noise[0].shape), (shape, noise[0].shape)
+        return noise[0].clone()
+
+    torch.randn = randn
+    try:
+        with torch.no_grad():
+            out = rf(cond, infer_step=case["infer_step"], infer=True)
+    finally:
+        torch.randn = real_randn
+        h.remove()
+    return dict(out=out.contiguous().numpy(), v=torch.stack(vs).numpy(), digest=np.array(synth.digest(state, cond, noise[0])))
+
+
 def main():
-    from oracle.golden_cases import SAMPLE_CASES, DENOISE_CASES
+    from oracle.golden_cases import SAMPLE_CASES, DENOISE_CASES, REFLOW_CASES
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     out_dir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
@@ -108,6 +144,10 @@ def main():
         r = run_reference_denoise(case)
         np.savez(os.path.join(out_dir, f"denoise_{name}.npz"), **r)
         print(f"denoise_{name}: out {r['out'].shape} |out|max {np.abs(r['out']).max():.3f}")
+    for name, case in REFLOW_CASES.items():
+        r = run_reference_reflow(case)
+        np.savez(os.path.join(out_dir, f"reflow_{name}.npz"), **r)
+        print(f"reflow_{name}: out {r['out'].shape} v {r['v'].shape} |v|max {np.abs(r['v']).max():.3f}")
 
 
 if __name__ == "__main__":

@@ -217,3 +217,72 @@ def sample(state: State, tables, cond, x_T, noise, infer_step: int, num_timestep
         x0s.append(x_0_pred)
         x = q_posterior_sample(tables, x_0_pred, x, t, noise[j])
     return x[:, 0].transpose(1, 2), x0s
+
+
+# --------------------------------------------------------------------------------------
+# rectified-flow sampler over the same denoiser
+#     /root/reference/modules/diffusion/reflow.py:48-107
+# --------------------------------------------------------------------------------------
+REFLOW_ALGORITHMS = ("euler", "rk2", "rk4", "rk5")
+
+
+@torch.no_grad()
+def reflow_sample(state: State, cond, x_start, infer_step: int, algorithm: str, time_scale,
+                  spec_min, spec_max, dilation_cycle_length: int) -> Tuple[torch.Tensor, List[torch.Tensor]]:
+    """RectifiedFlow.forward(infer=True) = inference + denorm_spec (reflow.py:32-46, 86-107).
+
+    cond [B,T,H]; x_start [B,1,M,T] replaces the torch.randn at :88; ``spec_min`` / ``spec_max`` are the
+    per-bin lists the constructor takes (:20-23).  The four integrators follow sample_euler / sample_rk2 /
+    sample_rk4 / sample_rk5 (:48-84) expression by expression, including the fp32 tensor ``dts`` the loop
+    multiplies the step index with (:97-99) and the in-place ``x +=``.  An unknown algorithm falls back to
+    euler as the reference's ``dict.get`` does (:95).
+    Returns (mel [B,T,M] after denorm_spec, [velocity of every denoiser evaluation, in call order]).
+    """
+    cond = cond.transpose(1, 2)
+    M = x_start.shape[2]
+    vs: List[torch.Tensor] = []
+
+    def velocity_fn(x, t):
+        v = wavenet_forward(state, x, t, cond, dilation_cycle_length)
+        vs.append(v)
+        return v
+
+    def sample_euler(x, t, dt):
+        x += velocity_fn(x, time_scale * t) * dt
+        return x
+
+    def sample_rk2(x, t, dt):
+        k_1 = velocity_fn(x, time_scale * t)
+        k_2 = velocity_fn(x + 0.5 * k_1 * dt, time_scale * (t + 0.5 * dt))
+        x += k_2 * dt
+        return x
+
+    def sample_rk4(x, t, dt):
+        k_1 = velocity_fn(x, time_scale * t)
+        k_2 = velocity_fn(x + 0.5 * k_1 * dt, time_scale * (t + 0.5 * dt))
+        k_3 = velocity_fn(x + 0.5 * k_2 * dt, time_scale * (t + 0.5 * dt))
+        k_4 = velocity_fn(x + k_3 * dt, time_scale * (t + dt))
+        x += (k_1 + 2 * k_2 + 2 * k_3 + k_4) * dt / 6
+        return x
+
+    def sample_rk5(x, t, dt):
+        k_1 = velocity_fn(x, time_scale * t)
+        k_2 = velocity_fn(x + 0.25 * k_1 * dt, time_scale * (t + 0.25 * dt))
+        k_3 = velocity_fn(x + 0.125 * (k_2 + k_1) * dt, time_scale * (t + 0.25 * dt))
+        k_4 = velocity_fn(x + 0.5 * (-k_2 + 2 * k_3) * dt, time_scale * (t + 0.5 * dt))
+        k_5 = velocity_fn(x + 0.0625 * (3 * k_1 + 9 * k_4) * dt, time_scale * (t + 0.75 * dt))
+        k_6 = velocity_fn(x + (-3 * k_1 + 2 * k_2 + 12 * k_3 - 12 * k_4 + 8 * k_5) * dt / 7, time_scale * (t + dt))
+        x += (7 * k_1 + 32 * k_3 + 12 * k_4 + 32 * k_5 + 7 * k_6) * dt / 90
+        return x
+
+    fn = {"euler": sample_euler, "rk2": sample_rk2, "rk4": sample_rk4, "rk5": sample_rk5}.get(algorithm, sample_euler)
+    x = x_start.clone()
+    dt = 1.0 / max(1, infer_step)
+    dts = torch.tensor([dt]).to(x)
+    for i in range(infer_step):
+        x = fn(x, i * dts, dt)
+    x = x.float()
+    x = x.transpose(2, 3).squeeze(1)                                  # [B,1,M,T] -> [B,T,M]
+    smin = torch.FloatTensor(spec_min)[None, None, :M].transpose(-3, -2)
+    smax = torch.FloatTensor(spec_max)[None, None, :M].transpose(-3, -2)
+    return (x + 1) / 2 * (smax - smin) + smin, vs

@@ -5,12 +5,15 @@ Public surface (mirrors the reference's module API for this path, SURVEY.md sect
     WaveNet(in_dims, hidden_size, residual_layers, residual_channels, dilation_cycle_length).forward(spec, step, cond)
     GaussianDiffusion(out_dims, denoise_fn, timesteps, time_scale, betas, schedule_type, max_beta, spec_min, spec_max)
         .forward(cond, src_spec=None, gt_spec=None, infer_step=4, infer=False)
+    RectifiedFlow(out_dims, denoise_fn, time_scale, num_features, sampling_algorithm, spec_min, spec_max)
+        .forward(cond, gt_spec=None, infer_step=20, infer=True)          (PitchRectifiedFlow likewise)
 
 ``install()`` swaps these classes into the reference's own modules so that ``ProDiffTeacher``, the SVS inferer
 (``handler/infer/handler.py``), ``main.py infer`` and the vocoder hand-off run unchanged on top of them.
 """
 from .wavenet import WaveNet
 from .diffusion import GaussianDiffusion
+from .reflow import RectifiedFlow, PitchRectifiedFlow
 from .synth import DiffNetConfig
 
 __version__ = "0.1.0"
@@ -23,7 +26,10 @@ def install():
     gd = importlib.import_module("modules.diffusion.prodiff")
     wn.WaveNet = WaveNet
     gd.GaussianDiffusion = GaussianDiffusion
+    rf = importlib.import_module("modules.diffusion.reflow")
+    rf.RectifiedFlow = RectifiedFlow
+    rf.PitchRectifiedFlow = PitchRectifiedFlow
     return wn, gd
 
 
-__all__ = ["WaveNet", "GaussianDiffusion", "DiffNetConfig", "install"]
+__all__ = ["WaveNet", "GaussianDiffusion", "RectifiedFlow", "PitchRectifiedFlow", "DiffNetConfig", "install"]

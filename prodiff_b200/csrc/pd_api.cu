@@ -956,6 +956,95 @@ extern "C" int pd_sample(pd_plan* p, const float* cond, float* x, const float* n
   return 0;
 }
 
+// ------------------------------------------------------------------ rectified-flow sampler (reflow.py:48-101)
+namespace {
+struct RkTableau {
+  int stages;
+  // stage i (i >= 1) evaluates the velocity at x + (((sum_j a[i][j] k_j) * mult[i]) * dt) / div[i], time t + c[i] * dt;
+  // row `stages` is the final update.  Written exactly as the reference expressions are (reflow.py:49-84).
+  double c[6];
+  float a[7][6];
+  float mult[7], div[7];
+};
+const RkTableau kEuler = {1, {0}, {{0}, {1}}, {1, 1}, {1, 1}};
+const RkTableau kRk2 = {2, {0, 0.5}, {{0}, {1}, {0, 1}}, {1, 0.5f, 1}, {1, 1, 1}};
+const RkTableau kRk4 = {4, {0, 0.5, 0.5, 1.0}, {{0}, {1}, {0, 1}, {0, 0, 1}, {1, 2, 2, 1}}, {1, 0.5f, 0.5f, 1, 1}, {1, 1, 1, 1, 6}};
+const RkTableau kRk5 = {6,
+                        {0, 0.25, 0.25, 0.5, 0.75, 1.0},
+                        {{0}, {1}, {1, 1}, {0, -1, 2}, {3, 0, 0, 9}, {-3, 2, 12, -12, 8}, {7, 0, 32, 12, 32, 7}},
+                        {1, 0.25f, 0.125f, 0.5f, 0.0625f, 1, 1},
+                        {1, 1, 1, 1, 1, 7, 90}};
+}  // namespace
+
+static int rk_stage(pd_plan* p, const RkTableau& tb, int row, float* const* k, float dt, const float* x, float* x_out, bool want_xin,
+                    cudaStream_t s) {
+  const pd_config& c = p->m->cfg;
+  RkStage st;
+  memset(&st, 0, sizeof(st));
+  // terms with a zero weight are skipped like the reference's expressions skip them; order of the others is kept
+  for (int j = 0; j < 6; ++j)
+    if (tb.a[row][j] != 0.f) {
+      st.k[st.n_k] = k[j];
+      st.w[st.n_k] = tb.a[row][j];
+      ++st.n_k;
+    }
+  st.mult = tb.mult[row];
+  st.dt = dt;
+  st.div = tb.div[row];
+  const dim3 grid((p->T + 31) / 32, (c.in_dims + 31) / 32, p->B), block(32, 8);
+  if (c.dtype == PD_FP16) k_rk_stage<__half><<<grid, block, 0, s>>>(want_xin ? p->ptr<__half>("xin") : nullptr, x_out, x, st, c.in_dims, c.in_dims, p->T);
+  else k_rk_stage<__nv_bfloat16><<<grid, block, 0, s>>>(want_xin ? p->ptr<__nv_bfloat16>("xin") : nullptr, x_out, x, st, c.in_dims, c.in_dims, p->T);
+  PD_LAUNCH_CHECK("k_rk_stage");
+  return 0;
+}
+
+extern "C" int pd_reflow_sample(pd_plan* p, const float* cond, float* x, int algorithm, int n_steps, float time_scale,
+                                float* k_scratch, const float* spec_min, const float* spec_max, int n_spec, float* v_trace,
+                                void* stream) {
+  if (!p || !cond || !x || !k_scratch) return fail("null argument");
+  if (algorithm < 0 || algorithm > 3) return fail("algorithm %d is not one of 0 euler, 1 rk2, 2 rk4, 3 rk5", algorithm);
+  if (n_steps < 1) return fail("n_steps=%d must be >= 1", n_steps);
+  const RkTableau& tb = algorithm == 0 ? kEuler : algorithm == 1 ? kRk2 : algorithm == 2 ? kRk4 : kRk5;
+  if (p->E < tb.stages) return fail("plan was created with max_entries=%d < %d stages of this integrator", p->E, tb.stages);
+  const pd_config& c = p->m->cfg;
+  if ((spec_min == nullptr) != (spec_max == nullptr) || (spec_min && n_spec != 1 && n_spec < c.in_dims))
+    return fail("spec_min / spec_max must both be given with 1 or >= in_dims entries");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t state_elems = (size_t)p->B * c.in_dims * p->T;
+  const double dt = 1.0 / (double)n_steps;   // reflow.py:89
+  const float dtf = (float)dt;               // the fp32 tensor `dts` (:97)
+  if (pd_cond_project(p, cond, stream)) return 1;  // once per utterance, reused by every evaluation
+  if (spec_to_xin(p, x, s)) return 1;
+  for (int n = 0; n < n_steps; ++n) {
+    // times of this step's evaluations, in the reference's fp32 arithmetic: time_scale * (i * dts + c * dt)
+    StepVals sv;
+    const float tn = (float)n * dtf;
+    for (int i = 0; i < tb.stages; ++i) sv.v[i] = time_scale * (i == 0 ? tn : tn + (float)(tb.c[i] * dt));
+    k_set_steps<<<1, 64, 0, s>>>(p->ptr<float>("steps"), sv, tb.stages);
+    PD_LAUNCH_CHECK("k_set_steps");
+    if (run_step_tables(p, tb.stages, s)) return 1;
+    float* k[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    for (int i = 0; i < tb.stages; ++i)
+      k[i] = v_trace ? v_trace + ((size_t)n * tb.stages + i) * state_elems : k_scratch + (size_t)i * state_elems;
+    for (int i = 0; i < tb.stages; ++i) {
+      OutStage os;
+      memset(&os, 0, sizeof(os));
+      os.x0_out = k[i];   // the denoiser output is the velocity (reflow.py:50)
+      if (run_denoiser(p, i, 0, os, s)) return 1;
+      if (i + 1 < tb.stages) {
+        if (rk_stage(p, tb, i + 1, k, dtf, x, nullptr, true, s)) return 1;          // next evaluation point -> xin
+      } else {
+        if (rk_stage(p, tb, tb.stages, k, dtf, x, x, n + 1 < n_steps, s)) return 1;  // x += ..., and xin for the next step
+      }
+    }
+  }
+  if (spec_min != nullptr) {
+    k_denorm_spec<<<p->m->sm_count * 4, 256, 0, s>>>(x, spec_min, spec_max, n_spec, c.in_dims, p->T, (long long)state_elems);
+    PD_LAUNCH_CHECK("k_denorm_spec");
+  }
+  return 0;
+}
+
 // ------------------------------------------------------------------ test hook
 extern "C" int pd_debug_gemm(int dtype, const void* a, int B, int T, int Cin, int taps, int dil, const void* w, int N,
                              const float* bias, float* out, void* stream) {

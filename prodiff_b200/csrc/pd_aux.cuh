@@ -106,6 +106,52 @@ __global__ void k_spec_to_xin(T* __restrict__ xin, const float* __restrict__ spe
   }
 }
 
+// One stage of the rectified-flow integrators (reflow.py:48-84): y = x + (((sum_j w_j k_j) * mult) * dt) / div, the same
+// operation order as the reference expressions (e.g. 0.0625 * (3 k1 + 9 k4) * dt, or (...) * dt / 7), with explicit
+// round-to-nearest mul/add so nothing is contracted into an fma.  Writes y as fp32 in the state layout [B,1,M,T] (x_out,
+// optional; may alias x) and/or as the 16-bit, frame-major input-projection operand xin [B*T, Mp] (optional).
+struct RkStage {
+  const float* k[6];
+  float w[6];
+  int n_k;
+  float mult, dt, div;
+};
+template <typename T>
+__global__ void k_rk_stage(T* __restrict__ xin, float* x_out, const float* x, RkStage st, int M, int Mp, int Tn) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, m0 = blockIdx.y * 32, t0 = blockIdx.x * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+  for (int i = ty; i < 32; i += 8) {
+    const int m = m0 + i, t = t0 + tx;
+    float y = 0.f;
+    if (m < M && t < Tn) {
+      const long long idx = ((long long)b * M + m) * Tn + t;
+      float sum = __fmul_rn(st.w[0], st.k[0][idx]);
+      for (int j = 1; j < st.n_k; ++j) sum = __fadd_rn(sum, __fmul_rn(st.w[j], st.k[j][idx]));
+      y = __fadd_rn(x[idx], __fdiv_rn(__fmul_rn(__fmul_rn(sum, st.mult), st.dt), st.div));
+      if (x_out != nullptr) x_out[idx] = y;
+    }
+    tile[i][tx] = y;
+  }
+  if (xin == nullptr) return;
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int t = t0 + i, m = m0 + tx;
+    if (t < Tn && m < Mp) xin[((long long)b * Tn + t) * Mp + m] = from_float<T>(tile[tx][i]);
+  }
+}
+
+// RectifiedFlow.denorm_spec (reflow.py:106-107) in place on the state [B,1,M,T]: (x + 1) / 2 * (max - min) + min per mel bin.
+__global__ void k_denorm_spec(float* __restrict__ x, const float* __restrict__ spec_min, const float* __restrict__ spec_max,
+                              int n_spec, int M, int Tn, long long total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int m = (int)((i / Tn) % M);
+    const int j = n_spec == 1 ? 0 : m;
+    const float lo = spec_min[j], hi = spec_max[j];
+    x[i] = __fadd_rn(__fmul_rn(__fdiv_rn(__fadd_rn(x[i], 1.f), 2.f), __fadd_rn(hi, -lo)), lo);
+  }
+}
+
 struct StepVals {
   float v[64];
 };

@@ -142,6 +142,27 @@ class Engine:
                                           x0_trace.data_ptr() if x0_trace is not None else None, self._stream()), "pd_sample")
         return x
 
+    REFLOW_ALGORITHMS = {"euler": (0, 1), "rk2": (1, 2), "rk4": (2, 4), "rk5": (3, 6)}   # name -> (C-ABI id, stages)
+
+    def reflow(self, cond_bth: torch.Tensor, x: torch.Tensor, algorithm: str, n_steps: int, time_scale: float,
+               spec_min: Optional[torch.Tensor], spec_max: Optional[torch.Tensor],
+               v_trace: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """The rectified-flow ODE loop (pd_reflow_sample), in place on x [B,1,M,T] (in: N(0,1) start, out: denormalised)."""
+        B, _, M, T = x.shape
+        algo, stages = self.REFLOW_ALGORITHMS.get(algorithm, self.REFLOW_ALGORITHMS["euler"])   # reflow.py:95 falls back to euler
+        p = self.plan(B, T, 6)
+        scratch = None if v_trace is not None else torch.empty(stages, B, 1, M, T, dtype=torch.float32, device=self.device)
+        k_ptr = v_trace.data_ptr() if v_trace is not None else scratch.data_ptr()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.pd_reflow_sample(
+                p.handle, cond_bth.data_ptr(), x.data_ptr(), algo, int(n_steps), float(time_scale), k_ptr,
+                spec_min.data_ptr() if spec_min is not None else None, spec_max.data_ptr() if spec_max is not None else None,
+                int(spec_min.numel()) if spec_min is not None else 0,
+                v_trace.data_ptr() if v_trace is not None else None, self._stream()), "pd_reflow_sample")
+            if scratch is not None:
+                scratch.record_stream(torch.cuda.current_stream(self.device))
+        return x
+
     def __del__(self):
         try:
             self.plans.clear()

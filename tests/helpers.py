@@ -5,7 +5,7 @@ import numpy as np
 import torch
 
 from oracle import prodiff_oracle as oracle
-from oracle.golden_cases import SAMPLE_CASES, DENOISE_CASES
+from oracle.golden_cases import SAMPLE_CASES, DENOISE_CASES, REFLOW_CASES, reflow_spec_range
 from prodiff_b200 import synth
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -35,3 +35,21 @@ def oracle_sample(case, cfg, state, cond, x_T, noise):
     tables = oracle.diffusion_tables(case["timesteps"], case["schedule_type"], case["max_beta"])
     return oracle.sample(state, tables, cond, x_T, noise, case["infer_step"], case["timesteps"],
                          cfg.dilation_cycle_length)
+
+
+def regen_reflow_case(name):
+    case = REFLOW_CASES[name]
+    cfg = case["cfg"]
+    state = synth.make_state(cfg, case["wseed"], case["out_init"])
+    cond, _, noise = synth.make_inputs(cfg, case["B"], case["T"], 1, case["iseed"])
+    return case, cfg, state, cond, noise[0]
+
+
+def oracle_reflow(case, cfg, state, cond, x_start):
+    """(denormalised output, velocities) of the oracle; the pitch flavour applies reflow.py:143 on top."""
+    smin, smax = reflow_spec_range(case)
+    out, vs = oracle.reflow_sample(state, cond, x_start, case["infer_step"], case["algorithm"], case["time_scale"],
+                                   smin, smax, cfg.dilation_cycle_length)
+    if case["spec"] == "pitch":
+        out = out.mean(dim=-1).clamp(-12.0, 12.0)
+    return out, vs

@@ -214,6 +214,55 @@ def test_fused_sampler_tail_equals_separate_kernels():
     assert float((res[0][2][K - 1] - x0s[K - 1]).abs().max()) <= STEP_TOL * 4   # last step: errors of K - 1 updates ride along
 
 
+@pytest.mark.parametrize("name", ["euler", "rk2", "rk4", "rk5", "pitch64"])
+def test_reflow_matches_oracle_and_fixture(name):
+    """RectifiedFlow / PitchRectifiedFlow .forward(infer=True) through pd_reflow_sample against the oracle
+    (same injected start noise) and the reference-made fixture.  Bar: every velocity (= denoiser output) within max-abs
+    1e-2 (x output scale for the Kaiming case), final result L1 within 1e-2 in normalised units, i.e. x (max - min) / 2
+    after denorm_spec."""
+    import prodiff_b200 as pb
+    case, cfg, state, cond, x_start = helpers.regen_reflow_case(name)
+    out_ref, vs_ref = helpers.oracle_reflow(case, cfg, state, cond, x_start)
+    g = helpers.load_golden("reflow", name)
+    wn = _build(cfg, state)
+    smin, smax = helpers.reflow_spec_range(case)
+    if case["spec"] == "pitch":
+        rf = pb.PitchRectifiedFlow(cfg.in_dims, wn, time_scale=case["time_scale"], sampling_algorithm=case["algorithm"],
+                                   spec_min=smin[0], spec_max=smax[0]).cuda().eval()
+    else:
+        rf = pb.RectifiedFlow(cfg.in_dims, wn, time_scale=case["time_scale"], sampling_algorithm=case["algorithm"],
+                              spec_min=smin, spec_max=smax).cuda().eval()
+    n_eval = len(vs_ref)
+    tr = torch.empty(n_eval, case["B"], 1, cfg.in_dims, case["T"], device="cuda")
+    with torch.no_grad():
+        out = rf(cond.cuda(), infer_step=case["infer_step"], infer=True, x_start=x_start.cuda(), v_trace=tr).cpu()
+        out2 = rf(cond.cuda(), infer_step=case["infer_step"], infer=True, x_start=x_start.cuda()).cpu()   # scratch path
+    assert out.shape == out_ref.shape and torch.equal(out, out2)
+    scale = _scale(case["out_init"])
+    v_err = float((tr.cpu() - torch.stack(vs_ref)).abs().max())
+    assert v_err <= STEP_TOL * scale, f"velocity max-abs {v_err:.4g}"
+    half_range = (max(smax) - min(smin)) / 2
+    l1 = float((out - out_ref).abs().mean())
+    assert l1 <= MEL_L1_TOL * half_range * scale, f"final L1 {l1:.4g}"
+    assert float((out - torch.from_numpy(g["out"])).abs().mean()) <= MEL_L1_TOL * half_range * scale
+
+
+def test_reflow_inference_is_normalised_and_random_start():
+    """``inference`` returns the normalised result like reflow.py:86-101 (denorm_spec is forward's job), and without
+    ``x_start`` the start is torch.randn: two calls differ."""
+    import prodiff_b200 as pb
+    case, cfg, state, cond, x_start = helpers.regen_reflow_case("rk2")
+    wn = _build(cfg, state)
+    rf = pb.RectifiedFlow(cfg.in_dims, wn, time_scale=1000, sampling_algorithm="rk2", spec_min=[-12.0], spec_max=[0.0]).cuda().eval()
+    with torch.no_grad():
+        full = rf(cond.cuda(), infer_step=3, infer=True, x_start=x_start.cuda())
+        norm = rf.inference(cond.cuda().transpose(1, 2), b=1, infer_step=3, x_start=x_start.cuda())
+        assert torch.allclose(rf.denorm_spec(norm), full, atol=1e-5)
+        a = rf(cond.cuda(), infer_step=2, infer=True)
+        b = rf(cond.cuda(), infer_step=2, infer=True)
+    assert a.shape == (1, case["T"], 128) and float((a - b).abs().mean()) > 1e-3
+
+
 def test_full_size_roundtrip_properties():
     """BASELINE config-2 size (64 x 1000, K = 4), properties that need no oracle run:
     determinism per seed, batch-row independence (a row sampled alone equals the same row inside the batch, which is

@@ -10,7 +10,7 @@ import pytest
 import torch
 
 from oracle import prodiff_oracle as oracle
-from oracle.golden_cases import SAMPLE_CASES, DENOISE_CASES
+from oracle.golden_cases import SAMPLE_CASES, DENOISE_CASES, REFLOW_CASES
 from prodiff_b200 import synth
 from tests import helpers
 
@@ -52,6 +52,29 @@ def test_denoise_matches_reference_fixture(name):
         out = oracle.wavenet_forward(state, x_T, steps, cond.transpose(1, 2), cfg.dilation_cycle_length)
     assert out.shape == (case["B"], 1, cfg.in_dims, case["T"])
     assert np.abs(out.numpy() - g["out"]).max() <= TOL
+
+
+@pytest.mark.parametrize("name", sorted(REFLOW_CASES))
+def test_reflow_matches_reference_fixture(name):
+    """RectifiedFlow / PitchRectifiedFlow .forward(infer=True) of the reference (reflow.py:32-107, :110-143): every
+    velocity in call order and the denormalised result.  The denorm multiplies errors by (max - min) / 2 <= 8."""
+    case, cfg, state, cond, x_start = helpers.regen_reflow_case(name)
+    g = helpers.load_golden("reflow", name)
+    assert str(g["digest"]) == synth.digest(state, cond, x_start), "regenerated inputs differ from the fixture's"
+    out, vs = helpers.oracle_reflow(case, cfg, state, cond, x_start)
+    stages = {"euler": 1, "rk2": 2, "rk4": 4, "rk5": 6}[case["algorithm"]]
+    assert len(vs) == case["infer_step"] * stages and g["v"].shape[0] == len(vs)
+    assert np.abs(torch.stack(vs).numpy() - g["v"]).max() <= TOL
+    assert out.shape == g["out"].shape and np.abs(out.numpy() - g["out"]).max() <= 8 * TOL
+    assert np.abs(g["v"]).max() > 0.1
+
+
+def test_reflow_unknown_algorithm_is_euler():
+    """reflow.py:90-95: ``dict.get(name, self.sample_euler)``."""
+    case, cfg, state, cond, x_start = helpers.regen_reflow_case("euler")
+    a, _ = helpers.oracle_reflow(case, cfg, state, cond, x_start)
+    b, _ = helpers.oracle_reflow(dict(case, algorithm="heun?"), cfg, state, cond, x_start)
+    assert torch.equal(a, b)
 
 
 def test_default_schedule_values():

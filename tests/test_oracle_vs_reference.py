@@ -46,6 +46,17 @@ def test_denoise_bit_exact(mg, name):
     assert np.array_equal(out.numpy(), ref["out"])
 
 
+@pytest.mark.parametrize("name", ["euler", "rk2", "rk4", "rk5", "pitch64"])
+def test_reflow_bit_exact(mg, name):
+    from oracle.golden_cases import REFLOW_CASES
+    from tests import helpers
+    case, cfg, state, cond, x_start = helpers.regen_reflow_case(name)
+    ref = mg.run_reference_reflow(REFLOW_CASES[name])
+    out, vs = helpers.oracle_reflow(case, cfg, state, cond, x_start)
+    assert np.array_equal(torch.stack(vs).numpy(), ref["v"])
+    assert np.array_equal(out.contiguous().numpy(), ref["out"])
+
+
 def test_reference_init_distribution_matches_synth(mg):
     """synth.make_state mirrors the reference's init *distributions* (not its torch RNG stream)."""
     from prodiff_b200 import synth
