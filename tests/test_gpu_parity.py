@@ -263,6 +263,38 @@ def test_reflow_inference_is_normalised_and_random_start():
     assert a.shape == (1, case["T"], 128) and float((a - b).abs().mean()) > 1e-3
 
 
+def test_large_batches_are_walked_in_row_blocks():
+    """Engine.sample splits batches above FRAMES_PER_CALL into row blocks; utterances are independent, so the blocked
+    result must equal the one-call result up to fp32 accumulation order (tiles pair up differently), including the
+    injected-noise and x0-trace plumbing of the blocks."""
+    from prodiff_b200 import synth
+    from prodiff_b200.engine import Engine
+    cfg = synth.DiffNetConfig(128, 256, 4, 256, 2)
+    state = synth.make_state(cfg, 41, "trained")
+    case = dict(timesteps=4, schedule_type="vpsde", max_beta=40)
+    B, T, K = 7, 150, 3
+    cond, x_T, noise = synth.make_inputs(cfg, B, T, K, 42)
+    gd = _build(cfg, state, case)
+    outs = []
+    old = Engine.FRAMES_PER_CALL
+    try:
+        for fpc in (old, 300):                      # 300 frames per call -> 2 rows per block -> 4 blocks
+            Engine.FRAMES_PER_CALL = fpc
+            tr = torch.empty(K, B, 1, 128, T, device="cuda")
+            with torch.no_grad():
+                mel = gd(cond.cuda(), infer_step=K, infer=True, x_T=x_T.cuda(), noise=noise.cuda(), x0_trace=tr).cpu()
+                cond2, x2 = cond.clone(), x_T.clone()
+                cond2[2], x2[2] = cond2[0], x2[0]                  # rows 0 and 2: same inputs, same position in their blocks
+                rnd = gd(cond2.cuda(), infer_step=K, infer=True, x_T=x2.cuda(), seed=9).cpu()
+            outs.append((mel, tr.cpu(), rnd))
+    finally:
+        Engine.FRAMES_PER_CALL = old
+    assert float((outs[0][0] - outs[1][0]).abs().max()) <= 2e-2 and float((outs[0][0] - outs[1][0]).abs().mean()) <= 1e-3
+    assert float((outs[0][1] - outs[1][1]).abs().max()) <= 2e-2
+    # in-kernel noise: every block has its own Philox stream, so identical rows in different blocks get different noise
+    assert float((outs[1][2][0] - outs[1][2][2]).abs().mean()) > 1e-2 and torch.isfinite(outs[1][2]).all()
+
+
 def test_full_size_roundtrip_properties():
     """BASELINE config-2 size (64 x 1000, K = 4), properties that need no oracle run:
     determinism per seed, batch-row independence (a row sampled alone equals the same row inside the batch, which is

@@ -130,3 +130,18 @@ def test_synth_is_deterministic_and_scaled():
     cond, xT, noise = synth.make_inputs(cfg, 2, 10, 3)
     assert cond.shape == (2, 10, 256) and xT.shape == (2, 1, 128, 10) and noise.shape == (3, 2, 1, 128, 10)
     assert 0 <= float(xT.min()) and float(xT.max()) < 1
+
+
+def test_row_chunks_cover_batch_in_balanced_blocks():
+    """Engine.sample walks large batches in row blocks (engine.row_chunks): contiguous, covering, balanced, bounded."""
+    from prodiff_b200.engine import row_chunks
+    assert row_chunks(64, 1000, 65536) == [(0, 64)]
+    assert row_chunks(96, 1000, 65536) == [(0, 96)]                # up to 1.5 x the block size stays one call
+    for B, T in ((256, 1000), (1024, 1000), (97, 1000), (8, 6000), (30, 6000), (5, 100000), (1, 10)):
+        ch = row_chunks(B, T, 65536)
+        assert ch[0][0] == 0 and ch[-1][1] == B and all(a[1] == b[0] for a, b in zip(ch, ch[1:]))
+        sizes = [e - s for s, e in ch]
+        assert min(sizes) >= 1 and max(sizes) - min(sizes) <= 1
+        if len(ch) > 1:
+            assert max(sizes) <= max(1, 65536 // T)
+    assert len(row_chunks(256, 1000, 65536)) == 4 and len(row_chunks(1024, 1000, 65536)) == 16
