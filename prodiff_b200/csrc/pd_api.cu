@@ -663,10 +663,16 @@ extern "C" int pd_cond_project(pd_plan* p, const float* cond, void* stream) {
     sh.trace = g_trace ? g_trace : nullptr;
     sh.idesc = make_idesc(c.dtype, 256, 256);
     return c.dtype == PD_FP16
-               ? launch_gemm_t<EPI_STORE, 256, __half, true, true>(p->tm_cond, m->tm_w_cond_h, p->tm_cond, p->tm_cond, sh, ep, m->sm_count, s, "gemm(cond_proj)", 0)
-               : launch_gemm_t<EPI_STORE, 256, __nv_bfloat16, true, true>(p->tm_cond, m->tm_w_cond_h, p->tm_cond, p->tm_cond, sh, ep, m->sm_count, s, "gemm(cond_proj)", 0);
+               ? launch_gemm_t<EPI_STORE_BLK, 256, __half, true, true>(p->tm_cond, m->tm_w_cond_h, p->tm_cond, p->tm_cond, sh, ep, m->sm_count, s, "gemm(cond_proj)", 0)
+               : launch_gemm_t<EPI_STORE_BLK, 256, __nv_bfloat16, true, true>(p->tm_cond, m->tm_w_cond_h, p->tm_cond, p->tm_cond, sh, ep, m->sm_count, s, "gemm(cond_proj)", 0);
   }
-  return launch_gemm<EPI_STORE, 256>(c.dtype, p->tm_cond, m->tm_w_cond, sh, ep, m->sm_count, s, "gemm(cond_proj)", 0);
+  static int blk = -1;   // PD_CP_DIRECT=1: the earlier epilogue with direct st.global (A/B only)
+  static int cp_pair = -1;   // PD_CP_PAIR=0: single-CTA tiles instead of cta_group::2 pairs
+  if (cp_pair < 0) { const char* e = getenv("PD_CP_PAIR"); cp_pair = (e && e[0] == '0') ? 0 : (pair_enabled() ? 1 : 0); }
+  if (blk < 0) { const char* e = getenv("PD_CP_DIRECT"); blk = (e && e[0] == '1') ? 0 : 1; }
+  if (!blk) return launch_gemm<EPI_STORE, 256>(c.dtype, p->tm_cond, m->tm_w_cond, sh, ep, m->sm_count, s, "gemm(cond_proj)", 0);
+  return launch_gemm<EPI_STORE_BLK, 256>(c.dtype, p->tm_cond, m->tm_w_cond, sh, ep, m->sm_count, s, "gemm(cond_proj)", 0, nullptr, nullptr,
+                                         cp_pair ? &m->tm_w_cond_h : nullptr);
 }
 
 // Step-embedding chain for `E` entries whose step values are already in the plan's "steps" buffer.

@@ -31,7 +31,7 @@ constexpr int kEpiWarps = 8;
 constexpr int kGemmThreads = 32 * (2 + kEpiWarps);
 constexpr uint32_t kTmemCols = 512;
 
-enum EpiKind { EPI_STORE = 0, EPI_GATE = 1, EPI_RES = 2, EPI_OUT = 3 };
+enum EpiKind { EPI_STORE = 0, EPI_GATE = 1, EPI_RES = 2, EPI_OUT = 3, EPI_STORE_BLK = 4 };
 enum OutType { OUT_T = 0, OUT_F16 = 1, OUT_F32 = 2 };
 
 struct GemmShape {
@@ -179,10 +179,12 @@ template <int EPI, int BN, bool kPair = false, bool kARes = false> struct GemmCf
   static constexpr uint32_t kABytes = kBlockM * kBlockK * 2;
   static constexpr uint32_t kBBytes = (kPair ? BN / 2 : BN) * kBlockK * 2;
   static constexpr uint32_t kStageBytes = (kARes ? 0 : kABytes) + kBBytes;
-  static constexpr uint32_t kExtraBytes = kARes ? 4 * kABytes : ((EPI == EPI_GATE) ? 2 * 16384 : (EPI == EPI_RES ? 4 * 16384 : 0));
+  static constexpr uint32_t kStagingBytes = (EPI == EPI_STORE_BLK) ? 65536 : 0;   // blocked-output tile staged for a bulk store
+  static constexpr uint32_t kExtraBytes = (kARes ? 4 * kABytes : ((EPI == EPI_GATE) ? 2 * 16384 : (EPI == EPI_RES ? 4 * 16384 : 0))) + kStagingBytes;
   // smem ring depth: as many stages as fit next to the epilogue's operand/output tile (cap 8)
   static constexpr int kStagesFit = (int)((227u * 1024u - 1024u - 256u - kExtraBytes) / kStageBytes);
-  static constexpr int kStages = (kPair || kARes) ? (kStagesFit > 8 ? 8 : kStagesFit) : ((EPI == EPI_RES) ? 3 : (BN == 256 ? 4 : 6));
+  static constexpr int kStagesWant = (kPair || kARes) ? 8 : ((EPI == EPI_RES) ? 3 : (BN == 256 ? 4 : 6));
+  static constexpr int kStages = kStagesFit < kStagesWant ? kStagesFit : kStagesWant;
   static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kExtraBytes + 1024 + 256;  // + alignment slack + barriers
 };
 
@@ -200,7 +202,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmX, const GemmShape sh,
             const EpiArgs ep) {
   using Cfg = GemmCfg<EPI, BN, kPair, kARes>;
-  static_assert(!kARes || EPI == EPI_STORE, "A-resident mode is for the plain store epilogue");
+  static_assert(!kARes || EPI == EPI_STORE || EPI == EPI_STORE_BLK, "A-resident mode is for the plain store epilogues");
+  static_assert(EPI != EPI_STORE_BLK || BN == 256, "blocked-output staging is 256 columns wide");
   constexpr int kStages = Cfg::kStages;
   static_assert(BN == 256 || BN == 128, "tile width");
   static_assert(EPI != EPI_GATE || BN == 256, "gate epilogue pairs 128 gate with 128 filter columns");
@@ -423,7 +426,57 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       tc_fence_after();
       if (sh.trace && blockIdx.x == 0 && warp == 2 && lane == 0) sh.trace[ti * 16 + 6] = clock64();
 
-      if constexpr (EPI == EPI_STORE) {
+      if constexpr (EPI == EPI_STORE_BLK) {
+        // Tile-blocked 16-bit output ([tile][16-byte chunk][128 rows][8], see blocked_off): the (m-tile, n-tile) block of this
+        // column half is ONE contiguous 32 KB range in global memory, so it is staged in the same order in shared memory
+        // (conflict-free 16-byte stores, one thread per row) and leaves as a single bulk copy.  Direct st.global from the
+        // epilogue threads made this kernel epilogue-bound (6.7 k cycles per tile against 2 k of MMA).
+        uint8_t* stg = extra + (kARes ? 4 * Cfg::kABytes : 0) + h * 32768;
+        const bool store_thread = (q == 0 && lane == 0);
+        if (store_thread) tma_store_wait_read<0>();   // the previous tile's copy has finished reading the staging half
+        named_bar_sync(1 + h, 4 * 32);
+        uint32_t rr[2][32];
+        tmem_ld_x32(trow + h * 128, rr[0]);
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci) {
+          const int c = h * 128 + ci * 32;
+          tmem_ld_wait();
+          if (ci < 3) tmem_ld_x32(trow + c + 32, rr[(ci + 1) & 1]);
+          const uint32_t (&r)[32] = rr[ci & 1];
+          const int g = n_tile * BN + c;
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 bv = __ldg(reinterpret_cast<const float4*>(ep.bias + g + j));
+            v[j + 0] = (__uint_as_float(r[j + 0]) + bv.x) * ep.scale;
+            v[j + 1] = (__uint_as_float(r[j + 1]) + bv.y) * ep.scale;
+            v[j + 2] = (__uint_as_float(r[j + 2]) + bv.z) * ep.scale;
+            v[j + 3] = (__uint_as_float(r[j + 3]) + bv.w) * ep.scale;
+          }
+          if (ep.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint4 o = ep.out_type == OUT_F16
+                                ? make_uint4(Cvt<__half>::pack(v[8 * j], v[8 * j + 1]), Cvt<__half>::pack(v[8 * j + 2], v[8 * j + 3]),
+                                             Cvt<__half>::pack(v[8 * j + 4], v[8 * j + 5]), Cvt<__half>::pack(v[8 * j + 6], v[8 * j + 7]))
+                                : make_uint4(Cvt<T>::pack(v[8 * j], v[8 * j + 1]), Cvt<T>::pack(v[8 * j + 2], v[8 * j + 3]),
+                                             Cvt<T>::pack(v[8 * j + 4], v[8 * j + 5]), Cvt<T>::pack(v[8 * j + 6], v[8 * j + 7]));
+            *reinterpret_cast<uint4*>(stg + (ci * 4 + j) * 2048 + row * 16) = o;
+          }
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(3 + h, 4 * 32);
+        if (store_thread && m_tile < num_m_tiles) {
+          const int g0 = n_tile * BN + h * 128;
+          const int slab = g0 / ep.ld, within0 = g0 - slab * ep.ld;
+          const long long tile_b = (long long)slab * num_m_tiles + m_tile;
+          bulk_store(static_cast<uint16_t*>(ep.out) + blocked_off(tile_b, ep.ld >> 3, within0 >> 3, 0), stg, 32768);
+          tma_store_commit();
+        }
+      } else if constexpr (EPI == EPI_STORE) {
         const long long nfr = (long long)sh.B * sh.T;
         // two register buffers: the TMEM load of chunk i+1 is in flight while chunk i is converted and stored
         uint32_t rr[2][32];
@@ -634,6 +687,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     if constexpr (EPI == EPI_GATE || EPI == EPI_RES) {
       if (issuer) tma_store_wait_all();  // all bulk stores complete before the CTA retires
+    }
+    if constexpr (EPI == EPI_STORE_BLK) {
+      if (q == 0 && lane == 0) tma_store_wait_all();
     }
   }
 

@@ -142,6 +142,10 @@ __device__ __forceinline__ uint4 ldg_stream_v4(const void* p, uint64_t policy) {
                : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(policy));
   return v;
 }
+// Plain (non-tensor) bulk copy shared -> global, tracked by the same bulk async-groups as the tensor stores.
+__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 // Named barrier among a subset of the CTA's warps (id 1..15; id 0 is __syncthreads).
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
