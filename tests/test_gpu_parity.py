@@ -295,6 +295,51 @@ def test_large_batches_are_walked_in_row_blocks():
     assert float((outs[1][2][0] - outs[1][2][2]).abs().mean()) > 1e-2 and torch.isfinite(outs[1][2]).all()
 
 
+@pytest.mark.parametrize("T", [130, 333])
+def test_no_writes_outside_the_caller_tensors(T):
+    """The kernels write the caller's state / trace tensors with plain stores guarded by a frame-validity test (the TMA
+    stores clip by construction).  Each tensor is carved out of a larger sentinel-filled buffer; after a ProDiff sampling
+    call and a rectified-flow call on a ragged length (T not a multiple of the 128-frame tile, nor of 4) every sentinel
+    byte must be intact.  (compute-sanitizer is not available on the GPU pool.)"""
+    import prodiff_b200 as pb
+    from prodiff_b200 import synth
+    cfg = synth.DiffNetConfig(128, 256, 3, 256, 2)
+    state = synth.make_state(cfg, 51, "trained")
+    case = dict(timesteps=4, schedule_type="vpsde", max_beta=40)
+    B, K, pad = 3, 3, 4096
+    cond, x_T, noise = synth.make_inputs(cfg, B, T, K, 52)
+
+    def carve(shape):
+        n = int(np.prod(shape))
+        big = torch.full((n + 2 * pad,), -12345.0, device="cuda")
+        return big, big[pad:pad + n].view(shape)
+
+    gd = _build(cfg, state, case)
+    eng = gd.denoise_fn.engine()
+    big_x, x = carve((B, 1, 128, T))
+    big_t, tr = carve((K, B, 1, 128, T))
+    x.copy_(x_T)
+    tabs = gd._tables_on_host()
+    with torch.no_grad():
+        eng.sample(cond.cuda().contiguous(), x, list(range(K - 1, -1, -1)), *tabs, noise=noise.cuda(), x0_trace=tr)
+    torch.cuda.synchronize()
+    for big in (big_x, big_t):
+        assert bool((big[:pad] == -12345.0).all()) and bool((big[-pad:] == -12345.0).all())
+    assert torch.isfinite(x).all() and torch.isfinite(tr).all() and not bool((tr == -12345.0).any())
+    # rectified flow: state, velocity trace
+    big_x2, x2 = carve((B, 1, 128, T))
+    big_v, vt = carve((2 * 4, B, 1, 128, T))
+    x2.copy_(noise[0])
+    smin = torch.full((1,), -12.0, device="cuda")
+    smax = torch.zeros(1, device="cuda")
+    with torch.no_grad():
+        eng.reflow(cond.cuda().contiguous(), x2, "rk4", 2, 1000.0, smin, smax, vt)
+    torch.cuda.synchronize()
+    for big in (big_x2, big_v):
+        assert bool((big[:pad] == -12345.0).all()) and bool((big[-pad:] == -12345.0).all())
+    assert torch.isfinite(x2).all() and not bool((vt == -12345.0).any())
+
+
 def test_full_size_roundtrip_properties():
     """BASELINE config-2 size (64 x 1000, K = 4), properties that need no oracle run:
     determinism per seed, batch-row independence (a row sampled alone equals the same row inside the batch, which is
