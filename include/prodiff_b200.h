@@ -99,6 +99,15 @@ int pd_sample(pd_plan* p, const float* cond, float* x, const float* noise, uint6
               const int32_t* t_list, const float* coef1, const float* coef2, const float* logvar, int n_table,
               float* x0_trace, void* stream);
 
+/* Ragged batches (no counterpart in the reference, which pads and processes every row at the full T, SURVEY appendix A.7;
+ * needed to batch its one-utterance-at-a-time offline sampling loop, component/binarizer/svs.py:193-223, without changing
+ * results): lengths[b] <= T is the number of valid frames of utterance b (host array of B entries, copied by value).
+ * Subsequent pd_denoise / pd_sample / pd_reflow_sample calls on this plan keep every layer's activations at zero past
+ * lengths[b] and choose the step-bias edge slots from lengths[b], so frames t < lengths[b] get exactly what a run of that
+ * utterance alone at T = lengths[b] computes (zero padding of x + d at its own end, wavenet.py:63-65); outputs at
+ * t >= lengths[b] are unspecified.  NULL restores full-length rows.  Needs the fused layer kernel (C = 256). */
+int pd_plan_set_lengths(pd_plan* p, const int32_t* lengths, void* stream);
+
 /* RectifiedFlow.forward(infer=True) (/root/reference/modules/diffusion/reflow.py:32-46, 86-107): the rectified-flow ODE
  * x' = v(x, time_scale * t) integrated from t = 0 to 1 in n_steps steps of dt = 1 / n_steps with sample_euler (:48-52),
  * sample_rk2 (:54-60), sample_rk4 (:62-70) or sample_rk5 (:72-84), the velocity being the same DiffNet denoiser
@@ -127,7 +136,7 @@ int pd_profile_begin(void);
 int pd_profile_end(float* ms_by_kind, int* count_by_kind, int n_kinds);
 
 /* Introspection for tests: byte offset/size of a named scratch buffer inside the plan's workspace.
- * Names: "cond16","cp","xin","xa","xb","ybuf","s1","s2","steps","emb0","hid","emb","dvec","sb","flags". Returns 0 if found. */
+ * Names: "cond16","cp","xin","xa","xb","ybuf","s1","s2","steps","emb0","hid","emb","dvec","sb","flags","lens". Returns 0 if found. */
 int pd_plan_buffer(const pd_plan* p, const char* name, size_t* offset, size_t* bytes);
 
 /* Test hook: one implicit-GEMM launch of the production kernel with a plain fp32 store epilogue.

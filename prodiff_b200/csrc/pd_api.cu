@@ -334,6 +334,7 @@ struct pd_plan {
   CUtensorMap tm_xa_st, tm_xb_st, tm_y_st;    // box (64, 32): per-warp TMA stores
   bool fused_ok;
   bool tail_ok;
+  bool ragged;   // pd_plan_set_lengths installed per-utterance lengths
   size_t off(const char* n) const {
     for (const Buf& b : bufs)
       if (!strcmp(b.name, n)) return b.off;
@@ -365,6 +366,7 @@ static size_t plan_layout(const pd_config& c, int B, int T, int E, std::vector<B
   take("dvec", (size_t)E * L * C * 4);
   take("sb", (size_t)E * L * 4 * 2 * C * 4);
   take("flags", L * mtiles * 4);  // multi-layer kernel: per (layer, tile) completion counters
+  take("lens", (size_t)B * 4);      // optional per-utterance valid lengths (pd_plan_set_lengths)
   return o;
 }
 
@@ -407,7 +409,8 @@ extern "C" int pd_plan_create(const pd_model* m, int B, int T, int max_entries, 
   }
   // fused layer kernel (C = 256, dilations <= 16): haloed loads and 32-row store boxes
   p->fused_ok = (C == kLayerC) && (1 << (c.dilation_cycle_length - 1)) <= kLayerMaxDil;
-  p->tail_ok = p->fused_ok && c.in_dims == 128;   // fused sampler tail (pd_tail.cuh) is specialised for C = 256, M = 128
+  p->tail_ok = p->fused_ok && c.in_dims == 128;
+  p->ragged = false;   // fused sampler tail (pd_tail.cuh) is specialised for C = 256, M = 128
   if (p->fused_ok) {
     for (int i = 0; i < 5 && i < c.dilation_cycle_length; ++i)
       if (make_act_map(&p->tm_xa_halo[i], dt, p->ptr<void>("xa"), C, T, B, 1, kBlockM + 2 * (1 << i)) ||
@@ -637,6 +640,33 @@ static int launch_tail_t(const CUtensorMap& s1, const CUtensorMap& wsp, const CU
 }
 
 // ------------------------------------------------------------------ hot-path sequences
+struct LenVals {
+  int v[64];
+};
+__global__ void k_set_lens(int* __restrict__ dst, LenVals vals, int n) {
+  if (threadIdx.x < n) dst[threadIdx.x] = vals.v[threadIdx.x];
+}
+extern "C" int pd_plan_set_lengths(pd_plan* p, const int32_t* lengths, void* stream) {
+  if (!p) return fail("null argument");
+  if (lengths == nullptr) {
+    p->ragged = false;
+    return 0;
+  }
+  if (!p->fused_ok) return fail("per-utterance lengths need the fused layer kernel (C = 256, dilation <= 16)");
+  for (int b = 0; b < p->B; ++b)
+    if (lengths[b] < 0 || lengths[b] > p->T) return fail("lengths[%d]=%d outside [0, T=%d]", b, lengths[b], p->T);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  for (int b0 = 0; b0 < p->B; b0 += 64) {   // by-value kernel arguments: no host memory is read asynchronously
+    LenVals lv;
+    const int n = p->B - b0 < 64 ? p->B - b0 : 64;
+    for (int j = 0; j < n; ++j) lv.v[j] = lengths[b0 + j];
+    k_set_lens<<<1, 64, 0, s>>>(p->ptr<int>("lens") + b0, lv, n);
+    PD_LAUNCH_CHECK("k_set_lens");
+  }
+  p->ragged = true;
+  return 0;
+}
+
 extern "C" int pd_cond_project(pd_plan* p, const float* cond, void* stream) {
   if (!p || !cond) return fail("null argument");
   const pd_model* m = p->m;
@@ -729,10 +759,12 @@ static int run_denoiser(pd_plan* p, int entry_base, int entry_per_b, const OutSt
     ep.bias = (const float*)(pk + lay.b_in);
     ep.ld = C;
     ep.relu = 1;
+    ep.lens = p->ragged ? p->ptr<int>("lens") : nullptr;
     if (launch_gemm<EPI_STORE, 256>(dt, p->tm_xin, m->tm_w_in, sh, ep, sms, s, "gemm(input_proj)", 1)) return 1;
   }
   bool cur_is_a = true;
   const bool fused = p->fused_ok && fused_enabled();
+  if (p->ragged && !fused) return fail("per-utterance lengths need the fused layer kernel (C = 256, dilation <= 16, PD_FUSED != 0)");
   for (int l = 0; l < L; ++l) {
     const int dil = 1 << (l % c.dilation_cycle_length);
     if (fused) {  // ResidualBlocks as the fused 2-CTA kernel: all layers in one persistent launch, or one launch per layer
@@ -774,6 +806,7 @@ static int run_denoiser(pd_plan* p, int entry_base, int entry_per_b, const OutSt
       lp.sb_entry_per_b = entry_per_b;
       lp.b_res = (const float*)(pk + lay.b_res);
       lp.scale = 0.70710678118654752440f;
+      lp.lens = p->ragged ? p->ptr<int>("lens") : nullptr;
       lp.trace = g_trace ? g_trace + 8 * 1024 : nullptr;
       static int hyb = -1;
       if (hyb < 0) { const char* e = getenv("PD_HYBRID"); hyb = (e && e[0] == '1') ? 1 : 0; }
@@ -868,6 +901,7 @@ static int run_denoiser(pd_plan* p, int entry_base, int entry_per_b, const OutSt
     tp.sigma = os.sigma;
     tp.seed = os.seed;
     tp.step_id = os.step_id;
+    tp.lens = p->ragged ? p->ptr<int>("lens") : nullptr;
     tp.trace = g_trace ? g_trace + 10 * 1024 : nullptr;
     return dt == PD_FP16 ? launch_tail_t<__half>(p->tm_s1, m->tm_w_sp, m->tm_w_out, m->tm_w_in, p->tm_xa_st, tp, sms, s)
                          : launch_tail_t<__nv_bfloat16>(p->tm_s1, m->tm_w_sp, m->tm_w_out, m->tm_w_in, p->tm_xa_st, tp, sms, s);

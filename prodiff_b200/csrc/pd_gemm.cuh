@@ -59,6 +59,7 @@ struct EpiArgs {
   int out_blocked;  // STORE: write the tile-blocked layout (see blocked_off) instead of row-major
   int out_slab;     // GATE: 4th TMA coordinate (layer) of the gated-activation store
   float scale;  // STORE: multiplier after bias; RES: 1/sqrt(2)
+  const int* lens;  // optional per-utterance valid lengths (ragged batch): STORE writes zeros for frames >= lens[b]
   int relu;
   int out_type;
   // EPI_OUT
@@ -502,6 +503,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             if (ep.relu) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+            if (ep.lens != nullptr && t >= __ldg(ep.lens + b)) {   // ragged batch: frames past this utterance's end stay zero
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = 0.f;
             }
             if (ep.out_type == OUT_F32) {
               float4* dst = reinterpret_cast<float4*>(static_cast<float*>(ep.out) + ((long long)slab * nfr + n) * ep.ld + within);

@@ -74,6 +74,7 @@ struct LayerParams {
   int sb_entry_base, sb_entry_per_b;
   const float* b_res;     // residual-half bias of output_projection, [L][C]
   float scale;            // 1/sqrt(2)
+  const int* lens;        // optional per-utterance valid lengths (ragged batch, see pd_plan_set_lengths); nullptr = all T
   long long* trace;
 };
 
@@ -381,7 +382,10 @@ layer_kernel(const __grid_constant__ LayerMaps mp,
       const bool valid = (m_tile < num_m_tiles) && (t < lp.T);
       const int entry = lp.sb_entry_base + (b < lp.B ? b : 0) * lp.sb_entry_per_b;
       // step-bias slot of this frame (all taps / no tap 0 / no tap 2 / centre tap only), see k_step_taps
-      const int slot = (t < dil ? 1 : 0) + (t + dil >= lp.T ? 2 : 0);
+      // ragged batch: the utterance ends at len_b <= T; frames past it are kept at zero in every layer (epilogue 2), so the
+      // frames before it see exactly the zero padding a single-utterance run would
+      const int len_b = (lp.lens != nullptr && b < lp.B) ? __ldg(lp.lens + b) : lp.T;
+      const int slot = (t < dil ? 1 : 0) + (t + dil >= len_b ? 2 : 0);
       const float* sb_row = lp.sb + (long long)entry * lp.sb_entry_stride + (long long)l * (4 * 2 * kLayerC) + slot * (2 * kLayerC);
       const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
 
@@ -526,6 +530,7 @@ layer_kernel(const __grid_constant__ LayerMaps mp,
         tc_fence_after();
         if (tr && warp == 2 && lane == 0) lp.trace[(ti & 31) * 16 + 10] = clock64();
         const uint32_t trow = lane_base + colA;
+        const float sc2 = t < len_b ? lp.scale : 0.f;
         uint32_t rr[2][32];   // the TMEM load of group i+1 is in flight while group i is converted and stored
         tmem_ld_x32(trow + h * 64, rr[0]);
 #pragma unroll
@@ -545,8 +550,8 @@ layer_kernel(const __grid_constant__ LayerMaps mp,
               for (int u = 0; u < 4; u += 2) {
                 const float4 bv = __ldg(reinterpret_cast<const float4*>(b_res + c + 8 * u4 + 2 * u));
                 const int col = 8 * u4 + 2 * u;
-                ow[u] = Cvt<T>::pack((__uint_as_float(r[col]) + bv.x) * lp.scale, (__uint_as_float(r[col + 1]) + bv.y) * lp.scale);
-                ow[u + 1] = Cvt<T>::pack((__uint_as_float(r[col + 2]) + bv.z) * lp.scale, (__uint_as_float(r[col + 3]) + bv.w) * lp.scale);
+                ow[u] = Cvt<T>::pack((__uint_as_float(r[col]) + bv.x) * sc2, (__uint_as_float(r[col + 1]) + bv.y) * sc2);
+                ow[u + 1] = Cvt<T>::pack((__uint_as_float(r[col + 2]) + bv.z) * sc2, (__uint_as_float(r[col + 3]) + bv.w) * sc2);
               }
               *sw128_chunk(ytile, row, ci * 4 + u4) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
             }

@@ -41,6 +41,7 @@ struct TailParams {
   float c1, c2, sigma;
   unsigned long long seed;
   unsigned int step_id;
+  const int* lens;           // optional per-utterance valid lengths: xa rows past them are written as zeros
   long long* trace;
 };
 
@@ -297,6 +298,7 @@ tail_kernel(const __grid_constant__ CUtensorMap tmS1, const __grid_constant__ CU
         mbar_wait(&acc_bar[2], par, 8);
         tc_fence_after();
         if (tr && warp == 2 && lane == 0) tp.trace[trow_i(ti) * 16 + 2] = clock64();
+        const bool live = tp.lens == nullptr || t < __ldg(tp.lens + b);   // ragged batch: layer-0 input stays zero past the end
         uint32_t rr[2][32];
         tmem_ld_x32(lane_base + 256 + h * 128, rr[0]);
 #pragma unroll
@@ -317,7 +319,7 @@ tail_kernel(const __grid_constant__ CUtensorMap tmS1, const __grid_constant__ CU
               ow[u] = Cvt<T>::pack(fmaxf(__uint_as_float(r[col]) + bv.x, 0.f), fmaxf(__uint_as_float(r[col + 1]) + bv.y, 0.f));
               ow[u + 1] = Cvt<T>::pack(fmaxf(__uint_as_float(r[col + 2]) + bv.z, 0.f), fmaxf(__uint_as_float(r[col + 3]) + bv.w, 0.f));
             }
-            *sw128_chunk(st, row, ch0 + j) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+            *sw128_chunk(st, row, ch0 + j) = live ? make_uint4(ow[0], ow[1], ow[2], ow[3]) : make_uint4(0u, 0u, 0u, 0u);
           }
         }
         tc_fence_before();

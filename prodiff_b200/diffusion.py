@@ -3,7 +3,8 @@
 Constructor, persistent buffers (names, order, values) and method signatures are the reference's.  The inference
 branch of ``forward`` hands the whole K-step reverse loop to the C-ABI library (``pd_sample``): condition projection
 once, K denoiser evaluations and K fused posterior updates, all sm_100a kernels.  Extra keyword-only arguments allow
-injecting ``x_T`` / per-step noise (the parity tests need identical randomness) and tracing per-step x0 predictions.
+injecting ``x_T`` / per-step noise (the parity tests need identical randomness), tracing per-step x0 predictions, and
+``lengths`` (per-utterance frame counts of a padded batch: each row is then computed exactly as that utterance alone).
 """
 from __future__ import annotations
 
@@ -95,7 +96,7 @@ class GaussianDiffusion(nn.Module):
         return self._host_tables[1:]
 
     def forward(self, cond, src_spec=None, gt_spec=None, infer_step=4, infer=False, *, x_T=None, noise=None,
-                seed: Optional[int] = None, x0_trace: Optional[torch.Tensor] = None):
+                seed: Optional[int] = None, x0_trace: Optional[torch.Tensor] = None, lengths=None):
         b, device = cond.shape[0], cond.device
         if not infer:
             # training branch: one denoiser call at a random step; the denoiser itself refuses autograd (see WaveNet)
@@ -124,7 +125,8 @@ class GaussianDiffusion(nn.Module):
         c1, c2, lv = self._tables_on_host()
         cond_bth = cond.detach().to(dtype=torch.float32).contiguous()
         t_list = list(range(infer_step - 1, -1, -1))
-        self.denoise_fn.engine().sample(cond_bth, x, t_list, c1, c2, lv, noise=noise, seed=seed, x0_trace=x0_trace)
+        self.denoise_fn.engine().sample(cond_bth, x, t_list, c1, c2, lv, noise=noise, seed=seed, x0_trace=x0_trace,
+                                        lengths=lengths)
         x = x[:, 0].transpose(1, 2)
         return self.denorm_spec(x)
 

@@ -136,21 +136,34 @@ class Engine:
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream
 
+    def _set_lengths(self, p: Plan, lengths, s: int, e: int) -> None:
+        """Install (or clear) the per-utterance valid lengths of rows [s, e) on a plan (pd_plan_set_lengths)."""
+        if lengths is None:
+            _lib.check(self.lib.pd_plan_set_lengths(p.handle, None, self._stream()), "pd_plan_set_lengths")
+            return
+        arr = (C.c_int32 * (e - s))(*[int(v) for v in lengths[s:e]])
+        _lib.check(self.lib.pd_plan_set_lengths(p.handle, arr, self._stream()), "pd_plan_set_lengths")
+
     def denoise(self, spec: torch.Tensor, step: torch.Tensor, cond_bth: torch.Tensor) -> torch.Tensor:
         """spec [B,1,M,T] fp32, step [B] fp32, cond_bth [B,T,H] fp32 contiguous -> [B,1,M,T] fp32."""
         B, _, M, T = spec.shape
         p = self.plan(B, T, B)
         out = torch.empty_like(spec)
         with torch.cuda.device(self.device):
+            self._set_lengths(p, None, 0, B)
             _lib.check(self.lib.pd_cond_project(p.handle, cond_bth.data_ptr(), self._stream()), "pd_cond_project")
             _lib.check(self.lib.pd_denoise(p.handle, spec.data_ptr(), step.data_ptr(), out.data_ptr(), self._stream()),
                        "pd_denoise")
         return out
 
     def sample(self, cond_bth: torch.Tensor, x: torch.Tensor, t_list: Sequence[int], coef1, coef2, logvar,
-               noise: Optional[torch.Tensor] = None, seed: int = 0, x0_trace: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """The whole reverse loop, in place on x [B,1,M,T] (in: x_T, out: x_0)."""
+               noise: Optional[torch.Tensor] = None, seed: int = 0, x0_trace: Optional[torch.Tensor] = None,
+               lengths: Optional[Sequence[int]] = None) -> torch.Tensor:
+        """The whole reverse loop, in place on x [B,1,M,T] (in: x_T, out: x_0).  ``lengths`` (B ints <= T): ragged batch,
+        row b is computed exactly as an utterance of lengths[b] frames; frames past it are unspecified."""
         B, _, M, T = x.shape
+        if lengths is not None and len(lengths) != B:
+            raise ValueError(f"lengths must have {B} entries")
         K = len(t_list)
         tl = (C.c_int32 * K)(*[int(t) for t in t_list])
         n = len(coef1)
@@ -164,6 +177,7 @@ class Engine:
                 nz = None if noise is None else (noise if whole else noise[:, s:e].contiguous())
                 tr = None if x0_trace is None else (x0_trace if whole else torch.empty_like(x0_trace[:, s:e]))
                 p = self.plan(e - s, T, K)
+                self._set_lengths(p, lengths, s, e)
                 # every block draws from its own Philox stream (the kernel counts frames from 0 inside a call)
                 sd = (seed + ci * 0x9E3779B97F4A7C15) & (2 ** 64 - 1)
                 _lib.check(self.lib.pd_sample(p.handle, cond_bth[s:e].data_ptr(), x[s:e].data_ptr(),
@@ -180,7 +194,7 @@ class Engine:
 
     def reflow(self, cond_bth: torch.Tensor, x: torch.Tensor, algorithm: str, n_steps: int, time_scale: float,
                spec_min: Optional[torch.Tensor], spec_max: Optional[torch.Tensor],
-               v_trace: Optional[torch.Tensor] = None) -> torch.Tensor:
+               v_trace: Optional[torch.Tensor] = None, lengths: Optional[Sequence[int]] = None) -> torch.Tensor:
         """The rectified-flow ODE loop (pd_reflow_sample), in place on x [B,1,M,T] (in: N(0,1) start, out: denormalised)."""
         B, _, M, T = x.shape
         algo, stages = self.REFLOW_ALGORITHMS.get(algorithm, self.REFLOW_ALGORITHMS["euler"])   # reflow.py:95 falls back to euler
@@ -189,6 +203,7 @@ class Engine:
             for s, e in chunks:
                 whole = len(chunks) == 1
                 p = self.plan(e - s, T, 6)
+                self._set_lengths(p, lengths, s, e)
                 tr = None if v_trace is None else (v_trace if whole else torch.empty_like(v_trace[:, s:e]))
                 scratch = None if tr is not None else torch.empty(stages, e - s, 1, M, T, dtype=torch.float32, device=self.device)
                 _lib.check(self.lib.pd_reflow_sample(

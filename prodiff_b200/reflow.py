@@ -48,7 +48,7 @@ class RectifiedFlow(nn.Module):
         return v_pred, x_end - x_start
 
     def forward(self, cond, gt_spec=None, infer_step=20, infer=True, *, x_start: Optional[torch.Tensor] = None,
-                v_trace: Optional[torch.Tensor] = None):
+                v_trace: Optional[torch.Tensor] = None, lengths=None):
         b, device = cond.shape[0], cond.device
         if not infer:
             spec = self.norm_spec(gt_spec).transpose(-2, -1)
@@ -58,7 +58,7 @@ class RectifiedFlow(nn.Module):
             v_pred, v_gt = self.p_losses(spec, t, cond=cond.transpose(1, 2))
             return v_pred, v_gt, t
         # denorm_spec (reflow.py:106-107) runs as the last kernel of the sequence, on the state, before the view is taken
-        x = self._run(cond.transpose(1, 2), b, infer_step, device, x_start, v_trace, denorm=True)
+        x = self._run(cond.transpose(1, 2), b, infer_step, device, x_start, v_trace, denorm=True, lengths=lengths)
         return self._finish(x)
 
     @torch.no_grad()
@@ -67,7 +67,7 @@ class RectifiedFlow(nn.Module):
         return self._run(cond, b, infer_step, device, x_start, v_trace, denorm=False)
 
     @torch.no_grad()
-    def _run(self, cond, b, infer_step, device, x_start, v_trace, denorm):
+    def _run(self, cond, b, infer_step, device, x_start, v_trace, denorm, lengths=None):
         device = cond.device if device is None else device
         T = cond.shape[2]
         if x_start is None:
@@ -86,7 +86,8 @@ class RectifiedFlow(nn.Module):
         smax = self.spec_max.detach().to(device=device, dtype=torch.float32).reshape(-1).contiguous()
         if not denorm:
             smin = smax = None
-        self.velocity_fn.engine().reflow(cond_bth, x, self.sampling_algorithm, n, float(self.time_scale), smin, smax, v_trace)
+        self.velocity_fn.engine().reflow(cond_bth, x, self.sampling_algorithm, n, float(self.time_scale), smin, smax, v_trace,
+                                         lengths=lengths)
         return x.transpose(2, 3).squeeze(1)
 
     def _finish(self, x):

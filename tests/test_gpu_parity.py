@@ -340,6 +340,42 @@ def test_no_writes_outside_the_caller_tensors(T):
     assert torch.isfinite(x2).all() and not bool((vt == -12345.0).any())
 
 
+def test_ragged_batch_rows_equal_single_utterance_runs():
+    """pd_plan_set_lengths: a padded batch with per-utterance lengths must give every row, up to its length, what that
+    utterance gets when sampled alone at T = its length (the reference's offline loop, binarizer/svs.py:193-223, runs them
+    one at a time).  Checked against single runs of the CUDA path (fp32 accumulation order is the only difference) and
+    against the oracle per utterance, for the ProDiff loop and a rectified-flow integrator; dilations up to 4."""
+    import prodiff_b200 as pb
+    from prodiff_b200 import synth
+    cfg = synth.DiffNetConfig(128, 256, 6, 256, 3)
+    state = synth.make_state(cfg, 61, "trained")
+    case = dict(timesteps=4, schedule_type="vpsde", max_beta=40, infer_step=3)
+    lens = [300, 129, 37, 256, 1]
+    B, T, K = len(lens), 300, 3
+    cond, x_T, noise = synth.make_inputs(cfg, B, T, K, 62)
+    gd = _build(cfg, state, case)
+    rf = pb.RectifiedFlow(128, gd.denoise_fn, time_scale=1000, sampling_algorithm="rk2", spec_min=[-12.0], spec_max=[0.0]).cuda().eval()
+    with torch.no_grad():
+        mel = gd(cond.cuda(), infer_step=K, infer=True, x_T=x_T.cuda(), noise=noise.cuda(), lengths=lens).cpu()
+        flow = rf(cond.cuda(), infer_step=2, infer=True, x_start=noise[0].cuda(), lengths=lens).cpu()
+        padded = gd(cond.cuda(), infer_step=K, infer=True, x_T=x_T.cuda(), noise=noise.cuda()).cpu()
+    differs = 0.0
+    for b, n in enumerate(lens):
+        c1, x1, n1 = cond[b:b + 1, :n], x_T[b:b + 1, :, :, :n].contiguous(), noise[:, b:b + 1, :, :, :n].contiguous()
+        with torch.no_grad():
+            solo = gd(c1.cuda(), infer_step=K, infer=True, x_T=x1.cuda(), noise=n1.cuda()).cpu()
+            solo_flow = rf(c1.cuda(), infer_step=2, infer=True, x_start=n1[0].cuda()).cpu()
+        d = (mel[b:b + 1, :n] - solo).abs()
+        assert float(d.max()) <= 2e-2 and float(d.mean()) <= 1e-3, (b, n, float(d.max()), float(d.mean()))
+        d = (flow[b:b + 1, :n] - solo_flow).abs()
+        assert float(d.max()) <= 6 * 2e-2 and float(d.mean()) <= 6 * 1e-3, (b, n, float(d.max()), float(d.mean()))
+        ref, _ = helpers.oracle_sample(case, cfg, state, c1, x1, n1)
+        assert float((mel[b:b + 1, :n] - ref).abs().mean()) <= MEL_L1_TOL
+        if n < T:
+            differs = max(differs, float((padded[b, :n] - mel[b, :n]).abs().max()))
+    assert differs > 1e-3     # without lengths the padded frames do leak into the last frames of short rows
+
+
 def test_full_size_roundtrip_properties():
     """BASELINE config-2 size (64 x 1000, K = 4), properties that need no oracle run:
     determinism per seed, batch-row independence (a row sampled alone equals the same row inside the batch, which is
