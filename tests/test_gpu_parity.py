@@ -376,6 +376,36 @@ def test_ragged_batch_rows_equal_single_utterance_runs():
     assert differs > 1e-3     # without lengths the padded frames do leak into the last frames of short rows
 
 
+def test_offline_sample_items_matches_single_utterance_loop():
+    """offline.sample_items: the batched form of the reference's per-item teacher sampling loop
+    (binarizer/svs.py:214-222) returns, per item, the condition, the x_T it drew and an x_0 equal to sampling that item
+    alone from that x_T (use_x_T=True; rectified flow, euler, so the run is deterministic given x_T)."""
+    import prodiff_b200 as pb
+    from prodiff_b200 import offline, synth
+    cfg = synth.DiffNetConfig(128, 256, 4, 256, 2)
+    state = synth.make_state(cfg, 71, "trained")
+    wn = _build(cfg, state)
+    rf = pb.RectifiedFlow(128, wn, time_scale=1000, sampling_algorithm="euler", spec_min=[-12.0], spec_max=[0.0]).cuda().eval()
+    g = torch.Generator().manual_seed(5)
+    lens = [200, 64, 131, 199, 17, 260]
+    conds = [torch.randn(n, 256, generator=g) for n in lens]
+    gen = torch.Generator(device="cuda").manual_seed(6)
+    res = offline.sample_items(rf, conds, infer_step=3, use_x_T=True, generator=gen, frames_per_batch=768)
+    assert sorted(res) == list(range(len(lens)))
+    for i, n in enumerate(lens):
+        it = res[i]
+        assert it["condition"].shape == (n, 256) and it["x_T"].shape == (n, 128) and it["x_0"].shape == (n, 128)
+        assert np.array_equal(it["condition"], conds[i].numpy())
+        x_start = torch.from_numpy(it["x_T"]).t()[None, None].contiguous().cuda()
+        with torch.no_grad():
+            solo = rf(conds[i][None].cuda(), infer_step=3, infer=True, x_start=x_start).cpu().numpy()[0]
+        d = np.abs(solo - it["x_0"])
+        assert d.max() <= 6 * 2e-2 and d.mean() <= 6 * 1e-3, (i, n, d.max(), d.mean())
+    # as written in the reference (use_x_T=False) the sampler ignores the x_T it is handed and draws its own start
+    res2 = offline.sample_items(rf, conds[:2], infer_step=2, use_x_T=False, generator=gen)
+    assert res2[0]["x_0"].shape == (lens[0], 128) and np.isfinite(res2[0]["x_0"]).all()
+
+
 def test_full_size_roundtrip_properties():
     """BASELINE config-2 size (64 x 1000, K = 4), properties that need no oracle run:
     determinism per seed, batch-row independence (a row sampled alone equals the same row inside the batch, which is

@@ -145,3 +145,66 @@ def test_row_chunks_cover_batch_in_balanced_blocks():
         if len(ch) > 1:
             assert max(sizes) <= max(1, 65536 // T)
     assert len(row_chunks(256, 1000, 65536)) == 4 and len(row_chunks(1024, 1000, 65536)) == 16
+
+
+def test_indexed_dataset_roundtrip_and_reference_bytes(tmp_path):
+    """offline.IndexedDatasetBuilder writes the reference's on-disk format (utils/indexed_datasets.py:51-76): round trip
+    through our reader, across a segment boundary; when the reference is mounted, the files are byte-identical to the ones
+    its own builder writes and its own reader returns the same items."""
+    import os
+    import sys
+    import numpy as np
+    from prodiff_b200 import offline
+    rng = np.random.default_rng(0)
+    items = [{"item_name": f"utt{i}", "x_0": rng.normal(size=(5 + i, 4)).astype(np.float32), "spk_id": i % 3} for i in range(7)]
+    a = tmp_path / "ours"
+    a.mkdir()
+    b = offline.IndexedDatasetBuilder(str(a), "train", segment_size=3)
+    for it in items:
+        b.add_item(it)
+    b.finalize()
+    assert sorted(os.listdir(a)) == ["train_0.data", "train_0.idx", "train_1.data", "train_1.idx", "train_2.data", "train_2.idx"]
+    ds = offline.IndexedDataset(str(a), "train", segment_size=3)
+    assert len(ds) == 7
+    for i, it in enumerate(items):
+        got = ds[i]
+        assert got["item_name"] == it["item_name"] and np.array_equal(got["x_0"], it["x_0"])
+    with pytest.raises(IndexError):
+        ds[7]
+    ds.close()
+    ref_root = "/root/reference"
+    if os.path.isdir(os.path.join(ref_root, "utils")):
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("ref_indexed_datasets", os.path.join(ref_root, "utils", "indexed_datasets.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        r = tmp_path / "ref"
+        r.mkdir()
+        rb = mod.IndexedDatasetBuilder(str(r), "train", segment_size=3)
+        for it in items:
+            rb.add_item(it)
+        rb.finalize()
+        for f in sorted(os.listdir(r)):
+            assert (r / f).read_bytes() == (a / f).read_bytes(), f
+        rds = mod.IndexedDataset(str(a), "train", segment_size=3)      # the reference reader on OUR files
+        assert np.array_equal(rds[4]["x_0"], items[4]["x_0"])
+
+
+def test_bucket_by_length_properties():
+    from prodiff_b200 import offline
+    rng = np.random.default_rng(1)
+    lengths = [int(v) for v in rng.integers(20, 3000, size=200)]
+    batches = offline.bucket_by_length(lengths, frames_per_batch=65536, max_rows=64)
+    flat = [i for b in batches for i in b]
+    assert sorted(flat) == list(range(200))
+    for b in batches:
+        ls = [lengths[i] for i in b]
+        assert ls == sorted(ls, reverse=True) and len(b) <= 64
+        T = -(-ls[0] // 128) * 128
+        assert len(b) == 1 or len(b) * T <= 65536
+    # padding waste stays small because neighbours in a batch have similar lengths
+    waste = sum(len(b) * lengths[b[0]] - sum(lengths[i] for i in b) for b in batches) / sum(lengths)
+    assert waste < 0.25
+    assert offline.my_batches(10, rank=1, world=4) == [1, 5, 9] and offline.my_batches(3, rank=0, world=1) == [0, 1, 2]
+    with pytest.raises(ValueError):
+        offline.bucket_by_length([10, 0, 5])
