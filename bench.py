@@ -234,12 +234,14 @@ def main():
 
     # ---------------- e2e: host buffers -> public API -> host result, copies inside the timed region
     cond_pin = cond_h.pin_memory()
-    mel_pin = torch.empty(B, T, M, dtype=torch.float32).pin_memory()
+    # the sampler's result is the [B,T,M] VIEW of a [B,M,T] buffer (prodiff.py:151 returns such a view too); the host copy keeps
+    # that physical layout, so the D2H is one contiguous DMA and the host-side result is the same transposed view
+    mel_pin = torch.empty(B, M, T, dtype=torch.float32).pin_memory()
     # two-deep software pipeline: the H2D of step i+1 and the D2H of step i-1 overlap the sampling of step i
     copy_s = torch.cuda.Stream(device)
     comp_s = torch.cuda.current_stream(device)
     cond_bufs = [torch.empty_like(cond_d), torch.empty_like(cond_d)]
-    mel_bufs = [torch.empty(B, T, M, device=device), torch.empty(B, T, M, device=device)]
+    mel_hold = [None, None]   # device results whose D2H may still be in flight
     h2d_done = [torch.cuda.Event(), torch.cuda.Event()]
     comp_done = [torch.cuda.Event(), torch.cuda.Event()]
     d2h_done = [torch.cuda.Event(), torch.cuda.Event()]
@@ -251,11 +253,10 @@ def main():
         for i in range(n):
             cur = i & 1
             comp_s.wait_event(h2d_done[cur])
-            if i >= 2:
-                comp_s.wait_event(d2h_done[cur])  # mel_bufs[cur] is free again
             with torch.no_grad():
                 mel = gd(cond_bufs[cur], infer_step=K, infer=True, seed=2000 + i)
-            mel_bufs[cur].copy_(mel)  # [B,T,M]-contiguous result for the host
+            mel_hold[cur] = mel.transpose(1, 2)   # the contiguous [B,M,T] storage behind the returned view
+            assert mel_hold[cur].is_contiguous()
             comp_done[cur].record(comp_s)
             with torch.cuda.stream(copy_s):
                 if i + 1 < n:
@@ -264,7 +265,8 @@ def main():
                     cond_bufs[cur ^ 1].copy_(cond_pin, non_blocking=True)
                     h2d_done[cur ^ 1].record(copy_s)
                 copy_s.wait_event(comp_done[cur])
-                mel_pin.copy_(mel_bufs[cur], non_blocking=True)
+                mel_pin.copy_(mel_hold[cur], non_blocking=True)
+                mel_hold[cur].record_stream(copy_s)
                 d2h_done[cur].record(copy_s)
         comp_s.wait_stream(copy_s)
 
