@@ -130,8 +130,9 @@ long long pd_launch_count(int reset);
  * bracketed by a CUDA-event pair on its stream.  pd_profile_end synchronises and returns, per kernel kind, the summed
  * milliseconds and the launch count.  Kinds: 0 cond_proj, 1 input_proj, 2 dilated_conv+gate, 3 res_proj, 4 skip_sum,
  * 5 skip_proj, 6 output_proj+posterior, 7 debug. */
-#define PD_N_KINDS 10  /* kind 8 = fused ResidualBlock layer kernel (2-CTA); kind 9 = fused sampler tail (skip_projection +
-                          output_projection + q-posterior + next step's input_projection, pd_sample only) */
+#define PD_N_KINDS 11  /* kind 8 = fused ResidualBlock layer kernel (2-CTA); kind 9 = fused sampler tail (skip_projection +
+                          output_projection + q-posterior + next step's input_projection, pd_sample only); kind 10 = skip sum +
+                          that tail as one kernel */
 int pd_profile_begin(void);
 int pd_profile_end(float* ms_by_kind, int* count_by_kind, int n_kinds);
 
@@ -157,6 +158,12 @@ int pd_set_stack(int on);
  * shared memory (1, default when C = 256 and M = 128; env PD_TAIL=0 also disables) or as separate GEMM launches (0).
  * Returns the previous value. */
 int pd_set_tail(int on);
+
+/* pd_sample only: additionally run the deferred skip sum (wavenet.py:119) inside the same kernel as the tail above, the
+ * tail chain of one frame tile overlapping the skip-sum K loop of the next (1; env PD_SUMTAIL=1 also enables; needs the tail,
+ * cta_group::2 pairs and at least two frame tiles) or keep skip_sum a separate GEMM launch (0, default: the fused form is
+ * bit-identical but measured no faster).  Returns the previous value. */
+int pd_set_sumtail(int on);
 
 /* Debug: when set to a device buffer of 12 x 1024 int64, CTA 0 of every GEMM launch writes clock64() stamps of its
  * pipeline events at [kind * 1024 + tile * 16 + slot] (slots: 0/1 first/last TMA issue, 2 accumulator free, 3/4 first/

@@ -17,7 +17,7 @@ PD_BF16, PD_FP16 = 0, 1
 SYMBOLS = [
     "pd_state_count", "pd_last_error", "pd_abi_version", "pd_packed_bytes", "pd_model_create", "pd_model_destroy",
     "pd_workspace_bytes", "pd_plan_create", "pd_plan_destroy", "pd_cond_project", "pd_denoise", "pd_sample",
-    "pd_launch_count", "pd_plan_buffer", "pd_debug_gemm", "pd_profile_begin", "pd_profile_end", "pd_debug_shift", "pd_debug_set_trace", "pd_set_fused", "pd_set_stack", "pd_set_tail", "pd_reflow_sample", "pd_plan_set_lengths",
+    "pd_launch_count", "pd_plan_buffer", "pd_debug_gemm", "pd_profile_begin", "pd_profile_end", "pd_debug_shift", "pd_debug_set_trace", "pd_set_fused", "pd_set_stack", "pd_set_tail", "pd_set_sumtail", "pd_reflow_sample", "pd_plan_set_lengths",
 ]
 
 
@@ -67,6 +67,7 @@ def load() -> C.CDLL:
     lib.pd_set_fused.argtypes = [C.c_int]; lib.pd_set_fused.restype = C.c_int
     lib.pd_set_stack.argtypes = [C.c_int]; lib.pd_set_stack.restype = C.c_int
     lib.pd_set_tail.argtypes = [C.c_int]; lib.pd_set_tail.restype = C.c_int
+    lib.pd_set_sumtail.argtypes = [C.c_int]; lib.pd_set_sumtail.restype = C.c_int
     lib.pd_profile_begin.argtypes = []; lib.pd_profile_begin.restype = C.c_int
     lib.pd_profile_end.argtypes = [P(C.c_float), P(C.c_int), C.c_int]; lib.pd_profile_end.restype = C.c_int
     if lib.pd_abi_version() != 1:
@@ -76,7 +77,7 @@ def load() -> C.CDLL:
 
 
 KIND_NAMES = ["cond_proj", "input_proj", "dilated_conv+gate", "res_proj", "skip_sum", "skip_proj", "output_proj+posterior",
-              "debug", "residual_layer(fused)", "sampler_tail(fused)"]
+              "debug", "residual_layer(fused)", "sampler_tail(fused)", "skip_sum+tail(fused)"]
 
 
 def profile_begin() -> None:
@@ -85,10 +86,10 @@ def profile_begin() -> None:
 
 def profile_end() -> dict:
     """{kind name: (total ms, launches)} for every GEMM launched since profile_begin()."""
-    ms = (C.c_float * 10)()
-    cnt = (C.c_int * 10)()
-    check(load().pd_profile_end(ms, cnt, 10), "pd_profile_end")
-    return {KIND_NAMES[i]: (float(ms[i]), int(cnt[i])) for i in range(10) if cnt[i]}
+    ms = (C.c_float * 11)()
+    cnt = (C.c_int * 11)()
+    check(load().pd_profile_end(ms, cnt, 11), "pd_profile_end")
+    return {KIND_NAMES[i]: (float(ms[i]), int(cnt[i])) for i in range(11) if cnt[i]}
 
 
 def check(rc: int, what: str) -> None:

@@ -4,6 +4,7 @@
 #include "pd_aux.cuh"
 #include "pd_layer.cuh"
 #include "pd_tail.cuh"
+#include "pd_sumtail.cuh"
 
 #include <math.h>
 #include <stdarg.h>
@@ -639,6 +640,55 @@ static int launch_tail_t(const CUtensorMap& s1, const CUtensorMap& wsp, const CU
   return 0;
 }
 
+static int g_sumtail = -1;  // -1: read PD_SUMTAIL from the environment on first use
+extern "C" int pd_set_sumtail(int on) {
+  const int prev = g_sumtail;
+  g_sumtail = on ? 1 : 0;
+  return prev;
+}
+static bool sumtail_enabled() {
+  if (g_sumtail < 0) {
+    // Off by default: measured equal to skip_sum + tail as two launches (0.95-0.97 vs 0.96-0.98 ms per 4-step sample;
+    // 198.7 vs 134.8 + 62.7 us under ncu).  The tail chain does hide behind the next tile's K loop, but that loop runs ~20 %
+    // slower next to it (4 instead of 7 ring stages, x / xa writes mixed into a read stream), S is single-buffered and
+    // the last tile's chain is exposed.
+    const char* e = getenv("PD_SUMTAIL");
+    g_sumtail = (e && e[0] == '1') ? 1 : 0;
+  }
+  return g_sumtail == 1;
+}
+template <typename T>
+static int launch_sumtail_t(const CUtensorMap& y, const CUtensorMap& wskip, const CUtensorMap& wsp, const CUtensorMap& wout,
+                            const CUtensorMap& win, const CUtensorMap& xst, const SumTailParams& sp, int sms, cudaStream_t s) {
+  auto kern = sumtail_kernel<T>;
+  static bool configured[64] = {false};
+  int dev = 0;
+  PD_CUDA(cudaGetDevice(&dev));
+  if (!configured[dev & 63]) {
+    PD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSumTailSmemBytes));
+    configured[dev & 63] = true;
+  }
+  const int pairs = (sp.tp.B * sp.tp.m_tiles_per_row + 1) / 2;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(2 * (pairs < sms / 2 ? pairs : sms / 2));
+  cfg.blockDim = dim3(kSumTailThreads);
+  cfg.dynamicSmemBytes = kSumTailSmemBytes;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  prof_before(10, s);
+  PD_CUDA(cudaLaunchKernelEx(&cfg, kern, y, wskip, wsp, wout, win, xst, sp));
+  prof_after(s);
+  PD_LAUNCH_CHECK("sumtail_kernel");
+  return 0;
+}
+
 // ------------------------------------------------------------------ hot-path sequences
 struct LenVals {
   int v[64];
@@ -867,6 +917,38 @@ static int run_denoiser(pd_plan* p, int entry_base, int entry_per_b, const OutSt
       if (launch_gemm<EPI_RES, 256>(dt, p->tm_y, m->tm_w_res, sh, ep, sms, s, "gemm(res_proj)", 3, &tm_nxt, &tm_cur, &m->tm_w_res128)) return 1;
     }
     cur_is_a = !cur_is_a;
+  }
+  if (os.x_state != nullptr && p->tail_ok && tail_enabled() && sumtail_enabled() && pair_enabled() && B * ((T + kBlockM - 1) / kBlockM) >= 2) {
+    // sampling loop: skip sum, skip_projection, output_projection, q-posterior and the next step's input_projection as one
+    // kernel (pd_sumtail.cuh): the tail chain of tile t runs on the epilogue warps while the skip-sum K loop of tile t+1 streams
+    SumTailParams sp;
+    memset(&sp, 0, sizeof(sp));
+    TailParams& tp = sp.tp;
+    tp.B = B;
+    tp.T = T;
+    tp.m_tiles_per_row = (T + kBlockM - 1) / kBlockM;
+    tp.do_in = os.write_xin ? 1 : 0;
+    tp.b_sp = (const float*)(pk + lay.b_sp);
+    tp.b_out = (const float*)(pk + lay.b_out);
+    tp.b_in = (const float*)(pk + lay.b_in);
+    tp.M = M;
+    tp.x0_out = os.x0_out;
+    tp.x_state = os.x_state;
+    tp.noise = os.noise;
+    tp.c1 = os.c1;
+    tp.c2 = os.c2;
+    tp.sigma = os.sigma;
+    tp.seed = os.seed;
+    tp.step_id = os.step_id;
+    tp.lens = p->ragged ? p->ptr<int>("lens") : nullptr;
+    tp.trace = (g_trace && os.write_xin) ? g_trace + 10 * 1024 : nullptr;   // trace a launch that includes the input_proj GEMM
+    sp.L = L;
+    sp.idesc256 = make_idesc(dt, 256, 256);
+    sp.idesc128 = make_idesc(dt, 128, 256);
+    sp.b_sum = (const float*)(pk + lay.b_skipsum);
+    sp.scale = 1.0f / sqrtf((float)L);
+    return dt == PD_FP16 ? launch_sumtail_t<__half>(p->tm_y, m->tm_w_skip_h, m->tm_w_sp_h, m->tm_w_out_h, m->tm_w_in_h, p->tm_xa_st, sp, sms, s)
+                         : launch_sumtail_t<__nv_bfloat16>(p->tm_y, m->tm_w_skip_h, m->tm_w_sp_h, m->tm_w_out_h, m->tm_w_in_h, p->tm_xa_st, sp, sms, s);
   }
   {  // sum of the L skip halves as ONE GEMM with K = L*C, then / sqrt(L)  (wavenet.py:119)
     GemmShape sh = base_shape(B, T, C / 256, C / 64);

@@ -54,6 +54,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity, ui
       : "memory");
   return ok != 0;
 }
+// Non-blocking test of a phase (mbarrier.test_wait never suspends the thread, unlike try_wait).
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // Wait for the phase with the given parity to complete.  `tag` identifies the call site in the trap message.
 // A waiter that is not ready backs off with nanosleep so it does not burn issue slots of the warps sharing its SM
 // sub-partition (the waiting control warps have the highest arbiter priority).

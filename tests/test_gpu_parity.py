@@ -183,8 +183,10 @@ def test_fused_layer_kernel_equals_unfused_pair():
     assert float((outs[0] - ref).abs().max()) <= STEP_TOL and float((outs[1] - ref).abs().max()) <= STEP_TOL
 
 
-def test_fused_sampler_tail_equals_separate_kernels():
-    """pd_sample with the fused tail kernel (skip_projection -> output_projection -> q-posterior -> next step's
+@pytest.mark.parametrize("mode", ["sumtail", "tail"])
+def test_fused_sampler_tail_equals_separate_kernels(mode):
+    """(mode "sumtail": the skip sum runs in the same kernel as well, pd_sumtail.cuh.)
+    pd_sample with the fused tail kernel (skip_projection -> output_projection -> q-posterior -> next step's
     input_projection, intermediates in shared memory) against the same loop running those as separate GEMM launches.
     Identical operands, identical K order and identical 16-bit rounding points, so the mel must agree exactly; both
     injected noise and the in-kernel Philox stream are covered, and the per-step x0 trace as well."""
@@ -196,8 +198,9 @@ def test_fused_sampler_tail_equals_separate_kernels():
     B, T, K = 3, 333, 4                                     # ragged last tile per utterance
     cond, x_T, noise = synth.make_inputs(cfg, B, T, K, 24)
     res = []
-    for tail in (1, 0):
+    for tail, sumtail in ((1, mode == "sumtail"), (0, 0)):
         prev = lib.pd_set_tail(tail)
+        prev_st = lib.pd_set_sumtail(1 if sumtail else 0)
         try:
             gd = _build(cfg, state, case)
             with torch.no_grad():
@@ -207,6 +210,7 @@ def test_fused_sampler_tail_equals_separate_kernels():
                 res.append((a, b, tr.cpu()))
         finally:
             lib.pd_set_tail(1 if prev != 0 else 0)
+            lib.pd_set_sumtail(1 if prev_st != 0 else 0)
     assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
     assert torch.equal(res[0][2], res[1][2])
     mel_ref, x0s = helpers.oracle_sample(dict(case, infer_step=K), cfg, state, cond, x_T, noise)
