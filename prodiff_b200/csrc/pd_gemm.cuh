@@ -138,7 +138,7 @@ __device__ __forceinline__ float4 philox_normal4(unsigned long long seed, uint32
   const float k = 2.3283064365386963e-10f;  // 2^-32
   const float u0 = ((float)r.x + 1.0f) * k, u1 = (float)r.y * k;
   const float u2 = ((float)r.z + 1.0f) * k, u3 = (float)r.w * k;
-  const float r0 = sqrtf(-2.f * __logf(fminf(u0, 1.f))), r1 = sqrtf(-2.f * __logf(fminf(u2, 1.f)));
+  const float r0 = sqrt_approx(-2.f * __logf(fminf(u0, 1.f))), r1 = sqrt_approx(-2.f * __logf(fminf(u2, 1.f)));
   float s0, c0f, s1, c1f;
   __sincosf(6.283185307179586f * u1, &s0, &c0f);
   __sincosf(6.283185307179586f * u3, &s1, &c1f);
