@@ -237,8 +237,10 @@ def main():
     # the sampler's result is the [B,T,M] VIEW of a [B,M,T] buffer (prodiff.py:151 returns such a view too); the host copy keeps
     # that physical layout, so the D2H is one contiguous DMA and the host-side result is the same transposed view
     mel_pin = torch.empty(B, M, T, dtype=torch.float32).pin_memory()
-    # two-deep software pipeline: the H2D of step i+1 and the D2H of step i-1 overlap the sampling of step i
+    # two-deep software pipeline: the H2D of step i+1 and the D2H of step i-1 overlap the sampling of step i; one stream per
+    # direction (PCIe is full duplex: serialising both on one stream made the loop copy-bound whenever the link ran slow)
     copy_s = torch.cuda.Stream(device)
+    d2h_s = torch.cuda.Stream(device)
     comp_s = torch.cuda.current_stream(device)
     cond_bufs = [torch.empty_like(cond_d), torch.empty_like(cond_d)]
     mel_hold = [None, None]   # device results whose D2H may still be in flight
@@ -264,11 +266,13 @@ def main():
                         copy_s.wait_event(comp_done[cur ^ 1])  # cond_bufs[cur^1] no longer read by step i-1
                     cond_bufs[cur ^ 1].copy_(cond_pin, non_blocking=True)
                     h2d_done[cur ^ 1].record(copy_s)
-                copy_s.wait_event(comp_done[cur])
+            with torch.cuda.stream(d2h_s):
+                d2h_s.wait_event(comp_done[cur])
                 mel_pin.copy_(mel_hold[cur], non_blocking=True)
-                mel_hold[cur].record_stream(copy_s)
-                d2h_done[cur].record(copy_s)
+                mel_hold[cur].record_stream(d2h_s)
+                d2h_done[cur].record(d2h_s)
         comp_s.wait_stream(copy_s)
+        comp_s.wait_stream(d2h_s)
 
     e2e_loop(3)
     barrier()

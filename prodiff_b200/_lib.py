@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libprodiff_b200.so")
+# PRODIFF_B200_LIB: developer hook to A/B two builds of the same ABI inside one GPU session
+LIB_PATH = os.environ.get("PRODIFF_B200_LIB") or os.path.join(_HERE, "csrc", "libprodiff_b200.so")
 
 PD_BF16, PD_FP16 = 0, 1
 
