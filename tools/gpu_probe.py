@@ -124,7 +124,7 @@ def check_trace():
     lib = _lib.load()
     gd, cfg, _ = bench.build_model(torch.device("cuda"))
     from prodiff_b200 import synth
-    cond, _, _ = synth.make_inputs(cfg, 64, 1000, 1, 5)
+    cond, _, _ = synth.make_inputs(cfg, int(os.environ.get("PROBE_B", "64")), 1000, 1, 5)
     cond = cond.cuda()
     with torch.no_grad():
         gd(cond, infer_step=4, infer=True, seed=1)
