@@ -255,6 +255,11 @@ def main():
         for i in range(n):
             cur = i & 1
             comp_s.wait_event(h2d_done[cur])
+            if i >= 2:
+                # the result of step i-2 (released just below) may only be recycled by the allocator once its D2H is done;
+                # ordering the compute stream after that copy keeps the reuse stream-ordered without record_stream(), which
+                # would park every freed block until the GPU catches up and make each step cudaMalloc a fresh state tensor
+                comp_s.wait_event(d2h_done[cur])
             with torch.no_grad():
                 mel = gd(cond_bufs[cur], infer_step=K, infer=True, seed=2000 + i)
             mel_hold[cur] = mel.transpose(1, 2)   # the contiguous [B,M,T] storage behind the returned view
@@ -269,7 +274,6 @@ def main():
             with torch.cuda.stream(d2h_s):
                 d2h_s.wait_event(comp_done[cur])
                 mel_pin.copy_(mel_hold[cur], non_blocking=True)
-                mel_hold[cur].record_stream(d2h_s)
                 d2h_done[cur].record(d2h_s)
         comp_s.wait_stream(copy_s)
         comp_s.wait_stream(d2h_s)
