@@ -88,7 +88,7 @@ int pd_cond_project(pd_plan* p, const float* cond, void* stream);
 int pd_denoise(pd_plan* p, const float* spec, const float* diffusion_step, float* out, void* stream);
 
 /* GaussianDiffusion.forward(infer=True) (prodiff.py:145-153): the whole K-step reverse loop.
- *   cond   [B,T,H] fp32
+ *   cond   [B,T,H] fp32 (NULL: the projection is already in the plan -- pd_cond_project / pd_cond_assemble ran for this batch)
  *   x      [B,1,M,T] fp32: in = x_T (the reference draws it with torch.rand, :147), out = x_0
  *   noise  [K,B,1,M,T] fp32 or NULL: noise[j] is used by the j-th iteration (replaces torch.randn, :118);
  *          NULL = in-kernel Philox4x32-10 keyed by `seed`
@@ -98,6 +98,21 @@ int pd_denoise(pd_plan* p, const float* spec, const float* diffusion_step, float
 int pd_sample(pd_plan* p, const float* cond, float* x, const float* noise, uint64_t seed, int K,
               const int32_t* t_list, const float* coef1, const float* coef2, const float* logvar, int n_table,
               float* x0_trace, void* stream);
+
+/* Frame-level half of ProDiffTeacher.forward_condition (/root/reference/modules/svs/prodiff_teacher.py:127-149; SURVEY 8f
+ * N1): length regulation (F.pad + gather by mel2ph, :128-130), + pitch_embed(log(1 + f0 / 700)) (:98-101, :132), + up to two
+ * utterance-level embedding rows (speaker :135, gender :137), + an optional frame-level embedding (a per-frame speaker mix),
+ * + the sum of up to two Linear(1,H) variance embeddings (voicing, breath, :139-147), times the non-padding mask
+ * (mel2ph > 0, :148-149) -- written straight into the plan's 16-bit condition operand, followed by the condition projection
+ * of every layer (what pd_cond_project does after its cast).  The token-level encoder stays with the caller.
+ *   encoder_out [B,Tph,H] fp32; mel2ph [B,T] int64 (0 = padding, i > 0 = token i - 1); f0 [B,T] fp32;
+ *   w_pitch / b_pitch [H] (pitch_embed.weight[:, 0], .bias); utt0 / utt1 optional [B,H]; var_x[j] [B,T], var_w[j] / var_b[j] [H]
+ *   for j < n_var <= 2; frame_embed optional [B,T,H]; cond_out optional [B,T,H] fp32 (the condition forward_condition
+ *   returns).  All device pointers.  Afterwards pd_sample / pd_reflow_sample are called with cond = NULL. */
+int pd_cond_assemble(pd_plan* p, const float* encoder_out, int Tph, const long long* mel2ph, const float* f0,
+                     const float* w_pitch, const float* b_pitch, const float* utt0, const float* utt1, int n_var,
+                     const float* const* var_x, const float* const* var_w, const float* const* var_b,
+                     const float* frame_embed, float* cond_out, void* stream);
 
 /* Ragged batches (no counterpart in the reference, which pads and processes every row at the full T, SURVEY appendix A.7;
  * needed to batch its one-utterance-at-a-time offline sampling loop, component/binarizer/svs.py:193-223, without changing
@@ -112,7 +127,8 @@ int pd_plan_set_lengths(pd_plan* p, const int32_t* lengths, void* stream);
  * x' = v(x, time_scale * t) integrated from t = 0 to 1 in n_steps steps of dt = 1 / n_steps with sample_euler (:48-52),
  * sample_rk2 (:54-60), sample_rk4 (:62-70) or sample_rk5 (:72-84), the velocity being the same DiffNet denoiser
  * (WaveNet.forward with a float diffusion step shared by the batch), followed by denorm_spec (:106-107).
- *   cond      [B,T,H] fp32 device; projected once and reused by every evaluation.
+ *   cond      [B,T,H] fp32 device; projected once and reused by every evaluation (NULL: pd_cond_project / pd_cond_assemble
+ *             already ran on this plan for this batch).
  *   x         [B,1,M,T] fp32 device, in place: in = the N(0,1) start the reference draws at :88, out = denormalised result
  *             (the caller returns the [B,T,M] view x[:,0].transpose(1,2) like :100).
  *   algorithm 0 euler, 1 rk2, 2 rk4, 3 rk5 (the caller maps unknown names to euler as the reference's dict.get does, :95).

@@ -64,3 +64,36 @@ def reflow_spec_range(case):
     if case["spec"] == "pitch":
         return [-8.0], [8.0]
     return [-12.0], [0.0]
+
+
+# Frame-level half of ProDiffTeacher.forward_condition (prodiff_teacher.py:127-149): inputs are drawn by
+# make_condition_inputs below, the fixture stores what the reference method returned for them.
+CONDITION_CASES = {
+    # speaker + gender rows, both variance embeddings, trailing padding of different lengths
+    "full": dict(B=3, T=150, Tph=23, H=256, spk=True, gender=True, n_var=2, frame_mix=False, seed=111),
+    # speaker mix given per frame ([B,T,H]) as the web handler does, no gender, one variance embedding
+    "frame_mix": dict(B=2, T=77, Tph=9, H=256, spk=True, gender=False, n_var=1, frame_mix=True, seed=112),
+    # nothing optional
+    "bare": dict(B=1, T=40, Tph=5, H=256, spk=False, gender=False, n_var=0, frame_mix=False, seed=113),
+}
+
+
+def make_condition_inputs(case):
+    """Seeded inputs of a CONDITION case (numpy PCG64 like prodiff_b200.synth, reproducible anywhere)."""
+    import numpy as np
+    import torch
+    rng = np.random.default_rng(case["seed"])
+    B, T, Tph, H = case["B"], case["T"], case["Tph"], case["H"]
+    f32 = lambda a: torch.from_numpy(np.asarray(a, dtype=np.float32))
+    d = dict(encoder_out=f32(rng.normal(size=(B, Tph, H))), pitch_w=f32(rng.normal(size=(H, 1)) * 0.3), pitch_b=f32(rng.normal(size=(H,)) * 0.1))
+    mel2ph = np.zeros((B, T), dtype=np.int64)
+    for b in range(B):
+        n = T - (b * 17) % max(1, T // 2)                       # valid frames of row b; the rest is padding (0)
+        mel2ph[b, :n] = np.sort(rng.integers(1, Tph + 1, size=n))
+    d["mel2ph"] = torch.from_numpy(mel2ph)
+    d["f0"] = f32(np.where(rng.random((B, T)) < 0.2, 0.0, rng.uniform(80, 800, size=(B, T))))   # unvoiced frames have f0 = 0
+    d["spk"] = (f32(rng.normal(size=(B, T if case["frame_mix"] else 1, H))) if case["spk"] else None)
+    d["gender"] = f32(rng.normal(size=(B, 1, H))) if case["gender"] else None
+    d["variances"] = [(f32(rng.random((B, T))), f32(rng.normal(size=(H, 1)) * 0.3), f32(rng.normal(size=(H,)) * 0.1))
+                      for _ in range(case["n_var"])]
+    return d

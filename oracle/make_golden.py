@@ -131,8 +131,47 @@ def run_reference_reflow(case):
     return dict(out=out.contiguous().numpy(), v=torch.stack(vs).numpy(), digest=np.array(synth.digest(state, cond, noise[0])))
 
 
+def run_reference_condition(case):
+    """The reference's own ``ProDiffTeacher.forward_condition`` (prodiff_teacher.py:103-149), unmodified, run on a stub
+    ``self`` whose encoder returns the injected ``encoder_out`` -- the frame-level half is what the fixture pins."""
+    import types
+    from oracle.golden_cases import make_condition_inputs
+    load_reference()
+    sys.modules.setdefault("chardet", types.ModuleType("chardet"))      # utils/__init__.py imports it; unused here
+    from modules.svs.prodiff_teacher import ProDiffTeacher              # noqa
+    d = make_condition_inputs(case)
+    H = case["H"]
+
+    def linear(w, b):
+        m = torch.nn.Linear(1, H)
+        with torch.no_grad():
+            m.weight.copy_(w)
+            m.bias.copy_(b)
+        return m
+
+    stub = types.SimpleNamespace(
+        with_dur_embed=True, dur_embed=lambda dur: torch.zeros(1), with_lang_embed=False,
+        encoder=lambda txt_tokens, extra_embed: d["encoder_out"].clone(),
+        pitch_embed=linear(d["pitch_w"], d["pitch_b"]),
+        with_spk_embed=case["spk"], with_gender_embed=case["gender"],
+        with_voicing_embed=case["n_var"] >= 1, with_breath_embed=case["n_var"] >= 2)
+    if case["n_var"] >= 1:
+        stub.voicing_embed = linear(d["variances"][0][1], d["variances"][0][2])
+    if case["n_var"] >= 2:
+        stub.breath_embed = linear(d["variances"][1][1], d["variances"][1][2])
+    for name in ("add_pitch", "add_spk_embed", "add_gender_embed"):
+        setattr(stub, name, types.MethodType(getattr(ProDiffTeacher, name), stub))
+    txt = torch.ones(case["B"], case["Tph"], dtype=torch.long)
+    with torch.no_grad():
+        out = ProDiffTeacher.forward_condition(
+            stub, txt, d["mel2ph"], d["f0"], spk_mix_embed=d["spk"], gender_mix_embed=d["gender"],
+            voicing=d["variances"][0][0] if case["n_var"] >= 1 else None,
+            breath=d["variances"][1][0] if case["n_var"] >= 2 else None)
+    return dict(out=out.numpy())
+
+
 def main():
-    from oracle.golden_cases import SAMPLE_CASES, DENOISE_CASES, REFLOW_CASES
+    from oracle.golden_cases import SAMPLE_CASES, DENOISE_CASES, REFLOW_CASES, CONDITION_CASES
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     out_dir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
@@ -148,6 +187,10 @@ def main():
         r = run_reference_reflow(case)
         np.savez(os.path.join(out_dir, f"reflow_{name}.npz"), **r)
         print(f"reflow_{name}: out {r['out'].shape} v {r['v'].shape} |v|max {np.abs(r['v']).max():.3f}")
+    for name, case in CONDITION_CASES.items():
+        r = run_reference_condition(case)
+        np.savez(os.path.join(out_dir, f"condition_{name}.npz"), **r)
+        print(f"condition_{name}: out {r['out'].shape} |out|max {np.abs(r['out']).max():.3f}")
 
 
 if __name__ == "__main__":

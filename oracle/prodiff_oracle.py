@@ -286,3 +286,34 @@ def reflow_sample(state: State, cond, x_start, infer_step: int, algorithm: str, 
     smin = torch.FloatTensor(spec_min)[None, None, :M].transpose(-3, -2)
     smax = torch.FloatTensor(spec_max)[None, None, :M].transpose(-3, -2)
     return (x + 1) / 2 * (smax - smin) + smin, vs
+
+
+# --------------------------------------------------------------------------------------
+# frame-level half of the condition assembly
+#     /root/reference/modules/svs/prodiff_teacher.py:98-101 (add_pitch), :127-149 (forward_condition after the encoder)
+# --------------------------------------------------------------------------------------
+@torch.no_grad()
+def assemble_condition(encoder_out, mel2ph, f0, pitch_w, pitch_b, spk_embed=None, gender_embed=None,
+                       variances=()) -> torch.Tensor:
+    """``forward_condition`` from the length regulator on (prodiff_teacher.py:127-149).
+
+    encoder_out [B,Tph,H] (what ``self.encoder`` returned), mel2ph [B,T] int64 (0 = padding), f0 [B,T];
+    pitch_w [H,1] / pitch_b [H] = ``pitch_embed`` (a Linear(1,H)); spk_embed / gender_embed: what add_spk_embed /
+    add_gender_embed return ([B,1,H] looked-up rows or a caller-supplied mix that may be [B,T,H]); variances: sequence of
+    (x [B,T], weight [H,1], bias [H]) for the voicing / breath embeddings, summed through torch.stack(...).sum(-1) like
+    :146-147.  Returns the condition [B,T,H].
+    """
+    condition = F.pad(encoder_out, [0, 0, 1, 0])                                  # :128
+    mel2ph_ = mel2ph[..., None].repeat([1, 1, encoder_out.shape[-1]])             # :129
+    condition = torch.gather(condition, 1, mel2ph_)                               # :130
+    f0_mel = (1 + f0 / 700).log()                                                 # :99
+    condition += F.linear(f0_mel[:, :, None], pitch_w, pitch_b)                   # :100, :132
+    if spk_embed is not None:
+        condition += spk_embed                                                    # :135
+    if gender_embed is not None:
+        condition += gender_embed                                                 # :137
+    variance_embeds = [F.linear(x[:, :, None], w, b) for x, w, b in variances]    # :141-145
+    if len(variance_embeds) > 0:
+        condition += torch.stack(variance_embeds, dim=-1).sum(-1)                 # :147
+    nonpadding = (mel2ph > 0).float()[:, :, None]                                 # :148
+    return condition * nonpadding                                                 # :149

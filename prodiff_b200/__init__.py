@@ -14,6 +14,7 @@ Public surface (mirrors the reference's module API for this path, SURVEY.md sect
 from .wavenet import WaveNet
 from .diffusion import GaussianDiffusion
 from .reflow import RectifiedFlow, PitchRectifiedFlow
+from .conditioning import AssembledCondition, forward_condition
 from .synth import DiffNetConfig
 
 __version__ = "0.1.0"
@@ -32,4 +33,5 @@ def install():
     return wn, gd
 
 
-__all__ = ["WaveNet", "GaussianDiffusion", "RectifiedFlow", "PitchRectifiedFlow", "DiffNetConfig", "install"]
+__all__ = ["WaveNet", "GaussianDiffusion", "RectifiedFlow", "PitchRectifiedFlow", "AssembledCondition", "forward_condition",
+           "DiffNetConfig", "install"]

@@ -18,7 +18,7 @@ PD_BF16, PD_FP16 = 0, 1
 SYMBOLS = [
     "pd_state_count", "pd_last_error", "pd_abi_version", "pd_packed_bytes", "pd_model_create", "pd_model_destroy",
     "pd_workspace_bytes", "pd_plan_create", "pd_plan_destroy", "pd_cond_project", "pd_denoise", "pd_sample",
-    "pd_launch_count", "pd_plan_buffer", "pd_debug_gemm", "pd_profile_begin", "pd_profile_end", "pd_debug_shift", "pd_debug_set_trace", "pd_set_fused", "pd_set_stack", "pd_set_tail", "pd_set_sumtail", "pd_reflow_sample", "pd_plan_set_lengths",
+    "pd_launch_count", "pd_plan_buffer", "pd_debug_gemm", "pd_profile_begin", "pd_profile_end", "pd_debug_shift", "pd_debug_set_trace", "pd_set_fused", "pd_set_stack", "pd_set_tail", "pd_set_sumtail", "pd_reflow_sample", "pd_plan_set_lengths", "pd_cond_assemble",
 ]
 
 
@@ -59,6 +59,8 @@ def load() -> C.CDLL:
     lib.pd_reflow_sample.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_float, vp, vp, vp, C.c_int, vp, vp]
     lib.pd_reflow_sample.restype = C.c_int
     lib.pd_plan_set_lengths.argtypes = [vp, P(C.c_int32), vp]; lib.pd_plan_set_lengths.restype = C.c_int
+    lib.pd_cond_assemble.argtypes = [vp, vp, C.c_int, vp, vp, vp, vp, vp, vp, C.c_int, P(vp), P(vp), P(vp), vp, vp, vp]
+    lib.pd_cond_assemble.restype = C.c_int
     lib.pd_launch_count.argtypes = [C.c_int]; lib.pd_launch_count.restype = C.c_longlong
     lib.pd_plan_buffer.argtypes = [vp, cp, P(sz), P(sz)]; lib.pd_plan_buffer.restype = C.c_int
     lib.pd_debug_gemm.argtypes = [C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp, vp, vp]

@@ -717,16 +717,61 @@ extern "C" int pd_plan_set_lengths(pd_plan* p, const int32_t* lengths, void* str
   return 0;
 }
 
+static int cond_project_from16(pd_plan* p, cudaStream_t s);
+
 extern "C" int pd_cond_project(pd_plan* p, const float* cond, void* stream) {
   if (!p || !cond) return fail("null argument");
-  const pd_model* m = p->m;
-  const pd_config& c = m->cfg;
+  const pd_config& c = p->m->cfg;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const long long n4 = (long long)p->B * p->T * c.hidden_size / 4;
   const int blocks = (int)std::min<long long>((n4 + 255) / 256, 148 * 16);
   if (c.dtype == PD_FP16) k_cast<__half><<<blocks, 256, 0, s>>>(p->ptr<__half>("cond16"), cond, n4);
   else k_cast<__nv_bfloat16><<<blocks, 256, 0, s>>>(p->ptr<__nv_bfloat16>("cond16"), cond, n4);
   PD_LAUNCH_CHECK("k_cast(cond)");
+  return cond_project_from16(p, s);
+}
+
+extern "C" int pd_cond_assemble(pd_plan* p, const float* encoder_out, int Tph, const long long* mel2ph, const float* f0,
+                                const float* w_pitch, const float* b_pitch, const float* utt0, const float* utt1, int n_var,
+                                const float* const* var_x, const float* const* var_w, const float* const* var_b,
+                                const float* frame_embed, float* cond_out, void* stream) {
+  if (!p || !encoder_out || !mel2ph || !f0 || !w_pitch || !b_pitch) return fail("null argument");
+  if (Tph < 1 || n_var < 0 || n_var > 2) return fail("bad Tph=%d / n_var=%d", Tph, n_var);
+  if (n_var > 0 && (!var_x || !var_w || !var_b)) return fail("variance embeddings: null argument");
+  const pd_config& c = p->m->cfg;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CondAssemble a;
+  memset(&a, 0, sizeof(a));
+  a.enc = encoder_out;
+  a.mel2ph = mel2ph;
+  a.f0 = f0;
+  a.w_pitch = w_pitch;
+  a.b_pitch = b_pitch;
+  a.utt[0] = utt0;
+  a.utt[1] = utt1;
+  for (int j = 0; j < n_var; ++j) {
+    if (!var_x[j] || !var_w[j] || !var_b[j]) return fail("variance embedding %d: null argument", j);
+    a.var_x[j] = var_x[j];
+    a.var_w[j] = var_w[j];
+    a.var_b[j] = var_b[j];
+  }
+  a.frame = frame_embed;
+  a.Tph = Tph;
+  a.T = p->T;
+  a.H = c.hidden_size;
+  a.n_var = n_var;
+  const long long n4 = (long long)p->B * p->T * c.hidden_size / 4;
+  const int blocks = (int)std::min<long long>((n4 + 255) / 256, 148 * 16);
+  if (c.dtype == PD_FP16) k_assemble_cond<__half><<<blocks, 256, 0, s>>>(p->ptr<__half>("cond16"), cond_out, a, n4);
+  else k_assemble_cond<__nv_bfloat16><<<blocks, 256, 0, s>>>(p->ptr<__nv_bfloat16>("cond16"), cond_out, a, n4);
+  PD_LAUNCH_CHECK("k_assemble_cond");
+  return cond_project_from16(p, s);
+}
+
+// cond16 (the 16-bit [B,T,H] operand in the plan) -> hoisted condition projection of all layers
+static int cond_project_from16(pd_plan* p, cudaStream_t s) {
+  const pd_model* m = p->m;
+  const pd_config& c = m->cfg;
   const int C2 = 2 * c.residual_channels;
   GemmShape sh = base_shape(p->B, p->T, c.residual_layers * C2 / 256, c.hidden_size / 64);
   EpiArgs ep = base_epi();
@@ -1042,7 +1087,7 @@ extern "C" int pd_denoise(pd_plan* p, const float* spec, const float* diffusion_
 extern "C" int pd_sample(pd_plan* p, const float* cond, float* x, const float* noise, uint64_t seed, int K,
                          const int32_t* t_list, const float* coef1, const float* coef2, const float* logvar, int n_table,
                          float* x0_trace, void* stream) {
-  if (!p || !cond || !x || !t_list || !coef1 || !coef2 || !logvar) return fail("null argument");
+  if (!p || !x || !t_list || !coef1 || !coef2 || !logvar) return fail("null argument");
   if (K < 1 || K > p->E) return fail("K=%d outside [1, max_entries=%d] of this plan", K, p->E);
   for (int j = 0; j < K; ++j)
     if (t_list[j] < 0 || t_list[j] >= n_table) return fail("t_list[%d]=%d outside the %d-entry tables", j, t_list[j], n_table);
@@ -1058,7 +1103,9 @@ extern "C" int pd_sample(pd_plan* p, const float* cond, float* x, const float* n
     PD_LAUNCH_CHECK("k_set_steps");
   }
   if (run_step_tables(p, K, s)) return 1;
-  if (pd_cond_project(p, cond, stream)) return 1;  // once per utterance, reused by all K steps
+  // once per utterance, reused by all K steps; cond == NULL: the projection is already in the plan (pd_cond_project /
+  // pd_cond_assemble was called on it for this batch)
+  if (cond != nullptr && pd_cond_project(p, cond, stream)) return 1;
   if (spec_to_xin(p, x, s)) return 1;
   for (int j = 0; j < K; ++j) {
     const int t = t_list[j];
@@ -1123,7 +1170,7 @@ static int rk_stage(pd_plan* p, const RkTableau& tb, int row, float* const* k, f
 extern "C" int pd_reflow_sample(pd_plan* p, const float* cond, float* x, int algorithm, int n_steps, float time_scale,
                                 float* k_scratch, const float* spec_min, const float* spec_max, int n_spec, float* v_trace,
                                 void* stream) {
-  if (!p || !cond || !x || !k_scratch) return fail("null argument");
+  if (!p || !x || !k_scratch) return fail("null argument");
   if (algorithm < 0 || algorithm > 3) return fail("algorithm %d is not one of 0 euler, 1 rk2, 2 rk4, 3 rk5", algorithm);
   if (n_steps < 1) return fail("n_steps=%d must be >= 1", n_steps);
   const RkTableau& tb = algorithm == 0 ? kEuler : algorithm == 1 ? kRk2 : algorithm == 2 ? kRk4 : kRk5;
@@ -1135,7 +1182,7 @@ extern "C" int pd_reflow_sample(pd_plan* p, const float* cond, float* x, int alg
   const size_t state_elems = (size_t)p->B * c.in_dims * p->T;
   const double dt = 1.0 / (double)n_steps;   // reflow.py:89
   const float dtf = (float)dt;               // the fp32 tensor `dts` (:97)
-  if (pd_cond_project(p, cond, stream)) return 1;  // once per utterance, reused by every evaluation
+  if (cond != nullptr && pd_cond_project(p, cond, stream)) return 1;  // once per utterance, reused by every evaluation (NULL: already projected)
   if (spec_to_xin(p, x, s)) return 1;
   for (int n = 0; n < n_steps; ++n) {
     // times of this step's evaluations, in the reference's fp32 arithmetic: time_scale * (i * dts + c * dt)

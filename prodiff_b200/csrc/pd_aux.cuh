@@ -152,6 +152,72 @@ __global__ void k_denorm_spec(float* __restrict__ x, const float* __restrict__ s
   }
 }
 
+// Frame-level half of ProDiffTeacher.forward_condition (prodiff_teacher.py:127-146): length regulation
+// (F.pad + gather by mel2ph), + pitch embedding Linear(1,H) of log(1 + f0 / 700) (:98-101), + up to two utterance-level
+// embeddings (speaker, gender: [B,H] rows, :134-137), + the sum of up to two variance embeddings Linear(1,H) (voicing,
+// breath, :139-147), + an optional frame-level embedding ([B,T,H], the frame-wise speaker mixes of the web handler), all
+// times the non-padding mask (mel2ph > 0, :148-149) -- in the reference's order of fp32 additions.  Writes the fp32
+// condition (optional) and the 16-bit operand of the condition-projection GEMM directly, so the [B,T,H] fp32 tensor never
+// has to be materialised, cast and re-read.  One thread per (frame, 4 channels).
+struct CondAssemble {
+  const float* enc;        // encoder_out [B, Tph, H]
+  const long long* mel2ph; // [B, T], 0 = padding, i > 0 -> token i - 1
+  const float* f0;         // [B, T]
+  const float* w_pitch;    // [H] (Linear(1,H).weight[:, 0])
+  const float* b_pitch;    // [H]
+  const float* utt[2];     // optional [B, H]
+  const float* var_x[2];   // optional [B, T]
+  const float* var_w[2];   // [H]
+  const float* var_b[2];   // [H]
+  const float* frame;      // optional [B, T, H]
+  int Tph, T, H, n_var;
+};
+template <typename T>
+__global__ void k_assemble_cond(T* __restrict__ cond16, float* __restrict__ cond32, CondAssemble a, long long total4) {
+  const int H4 = a.H >> 2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / H4;            // frame index b * T + t
+    const int h = (int)(i - n * H4) * 4;
+    const int b = (int)(n / a.T);
+    const long long tok = a.mel2ph[n];
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (tok > 0) {
+      const float4 e = __ldg(reinterpret_cast<const float4*>(a.enc + ((long long)b * a.Tph + (tok - 1)) * a.H + h));
+      v[0] = e.x; v[1] = e.y; v[2] = e.z; v[3] = e.w;
+    }
+    const float f0_mel = logf(1.f + a.f0[n] / 700.f);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = __fadd_rn(v[u], __fadd_rn(__fmul_rn(f0_mel, a.w_pitch[h + u]), a.b_pitch[h + u]));
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+      if (a.utt[j] != nullptr) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = __fadd_rn(v[u], a.utt[j][(long long)b * a.H + h + u]);
+      }
+    if (a.frame != nullptr) {
+      const float4 f = __ldg(reinterpret_cast<const float4*>(a.frame + n * a.H + h));
+      v[0] = __fadd_rn(v[0], f.x); v[1] = __fadd_rn(v[1], f.y); v[2] = __fadd_rn(v[2], f.z); v[3] = __fadd_rn(v[3], f.w);
+    }
+    if (a.n_var > 0) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float s = __fadd_rn(__fmul_rn(a.var_x[0][n], a.var_w[0][h + u]), a.var_b[0][h + u]);
+        if (a.n_var > 1) s = __fadd_rn(s, __fadd_rn(__fmul_rn(a.var_x[1][n], a.var_w[1][h + u]), a.var_b[1][h + u]));
+        v[u] = __fadd_rn(v[u], s);
+      }
+    }
+    if (tok <= 0) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = 0.f;   // nonpadding mask
+    }
+    if (cond32 != nullptr) reinterpret_cast<float4*>(cond32)[i] = make_float4(v[0], v[1], v[2], v[3]);
+    uint2 o;
+    o.x = Cvt<T>::pack(v[0], v[1]);
+    o.y = Cvt<T>::pack(v[2], v[3]);
+    reinterpret_cast<uint2*>(cond16)[i] = o;
+  }
+}
+
 struct StepVals {
   float v[64];
 };

@@ -123,7 +123,8 @@ class GaussianDiffusion(nn.Module):
         if seed is None:
             seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if noise is None else 0
         c1, c2, lv = self._tables_on_host()
-        cond_bth = cond.detach().to(dtype=torch.float32).contiguous()
+        # a conditioning.AssembledCondition (frame-level assembly deferred to the kernels) passes through as it is
+        cond_bth = cond.detach().to(dtype=torch.float32).contiguous() if isinstance(cond, torch.Tensor) else cond
         t_list = list(range(infer_step - 1, -1, -1))
         self.denoise_fn.engine().sample(cond_bth, x, t_list, c1, c2, lv, noise=noise, seed=seed, x0_trace=x0_trace,
                                         lengths=lengths)

@@ -136,6 +136,31 @@ class Engine:
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream
 
+    def assemble(self, ac, cond_out: Optional[torch.Tensor] = None, plan: Optional[Plan] = None, entries: int = 1) -> None:
+        """pd_cond_assemble: frame-level condition assembly + condition projection of all layers for the rows of ``ac`` (a
+        conditioning.AssembledCondition), into ``plan`` (default: a plan of its shape); ``cond_out`` receives the dense
+        fp32 condition when given."""
+        B, T, _ = ac.shape
+        p = plan if plan is not None else self.plan(B, T, entries)
+        vp = C.c_void_p
+        nv = len(ac.variances)
+        arr = lambda k: (vp * 2)(*[ac.variances[j][k].data_ptr() if j < nv else None for j in range(2)])
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.pd_cond_assemble(
+                p.handle, ac.encoder_out.data_ptr(), int(ac.encoder_out.shape[1]), ac.mel2ph.data_ptr(), ac.f0.data_ptr(),
+                ac.pitch_w.data_ptr(), ac.pitch_b.data_ptr(),
+                ac.utt[0].data_ptr() if len(ac.utt) > 0 else None, ac.utt[1].data_ptr() if len(ac.utt) > 1 else None,
+                nv, arr(0), arr(1), arr(2), ac.frame.data_ptr() if ac.frame is not None else None,
+                cond_out.data_ptr() if cond_out is not None else None, self._stream()), "pd_cond_assemble")
+
+    def _cond_arg(self, p: Plan, cond, s: int, e: int):
+        """The ``cond`` argument of pd_sample / pd_reflow_sample for rows [s, e): a pointer to the dense fp32 tensor, or
+        NULL after assembling + projecting an AssembledCondition into the plan."""
+        if isinstance(cond, torch.Tensor):
+            return cond[s:e].data_ptr()
+        self.assemble(cond.rows(s, e), None, plan=p)
+        return None
+
     def _set_lengths(self, p: Plan, lengths, s: int, e: int) -> None:
         """Install (or clear) the per-utterance valid lengths of rows [s, e) on a plan (pd_plan_set_lengths)."""
         if lengths is None:
@@ -180,7 +205,7 @@ class Engine:
                 self._set_lengths(p, lengths, s, e)
                 # every block draws from its own Philox stream (the kernel counts frames from 0 inside a call)
                 sd = (seed + ci * 0x9E3779B97F4A7C15) & (2 ** 64 - 1)
-                _lib.check(self.lib.pd_sample(p.handle, cond_bth[s:e].data_ptr(), x[s:e].data_ptr(),
+                _lib.check(self.lib.pd_sample(p.handle, self._cond_arg(p, cond_bth, s, e), x[s:e].data_ptr(),
                                               nz.data_ptr() if nz is not None else None, C.c_uint64(sd),
                                               K, tl, c1, c2, lv, n, tr.data_ptr() if tr is not None else None, self._stream()),
                            "pd_sample")
@@ -207,7 +232,7 @@ class Engine:
                 tr = None if v_trace is None else (v_trace if whole else torch.empty_like(v_trace[:, s:e]))
                 scratch = None if tr is not None else torch.empty(stages, e - s, 1, M, T, dtype=torch.float32, device=self.device)
                 _lib.check(self.lib.pd_reflow_sample(
-                    p.handle, cond_bth[s:e].data_ptr(), x[s:e].data_ptr(), algo, int(n_steps), float(time_scale),
+                    p.handle, self._cond_arg(p, cond_bth, s, e), x[s:e].data_ptr(), algo, int(n_steps), float(time_scale),
                     (tr if tr is not None else scratch).data_ptr(),
                     spec_min.data_ptr() if spec_min is not None else None, spec_max.data_ptr() if spec_max is not None else None,
                     int(spec_min.numel()) if spec_min is not None else 0,

@@ -58,7 +58,8 @@ class RectifiedFlow(nn.Module):
             v_pred, v_gt = self.p_losses(spec, t, cond=cond.transpose(1, 2))
             return v_pred, v_gt, t
         # denorm_spec (reflow.py:106-107) runs as the last kernel of the sequence, on the state, before the view is taken
-        x = self._run(cond.transpose(1, 2), b, infer_step, device, x_start, v_trace, denorm=True, lengths=lengths)
+        x = self._run(cond.transpose(1, 2) if isinstance(cond, torch.Tensor) else cond, b, infer_step, device, x_start, v_trace,
+                      denorm=True, lengths=lengths)
         return self._finish(x)
 
     @torch.no_grad()
@@ -68,8 +69,9 @@ class RectifiedFlow(nn.Module):
 
     @torch.no_grad()
     def _run(self, cond, b, infer_step, device, x_start, v_trace, denorm, lengths=None):
+        dense = isinstance(cond, torch.Tensor)   # else a conditioning.AssembledCondition ([B,T,H] inputs, assembled by the kernels)
         device = cond.device if device is None else device
-        T = cond.shape[2]
+        T = cond.shape[2] if dense else cond.shape[1]
         if x_start is None:
             x = torch.randn(b, self.num_features, self.out_dims, T, device=device)
         else:
@@ -81,7 +83,7 @@ class RectifiedFlow(nn.Module):
         if v_trace is not None and (v_trace.shape != (n * stages, b, 1, self.out_dims, T) or not v_trace.is_contiguous()
                                     or v_trace.dtype != torch.float32 or v_trace.device != x.device):
             raise ValueError(f"v_trace must be a contiguous fp32 {(n * stages, b, 1, self.out_dims, T)} tensor on cond's device")
-        cond_bth = cond.detach().transpose(1, 2).to(dtype=torch.float32).contiguous()
+        cond_bth = cond.detach().transpose(1, 2).to(dtype=torch.float32).contiguous() if dense else cond
         smin = self.spec_min.detach().to(device=device, dtype=torch.float32).reshape(-1).contiguous()
         smax = self.spec_max.detach().to(device=device, dtype=torch.float32).reshape(-1).contiguous()
         if not denorm:

@@ -5,7 +5,8 @@ import numpy as np
 import torch
 
 from oracle import prodiff_oracle as oracle
-from oracle.golden_cases import SAMPLE_CASES, DENOISE_CASES, REFLOW_CASES, reflow_spec_range
+from oracle.golden_cases import (SAMPLE_CASES, DENOISE_CASES, REFLOW_CASES, CONDITION_CASES, reflow_spec_range,
+                                 make_condition_inputs)
 from prodiff_b200 import synth
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -53,3 +54,11 @@ def oracle_reflow(case, cfg, state, cond, x_start):
     if case["spec"] == "pitch":
         out = out.mean(dim=-1).clamp(-12.0, 12.0)
     return out, vs
+
+
+def oracle_condition(name):
+    """(inputs dict, oracle condition [B,T,H]) of a CONDITION case."""
+    d = make_condition_inputs(CONDITION_CASES[name])
+    out = oracle.assemble_condition(d["encoder_out"], d["mel2ph"], d["f0"], d["pitch_w"], d["pitch_b"], d["spk"], d["gender"],
+                                    d["variances"])
+    return d, out

@@ -410,6 +410,79 @@ def test_offline_sample_items_matches_single_utterance_loop():
     assert res2[0]["x_0"].shape == (lens[0], 128) and np.isfinite(res2[0]["x_0"]).all()
 
 
+@pytest.mark.parametrize("name", ["full", "frame_mix", "bare"])
+def test_condition_assembly_kernel_matches_oracle_and_fixture(name):
+    """SURVEY 8f N1 (frame-level half): pd_cond_assemble against the oracle restatement of prodiff_teacher.py:127-149 and
+    the reference-made fixture; fp32 elementwise work, bound 1e-5 absolute (one-ulp differences of log / fma order)."""
+    import types
+    import prodiff_b200 as pb
+    from oracle.golden_cases import CONDITION_CASES
+    from prodiff_b200 import synth
+    case = CONDITION_CASES[name]
+    d, ref = helpers.oracle_condition(name)
+    g = helpers.load_golden("condition", name)
+    cfg = synth.DiffNetConfig(128, 256, 2, 256, 1)
+    wn = _build(cfg, synth.make_state(cfg, 5, "trained"))
+    cu = lambda t: None if t is None else t.cuda()
+    utt, frame = [], None
+    for e in (d["spk"], d["gender"]):
+        if e is None:
+            continue
+        if e.shape[1] == case["T"] and case["T"] != 1:
+            frame = e
+        else:
+            utt.append(e[:, 0])
+    ac = pb.AssembledCondition(cu(d["encoder_out"]), cu(d["mel2ph"]), cu(d["f0"]), cu(d["pitch_w"]), cu(d["pitch_b"]),
+                               [cu(u) for u in utt], cu(frame), [(cu(x), cu(w), cu(b)) for x, w, b in d["variances"]])
+    out = ac.materialize(wn.engine()).cpu()
+    assert out.shape == ref.shape
+    assert float((out - ref).abs().max()) <= 1e-5 and float((out - torch.from_numpy(g["out"])).abs().max()) <= 1e-5
+    assert ac.lengths() == [int(v) for v in (d["mel2ph"] > 0).sum(1)]
+    # the same through conditioning.forward_condition on a stand-in for the reference teacher module
+    lin = lambda w, b: types.SimpleNamespace(weight=cu(w), bias=cu(b))
+    teacher = types.SimpleNamespace(
+        with_dur_embed=False, with_lang_embed=False, encoder=lambda tok, extra: cu(d["encoder_out"]),
+        pitch_embed=lin(d["pitch_w"], d["pitch_b"]), with_spk_embed=d["spk"] is not None, with_gender_embed=d["gender"] is not None,
+        add_spk_embed=lambda i, mix: mix, add_gender_embed=lambda i, mix: mix,
+        with_voicing_embed=case["n_var"] >= 1, with_breath_embed=case["n_var"] >= 2)
+    if case["n_var"] >= 1:
+        teacher.voicing_embed = lin(d["variances"][0][1], d["variances"][0][2])
+    if case["n_var"] >= 2:
+        teacher.breath_embed = lin(d["variances"][1][1], d["variances"][1][2])
+    ac2 = pb.forward_condition(teacher, torch.ones(case["B"], case["Tph"], dtype=torch.long).cuda(), cu(d["mel2ph"]), cu(d["f0"]),
+                               spk_mix_embed=cu(d["spk"]), gender_mix_embed=cu(d["gender"]),
+                               voicing=cu(d["variances"][0][0]) if case["n_var"] >= 1 else None,
+                               breath=cu(d["variances"][1][0]) if case["n_var"] >= 2 else None)
+    assert float((ac2.materialize(wn.engine()).cpu() - ref).abs().max()) <= 1e-5
+
+
+def test_sampling_from_assembled_condition_equals_dense_condition():
+    """GaussianDiffusion / RectifiedFlow accept the AssembledCondition in place of the dense [B,T,H] tensor: the 16-bit
+    operand written by pd_cond_assemble is the rounding of the same fp32 values the dense path casts, so the samples are
+    identical; with lengths taken from mel2ph the batch is ragged as well."""
+    import prodiff_b200 as pb
+    from prodiff_b200 import synth
+    d, _ = helpers.oracle_condition("full")
+    cfg = synth.DiffNetConfig(128, 256, 4, 256, 2)
+    state = synth.make_state(cfg, 81, "trained")
+    case = dict(timesteps=4, schedule_type="vpsde", max_beta=40)
+    gd = _build(cfg, state, case)
+    rf = pb.RectifiedFlow(128, gd.denoise_fn, time_scale=1000, sampling_algorithm="euler", spec_min=[-12.0], spec_max=[0.0]).cuda().eval()
+    cu = lambda t: t.cuda()
+    ac = pb.AssembledCondition(cu(d["encoder_out"]), cu(d["mel2ph"]), cu(d["f0"]), cu(d["pitch_w"]), cu(d["pitch_b"]),
+                               [cu(d["spk"][:, 0]), cu(d["gender"][:, 0])], None, [(cu(x), cu(w), cu(b)) for x, w, b in d["variances"]])
+    dense = ac.materialize(gd.denoise_fn.engine())
+    B, T = dense.shape[:2]
+    _, x_T, noise = synth.make_inputs(cfg, B, T, 3, 82)
+    with torch.no_grad():
+        a = gd(ac, infer_step=3, infer=True, x_T=x_T.cuda(), noise=noise.cuda())
+        b = gd(dense, infer_step=3, infer=True, x_T=x_T.cuda(), noise=noise.cuda())
+        assert torch.equal(a, b)
+        fa = rf(ac, infer_step=2, infer=True, x_start=noise[0].cuda(), lengths=ac.lengths())
+        fb = rf(dense, infer_step=2, infer=True, x_start=noise[0].cuda(), lengths=ac.lengths())
+        assert torch.equal(fa, fb) and torch.isfinite(fa).all()
+
+
 def test_full_size_roundtrip_properties():
     """BASELINE config-2 size (64 x 1000, K = 4), properties that need no oracle run:
     determinism per seed, batch-row independence (a row sampled alone equals the same row inside the batch, which is

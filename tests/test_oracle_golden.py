@@ -10,7 +10,7 @@ import pytest
 import torch
 
 from oracle import prodiff_oracle as oracle
-from oracle.golden_cases import SAMPLE_CASES, DENOISE_CASES, REFLOW_CASES
+from oracle.golden_cases import SAMPLE_CASES, DENOISE_CASES, REFLOW_CASES, CONDITION_CASES
 from prodiff_b200 import synth
 from tests import helpers
 
@@ -75,6 +75,17 @@ def test_reflow_unknown_algorithm_is_euler():
     a, _ = helpers.oracle_reflow(case, cfg, state, cond, x_start)
     b, _ = helpers.oracle_reflow(dict(case, algorithm="heun?"), cfg, state, cond, x_start)
     assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("name", sorted(CONDITION_CASES))
+def test_condition_assembly_matches_reference_fixture(name):
+    """Frame-level half of ProDiffTeacher.forward_condition (prodiff_teacher.py:127-149): the fixture holds what the
+    reference method returned for the seeded inputs."""
+    d, out = helpers.oracle_condition(name)
+    g = helpers.load_golden("condition", name)
+    assert out.shape == g["out"].shape and np.abs(out.numpy() - g["out"]).max() <= TOL
+    pad = d["mel2ph"].numpy() == 0
+    assert not pad.any() or np.abs(out.numpy()[pad]).max() == 0.0      # non-padding mask, :148-149
 
 
 def test_default_schedule_values():

@@ -57,6 +57,15 @@ def test_reflow_bit_exact(mg, name):
     assert np.array_equal(out.contiguous().numpy(), ref["out"])
 
 
+@pytest.mark.parametrize("name", ["full", "frame_mix", "bare"])
+def test_condition_assembly_bit_exact(mg, name):
+    from oracle.golden_cases import CONDITION_CASES
+    from tests import helpers
+    ref = mg.run_reference_condition(CONDITION_CASES[name])
+    _, out = helpers.oracle_condition(name)
+    assert np.array_equal(out.numpy(), ref["out"])
+
+
 def test_reference_init_distribution_matches_synth(mg):
     """synth.make_state mirrors the reference's init *distributions* (not its torch RNG stream)."""
     from prodiff_b200 import synth
