@@ -483,6 +483,72 @@ def test_sampling_from_assembled_condition_equals_dense_condition():
         assert torch.equal(fa, fb) and torch.isfinite(fa).all()
 
 
+SHAPE_SWEEP = [
+    # (B, T, L, C, cycle, M, K, operand dtype, ragged)      what it stresses
+    (1, 1, 2, 256, 1, 128, 1, "bf16", False),               # a single frame, a single step
+    (2, 128, 3, 256, 2, 128, 2, "bf16", False),             # T exactly one tile, even tile count
+    (3, 129, 2, 256, 5, 128, 2, "bf16", True),              # one frame into the second tile, dilation up to 16, ragged
+    (5, 257, 3, 256, 3, 128, 3, "fp16", True),              # odd tile count (dummy peer tile), fp16 operands, ragged
+    (2, 200, 2, 256, 1, 64, 2, "bf16", False),              # 64 mel bins: unfused tail, fused layer stack
+    (1, 300, 2, 512, 2, 128, 2, "bf16", False),             # 512 channels: unfused conv+gate / res kernels
+    (4, 96, 4, 256, 4, 128, 4, "bf16", True),               # T shorter than a tile, dilation 8 > T / 16, ragged
+    (7, 40, 2, 256, 2, 128, 2, "fp16", False),              # many short rows
+]
+
+
+@pytest.mark.parametrize("B,T,L,C,cycle,M,K,dt,ragged", SHAPE_SWEEP)
+def test_shape_sweep_against_oracle(B, T, L, C, cycle, M, K, dt, ragged):
+    """Seeded sweep over shapes the fixtures do not cover (tile-boundary lengths, odd tile counts, the largest dilation,
+    64 mel bins, 512 channels, single frames / steps, ragged rows), each against the oracle on identical x_T and noise."""
+    from prodiff_b200 import synth
+    cfg = synth.DiffNetConfig(M, 256, L, C, cycle)
+    state = synth.make_state(cfg, 900 + B * 7 + T, "trained")
+    case = dict(timesteps=max(4, K), schedule_type="vpsde", max_beta=40, infer_step=K)
+    cond, x_T, noise = synth.make_inputs(cfg, B, T, K, 1000 + T)
+    gd = _build(cfg, state, case, dt)
+    lens = [max(1, T - (b * (T // 3 + 1)) % T) for b in range(B)] if ragged else None
+    tr = torch.empty(K, B, 1, M, T, device="cuda")
+    with torch.no_grad():
+        mel = gd(cond.cuda(), infer_step=K, infer=True, x_T=x_T.cuda(), noise=noise.cuda(), x0_trace=tr, lengths=lens).cpu()
+    tr = tr.cpu()
+    assert torch.isfinite(mel).all()
+    for b in range(B):
+        n = lens[b] if ragged else T
+        if ragged:      # the oracle of a ragged row is that utterance alone at its own length
+            ref, x0s = helpers.oracle_sample(case, cfg, state, cond[b:b + 1, :n], x_T[b:b + 1, :, :, :n].contiguous(),
+                                             noise[:, b:b + 1, :, :, :n].contiguous())
+        elif b == 0:
+            ref_all, x0s_all = helpers.oracle_sample(case, cfg, state, cond, x_T, noise)
+        if not ragged:
+            ref, x0s = ref_all[b:b + 1], [v[b:b + 1] for v in x0s_all]
+        e0 = float((tr[0, b:b + 1, :, :, :n] - x0s[0]).abs().max())
+        l1 = float((mel[b:b + 1, :n] - ref).abs().mean())
+        assert e0 <= STEP_TOL and l1 <= MEL_L1_TOL, (b, n, e0, l1)
+
+
+def test_unsupported_combinations_fail_loudly():
+    """No silent fallbacks: per-utterance lengths on a shape the fused layer kernel does not cover, a bad length, and a
+    v_trace of the wrong size are errors with a message, not a different code path."""
+    import prodiff_b200 as pb
+    from prodiff_b200 import synth
+    cfg = synth.DiffNetConfig(128, 256, 2, 512, 1)
+    gd = _build(cfg, synth.make_state(cfg, 3, "trained"), dict(timesteps=4, schedule_type="vpsde", max_beta=40))
+    cond = torch.zeros(2, 64, 256, device="cuda")
+    with pytest.raises(RuntimeError, match="fused layer kernel"):
+        gd(cond, infer_step=2, infer=True, lengths=[64, 10])
+    cfg2 = synth.DiffNetConfig(128, 256, 2, 256, 1)
+    gd2 = _build(cfg2, synth.make_state(cfg2, 3, "trained"), dict(timesteps=4, schedule_type="vpsde", max_beta=40))
+    with pytest.raises(RuntimeError, match="outside"):
+        gd2(cond, infer_step=2, infer=True, lengths=[64, 65])
+    with pytest.raises(ValueError):
+        gd2(cond, infer_step=2, infer=True, lengths=[64])
+    rf = pb.RectifiedFlow(128, gd2.denoise_fn, sampling_algorithm="rk4", spec_min=[-12.0], spec_max=[0.0]).cuda().eval()
+    with pytest.raises(ValueError, match="v_trace"):
+        rf(cond, infer_step=2, infer=True, v_trace=torch.empty(2, 2, 1, 128, 64, device="cuda"))
+    out = gd2(cond, infer_step=2, infer=True, lengths=[64, 10])      # and the plan is usable again afterwards
+    assert torch.isfinite(out).all()
+
+
 def test_full_size_roundtrip_properties():
     """BASELINE config-2 size (64 x 1000, K = 4), properties that need no oracle run:
     determinism per seed, batch-row independence (a row sampled alone equals the same row inside the batch, which is
