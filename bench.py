@@ -139,7 +139,7 @@ def run_reference(args, rank):
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
     torch.set_flush_denormal(True)
-    sample_B = 2
+    sample_B = 8   # same bounded sample as the cpu_baseline leg of our own arm (larger batches run the CPU more efficiently)
     cfg = synth.DiffNetConfig(w["in_dims"], w["hidden"], w["layers"], w["channels"], w["cycle"])
     state = synth.make_state(cfg, 1234, "trained")
     tables = oracle.diffusion_tables(w["timesteps"], w["schedule"], w["max_beta"])
