@@ -156,7 +156,7 @@ static int make_w_map(CUtensorMap* m, int dtype, const void* base, int K, int ro
 // ------------------------------------------------------------------ packed weight layout
 struct PackedLayout {
   // 16-bit operands (byte offsets)
-  size_t w_in, w_cond, w_dil, w_dil64, w_res, w_skip, w_sp, w_out;
+  size_t w_in, w_cond, w_dil, w_res, w_skip, w_sp, w_out;
   // fp32 biases
   size_t b_in, b_cp, b_res, b_skipsum, b_sp, b_out;
   // fp32 copies for the step-embedding chain
@@ -171,7 +171,6 @@ static PackedLayout packed_layout(const pd_config& c) {
   p.w_in = take(C * M * 2);
   p.w_cond = take(L * 2 * C * H * 2);
   p.w_dil = take(L * 2 * C * 3 * C * 2);
-  p.w_dil64 = take(L * 2 * C * 3 * C * 2);  // 64-channel gate/filter pairing (fused layer kernel)
   p.w_res = take((L + 1) * C * C * 2);  // + one [C x C] identity block (fused layer kernel: residual add on the tensor core)
   p.w_skip = take(C * L * C * 2);
   p.w_sp = take(C * C * 2);
@@ -218,7 +217,6 @@ struct pd_model {
   int device, sm_count;
   CUtensorMap tm_w_in, tm_w_cond, tm_w_dil, tm_w_res, tm_w_skip, tm_w_sp, tm_w_out;
   CUtensorMap tm_w_dil128, tm_w_res128;  // 128-row boxes: one CTA's half of a cta_group::2 weight block
-  CUtensorMap tm_w_dil64;                // 64-row boxes over the 64-channel-paired packing
   CUtensorMap tm_w_in_h, tm_w_cond_h, tm_w_skip_h, tm_w_sp_h, tm_w_out_h;  // half-height boxes for the cta_group::2 GEMMs
 };
 
@@ -253,8 +251,6 @@ static int pack_all(const pd_config& c, const PackedLayout& lay, uint8_t* pk, co
     const float* const* q = st + 10 + 8 * l;
     k_pack_dil<T><<<blocks(6ll * C * C), TB, 0, s>>>((T*)(pk + lay.w_dil) + (size_t)l * 2 * C * 3 * C, q[0], C);
     PD_LAUNCH_CHECK("k_pack_dil");
-    k_pack_dil64<T><<<blocks(6ll * C * C), TB, 0, s>>>((T*)(pk + lay.w_dil64) + (size_t)l * 2 * C * 3 * C, q[0], C);
-    PD_LAUNCH_CHECK("k_pack_dil64");
     k_pack_rows<T><<<blocks(2ll * C * H), TB, 0, s>>>((T*)(pk + lay.w_cond) + (size_t)l * 2 * C * H, H, 0, q[4], 2 * C, 0, 2 * C, H, C);
     PD_LAUNCH_CHECK("k_pack_rows(cond)");
     k_pack_rows<T><<<blocks((long long)C * C), TB, 0, s>>>((T*)(pk + lay.w_res) + (size_t)l * C * C, C, 0, q[6], 2 * C, 0, C, C, 0);
@@ -308,7 +304,6 @@ extern "C" int pd_model_create(const pd_config* cfg, const float* const* state, 
       make_w_map(&m->tm_w_skip, dt, pk + lay.w_skip, L * C, C, 256) || make_w_map(&m->tm_w_sp, dt, pk + lay.w_sp, C, C, 256) ||
       make_w_map(&m->tm_w_out, dt, pk + lay.w_out, C, 128, 128) ||
       make_w_map(&m->tm_w_dil128, dt, pk + lay.w_dil, 3 * C, L * 2 * C, 128) || make_w_map(&m->tm_w_res128, dt, pk + lay.w_res, C, (L + 1) * C, 128) ||
-      make_w_map(&m->tm_w_dil64, dt, pk + lay.w_dil64, 3 * C, L * 2 * C, 64) ||
       make_w_map(&m->tm_w_in_h, dt, pk + lay.w_in, M, C, 128) || make_w_map(&m->tm_w_cond_h, dt, pk + lay.w_cond, H, L * 2 * C, 128) ||
       make_w_map(&m->tm_w_skip_h, dt, pk + lay.w_skip, L * C, C, 128) || make_w_map(&m->tm_w_sp_h, dt, pk + lay.w_sp, C, C, 128) ||
       make_w_map(&m->tm_w_out_h, dt, pk + lay.w_out, C, 128, 64)) {
@@ -457,11 +452,11 @@ static bool pair_enabled() {
   return g_pair == 1;
 }
 
-template <int EPI, int BN, typename T, bool kPair, bool kARes = false>
+template <int EPI, int BN, typename T, bool kPair>
 static int launch_gemm_t(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, const CUtensorMap& x,
                          const GemmShape& sh, const EpiArgs& ep, int sms, cudaStream_t s, const char* name, int kind) {
-  auto kern = gemm_kernel<EPI, BN, T, kPair, kARes>;
-  using Cfg = GemmCfg<EPI, BN, kPair, kARes>;
+  auto kern = gemm_kernel<EPI, BN, T, kPair>;
+  using Cfg = GemmCfg<EPI, BN, kPair>;
   static bool configured[64] = {false};  // per instantiation, per device
   int dev = 0;
   PD_CUDA(cudaGetDevice(&dev));
@@ -563,9 +558,9 @@ static bool stack_enabled() {
 // Launch the fused ResidualBlock kernel for layers [lp.layer0, lp.layer0 + lp.n_layers).  n_layers > 1 is the persistent
 // multi-layer form: its clusters wait on one another through global flags, so every cluster must be co-resident --
 // `*ok_multi` reports whether the occupancy query allows that (the caller falls back to one launch per layer).
-template <typename T, bool kHybrid>
+template <typename T>
 static int launch_layer_t(const LayerMaps& mp, const LayerParams& lp, int sms, cudaStream_t s, bool* ok_multi) {
-  auto kern = layer_kernel<T, kHybrid>;
+  auto kern = layer_kernel<T>;
   static bool configured[64] = {false};
   int dev = 0;
   PD_CUDA(cudaGetDevice(&dev));
@@ -602,9 +597,8 @@ static int launch_layer_t(const LayerMaps& mp, const LayerParams& lp, int sms, c
   return 0;
 }
 
-static int launch_layer(int dt, bool hybrid, const LayerMaps& mp, const LayerParams& lp, int sms, cudaStream_t s, bool* ok_multi) {
-  if (dt == PD_FP16) return hybrid ? launch_layer_t<__half, true>(mp, lp, sms, s, ok_multi) : launch_layer_t<__half, false>(mp, lp, sms, s, ok_multi);
-  return hybrid ? launch_layer_t<__nv_bfloat16, true>(mp, lp, sms, s, ok_multi) : launch_layer_t<__nv_bfloat16, false>(mp, lp, sms, s, ok_multi);
+static int launch_layer(int dt, const LayerMaps& mp, const LayerParams& lp, int sms, cudaStream_t s, bool* ok_multi) {
+  return dt == PD_FP16 ? launch_layer_t<__half>(mp, lp, sms, s, ok_multi) : launch_layer_t<__nv_bfloat16>(mp, lp, sms, s, ok_multi);
 }
 
 // ------------------------------------------------------------------ fused sampler tail launch
@@ -780,17 +774,6 @@ static int cond_project_from16(pd_plan* p, cudaStream_t s) {
   ep.ld = C2;
   ep.out_type = OUT_F16;
   ep.out_blocked = 1;
-  // Optional (PD_ARES=1): keep the activation tile resident across its 40 N tiles and stream only (half) weight blocks,
-  // as cta_group::2 pairs.  Measured neutral (0.50 vs 0.47 ms): the kernel writes 1.34 GB and is HBM-write bound.
-  static int ares = -1;
-  if (ares < 0) { const char* e = getenv("PD_ARES"); ares = (e && e[0] == '1') ? 1 : 0; }
-  if (ares && c.hidden_size <= 256 && p->B * sh.m_tiles_per_row >= 2) {
-    sh.trace = g_trace ? g_trace : nullptr;
-    sh.idesc = make_idesc(c.dtype, 256, 256);
-    return c.dtype == PD_FP16
-               ? launch_gemm_t<EPI_STORE_BLK, 256, __half, true, true>(p->tm_cond, m->tm_w_cond_h, p->tm_cond, p->tm_cond, sh, ep, m->sm_count, s, "gemm(cond_proj)", 0)
-               : launch_gemm_t<EPI_STORE_BLK, 256, __nv_bfloat16, true, true>(p->tm_cond, m->tm_w_cond_h, p->tm_cond, p->tm_cond, sh, ep, m->sm_count, s, "gemm(cond_proj)", 0);
-  }
   static int blk = -1;   // PD_CP_DIRECT=1: the earlier epilogue with direct st.global (A/B only)
   static int cp_pair = -1;   // PD_CP_PAIR=0: single-CTA tiles instead of cta_group::2 pairs
   if (cp_pair < 0) { const char* e = getenv("PD_CP_PAIR"); cp_pair = (e && e[0] == '0') ? 0 : (pair_enabled() ? 1 : 0); }
@@ -845,7 +828,6 @@ static int run_denoiser(pd_plan* p, int entry_base, int entry_per_b, const OutSt
   const int C = c.residual_channels, L = c.residual_layers, M = c.in_dims, B = p->B, T = p->T, dt = c.dtype, sms = m->sm_count;
   const uint8_t* pk = m->packed;
   const PackedLayout& lay = m->lay;
-  const size_t N = (size_t)B * T;
   // input_projection + ReLU (wavenet.py:108-111)
   if (!os.have_xa) {
     GemmShape sh = base_shape(B, T, C / 256, M / 64);
@@ -873,7 +855,6 @@ static int run_denoiser(pd_plan* p, int entry_base, int entry_per_b, const OutSt
       mp.xs[0] = p->tm_xa_st;
       mp.xs[1] = p->tm_xb_st;
       mp.wd = m->tm_w_dil128;
-      mp.wq = m->tm_w_dil64;
       mp.wr = m->tm_w_res128;
       mp.ys = p->tm_y_st;
       LayerParams lp;
@@ -891,7 +872,6 @@ static int run_denoiser(pd_plan* p, int entry_base, int entry_per_b, const OutSt
         lp.ident_resident = (res_opt && layer_smem_bytes(lp.xsub, 1) <= kLayerSmemMax) ? 1 : 0;
       }
       lp.idesc = (1u << 4) | ((dt == PD_FP16 ? 0u : 1u) << 7) | ((dt == PD_FP16 ? 0u : 1u) << 10) | ((256u >> 3) << 17) | ((256u >> 4) << 24);
-      lp.idesc128 = (lp.idesc & ~(0x3Fu << 17)) | ((128u >> 3) << 17);
       lp.idesc64 = (lp.idesc & ~(0x3Fu << 17)) | ((64u >> 3) << 17);
       lp.cp = p->ptr<uint16_t>("cp");
       lp.cp_layer_stride = (long long)mtiles * kBlockM * 2 * C;
@@ -903,9 +883,6 @@ static int run_denoiser(pd_plan* p, int entry_base, int entry_per_b, const OutSt
       lp.scale = 0.70710678118654752440f;
       lp.lens = p->ragged ? p->ptr<int>("lens") : nullptr;
       lp.trace = g_trace ? g_trace + 8 * 1024 : nullptr;
-      static int hyb = -1;
-      if (hyb < 0) { const char* e = getenv("PD_HYBRID"); hyb = (e && e[0] == '1') ? 1 : 0; }
-      const bool hybrid = hyb == 1;
       bool done = false;
       if (stack_enabled() && L > 1) {
         // one persistent launch for the whole stack; tiles of consecutive layers synchronise through per-tile flags
@@ -915,7 +892,7 @@ static int run_denoiser(pd_plan* p, int entry_base, int entry_per_b, const OutSt
         lp.flags = p->ptr<unsigned int>("flags");
         PD_CUDA(cudaMemsetAsync(lp.flags, 0, (size_t)L * mtiles * 4, s));
         bool ok = false;
-        const int rc = launch_layer(dt, hybrid, mp, lp, sms, s, &ok);
+        const int rc = launch_layer(dt, mp, lp, sms, s, &ok);
         if (rc) return rc;
         done = ok;
       }
@@ -925,7 +902,7 @@ static int run_denoiser(pd_plan* p, int entry_base, int entry_per_b, const OutSt
         lp.n_layers = 1;
         for (int ll = 0; ll < L; ++ll) {
           lp.layer0 = ll;
-          const int rc = launch_layer(dt, hybrid, mp, lp, sms, s, nullptr);
+          const int rc = launch_layer(dt, mp, lp, sms, s, nullptr);
           if (rc) return rc;
         }
       }

@@ -30,21 +30,6 @@ __global__ void k_pack_dil(T* __restrict__ dst, const float* __restrict__ src, i
   }
 }
 
-// Second packing of dilated_conv.weight for the fused layer kernel's 64-channel chunks: packed row p = c * 128 + w holds
-// gate channel 64c + w (w < 64) or filter channel 64c + w - 64; K index = tap * C + channel as above.
-template <typename T>
-__global__ void k_pack_dil64(T* __restrict__ dst, const float* __restrict__ src, int C) {
-  const long long total = 2ll * C * 3 * C;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int p = (int)(i / (3 * C));
-    const int rem = (int)(i - (long long)p * 3 * C);
-    const int tap = rem / C, c = rem - tap * C;
-    const int chunk = p >> 7, w = p & 127;
-    const int orig = (w >> 6) * C + chunk * 64 + (w & 63);
-    dst[i] = from_float<T>(src[((long long)orig * C + c) * 3 + tap]);
-  }
-}
-
 // Generic row gather: dst[r * dst_ld + dst_col0 + c] = src[(rowmap(r) + src_row0) * cols + c], zero for rows
 // beyond src_rows.  gateC > 0 selects the gate-paired row order.
 template <typename T>

@@ -173,18 +173,15 @@ __device__ __forceinline__ void gate_chunk16(const uint32_t (&rg)[16], const uin
 // kPair: two CTAs of a cluster compute two adjacent 128-frame tiles with tcgen05.mma.cta_group::2 (M = 256); each CTA
 // stages its own A tile and only HALF of the weight block, which halves L2 -> SM weight traffic (the single-CTA form of
 // cond_proj / skip_sum re-streams the weights per 128-row tile and sits at the L2 throughput cap).
-// kARes ("A resident", K <= 256, no taps): the activation tile is loaded ONCE per frame tile into shared memory and
-// reused for every N tile; each CTA (pair) walks a contiguous chunk of (m, n) tiles so consecutive tiles share it, and
-// the ring carries weight blocks only.  For cond_proj (40 N tiles per frame tile) this removes 39/40 of the A traffic.
-template <int EPI, int BN, bool kPair = false, bool kARes = false> struct GemmCfg {
+template <int EPI, int BN, bool kPair = false> struct GemmCfg {
   static constexpr uint32_t kABytes = kBlockM * kBlockK * 2;
   static constexpr uint32_t kBBytes = (kPair ? BN / 2 : BN) * kBlockK * 2;
-  static constexpr uint32_t kStageBytes = (kARes ? 0 : kABytes) + kBBytes;
+  static constexpr uint32_t kStageBytes = kABytes + kBBytes;
   static constexpr uint32_t kStagingBytes = (EPI == EPI_STORE_BLK) ? 65536 : 0;   // blocked-output tile staged for a bulk store
-  static constexpr uint32_t kExtraBytes = (kARes ? 4 * kABytes : ((EPI == EPI_GATE) ? 2 * 16384 : (EPI == EPI_RES ? 4 * 16384 : 0))) + kStagingBytes;
+  static constexpr uint32_t kExtraBytes = ((EPI == EPI_GATE) ? 2 * 16384 : (EPI == EPI_RES ? 4 * 16384 : 0)) + kStagingBytes;
   // smem ring depth: as many stages as fit next to the epilogue's operand/output tile (cap 8)
   static constexpr int kStagesFit = (int)((227u * 1024u - 1024u - 256u - kExtraBytes) / kStageBytes);
-  static constexpr int kStagesWant = (kPair || kARes) ? 8 : ((EPI == EPI_RES) ? 3 : (BN == 256 ? 4 : 6));
+  static constexpr int kStagesWant = kPair ? 8 : ((EPI == EPI_RES) ? 3 : (BN == 256 ? 4 : 6));
   static constexpr int kStages = kStagesFit < kStagesWant ? kStagesFit : kStagesWant;
   static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kExtraBytes + 1024 + 256;  // + alignment slack + barriers
 };
@@ -197,13 +194,12 @@ __device__ __forceinline__ uint4* sw128_chunk(uint8_t* tile, int r, int c) {
 // ------------------------------------------------------------------ the kernel
 // tmA: A operand (activations); tmB: B operand (weights); tmO: TMA-store target (GATE: gated activations, RES: x_next);
 // tmX: RES only, x_cur tile load.  Unused maps are passed as copies of tmA.
-template <int EPI, int BN, typename T, bool kPair = false, bool kARes = false>
+template <int EPI, int BN, typename T, bool kPair = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmX, const GemmShape sh,
             const EpiArgs ep) {
-  using Cfg = GemmCfg<EPI, BN, kPair, kARes>;
-  static_assert(!kARes || EPI == EPI_STORE || EPI == EPI_STORE_BLK, "A-resident mode is for the plain store epilogues");
+  using Cfg = GemmCfg<EPI, BN, kPair>;
   static_assert(EPI != EPI_STORE_BLK || BN == 256, "blocked-output staging is 256 columns wide");
   constexpr int kStages = Cfg::kStages;
   static_assert(BN == 256 || BN == 128, "tile width");
@@ -245,7 +241,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], kPair ? 2 * kEpiWarps : kEpiWarps);
     }
-    mbar_init(xfull_bar, (kARes && kPair) ? 2 : 1);   // RES: x tile landed / A-resident: A tile landed (in both CTAs)
+    mbar_init(xfull_bar, 1);   // RES: x tile landed
     mbar_init(xempty_bar, 1);
     fence_mbar_init();
   }
@@ -267,17 +263,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int num_tiles = (kPair ? (num_m_tiles + 1) / 2 : num_m_tiles) * sh.n_tiles;
   const int n_units = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;   // CTAs or CTA pairs
   const int unit = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-  // strided tiles, or (A-resident) one contiguous chunk per unit so that consecutive tiles share the frame tile
-  const int chunk = (num_tiles + n_units - 1) / n_units;
-  const int tile_first = kARes ? unit * chunk : unit;
-  const int tile_step = kARes ? 1 : n_units;
-  const int tile_end = kARes ? (tile_first + chunk < num_tiles ? tile_first + chunk : num_tiles) : num_tiles;
+  const int tile_first = unit, tile_step = n_units, tile_end = num_tiles;
   const int k_blocks = sh.k_per_tap * sh.taps;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      uint32_t it = 0, ti = 0, ai = 0;
+      uint32_t it = 0, ti = 0;
       for (int tile = tile_first; tile < tile_end; tile += tile_step, ++ti) {
         const int n_tile = tile % sh.n_tiles;
         const int m_tile = kPair ? 2 * (tile / sh.n_tiles) + (int)rank : tile / sh.n_tiles;
@@ -290,39 +282,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
           for (int j = 0; j < 4; ++j) tma_load_4d(extra + j * 16384, &tmX, xfull_bar, n_tile * BN + j * 64, t0, b, 0);
         }
-        if constexpr (kARes) {
-          if (tile == tile_first || n_tile == 0) {   // a new frame tile: (re)load the resident A tile, k_blocks x [128 x 64]
-            mbar_wait(xempty_bar, (ai & 1u) ^ 1u, 7);
-            if constexpr (kPair) {
-              if (leader) mbar_arrive_expect_tx(xfull_bar, 2u * (uint32_t)k_blocks * Cfg::kABytes);
-              else mbar_arrive_leader(xfull_bar);
-              for (int kb = 0; kb < k_blocks; ++kb) tma_load_4d_2sm(extra + kb * Cfg::kABytes, &tmA, xfull_bar, kb * kBlockK, t0, b, sh.a_slab0);
-            } else {
-              mbar_arrive_expect_tx(xfull_bar, (uint32_t)k_blocks * Cfg::kABytes);
-              for (int kb = 0; kb < k_blocks; ++kb) tma_load_4d(extra + kb * Cfg::kABytes, &tmA, xfull_bar, kb * kBlockK, t0, b, sh.a_slab0);
-            }
-            ++ai;
-          }
-        }
         for (int kb = 0; kb < k_blocks; ++kb, ++it) {
           const uint32_t stage = it % kStages, parity = (it / kStages) & 1u;
           mbar_wait(&empty_bar[stage], parity ^ 1u, 1);
           if (sh.trace && blockIdx.x == 0 && (kb == 0 || kb == k_blocks - 1)) sh.trace[ti * 16 + (kb == 0 ? 0 : 1)] = clock64();
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
-          uint8_t* sb = kARes ? sa : sa + Cfg::kABytes;
+          uint8_t* sb = sa + Cfg::kABytes;
           const int grp = kb / sh.k_per_tap, kc = kb - grp * sh.k_per_tap;
           const int t = sh.tap_mode ? t0 + (grp - (sh.taps >> 1)) * sh.dil : t0;
           const int slab = sh.tap_mode ? sh.a_slab0 : sh.a_slab0 + grp;
-          if constexpr (kARes) {
-            if constexpr (kPair) {
-              if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
-              else mbar_arrive_leader(&full_bar[stage]);
-              tma_load_2d_2sm(sb, &tmB, &full_bar[stage], kb * kBlockK, sh.b_row0 + n_tile * BN + (int)rank * (BN / 2));
-            } else {
-              mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-              tma_load_2d(sb, &tmB, &full_bar[stage], kb * kBlockK, sh.b_row0 + n_tile * BN);
-            }
-          } else if constexpr (kPair) {
+          if constexpr (kPair) {
             if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
             else mbar_arrive_leader(&full_bar[stage]);
             tma_load_4d_2sm(sa, &tmA, &full_bar[stage], kc * kBlockK, t, b, slab);
@@ -338,15 +307,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   } else if (warp == 1) {
     // ===================== MMA issuer (pair mode: leader CTA only) =====================
     if (lane == 0 && leader) {
-      uint32_t it = 0, ti = 0, ai = 0;
+      uint32_t it = 0, ti = 0;
       for (int tile = tile_first; tile < tile_end; tile += tile_step, ++ti) {
         const uint32_t as = ti & 1u, aph = (ti >> 1) & 1u;
-        if constexpr (kARes) {
-          if (tile == tile_first || tile % sh.n_tiles == 0) {   // wait for this frame tile's resident A
-            mbar_wait(xfull_bar, ai & 1u, 8);
-            ++ai;
-          }
-        }
         mbar_wait(&tempty_bar[as], aph ^ 1u, 2);
         tc_fence_after();
         if (sh.trace && blockIdx.x == 0) sh.trace[ti * 16 + 2] = clock64();
@@ -357,8 +320,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           tc_fence_after();
           if (sh.trace && blockIdx.x == 0 && (kb == 0 || kb == k_blocks - 1)) sh.trace[ti * 16 + (kb == 0 ? 3 : 4)] = clock64();
           const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
-          const uint64_t adesc = make_sw128_kmajor_desc(kARes ? smem_u32(extra) + kb * Cfg::kABytes : sa);
-          const uint64_t bdesc = make_sw128_kmajor_desc(kARes ? sa : sa + Cfg::kABytes);
+          const uint64_t adesc = make_sw128_kmajor_desc(sa);
+          const uint64_t bdesc = make_sw128_kmajor_desc(sa + Cfg::kABytes);
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k) {
             if constexpr (kPair) umma_f16_2sm(d_tmem, desc_advance_k(adesc, k), desc_advance_k(bdesc, k), sh.idesc, (kb | k) != 0 ? 1u : 0u);
@@ -371,13 +334,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         // accumulator complete
         if constexpr (kPair) umma_commit_2sm(&tfull_bar[as]);
         else umma_commit(&tfull_bar[as]);
-        if constexpr (kARes) {
-          // last N tile of this frame tile inside the chunk: the resident A tile may be replaced once these MMAs are done
-          if (tile + 1 >= tile_end || (tile + 1) % sh.n_tiles == 0) {
-            if constexpr (kPair) umma_commit_2sm(xempty_bar);
-            else umma_commit(xempty_bar);
-          }
-        }
       }
     }
   } else {
@@ -432,7 +388,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         // column half is ONE contiguous 32 KB range in global memory, so it is staged in the same order in shared memory
         // (conflict-free 16-byte stores, one thread per row) and leaves as a single bulk copy.  Direct st.global from the
         // epilogue threads made this kernel epilogue-bound (6.7 k cycles per tile against 2 k of MMA).
-        uint8_t* stg = extra + (kARes ? 4 * Cfg::kABytes : 0) + h * 32768;
+        uint8_t* stg = extra + h * 32768;
         const bool store_thread = (q == 0 && lane == 0);
         if (store_thread) tma_store_wait_read<0>();   // the previous tile's copy has finished reading the staging half
         named_bar_sync(1 + h, 4 * 32);

@@ -4,7 +4,7 @@
 //   x_next = (x + W_res y + b_res) / sqrt(2)                                                    (MMA2 + epilogue 2)
 //            where "x +" is itself part of MMA2: an identity weight block over the centre view of the resident x tile
 //            initialises the accumulator (exact: bf16 x times 1.0 in fp32).  That work runs on the tensor pipe while
-//            the epilogue drains the last gate chunk (when the pipe would otherwise idle), and it lets the x tile be
+//            the epilogue drains the second gate chunk (when the pipe would otherwise idle), and it lets the x tile be
 //            released -- and the next one prefetched -- before the epilogue has finished.
 //
 // and leaves y in HBM for the deferred skip GEMM.  C = 256 residual channels.
@@ -18,11 +18,12 @@
 //   descriptor base_offset 0: the 128B swizzle is a function of absolute smem address bits; profiles/r01_probe_shift.json).
 // * The gated activations are written by the epilogue straight into a swizzled K-major shared-memory tile, which is
 //   both the A operand of MMA2 and the source of the TMA store to HBM; x_next is staged in the same tile afterwards.
-// * TMEM (512 columns) holds three accumulators per tile: channels 0..127 as one N = 256 chunk ("c01", 128 gate +
-//   128 filter columns), channels 128..191 and 192..255 as two N = 128 chunks ("c2", "c3"), and later D2 in c01's
-//   columns.  The column assignment mirrors every tile (c01 lands where the previous tile's c2+c3 were), and only the
-//   LAST QUARTER of the gate epilogue is not hidden behind dilated-conv MMAs -- that quarter overlaps the identity and
-//   first residual K-blocks of MMA2, so the tensor pipe has no structural bubble.
+// * TMEM (512 columns) holds two dilated-conv accumulators per tile -- channels 0..127 ("c01") and 128..255 ("c23"), each
+//   one N = 256 chunk of 128 gate + 128 filter columns -- and later D2 in c01's columns.  The column assignment mirrors
+//   every tile (c01 lands where the previous tile's c23 was).  The gate epilogue of c01 hides behind c23's MMAs; c23's
+//   epilogue overlaps the identity part and the first two K blocks of MMA2.  (A 256 + 128 + 128 split exposes half as much
+//   epilogue, but N = 128 cta_group::2 MMAs take ~100 cycles instead of 64 -- operand fetch bound -- and two-warp shared
+//   slabs need named barriers: measured 5-8 % slower, removed.)
 //
 // Roles per CTA: warp 0 = weight-block TMA producer, warp 1 = MMA issuer (leader CTA only), warps 2..9 = epilogue,
 // warp 10 = x-tile TMA producer.  (Giving the control warps the highest warp ids -- the sub-partition arbiter favours
@@ -49,7 +50,6 @@ struct LayerMaps {
   CUtensorMap xh[2][5];   // haloed loads of the residual stream: [buffer (layer parity)][log2(dilation)], box (64, 128 + 2*dil)
   CUtensorMap xs[2];      // stores into the residual stream buffers, box (64, 32)
   CUtensorMap wd;         // W_dil  [L*2C][3C], 128-channel pairing, box (64, 128)
-  CUtensorMap wq;         // W_dil  [L*2C][3C], 64-channel pairing,  box (64, 64)
   CUtensorMap wr;         // W_res  [(L+1)*C][C] (+ identity block), box (64, 128)
   CUtensorMap ys;         // ybuf   [L][B][T][C], box (64, 32) (store)
 };
@@ -66,7 +66,6 @@ struct LayerParams {
                           //    traffic); 0: identity blocks are streamed through the weight ring like W_res (N = 256)
   uint32_t idesc64;       // N = 64 instruction descriptor for the resident-identity MMAs
   uint32_t idesc;         // cta_group::2 instruction descriptor (M = 256, N = 256)
-  uint32_t idesc128;      // same with N = 128 (the two 64-channel chunks)
   const void* cp;         // hoisted cond projection of layer 0, tile-blocked fp16
   long long cp_layer_stride;  // 16-bit elements between layers
   const float* sb;        // step-bias table, layer 0 (layers are 4 * 2C floats apart)
@@ -83,10 +82,7 @@ __device__ __forceinline__ long long global_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-// kHybrid: accumulator schedule, see the header comment.  true = 256 + 128 + 128 columns (c01, c2, c3); false = two
-// 256-column chunks (c01, c23): every dilated-conv MMA is a full-rate N = 256 instruction, but the whole second half of
-// the gate epilogue is exposed (only MMA2's identity + first residual K-blocks overlap it).
-template <typename T, bool kHybrid>
+template <typename T>
 __global__ void __launch_bounds__(kLayerThreads, 1)
 layer_kernel(const __grid_constant__ LayerMaps mp,
              const LayerParams lp) {
@@ -117,7 +113,6 @@ layer_kernel(const __grid_constant__ LayerMaps mp,
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mp.wd);
-    tma_prefetch_desc(&mp.wq);
     tma_prefetch_desc(&mp.wr);
     tma_prefetch_desc(&mp.ys);
   }
@@ -159,7 +154,7 @@ layer_kernel(const __grid_constant__ LayerMaps mp,
   // Every cluster walks the same weight blocks; starting each one at a different K block spreads the simultaneous
   // requests over different L2 lines instead of hammering one hot block (fp32 accumulation order differs per
   // cluster but is fixed for a given launch geometry, so results stay deterministic).
-  const int rot12 = cluster_id % 12, rot6 = cluster_id % 6, rot4 = cluster_id & 3;
+  const int rot12 = cluster_id % 12, rot4 = cluster_id & 3;
   const int l_end = lp.layer0 + lp.n_layers;
   // Multi-layer launches rotate the pair -> cluster assignment every layer, so the clusters that get the extra pair of a
   // partial wave change from layer to layer and the imbalance averages out over the stack.
@@ -180,15 +175,9 @@ layer_kernel(const __grid_constant__ LayerMaps mp,
           if (blk < 12) {          // c01: [128 rows = this CTA's gate (rank 0) or filter (rank 1) half] x 64 K
             const int kb = (blk + rot12) % 12;
             tma_load_2d_2sm(dst, &mp.wd, &full_bar[stage], kb * kBlockK, l * 2 * kLayerC + (int)rank * 128);
-          } else if (blk < 24 && !kHybrid) {   // c23: channels 128..255 as a second N = 256 chunk
+          } else if (blk < 24) {   // c23: channels 128..255 as a second N = 256 chunk
             const int kb = (blk - 12 + rot12) % 12;
             tma_load_2d_2sm(dst, &mp.wd, &full_bar[stage], kb * kBlockK, l * 2 * kLayerC + 256 + (int)rank * 128);
-          } else if (blk < 24) {   // c2 / c3: two [64 rows x 64 K] sub-blocks (K blocks 2*kq, 2*kq + 1) per stage
-            const int c = 2 + (blk - 12) / 6;
-            const int kq = ((blk - 12) % 6 + rot6) % 6;
-            const int row0 = l * 2 * kLayerC + c * 128 + (int)rank * 64;
-            tma_load_2d_2sm(dst, &mp.wq, &full_bar[stage], (2 * kq) * kBlockK, row0);
-            tma_load_2d_2sm(dst + 8192, &mp.wq, &full_bar[stage], (2 * kq + 1) * kBlockK, row0);
           } else if (blk < 28) {   // identity block: D2 starts as the x tile itself
             tma_load_2d_2sm(dst, &mp.wr, &full_bar[stage], ((blk - 24 + rot4) & 3) * kBlockK, lp.ident_row0 + (int)rank * 128);
           } else {
@@ -256,14 +245,12 @@ layer_kernel(const __grid_constant__ LayerMaps mp,
         const int dil = 1 << (l % lp.cycle);
         const uint32_t par = ti & 1u;                       // this tile's barrier phase parity and column layout
         const uint32_t colA = par ? 256u : 0u;              // c01, later D2 (the layout mirrors every tile)
-        const uint32_t colB1 = par ? 0u : 256u;             // c2
-        const uint32_t colB2 = colB1 + 128u;                // c3
+        const uint32_t colB1 = par ? 0u : 256u;             // c23
         mbar_wait(xfull_bar, par, 2);
         tc_fence_after();
         if (tr) lp.trace[(ti & 31) * 16 + 2] = clock64();
         // ---- MMA1, channels 0..127 (N = 256).  Its columns were the previous tile's c2 and c3.
         mbar_wait(&afree_bar[1], par ^ 1u, 3);
-        if constexpr (kHybrid) mbar_wait(&afree_bar[2], par ^ 1u, 3);
         tc_fence_after();
         for (int kk = 0; kk < 12; ++kk, ++it) {
           const int kb = (kk + rot12) % 12;
@@ -282,7 +269,7 @@ layer_kernel(const __grid_constant__ LayerMaps mp,
         // ---- MMA1, channels 128..191 and 192..255 (N = 128 each).  Their columns held the previous tile's D2.
         mbar_wait(&afree_bar[3], par ^ 1u, 5);
         tc_fence_after();
-        if constexpr (!kHybrid) {
+        {
           for (int kk = 0; kk < 12; ++kk, ++it) {
             const int kb = (kk + rot12) % 12;
             const uint32_t stage = it % kLayerStages, parity = (it / kLayerStages) & 1u;
@@ -297,27 +284,6 @@ layer_kernel(const __grid_constant__ LayerMaps mp,
           }
           umma_commit_2sm(&afull_bar[1]);
           if (tr) lp.trace[(ti & 31) * 16 + 4] = lp.trace[(ti & 31) * 16 + 5] = clock64();
-        }
-        for (int c = 0; c < (kHybrid ? 2 : 0); ++c) {
-          const uint32_t d_tmem = tmem_base + (c ? colB2 : colB1);
-          for (int kk = 0; kk < 6; ++kk, ++it) {
-            const int kq = (kk + rot6) % 6;
-            const uint32_t stage = it % kLayerStages, parity = (it / kLayerStages) & 1u;
-            { const long long w0 = tr ? clock64() : 0; mbar_wait(&full_bar[stage], parity, 6); if (tr) wfull += clock64() - w0; }
-            tc_fence_after();
-#pragma unroll
-            for (int sub = 0; sub < 2; ++sub) {
-              const int kb = 2 * kq + sub;
-              const uint64_t adesc = make_sw128_kmajor_desc(sXa + (kb & 3) * xsub + (uint32_t)((kb >> 2) * dil) * 128u);
-              const uint64_t bdesc = make_sw128_kmajor_desc(sWa + stage * 16384 + sub * 8192);
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_f16_2sm(d_tmem, desc_advance_k(adesc, k), desc_advance_k(bdesc, k), lp.idesc128, (kk | sub | k) != 0 ? 1u : 0u);
-            }
-            umma_commit_2sm(&empty_bar[stage]);
-          }
-          umma_commit_2sm(&afull_bar[1 + c]);
-          if (tr) lp.trace[(ti & 31) * 16 + 4 + c] = clock64();
         }
         // ---- MMA2: D2 = x_centre * I  +  Y * W_res^T, in c01's columns once epilogue(c01) has drained them
         mbar_wait(&afree_bar[0], par, 7);
@@ -340,7 +306,6 @@ layer_kernel(const __grid_constant__ LayerMaps mp,
             mbar_wait(&yready_bar[0], par, 8);
           }
           if (kb == 6) mbar_wait(&yready_bar[1], par, 8);
-          if (kHybrid && kb == 7) mbar_wait(&yready_bar[2], par, 8);
           if (tr) lp.trace[512 + (ti & 15) * 16 + 8 + (kb >> 1)] = clock64();
           const uint32_t stage = it % kLayerStages, parity = (it / kLayerStages) & 1u;
           { const long long w0 = tr ? clock64() : 0; mbar_wait(&full_bar[stage], parity, 9); if (tr) { const long long w1 = clock64(); wfull += w1 - w0; lp.trace[1024 + (ti & 7) * 128 + 32 + 24 + kb] = w1; lp.trace[1024 + (ti & 7) * 128 + 64 + 24 + kb] = w1 - w0; } }
@@ -392,7 +357,7 @@ layer_kernel(const __grid_constant__ LayerMaps mp,
       // ---------------- gate epilogue of a 128-channel chunk (j = 0: channels 0..127; j = 1, two-chunk schedule only:
       // channels 128..255): this warp does channels [128j + 64h, +64) -> Y sub-tile 2j + h
 #pragma unroll 1
-      for (int j = 0; j < (kHybrid ? 1 : 2); ++j) {
+      for (int j = 0; j < 2; ++j) {
         uint4 pre[16];
         if (valid) {   // hoisted cond projection: 64 gate + 64 filter pre-activations (coalesced, blocked layout)
 #pragma unroll
@@ -404,13 +369,8 @@ layer_kernel(const __grid_constant__ LayerMaps mp,
         if (valid && j == 0) {   // bring the cond-projection lines of the later sections into L2 now; they are loaded ~6-10k cycles later
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
-            if constexpr (kHybrid) {
-              prefetch_l2(cpb + blocked_off(m_tile, 64, 32 + h * 4 + (u & 3) + (u >> 2) * 8, row));      // gate chunks of c2, c3
-              prefetch_l2(cpb + blocked_off(m_tile, 64, 48 + h * 4 + (u & 3) + (u >> 2) * 8, row));      // filter chunks
-            } else {
-              prefetch_l2(cpb + blocked_off(m_tile, 64, 32 + h * 8 + u, row));
-              prefetch_l2(cpb + blocked_off(m_tile, 64, 48 + h * 8 + u, row));
-            }
+            prefetch_l2(cpb + blocked_off(m_tile, 64, 32 + h * 8 + u, row));
+            prefetch_l2(cpb + blocked_off(m_tile, 64, 48 + h * 8 + u, row));
           }
         }
         const uint32_t* prew = reinterpret_cast<const uint32_t*>(pre);
@@ -467,57 +427,6 @@ layer_kernel(const __grid_constant__ LayerMaps mp,
           mbar_arrive_leader(&yready_bar[j]);
           tma_store_4d_hint(&mp.ys, ytile + q * 4096, (2 * j + h) * 64, t0 + q * 32, b, l, pol_stream);   // 32 frames x 64 channels
           tma_store_commit();
-        }
-      }
-
-      // ---------------- gate epilogue, channels 128..191 (c = 0 -> Y sub-tile 2) and 192..255 (c = 1 -> sub-tile 3):
-      // the two warps of a lane quadrant split the 64 channels (32 each) and share the sub-tile's 32 rows
-#pragma unroll 1
-      for (int c = 0; c < (kHybrid ? 2 : 0); ++c) {
-        uint4 pre[8];
-        if (valid) {
-          const int cg = 32 + c * 8 + h * 4;   // 16-byte chunk of gate channel 128 + 64c + 32h in the 256-paired layout
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            pre[u] = __ldg(reinterpret_cast<const uint4*>(cpb + blocked_off(m_tile, 64, cg + u, row)));
-            pre[4 + u] = __ldg(reinterpret_cast<const uint4*>(cpb + blocked_off(m_tile, 64, cg + 16 + u, row)));
-          }
-        }
-        const uint32_t* prew = reinterpret_cast<const uint32_t*>(pre);
-        uint8_t* ytile = sY + (2 + c) * 16384;
-        // sub-tile 2 + c rows were last read by the x_next store issued by warp (q, h = c); its y(c01) store is newer
-        if (h == c && lane == 0) tma_store_wait_read<1>();
-        named_bar_sync(1 + q, 64);
-        mbar_wait(&afull_bar[1 + c], par, 11);
-        tc_fence_after();
-        if (tr && warp == 2 && lane == 0) lp.trace[(ti & 31) * 16 + 8 + c] = clock64();
-        const uint32_t trow = lane_base + colB1 + (uint32_t)c * 128u;
-        const float* sbp = sb_row + 256 + c * 64 + h * 32;
-#pragma unroll
-        for (int ci = 0; ci < 2; ++ci) {
-          uint32_t rg[16], rf[16];
-          tmem_ld_x16(trow + h * 32 + ci * 16, rg);
-          tmem_ld_x16(trow + 64 + h * 32 + ci * 16, rf);
-          tmem_ld_wait();
-          uint32_t packed[8];
-          gate_chunk16<T>(rg, rf, prew + ci * 8, prew + 16 + ci * 8, sbp + ci * 16, packed);
-          if (!valid) {
-#pragma unroll
-            for (int u = 0; u < 8; ++u) packed[u] = 0u;
-          }
-          *sw128_chunk(ytile, row, h * 4 + 2 * ci) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-          *sw128_chunk(ytile, row, h * 4 + 2 * ci + 1) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
-        }
-        tc_fence_before();
-        fence_proxy_async_smem();
-        named_bar_sync(1 + q, 64);   // both halves of the 32 x 64 slab are written
-        if (lane == 0) {
-          mbar_arrive_leader(&afree_bar[1 + c]);
-          mbar_arrive_leader(&yready_bar[1 + c]);
-          if (h == c) {
-            tma_store_4d(&mp.ys, ytile + q * 4096, (2 + c) * 64, t0 + q * 32, b, l);
-            tma_store_commit();
-          }
         }
       }
 

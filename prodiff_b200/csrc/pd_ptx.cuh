@@ -173,13 +173,6 @@ __device__ __forceinline__ float tanh_approx(float x) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// two tanh per MUFU op: tanh.approx.f16x2 on (a, b) packed as half2 (abs error ~2^-11, inputs rounded to fp16)
-__device__ __forceinline__ float2 tanh2_approx(float a, float b) {
-  uint32_t h;
-  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(b), "f"(a));  // first source -> upper half
-  asm("tanh.approx.f16x2 %0, %1;" : "=r"(h) : "r"(h));
-  return __half22float2(*reinterpret_cast<__half2*>(&h));
-}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void tma_store_wait_read() {
