@@ -166,7 +166,12 @@ int pd_debug_gemm(int dtype, const void* a, int B, int T, int Cin, int taps, int
  * conv+gate / res_proj pair (0).  Returns the previous setting (-1 = not yet decided). */
 int pd_set_fused(int on);
 /* With the fused kernel: run all layers of a denoiser call in ONE persistent launch whose tiles synchronise through
- * per-tile flags (1, default; env PD_STACK=0 also disables) or launch one kernel per layer (0). Returns the previous value. */
+ * per-tile flags (1, default; env PD_STACK=0 also disables) or launch one kernel per layer (0). Returns the previous value.
+ * The persistent form needs all its clusters resident at once: the library checks that against an otherwise idle GPU, so
+ * run ONE sampling call at a time per GPU (what the reference does, handler/infer/handler.py:373-378; one process per GPU
+ * for multi-GPU).  Two such launches racing for the same SMs from different streams or processes can each end up holding
+ * SMs the other's unscheduled clusters need; the in-kernel watchdog then traps (an error, not a hang).  A host that
+ * must overlap several calls on one GPU selects the per-layer form (0), which has no inter-cluster waits. */
 int pd_set_stack(int on);
 
 /* pd_sample only: run skip_projection (wavenet.py:120-121), output_projection (:122), the q-posterior update
