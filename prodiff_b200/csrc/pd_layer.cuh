@@ -99,10 +99,10 @@ layer_kernel(const __grid_constant__ LayerMaps mp,
   uint64_t* empty_bar = full_bar + kLayerStages;       // [S] local : MMAs finished reading the block
   uint64_t* xfull_bar = empty_bar + kLayerStages;      // leader: X landed in both CTAs
   uint64_t* xempty_bar = xfull_bar + 1;                // local : X reusable (all tensor-core reads of it completed)
-  // accumulators, indexed by kind: 0 = c01 (channels 0..127), 1 = c2 (128..191), 2 = c3 (192..255), 3 = D2
+  // accumulators, indexed by kind: 0 = c01 (channels 0..127), 1 = c23 (128..255), 3 = D2 (index 2 unused)
   uint64_t* afull_bar = xempty_bar + 1;                // [4] local : accumulator complete (MMA commit, both CTAs)
   uint64_t* afree_bar = afull_bar + 4;                 // [4] leader: accumulator drained by all 16 epilogue warps
-  uint64_t* yready_bar = afree_bar + 4;                // [3] leader: y of chunk c01 / c2 / c3 written in both CTAs
+  uint64_t* yready_bar = afree_bar + 4;                // [3] leader: y of chunk c01 / c23 written in both CTAs (index 2 unused)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(yready_bar + 3);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -186,7 +186,7 @@ layer_kernel(const __grid_constant__ LayerMaps mp,
           if (tr) lp.trace[1024 + (ti & 7) * 128 + blk] = clock64();   // weight-load latency trace: issue time
           ++it;
         };
-        // weight blocks per tile: 12 (c01) + 6 + 6 (c2, c3) [+ 4 streamed identity] + 4 residual 1x1
+        // weight blocks per tile: 12 (c01) + 12 (c23) [+ 4 streamed identity] + 4 residual 1x1
         for (int blk = 0; blk < 32; ++blk)
           if (!(lp.ident_resident && blk >= 24 && blk < 28)) load_block(blk);
         if (tr) lp.trace[(ti & 31) * 16 + 1] = clock64();
@@ -249,7 +249,7 @@ layer_kernel(const __grid_constant__ LayerMaps mp,
         mbar_wait(xfull_bar, par, 2);
         tc_fence_after();
         if (tr) lp.trace[(ti & 31) * 16 + 2] = clock64();
-        // ---- MMA1, channels 0..127 (N = 256).  Its columns were the previous tile's c2 and c3.
+        // ---- MMA1, channels 0..127 (N = 256).  Its columns were the previous tile's c23.
         mbar_wait(&afree_bar[1], par ^ 1u, 3);
         tc_fence_after();
         for (int kk = 0; kk < 12; ++kk, ++it) {
@@ -266,7 +266,7 @@ layer_kernel(const __grid_constant__ LayerMaps mp,
         }
         umma_commit_2sm(&afull_bar[0]);
         if (tr) lp.trace[(ti & 31) * 16 + 3] = clock64();
-        // ---- MMA1, channels 128..191 and 192..255 (N = 128 each).  Their columns held the previous tile's D2.
+        // ---- MMA1, channels 128..255 (N = 256).  Its columns held the previous tile's D2.
         mbar_wait(&afree_bar[3], par ^ 1u, 5);
         tc_fence_after();
         {
