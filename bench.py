@@ -333,6 +333,19 @@ def main():
                     "avg_launch_us": tot_ms / n * 1e3, "launches": n, "share_of_gemm_time": tot_ms / all_ms,
                     "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']})",
                     "per_kernel_ms_per_step": {k: v[0] / prof_steps for k, v in kinds.items()}}
+        # HBM-bound kernels of the step: ALGORITHMIC bytes per launch (operands that must cross HBM once) / measured
+        # mean launch time, against the measured copy bandwidth (a pure fill reaches ~3.9 TB/s, a pure read ~5.9 TB/s on these
+        # boxes, tools/hbm_probe.py; the copy figure counts read + write bytes)
+        frames = B * T
+        hbm_bytes = {"cond_proj": frames * (H * 2 + L * 2 * C * 2),                    # read 16-bit cond, write hoisted projection
+                     "skip_sum": frames * (L * C * 2 + C * 2),                         # read gated activations of all layers, write s1
+                     "sampler_tail(fused)": frames * (C * 2 + 2 * M * 4 + C * 2)}      # read s1 + x, write x + next layer-0 input
+        roofline["hbm_kernels"] = {
+            k: {"bytes_per_launch": hbm_bytes[k], "avg_launch_us": kinds[k][0] / kinds[k][1] * 1e3,
+                "achieved_gbs": hbm_bytes[k] / (kinds[k][0] / kinds[k][1] * 1e-3) / 1e9,
+                "frac_of_copy_peak": hbm_bytes[k] / (kinds[k][0] / kinds[k][1] * 1e-3) / 1e9 / peaks["hbm"]}
+            for k in hbm_bytes if k in kinds and kinds[k][1] > 0}
+        roofline["hbm_peak_gbs"] = peaks["hbm"]
 
     if rank == 0:
         F = flops_per_frame(M, H, L, C, K)
