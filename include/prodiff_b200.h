@@ -123,6 +123,15 @@ int pd_cond_assemble(pd_plan* p, const float* encoder_out, int Tph, const long l
  * t >= lengths[b] are unspecified.  NULL restores full-length rows.  Needs the fused layer kernel (C = 256). */
 int pd_plan_set_lengths(pd_plan* p, const int32_t* lengths, void* stream);
 
+/* Vocoder hand-off (first sub-step).  The reference's NsfHifiGAN.spec2wav_torch
+ * (/root/reference/component/vocoder/nsf_hifigan.py:49-52) transposes the sampler's [B,T,M] result back to [B,M,T] and
+ * multiplies it by 2.30259 (log10 -> ln mel) before Generator.forward -- two more passes over the mel.  [B,M,T] is the
+ * physical layout of the sampler state x, so with scale != 1 installed the LAST posterior update of pd_sample (or the
+ * denorm_spec kernel of pd_reflow_sample) stores fl(scale * x) instead of x: the state the call leaves behind is the
+ * generator's input, bit-identical to `2.30259 * mel.transpose(2, 1)` on the unscaled result (one extra fp32 rounding, no
+ * extra kernel, no extra HBM traffic).  scale = 1 (the default) restores the reference's return value. */
+int pd_plan_set_output_scale(pd_plan* p, float scale);
+
 /* RectifiedFlow.forward(infer=True) (/root/reference/modules/diffusion/reflow.py:32-46, 86-107): the rectified-flow ODE
  * x' = v(x, time_scale * t) integrated from t = 0 to 1 in n_steps steps of dt = 1 / n_steps with sample_euler (:48-52),
  * sample_rk2 (:54-60), sample_rk4 (:62-70) or sample_rk5 (:72-84), the velocity being the same DiffNet denoiser

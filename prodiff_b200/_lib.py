@@ -19,6 +19,7 @@ SYMBOLS = [
     "pd_state_count", "pd_last_error", "pd_abi_version", "pd_packed_bytes", "pd_model_create", "pd_model_destroy",
     "pd_workspace_bytes", "pd_plan_create", "pd_plan_destroy", "pd_cond_project", "pd_denoise", "pd_sample",
     "pd_launch_count", "pd_plan_buffer", "pd_debug_gemm", "pd_profile_begin", "pd_profile_end", "pd_debug_shift", "pd_debug_set_trace", "pd_set_fused", "pd_set_stack", "pd_set_tail", "pd_set_sumtail", "pd_reflow_sample", "pd_plan_set_lengths", "pd_cond_assemble",
+    "pd_plan_set_output_scale",
 ]
 
 
@@ -59,6 +60,7 @@ def load() -> C.CDLL:
     lib.pd_reflow_sample.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_float, vp, vp, vp, C.c_int, vp, vp]
     lib.pd_reflow_sample.restype = C.c_int
     lib.pd_plan_set_lengths.argtypes = [vp, P(C.c_int32), vp]; lib.pd_plan_set_lengths.restype = C.c_int
+    lib.pd_plan_set_output_scale.argtypes = [vp, C.c_float]; lib.pd_plan_set_output_scale.restype = C.c_int
     lib.pd_cond_assemble.argtypes = [vp, vp, C.c_int, vp, vp, vp, vp, vp, vp, C.c_int, P(vp), P(vp), P(vp), vp, vp, vp]
     lib.pd_cond_assemble.restype = C.c_int
     lib.pd_launch_count.argtypes = [C.c_int]; lib.pd_launch_count.restype = C.c_longlong

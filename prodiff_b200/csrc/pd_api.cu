@@ -331,6 +331,7 @@ struct pd_plan {
   bool fused_ok;
   bool tail_ok;
   bool ragged;   // pd_plan_set_lengths installed per-utterance lengths
+  float out_scale;   // pd_plan_set_output_scale: multiplier of the finished sample (vocoder hand-off), 1 = off
   size_t off(const char* n) const {
     for (const Buf& b : bufs)
       if (!strcmp(b.name, n)) return b.off;
@@ -406,7 +407,8 @@ extern "C" int pd_plan_create(const pd_model* m, int B, int T, int max_entries, 
   // fused layer kernel (C = 256, dilations <= 16): haloed loads and 32-row store boxes
   p->fused_ok = (C == kLayerC) && (1 << (c.dilation_cycle_length - 1)) <= kLayerMaxDil;
   p->tail_ok = p->fused_ok && c.in_dims == 128;
-  p->ragged = false;   // fused sampler tail (pd_tail.cuh) is specialised for C = 256, M = 128
+  p->ragged = false;
+  p->out_scale = 1.f;
   if (p->fused_ok) {
     for (int i = 0; i < 5 && i < c.dilation_cycle_length; ++i)
       if (make_act_map(&p->tm_xa_halo[i], dt, p->ptr<void>("xa"), C, T, B, 1, kBlockM + 2 * (1 << i)) ||
@@ -522,6 +524,7 @@ static EpiArgs base_epi() {
   EpiArgs e;
   memset(&e, 0, sizeof(e));
   e.scale = 1.f;
+  e.out_scale = 1.f;
   e.out_type = OUT_T;
   return e;
 }
@@ -711,6 +714,13 @@ extern "C" int pd_plan_set_lengths(pd_plan* p, const int32_t* lengths, void* str
   return 0;
 }
 
+extern "C" int pd_plan_set_output_scale(pd_plan* p, float scale) {
+  if (!p) return fail("null argument");
+  if (!(scale == scale) || scale == 0.f) return fail("output scale must be a non-zero number, got %g", (double)scale);
+  p->out_scale = scale;
+  return 0;
+}
+
 static int cond_project_from16(pd_plan* p, cudaStream_t s);
 
 extern "C" int pd_cond_project(pd_plan* p, const float* cond, void* stream) {
@@ -816,6 +826,7 @@ struct OutStage {  // what the final GEMM's epilogue does with x0
   bool write_xin;
   bool have_xa;    // layer-0 input already produced by the previous step's fused tail: skip input_projection
   float c1, c2, sigma;
+  float out_scale;
   unsigned long long seed;
   unsigned int step_id;
 };
@@ -960,6 +971,7 @@ static int run_denoiser(pd_plan* p, int entry_base, int entry_per_b, const OutSt
     tp.c1 = os.c1;
     tp.c2 = os.c2;
     tp.sigma = os.sigma;
+    tp.out_scale = os.out_scale;
     tp.seed = os.seed;
     tp.step_id = os.step_id;
     tp.lens = p->ragged ? p->ptr<int>("lens") : nullptr;
@@ -1003,6 +1015,7 @@ static int run_denoiser(pd_plan* p, int entry_base, int entry_per_b, const OutSt
     tp.c1 = os.c1;
     tp.c2 = os.c2;
     tp.sigma = os.sigma;
+    tp.out_scale = os.out_scale;
     tp.seed = os.seed;
     tp.step_id = os.step_id;
     tp.lens = p->ragged ? p->ptr<int>("lens") : nullptr;
@@ -1032,6 +1045,7 @@ static int run_denoiser(pd_plan* p, int entry_base, int entry_per_b, const OutSt
     ep.c1 = os.c1;
     ep.c2 = os.c2;
     ep.sigma = os.sigma;
+    ep.out_scale = os.out_scale;
     ep.seed = os.seed;
     ep.step_id = os.step_id;
     if (launch_gemm<EPI_OUT, 128>(dt, p->tm_s2, m->tm_w_out, sh, ep, sms, s, "gemm(output_proj+posterior)", 6)) return 1;
@@ -1057,6 +1071,7 @@ extern "C" int pd_denoise(pd_plan* p, const float* spec, const float* diffusion_
   if (spec_to_xin(p, spec, s)) return 1;
   OutStage os;
   memset(&os, 0, sizeof(os));
+  os.out_scale = 1.f;
   os.x0_out = out;
   return run_denoiser(p, 0, 1, os, s);
 }
@@ -1095,6 +1110,7 @@ extern "C" int pd_sample(pd_plan* p, const float* cond, float* x, const float* n
     os.c1 = coef1[t];
     os.c2 = coef2[t];
     os.sigma = t == 0 ? 0.f : expf(0.5f * logvar[t]);  // nonzero_mask * exp(0.5 * log_var), prodiff.py:120-121
+    os.out_scale = j + 1 == K ? p->out_scale : 1.f;
     os.seed = seed;
     os.step_id = (unsigned int)j;
     if (run_denoiser(p, j, 0, os, s)) return 1;
@@ -1175,6 +1191,7 @@ extern "C" int pd_reflow_sample(pd_plan* p, const float* cond, float* x, int alg
     for (int i = 0; i < tb.stages; ++i) {
       OutStage os;
       memset(&os, 0, sizeof(os));
+      os.out_scale = 1.f;
       os.x0_out = k[i];   // the denoiser output is the velocity (reflow.py:50)
       if (run_denoiser(p, i, 0, os, s)) return 1;
       if (i + 1 < tb.stages) {
@@ -1185,7 +1202,7 @@ extern "C" int pd_reflow_sample(pd_plan* p, const float* cond, float* x, int alg
     }
   }
   if (spec_min != nullptr) {
-    k_denorm_spec<<<p->m->sm_count * 4, 256, 0, s>>>(x, spec_min, spec_max, n_spec, c.in_dims, p->T, (long long)state_elems);
+    k_denorm_spec<<<p->m->sm_count * 4, 256, 0, s>>>(x, spec_min, spec_max, n_spec, c.in_dims, p->T, (long long)state_elems, p->out_scale);
     PD_LAUNCH_CHECK("k_denorm_spec");
   }
   return 0;

@@ -128,12 +128,13 @@ __global__ void k_rk_stage(T* __restrict__ xin, float* x_out, const float* x, Rk
 
 // RectifiedFlow.denorm_spec (reflow.py:106-107) in place on the state [B,1,M,T]: (x + 1) / 2 * (max - min) + min per mel bin.
 __global__ void k_denorm_spec(float* __restrict__ x, const float* __restrict__ spec_min, const float* __restrict__ spec_max,
-                              int n_spec, int M, int Tn, long long total) {
+                              int n_spec, int M, int Tn, long long total, float out_scale) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int m = (int)((i / Tn) % M);
     const int j = n_spec == 1 ? 0 : m;
     const float lo = spec_min[j], hi = spec_max[j];
-    x[i] = __fadd_rn(__fmul_rn(__fdiv_rn(__fadd_rn(x[i], 1.f), 2.f), __fadd_rn(hi, -lo)), lo);
+    const float v = __fadd_rn(__fmul_rn(__fdiv_rn(__fadd_rn(x[i], 1.f), 2.f), __fadd_rn(hi, -lo)), lo);
+    x[i] = out_scale != 1.f ? __fmul_rn(v, out_scale) : v;   // vocoder hand-off (pd_plan_set_output_scale)
   }
 }
 

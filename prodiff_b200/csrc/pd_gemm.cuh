@@ -69,6 +69,7 @@ struct EpiArgs {
   const float* noise;  // optional [B,1,M,T]
   void* xin_next;      // optional [B*T, Mp] 16-bit copy of x_{t-1} (next step's input-projection operand)
   float c1, c2, sigma;
+  float out_scale;     // the stored x is multiplied by this (pd_plan_set_output_scale; 1 otherwise)
   unsigned long long seed;
   unsigned int step_id;
 };
@@ -603,7 +604,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 }
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                  const float v = fmaf(ep.c1, xn[j + u], fmaf(ep.sigma, nzv[u], ep.c2 * xv[ci & 1][j + u]));   // same order as pd_tail.cuh
+                  float v = fmaf(ep.c1, xn[j + u], fmaf(ep.sigma, nzv[u], ep.c2 * xv[ci & 1][j + u]));   // same order as pd_tail.cuh
+                  if (ep.out_scale != 1.f) v = __fmul_rn(v, ep.out_scale);   // vocoder hand-off, last step only
                   ep.x_state[cbase + (long long)(j + u) * Tn] = v;
                   xn[j + u] = v;
                 }

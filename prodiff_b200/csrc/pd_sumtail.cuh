@@ -351,6 +351,7 @@ sumtail_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ 
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               xn[j] = fmaf(tp.c1, xn[j], pv[ci * 16 + j]);
+              if (tp.out_scale != 1.f) xn[j] = __fmul_rn(xn[j], tp.out_scale);   // vocoder hand-off, last step only
               tp.x_state[cbase + (long long)j * Tn] = xn[j];
             }
           }

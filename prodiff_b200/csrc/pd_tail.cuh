@@ -39,6 +39,7 @@ struct TailParams {
   float* x_state;            // [B,1,M,T], updated in place
   const float* noise;        // optional [B,1,M,T]; nullptr = in-kernel Philox
   float c1, c2, sigma;
+  float out_scale;           // the stored x is multiplied by this (1 except on the last step of a vocoder hand-off call)
   unsigned long long seed;
   unsigned int step_id;
   const int* lens;           // optional per-utterance valid lengths: xa rows past them are written as zeros
@@ -278,6 +279,7 @@ tail_kernel(const __grid_constant__ CUtensorMap tmS1, const __grid_constant__ CU
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               xn[j] = fmaf(tp.c1, xn[j], pv[ci * 16 + j]);
+              if (tp.out_scale != 1.f) xn[j] = __fmul_rn(xn[j], tp.out_scale);   // vocoder hand-off, last step only
               tp.x_state[cbase + (long long)j * Tn] = xn[j];
             }
           }

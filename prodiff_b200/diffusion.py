@@ -96,7 +96,11 @@ class GaussianDiffusion(nn.Module):
         return self._host_tables[1:]
 
     def forward(self, cond, src_spec=None, gt_spec=None, infer_step=4, infer=False, *, x_T=None, noise=None,
-                seed: Optional[int] = None, x0_trace: Optional[torch.Tensor] = None, lengths=None):
+                seed: Optional[int] = None, x0_trace: Optional[torch.Tensor] = None, lengths=None,
+                vocoder_scale: Optional[float] = None):
+        """prodiff.py:136-153.  ``vocoder_scale`` (keyword-only, inference): return the generator input of
+        ``NsfHifiGAN.spec2wav_torch`` (nsf_hifigan.py:50-52) instead of the mel -- a contiguous [B,M,T] tensor equal to
+        ``vocoder_scale * mel.transpose(2, 1)``, produced by the last posterior update itself (handoff.py)."""
         b, device = cond.shape[0], cond.device
         if not infer:
             # training branch: one denoiser call at a random step; the denoiser itself refuses autograd (see WaveNet)
@@ -127,7 +131,9 @@ class GaussianDiffusion(nn.Module):
         cond_bth = cond.detach().to(dtype=torch.float32).contiguous() if isinstance(cond, torch.Tensor) else cond
         t_list = list(range(infer_step - 1, -1, -1))
         self.denoise_fn.engine().sample(cond_bth, x, t_list, c1, c2, lv, noise=noise, seed=seed, x0_trace=x0_trace,
-                                        lengths=lengths)
+                                        lengths=lengths, out_scale=1.0 if vocoder_scale is None else float(vocoder_scale))
+        if vocoder_scale is not None:
+            return x[:, 0]   # denorm_spec is the identity here (prodiff.py:158), so scaling first changes nothing
         x = x[:, 0].transpose(1, 2)
         return self.denorm_spec(x)
 

@@ -183,9 +183,10 @@ class Engine:
 
     def sample(self, cond_bth: torch.Tensor, x: torch.Tensor, t_list: Sequence[int], coef1, coef2, logvar,
                noise: Optional[torch.Tensor] = None, seed: int = 0, x0_trace: Optional[torch.Tensor] = None,
-               lengths: Optional[Sequence[int]] = None) -> torch.Tensor:
+               lengths: Optional[Sequence[int]] = None, out_scale: float = 1.0) -> torch.Tensor:
         """The whole reverse loop, in place on x [B,1,M,T] (in: x_T, out: x_0).  ``lengths`` (B ints <= T): ragged batch,
-        row b is computed exactly as an utterance of lengths[b] frames; frames past it are unspecified."""
+        row b is computed exactly as an utterance of lengths[b] frames; frames past it are unspecified.  ``out_scale``:
+        the last posterior update stores out_scale * x_0 (vocoder hand-off, pd_plan_set_output_scale)."""
         B, _, M, T = x.shape
         if lengths is not None and len(lengths) != B:
             raise ValueError(f"lengths must have {B} entries")
@@ -203,6 +204,7 @@ class Engine:
                 tr = None if x0_trace is None else (x0_trace if whole else torch.empty_like(x0_trace[:, s:e]))
                 p = self.plan(e - s, T, K)
                 self._set_lengths(p, lengths, s, e)
+                _lib.check(self.lib.pd_plan_set_output_scale(p.handle, float(out_scale)), "pd_plan_set_output_scale")
                 # every block draws from its own Philox stream (the kernel counts frames from 0 inside a call)
                 sd = (seed + ci * 0x9E3779B97F4A7C15) & (2 ** 64 - 1)
                 _lib.check(self.lib.pd_sample(p.handle, self._cond_arg(p, cond_bth, s, e), x[s:e].data_ptr(),
@@ -219,8 +221,12 @@ class Engine:
 
     def reflow(self, cond_bth: torch.Tensor, x: torch.Tensor, algorithm: str, n_steps: int, time_scale: float,
                spec_min: Optional[torch.Tensor], spec_max: Optional[torch.Tensor],
-               v_trace: Optional[torch.Tensor] = None, lengths: Optional[Sequence[int]] = None) -> torch.Tensor:
-        """The rectified-flow ODE loop (pd_reflow_sample), in place on x [B,1,M,T] (in: N(0,1) start, out: denormalised)."""
+               v_trace: Optional[torch.Tensor] = None, lengths: Optional[Sequence[int]] = None,
+               out_scale: float = 1.0) -> torch.Tensor:
+        """The rectified-flow ODE loop (pd_reflow_sample), in place on x [B,1,M,T] (in: N(0,1) start, out: denormalised,
+        times ``out_scale`` -- applied by the denorm_spec kernel, so it needs spec_min / spec_max)."""
+        if out_scale != 1.0 and spec_min is None:
+            raise ValueError("out_scale is applied by the denorm_spec kernel: pass spec_min / spec_max")
         B, _, M, T = x.shape
         algo, stages = self.REFLOW_ALGORITHMS.get(algorithm, self.REFLOW_ALGORITHMS["euler"])   # reflow.py:95 falls back to euler
         chunks = row_chunks(B, T, self.FRAMES_PER_CALL)
@@ -229,6 +235,7 @@ class Engine:
                 whole = len(chunks) == 1
                 p = self.plan(e - s, T, 6)
                 self._set_lengths(p, lengths, s, e)
+                _lib.check(self.lib.pd_plan_set_output_scale(p.handle, float(out_scale)), "pd_plan_set_output_scale")
                 tr = None if v_trace is None else (v_trace if whole else torch.empty_like(v_trace[:, s:e]))
                 scratch = None if tr is not None else torch.empty(stages, e - s, 1, M, T, dtype=torch.float32, device=self.device)
                 _lib.check(self.lib.pd_reflow_sample(

@@ -48,7 +48,9 @@ class RectifiedFlow(nn.Module):
         return v_pred, x_end - x_start
 
     def forward(self, cond, gt_spec=None, infer_step=20, infer=True, *, x_start: Optional[torch.Tensor] = None,
-                v_trace: Optional[torch.Tensor] = None, lengths=None):
+                v_trace: Optional[torch.Tensor] = None, lengths=None, vocoder_scale: Optional[float] = None):
+        """reflow.py:32-46.  ``vocoder_scale``: as in GaussianDiffusion.forward -- the denorm_spec kernel also applies the
+        vocoder's log10 -> ln factor and the contiguous [B,M,T] generator input is returned."""
         b, device = cond.shape[0], cond.device
         if not infer:
             spec = self.norm_spec(gt_spec).transpose(-2, -1)
@@ -59,7 +61,9 @@ class RectifiedFlow(nn.Module):
             return v_pred, v_gt, t
         # denorm_spec (reflow.py:106-107) runs as the last kernel of the sequence, on the state, before the view is taken
         x = self._run(cond.transpose(1, 2) if isinstance(cond, torch.Tensor) else cond, b, infer_step, device, x_start, v_trace,
-                      denorm=True, lengths=lengths)
+                      denorm=True, lengths=lengths, out_scale=1.0 if vocoder_scale is None else float(vocoder_scale))
+        if vocoder_scale is not None:
+            return x.transpose(1, 2)   # back to the physical [B,M,T] layout (a contiguous view)
         return self._finish(x)
 
     @torch.no_grad()
@@ -68,7 +72,7 @@ class RectifiedFlow(nn.Module):
         return self._run(cond, b, infer_step, device, x_start, v_trace, denorm=False)
 
     @torch.no_grad()
-    def _run(self, cond, b, infer_step, device, x_start, v_trace, denorm, lengths=None):
+    def _run(self, cond, b, infer_step, device, x_start, v_trace, denorm, lengths=None, out_scale=1.0):
         dense = isinstance(cond, torch.Tensor)   # else a conditioning.AssembledCondition ([B,T,H] inputs, assembled by the kernels)
         device = cond.device if device is None else device
         T = cond.shape[2] if dense else cond.shape[1]
@@ -89,7 +93,7 @@ class RectifiedFlow(nn.Module):
         if not denorm:
             smin = smax = None
         self.velocity_fn.engine().reflow(cond_bth, x, self.sampling_algorithm, n, float(self.time_scale), smin, smax, v_trace,
-                                         lengths=lengths)
+                                         lengths=lengths, out_scale=out_scale)
         return x.transpose(2, 3).squeeze(1)
 
     def _finish(self, x):

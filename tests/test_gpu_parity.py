@@ -218,6 +218,43 @@ def test_fused_sampler_tail_equals_separate_kernels(mode):
     assert float((res[0][2][K - 1] - x0s[K - 1]).abs().max()) <= STEP_TOL * 4   # last step: errors of K - 1 updates ride along
 
 
+@pytest.mark.parametrize("path", ["tail", "separate", "unfused512", "reflow"])
+def test_vocoder_handoff_scale_is_fused_and_bit_identical(path):
+    """SURVEY 8f N3 (first sub-step): with ``vocoder_scale`` the last posterior update (denorm_spec kernel for rectified
+    flow) stores fl(2.30259 * x), so the call returns the contiguous [B,M,T] generator input of nsf_hifigan.py:50-52 --
+    bit-identical to ``2.30259 * mel.transpose(2, 1)`` of the unscaled call on the same x_T / noise / seed, in every
+    kernel variant that owns the final write; a later call without the scale is unaffected."""
+    import prodiff_b200 as pb
+    from prodiff_b200 import _lib, handoff, synth
+    lib = _lib.load()
+    C = 512 if path == "unfused512" else 256
+    cfg = synth.DiffNetConfig(128, 256, 3, C, 2)
+    state = synth.make_state(cfg, 31, "trained")
+    B, T, K = 2, 300, 3
+    cond, x_T, noise = synth.make_inputs(cfg, B, T, K, 32)
+    prev = lib.pd_set_tail(0 if path == "separate" else 1)
+    try:
+        if path == "reflow":
+            rf = pb.RectifiedFlow(128, _build(cfg, state), time_scale=1000, sampling_algorithm="rk2",
+                                  spec_min=[-12.0], spec_max=[0.0]).cuda().eval()
+            run = lambda **kw: rf(cond.cuda(), infer_step=2, infer=True, x_start=x_T.cuda(), **kw)
+            runs = [run]
+        else:
+            gd = _build(cfg, state, dict(timesteps=4, schedule_type="vpsde", max_beta=40))
+            runs = [lambda **kw: gd(cond.cuda(), infer_step=K, infer=True, x_T=x_T.cuda(), noise=noise.cuda(), **kw),
+                    lambda **kw: gd(cond.cuda(), infer_step=K, infer=True, x_T=x_T.cuda(), seed=5, **kw)]
+        with torch.no_grad():
+            for run in runs:
+                mel = run()
+                c = run(vocoder_scale=handoff.LOG10_TO_LN)
+                again = run()
+                assert c.shape == (B, 128, T) and c.is_contiguous()
+                assert torch.equal(c, handoff.generator_input(mel)) and torch.equal(again, mel)
+                assert float(c.abs().max()) > 0
+    finally:
+        lib.pd_set_tail(1 if prev != 0 else 0)
+
+
 @pytest.mark.parametrize("name", ["euler", "rk2", "rk4", "rk5", "pitch64"])
 def test_reflow_matches_oracle_and_fixture(name):
     """RectifiedFlow / PitchRectifiedFlow .forward(infer=True) through pd_reflow_sample against the oracle
