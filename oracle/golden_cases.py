@@ -4,7 +4,7 @@ Each case is regenerated from seeds by ``prodiff_b200.synth``; the ``.npz`` unde
 ``tests/golden/`` stores only what the *reference* produced (per-step x0 predictions and the
 final mel) plus a sha256 of the regenerated weights/inputs.
 """
-from prodiff_b200.synth import DiffNetConfig
+from prodiff_b200.synth import DiffNetConfig, EncoderConfig
 
 # name -> dict(cfg, timesteps, schedule_type, max_beta, infer_step, B, T, out_init, wseed, iseed)
 SAMPLE_CASES = {
@@ -97,3 +97,15 @@ def make_condition_inputs(case):
     d["variances"] = [(f32(rng.random((B, T))), f32(rng.normal(size=(H, 1)) * 0.3), f32(rng.normal(size=(H,)) * 0.1))
                       for _ in range(case["n_var"])]
     return d
+
+
+# FastSpeech text encoder (tts_modules.py:291-330; SURVEY §8f N1, token-level half): FastspeechEncoder.forward(txt_tokens,
+# extra_embed) in eval mode.  ``lengths`` = non-padding tokens per row (trailing PAD), extra = whether extra_embed is given.
+ENCODER_CASES = {
+    # the configured encoder (base_config.yaml:106-116: 4 layers, 2 heads, kernel 9), ragged rows
+    "base4": dict(cfg=EncoderConfig(64, 256, 4, 9, 2), Tph=50, lengths=[50, 37, 44], extra=True, wseed=121, iseed=122),
+    # rows longer than one 128-token tile, a one-token row, no extra_embed
+    "long_noextra": dict(cfg=EncoderConfig(40, 256, 2, 9, 2), Tph=200, lengths=[200, 1], extra=False, wseed=123, iseed=124),
+    # shorter than the conv kernel
+    "tiny": dict(cfg=EncoderConfig(30, 256, 1, 9, 2), Tph=5, lengths=[5, 3], extra=True, wseed=125, iseed=126),
+}

@@ -170,8 +170,33 @@ def run_reference_condition(case):
     return dict(out=out.numpy())
 
 
+def run_reference_encoder(case):
+    """The reference's own ``FastspeechEncoder`` (tts_modules.py:291-330), unmodified, in eval mode on seeded weights.
+    Parameters are frozen (requires_grad False, as an inference deployment would have them): ATen picks the Conv1d backend
+    from that flag, and the oracle's plain tensors take the same one, which is what makes bit-exact comparison possible."""
+    import types
+    from prodiff_b200 import synth
+    load_reference()
+    sys.modules.setdefault("chardet", types.ModuleType("chardet"))      # utils/__init__.py imports it; unused here
+    from modules.fastspeech.tts_modules import FastspeechEncoder       # noqa
+    cfg = case["cfg"]
+    state = synth.make_encoder_state(cfg, case["wseed"])
+    tok, extra = synth.make_encoder_inputs(cfg, case["lengths"], case["Tph"], case["iseed"])
+    enc = FastspeechEncoder(cfg.vocab_size, cfg.hidden_size, cfg.num_layers, cfg.kernel_size, dropout=0.1,
+                            num_heads=cfg.num_heads).eval()
+    missing = enc.load_state_dict(state, strict=False)
+    assert not missing.unexpected_keys and missing.missing_keys == ["embed_positions._float_tensor"], missing
+    for p in enc.parameters():
+        p.requires_grad_(False)
+    with torch.no_grad():
+        out = enc(tok, extra if case["extra"] else None)
+    return dict(out=out.contiguous().numpy(), digest=np.array(synth.digest(state, tok.float(), extra)))
+
+
 def main():
-    from oracle.golden_cases import SAMPLE_CASES, DENOISE_CASES, REFLOW_CASES, CONDITION_CASES
+    from oracle.golden_cases import SAMPLE_CASES, DENOISE_CASES, REFLOW_CASES, CONDITION_CASES, ENCODER_CASES
+    if "--encoder-only" in sys.argv:
+        SAMPLE_CASES, DENOISE_CASES, REFLOW_CASES, CONDITION_CASES = {}, {}, {}, {}
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     out_dir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
@@ -191,6 +216,10 @@ def main():
         r = run_reference_condition(case)
         np.savez(os.path.join(out_dir, f"condition_{name}.npz"), **r)
         print(f"condition_{name}: out {r['out'].shape} |out|max {np.abs(r['out']).max():.3f}")
+    for name, case in ENCODER_CASES.items():
+        r = run_reference_encoder(case)
+        np.savez(os.path.join(out_dir, f"encoder_{name}.npz"), **r)
+        print(f"encoder_{name}: out {r['out'].shape} |out|max {np.abs(r['out']).max():.3f}")
 
 
 if __name__ == "__main__":

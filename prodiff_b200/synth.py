@@ -100,3 +100,59 @@ def digest(*tensors) -> str:
         else:
             h.update(t.contiguous().numpy().tobytes())
     return h.hexdigest()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# FastSpeech text encoder (token-level half): constructor arguments of the reference ``FastspeechEncoder``
+# (`/root/reference/modules/fastspeech/tts_modules.py:291-303`) and seeded weights with its init distributions
+# (embedding N(0, H^-0.5) with a zero padding row, `common_layers.py:63-68`; xavier-uniform attention / ffn_2 weights,
+# `:86-91,225-233`; torch-default Conv1d init for ffn_1).  LayerNorm affine parameters and the zero-initialised biases get a
+# small perturbation ("trained-like"), otherwise they would not be exercised at all.
+@dataclass(frozen=True)
+class EncoderConfig:
+    vocab_size: int = 64
+    hidden_size: int = 256
+    num_layers: int = 4
+    kernel_size: int = 9
+    num_heads: int = 2
+
+    def dict(self):
+        return asdict(self)
+
+
+def make_encoder_state(cfg: EncoderConfig, seed: int = 1234) -> Dict[str, torch.Tensor]:
+    """A full ``FastspeechEncoder.state_dict()`` (same keys and shapes as the reference, minus the one-element
+    ``embed_positions._float_tensor`` device marker) from a seed."""
+    rng = np.random.default_rng(seed)
+    H, k = cfg.hidden_size, cfg.kernel_size
+    st: Dict[str, np.ndarray] = {}
+    xavier = lambda shape: _uniform(rng, shape, np.sqrt(6.0 / (shape[0] + shape[1])))
+    for i in range(cfg.num_layers):
+        p = f"layers.{i}.op."
+        for ln in ("layer_norm1", "layer_norm2"):
+            st[p + ln + ".weight"] = (1.0 + 0.1 * rng.standard_normal(H)).astype(np.float32)
+            st[p + ln + ".bias"] = (0.1 * rng.standard_normal(H)).astype(np.float32)
+        st[p + "self_attn.in_proj_weight"] = xavier((3 * H, H))
+        st[p + "self_attn.out_proj.weight"] = xavier((H, H))
+        st[p + "ffn.ffn_1.weight"] = _uniform(rng, (4 * H, H, k), 1.0 / np.sqrt(H * k))
+        st[p + "ffn.ffn_1.bias"] = _uniform(rng, (4 * H,), 1.0 / np.sqrt(H * k))
+        st[p + "ffn.ffn_2.weight"] = xavier((H, 4 * H))
+        st[p + "ffn.ffn_2.bias"] = (0.02 * rng.standard_normal(H)).astype(np.float32)
+    st["layer_norm.weight"] = (1.0 + 0.1 * rng.standard_normal(H)).astype(np.float32)
+    st["layer_norm.bias"] = (0.1 * rng.standard_normal(H)).astype(np.float32)
+    emb = (rng.standard_normal((cfg.vocab_size, H)) * H ** -0.5).astype(np.float32)
+    emb[0] = 0
+    st["embed_tokens.weight"] = emb
+    return {k_: torch.from_numpy(v) for k_, v in st.items()}
+
+
+def make_encoder_inputs(cfg: EncoderConfig, lengths, Tph: int, seed: int = 4321):
+    """txt_tokens [B,Tph] int64 (row b has lengths[b] non-padding tokens, then PAD = 0) and extra_embed [B,Tph,H]
+    (what dur_embed + lang_embed add, prodiff_teacher.py:112-120; small, like Linear(1,H) of a duration)."""
+    rng = np.random.default_rng(seed)
+    B = len(lengths)
+    tok = np.zeros((B, Tph), dtype=np.int64)
+    for b, n in enumerate(lengths):
+        tok[b, :n] = rng.integers(1, cfg.vocab_size, size=n)
+    extra = (0.3 * rng.standard_normal((B, Tph, cfg.hidden_size))).astype(np.float32)
+    return torch.from_numpy(tok), torch.from_numpy(extra)

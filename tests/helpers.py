@@ -5,8 +5,9 @@ import numpy as np
 import torch
 
 from oracle import prodiff_oracle as oracle
-from oracle.golden_cases import (SAMPLE_CASES, DENOISE_CASES, REFLOW_CASES, CONDITION_CASES, reflow_spec_range,
-                                 make_condition_inputs)
+from oracle import encoder_oracle
+from oracle.golden_cases import (SAMPLE_CASES, DENOISE_CASES, REFLOW_CASES, CONDITION_CASES, ENCODER_CASES,
+                                 reflow_spec_range, make_condition_inputs)
 from prodiff_b200 import synth
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -62,3 +63,17 @@ def oracle_condition(name):
     out = oracle.assemble_condition(d["encoder_out"], d["mel2ph"], d["f0"], d["pitch_w"], d["pitch_b"], d["spk"], d["gender"],
                                     d["variances"])
     return d, out
+
+
+def regen_encoder_case(name):
+    """(case, cfg, state, txt_tokens, extra_embed or None) of an ENCODER case; the digest always covers extra_embed."""
+    case = ENCODER_CASES[name]
+    cfg = case["cfg"]
+    state = synth.make_encoder_state(cfg, case["wseed"])
+    tok, extra = synth.make_encoder_inputs(cfg, case["lengths"], case["Tph"], case["iseed"])
+    return case, cfg, state, tok, extra
+
+
+def oracle_encoder(case, cfg, state, tok, extra, trace=None):
+    with torch.no_grad():
+        return encoder_oracle.encoder_forward(state, tok, extra if case["extra"] else None, cfg.num_heads, trace)

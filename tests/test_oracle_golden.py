@@ -10,7 +10,7 @@ import pytest
 import torch
 
 from oracle import prodiff_oracle as oracle
-from oracle.golden_cases import SAMPLE_CASES, DENOISE_CASES, REFLOW_CASES, CONDITION_CASES
+from oracle.golden_cases import SAMPLE_CASES, DENOISE_CASES, REFLOW_CASES, CONDITION_CASES, ENCODER_CASES
 from prodiff_b200 import synth
 from tests import helpers
 
@@ -109,3 +109,27 @@ def test_t0_noise_is_masked():
     noise2[-1] += 100.0
     mel_b, _ = helpers.oracle_sample(case, cfg, state, cond, x_T, noise2)
     assert torch.equal(mel_a, mel_b)
+
+
+@pytest.mark.parametrize("name", sorted(ENCODER_CASES))
+def test_encoder_matches_reference_fixture(name):
+    """FastspeechEncoder.forward of the reference (tts_modules.py:291-330; SURVEY 8f N1, token-level half)."""
+    case, cfg, state, tok, extra = helpers.regen_encoder_case(name)
+    g = helpers.load_golden("encoder", name)
+    assert str(g["digest"]) == synth.digest(state, tok.float(), extra), "regenerated inputs differ from the fixture's"
+    out = helpers.oracle_encoder(case, cfg, state, tok, extra)
+    assert out.shape == g["out"].shape == (len(case["lengths"]), case["Tph"], cfg.hidden_size)
+    assert np.abs(out.numpy() - g["out"]).max() <= TOL
+    for b, n in enumerate(case["lengths"]):           # padding tokens come out as exact zeros (FFTBlocks.forward :269-279)
+        assert not out[b, n:].any() and out[b, :n].abs().max() > 0.5
+
+
+def test_encoder_positions_and_durations():
+    """make_positions over ~padding_mask (tts_utils.py:6-18, tts_modules.py:322) and mel2ph_to_dur (tts_modules.py:223-229)."""
+    from oracle import encoder_oracle as eo
+    tok = torch.tensor([[5, 7, 0, 9, 0], [0, 0, 0, 0, 0]])
+    assert eo.make_positions(~tok.eq(0)).tolist() == [[1, 2, 0, 3, 0], [0, 0, 0, 0, 0]]
+    tab = eo.sinusoid_table(8, 6)
+    assert not tab[0].any() and torch.allclose(tab[1, :3], torch.sin(torch.tensor([1.0, 1e-2, 1e-4])), atol=1e-6)
+    mel2ph = torch.tensor([[1, 1, 2, 4, 4, 4, 0, 0]])
+    assert eo.mel2ph_to_dur(mel2ph, 4).tolist() == [[2, 1, 0, 3]]

@@ -66,6 +66,15 @@ def test_condition_assembly_bit_exact(mg, name):
     assert np.array_equal(out.numpy(), ref["out"])
 
 
+@pytest.mark.parametrize("name", ["base4", "long_noextra", "tiny"])
+def test_encoder_bit_exact(mg, name):
+    from oracle.golden_cases import ENCODER_CASES
+    from tests import helpers
+    ref = mg.run_reference_encoder(ENCODER_CASES[name])
+    out = helpers.oracle_encoder(*helpers.regen_encoder_case(name))
+    assert np.array_equal(out.contiguous().numpy(), ref["out"])
+
+
 def test_reference_init_distribution_matches_synth(mg):
     """synth.make_state mirrors the reference's init *distributions* (not its torch RNG stream)."""
     from prodiff_b200 import synth
