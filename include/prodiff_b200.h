@@ -148,6 +148,42 @@ int pd_plan_set_output_scale(pd_plan* p, float scale);
 int pd_reflow_sample(pd_plan* p, const float* cond, float* x, int algorithm, int n_steps, float time_scale,
                      float* k_scratch, const float* spec_min, const float* spec_max, int n_spec, float* v_trace, void* stream);
 
+/* ---- FastSpeech text encoder (token-level half) -------------------------------------------------------
+ * FastspeechEncoder.forward(txt_tokens, extra_embed) in eval mode (/root/reference/modules/fastspeech/tts_modules.py:291-330,
+ * FFTBlocks.forward :262-288, EncSALayer /root/reference/modules/commons/common_layers.py:625-673): what
+ * ProDiffTeacher.forward_condition calls at /root/reference/modules/svs/prodiff_teacher.py:122 to produce the
+ * `encoder_out` that pd_cond_assemble consumes.  Constructor arguments of the reference class plus the operand type. */
+typedef struct pd_encoder_config {
+  int32_t vocab_size;
+  int32_t hidden_size; /* 256 */
+  int32_t num_layers;
+  int32_t kernel_size; /* odd; the FFN's Conv1d (enc_ffn_kernel_size, 9) */
+  int32_t num_heads;   /* 1, 2 or 4 */
+  int32_t dtype;       /* PD_BF16 / PD_FP16 tensor-core operands; LayerNorm, softmax, residual stream in fp32 */
+} pd_encoder_config;
+typedef struct pd_encoder pd_encoder;
+
+/* Entries pd_encoder_create expects in `state`: 3 + 10 * num_layers device fp32 tensors, the reference's state_dict keys:
+ *   0 embed_tokens.weight [V,H]   1 layer_norm.weight [H]   2 layer_norm.bias [H]
+ *   then for layer i (base = 3 + 10*i) the keys of layers.{i}.op. in this order:
+ *   +0 layer_norm1.weight  +1 layer_norm1.bias  +2 self_attn.in_proj_weight [3H,H]  +3 self_attn.out_proj.weight [H,H]
+ *   +4 layer_norm2.weight  +5 layer_norm2.bias  +6 ffn.ffn_1.weight [4H,H,k]  +7 ffn.ffn_1.bias [4H]
+ *   +8 ffn.ffn_2.weight [H,4H]  +9 ffn.ffn_2.bias [H] */
+int pd_encoder_state_count(const pd_encoder_config* cfg);
+size_t pd_encoder_packed_bytes(const pd_encoder_config* cfg);
+/* Packs the weights into `packed` (device, 1024-byte aligned, pd_encoder_packed_bytes; owned by the caller, must outlive
+ * the handle).  Same ownership rules as pd_model_create. */
+int pd_encoder_create(const pd_encoder_config* cfg, const float* const* state, int n_state, void* packed,
+                      size_t packed_bytes, void* stream, pd_encoder** out);
+void pd_encoder_destroy(pd_encoder* e);
+size_t pd_encoder_workspace_bytes(const pd_encoder* e, int B, int T);
+/* txt_tokens [B,T] int64 device (0 = padding, tts_modules.py:311); extra_embed [B,T,H] fp32 device or NULL (what
+ * dur_embed + lang_embed add, prodiff_teacher.py:112-120); out [B,T,H] fp32 device: encoder_out, zeros at padding tokens.
+ * A row whose tokens are all padding comes out as zeros (the reference produces NaN there).  workspace: device scratch of
+ * pd_encoder_workspace_bytes(e, B, T), 1024-byte aligned, only used during the call's kernels. */
+int pd_encoder_forward(pd_encoder* e, const long long* txt_tokens, const float* extra_embed, float* out, int B, int T,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
 /* Number of kernels of this library launched by the calling thread since the last reset (bench evidence). */
 long long pd_launch_count(int reset);
 

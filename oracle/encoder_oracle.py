@@ -73,7 +73,7 @@ def self_attention(x_tbc: torch.Tensor, in_proj_weight: torch.Tensor, out_proj_w
     q = q.view(tgt_len, bsz * num_heads, head_dim).transpose(0, 1)
     k = k.view(tgt_len, bsz * num_heads, head_dim).transpose(0, 1)
     v = v.view(tgt_len, bsz * num_heads, head_dim).transpose(0, 1)
-    mask = torch.zeros(key_padding_mask.shape, dtype=x_tbc.dtype).masked_fill_(key_padding_mask, float("-inf"))
+    mask = torch.zeros(key_padding_mask.shape, dtype=x_tbc.dtype, device=x_tbc.device).masked_fill_(key_padding_mask, float("-inf"))
     mask = mask.view(bsz, 1, 1, tgt_len).expand(-1, num_heads, -1, -1).reshape(bsz * num_heads, 1, tgt_len)
     q_scaled = q * math.sqrt(1.0 / float(head_dim))
     w = torch.baddbmm(mask, q_scaled, k.transpose(-2, -1))

@@ -7,6 +7,8 @@ Public surface (mirrors the reference's module API for this path, SURVEY.md sect
         .forward(cond, src_spec=None, gt_spec=None, infer_step=4, infer=False)
     RectifiedFlow(out_dims, denoise_fn, time_scale, num_features, sampling_algorithm, spec_min, spec_max)
         .forward(cond, gt_spec=None, infer_step=20, infer=True)          (PitchRectifiedFlow likewise)
+    FastspeechEncoder(vocab_size, hidden_size, num_layers, kernel_size, dropout, num_heads, rel_pos)
+        .forward(txt_tokens, extra_embed=None)                           (the step before the sampler)
 
 ``install()`` swaps these classes into the reference's own modules so that ``ProDiffTeacher``, the SVS inferer
 (``handler/infer/handler.py``), ``main.py infer`` and the vocoder hand-off run unchanged on top of them.
@@ -15,6 +17,7 @@ from .wavenet import WaveNet
 from .diffusion import GaussianDiffusion
 from .reflow import RectifiedFlow, PitchRectifiedFlow
 from .conditioning import AssembledCondition, forward_condition
+from .encoder import FastspeechEncoder
 from .synth import DiffNetConfig
 
 __version__ = "0.1.0"
@@ -30,8 +33,10 @@ def install():
     rf = importlib.import_module("modules.diffusion.reflow")
     rf.RectifiedFlow = RectifiedFlow
     rf.PitchRectifiedFlow = PitchRectifiedFlow
+    tm = importlib.import_module("modules.fastspeech.tts_modules")   # prodiff_teacher.py:8 imports the name from here
+    tm.FastspeechEncoder = FastspeechEncoder
     return wn, gd
 
 
-__all__ = ["WaveNet", "GaussianDiffusion", "RectifiedFlow", "PitchRectifiedFlow", "AssembledCondition", "forward_condition",
+__all__ = ["WaveNet", "GaussianDiffusion", "RectifiedFlow", "PitchRectifiedFlow", "FastspeechEncoder", "AssembledCondition", "forward_condition",
            "DiffNetConfig", "install"]

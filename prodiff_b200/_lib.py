@@ -20,7 +20,14 @@ SYMBOLS = [
     "pd_workspace_bytes", "pd_plan_create", "pd_plan_destroy", "pd_cond_project", "pd_denoise", "pd_sample",
     "pd_launch_count", "pd_plan_buffer", "pd_debug_gemm", "pd_profile_begin", "pd_profile_end", "pd_debug_shift", "pd_debug_set_trace", "pd_set_fused", "pd_set_stack", "pd_set_tail", "pd_set_sumtail", "pd_reflow_sample", "pd_plan_set_lengths", "pd_cond_assemble",
     "pd_plan_set_output_scale",
+    "pd_encoder_state_count", "pd_encoder_packed_bytes", "pd_encoder_create", "pd_encoder_destroy",
+    "pd_encoder_workspace_bytes", "pd_encoder_forward",
 ]
+
+
+class pd_encoder_config(C.Structure):
+    _fields_ = [("vocab_size", C.c_int32), ("hidden_size", C.c_int32), ("num_layers", C.c_int32),
+                ("kernel_size", C.c_int32), ("num_heads", C.c_int32), ("dtype", C.c_int32)]
 
 
 class pd_config(C.Structure):
@@ -63,6 +70,12 @@ def load() -> C.CDLL:
     lib.pd_plan_set_output_scale.argtypes = [vp, C.c_float]; lib.pd_plan_set_output_scale.restype = C.c_int
     lib.pd_cond_assemble.argtypes = [vp, vp, C.c_int, vp, vp, vp, vp, vp, vp, C.c_int, P(vp), P(vp), P(vp), vp, vp, vp]
     lib.pd_cond_assemble.restype = C.c_int
+    lib.pd_encoder_state_count.argtypes = [P(pd_encoder_config)]; lib.pd_encoder_state_count.restype = C.c_int
+    lib.pd_encoder_packed_bytes.argtypes = [P(pd_encoder_config)]; lib.pd_encoder_packed_bytes.restype = sz
+    lib.pd_encoder_create.argtypes = [P(pd_encoder_config), P(vp), C.c_int, vp, sz, vp, P(vp)]; lib.pd_encoder_create.restype = C.c_int
+    lib.pd_encoder_destroy.argtypes = [vp]; lib.pd_encoder_destroy.restype = None
+    lib.pd_encoder_workspace_bytes.argtypes = [vp, C.c_int, C.c_int]; lib.pd_encoder_workspace_bytes.restype = sz
+    lib.pd_encoder_forward.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, vp, sz, vp]; lib.pd_encoder_forward.restype = C.c_int
     lib.pd_launch_count.argtypes = [C.c_int]; lib.pd_launch_count.restype = C.c_longlong
     lib.pd_plan_buffer.argtypes = [vp, cp, P(sz), P(sz)]; lib.pd_plan_buffer.restype = C.c_int
     lib.pd_debug_gemm.argtypes = [C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp, vp, vp]

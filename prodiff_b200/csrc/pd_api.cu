@@ -1297,3 +1297,6 @@ extern "C" int pd_debug_shift(int dtype, const void* a, int R, const void* w, in
   PD_LAUNCH_CHECK("k_shift_probe");
   return 0;
 }
+
+// ------------------------------------------------------------------ FastSpeech text encoder
+#include "pd_encoder_api.cuh"

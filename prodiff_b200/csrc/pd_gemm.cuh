@@ -20,6 +20,8 @@
 //               diffusion-step bias added first                 (ResidualBlock up to the gate)
 //   EPI_RES   : (x + acc + bias) / sqrt(2)                      (ResidualBlock residual path)
 //   EPI_OUT   : x0 = acc + bias, then the q-posterior update x_{t-1} = c1*x0 + c2*x_t + sigma*noise
+//   EPI_STORE_X : EPI_STORE plus what the text encoder's GEMMs need (pd_encoder.cuh): erf-GELU, an fp32 residual added
+//               after the activation, and a per-row keep mask (padding tokens come out as zeros)
 #pragma once
 #include "pd_ptx.cuh"
 
@@ -31,7 +33,7 @@ constexpr int kEpiWarps = 8;
 constexpr int kGemmThreads = 32 * (2 + kEpiWarps);
 constexpr uint32_t kTmemCols = 512;
 
-enum EpiKind { EPI_STORE = 0, EPI_GATE = 1, EPI_RES = 2, EPI_OUT = 3, EPI_STORE_BLK = 4 };
+enum EpiKind { EPI_STORE = 0, EPI_GATE = 1, EPI_RES = 2, EPI_OUT = 3, EPI_STORE_BLK = 4, EPI_STORE_X = 5 };
 enum OutType { OUT_T = 0, OUT_F16 = 1, OUT_F32 = 2 };
 
 struct GemmShape {
@@ -62,6 +64,10 @@ struct EpiArgs {
   const int* lens;  // optional per-utterance valid lengths (ragged batch): STORE writes zeros for frames >= lens[b]
   int relu;
   int out_type;
+  // EPI_STORE_X
+  int gelu;               // exact (erf) GELU after bias and scale (common_layers.py:575-576)
+  const float* resid;     // optional fp32 tensor in the output's own layout, added last (may alias `out`)
+  const uint8_t* keep;    // optional per-row flag [B*T]: rows with 0 are written as zeros
   // EPI_OUT
   int M, Mp;
   float* x0_out;       // optional [B,1,M,T]
@@ -434,7 +440,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           bulk_store(static_cast<uint16_t*>(ep.out) + blocked_off(tile_b, ep.ld >> 3, within0 >> 3, 0), stg, 32768);
           tma_store_commit();
         }
-      } else if constexpr (EPI == EPI_STORE) {
+      } else if constexpr (EPI == EPI_STORE || EPI == EPI_STORE_X) {
         const long long nfr = (long long)sh.B * sh.T;
         // two register buffers: the TMEM load of chunk i+1 is in flight while chunk i is converted and stored
         uint32_t rr[2][32];
@@ -464,6 +470,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             if (ep.lens != nullptr && t >= __ldg(ep.lens + b)) {   // ragged batch: frames past this utterance's end stay zero
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = 0.f;
+            }
+            if constexpr (EPI == EPI_STORE_X) {
+              if (ep.gelu) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = 0.5f * v[j] * (1.f + erff(v[j] * 0.70710678118654752f));
+              }
+              if (ep.resid != nullptr) {
+                const float4* rs = reinterpret_cast<const float4*>(ep.resid + ((long long)slab * nfr + n) * ep.ld + within);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float4 rv = rs[j];
+                  v[4 * j] += rv.x; v[4 * j + 1] += rv.y; v[4 * j + 2] += rv.z; v[4 * j + 3] += rv.w;
+                }
+              }
+              if (ep.keep != nullptr && !ep.keep[n]) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = 0.f;
+              }
             }
             if (ep.out_type == OUT_F32) {
               float4* dst = reinterpret_cast<float4*>(static_cast<float*>(ep.out) + ((long long)slab * nfr + n) * ep.ld + within);

@@ -520,6 +520,148 @@ def test_sampling_from_assembled_condition_equals_dense_condition():
         assert torch.equal(fa, fb) and torch.isfinite(fa).all()
 
 
+ENC_TOL = {"bf16": (2e-2, 3e-3), "fp16": (3e-3, 5e-4)}   # (max-abs, mean-abs) of encoder_out, whose entries are ~N(0,1) after the last LayerNorm
+
+
+def _build_encoder(cfg, state, operand_dtype="bf16"):
+    import prodiff_b200 as pb
+    enc = pb.FastspeechEncoder(cfg.vocab_size, cfg.hidden_size, cfg.num_layers, cfg.kernel_size, num_heads=cfg.num_heads,
+                               operand_dtype=operand_dtype)
+    missing = enc.load_state_dict(state, strict=False)
+    assert not missing.unexpected_keys and missing.missing_keys == ["embed_positions._float_tensor"]
+    return enc.cuda().eval()
+
+
+@pytest.mark.parametrize("operand_dtype", ["bf16", "fp16"])
+@pytest.mark.parametrize("name", ["base4", "long_noextra", "tiny"])
+def test_text_encoder_matches_oracle_and_fixture(name, operand_dtype):
+    """SURVEY 8f N1 (token-level half): FastspeechEncoder.forward through pd_encoder_forward against the oracle restatement
+    of tts_modules.py:291-330 and the reference-made fixture.  16-bit tensor-core operands for the four GEMMs of each block,
+    fp32 LayerNorm / softmax / residual stream: encoder_out (unit scale) within 2e-2 max-abs / 3e-3 mean-abs for bf16 operands
+    (measured <= 9.6e-3 / 1.4e-3), 3e-3 / 5e-4 for fp16 (measured 1.3e-3 / 1.6e-4); padding tokens are exact zeros."""
+    case, cfg, state, tok, extra = helpers.regen_encoder_case(name)
+    ref = helpers.oracle_encoder(case, cfg, state, tok, extra)
+    g = torch.from_numpy(helpers.load_golden("encoder", name)["out"])
+    enc = _build_encoder(cfg, state, operand_dtype)
+    with torch.no_grad():
+        out = enc(tok.cuda(), extra.cuda() if case["extra"] else None)
+        out2 = enc(tok.cuda(), extra.cuda() if case["extra"] else None)
+    assert out.shape == ref.shape and out.dtype == torch.float32 and torch.equal(out, out2)
+    out = out.cpu()
+    tol_max, tol_mean = ENC_TOL[operand_dtype]
+    for want in (ref, g):
+        assert float((out - want).abs().max()) <= tol_max, float((out - want).abs().max())
+        assert float((out - want).abs().mean()) <= tol_mean
+    for b, n in enumerate(case["lengths"]):
+        assert not out[b, n:].any()
+
+
+def test_text_encoder_ragged_rows_and_interior_padding():
+    """Rows are independent (each row equals that utterance run alone at its own length: attention masks padded keys, the
+    FFN convolution sees LayerNorm(0) = bias at padded positions inside T exactly like the reference), and a PAD token in
+    the middle of a row is handled like the reference handles it (masked key, zero output, positions skip it)."""
+    from prodiff_b200 import synth
+    cfg = synth.EncoderConfig(50, 256, 2, 9, 2)
+    state = synth.make_encoder_state(cfg, 131)
+    tok, extra = synth.make_encoder_inputs(cfg, [140, 90, 129], 140, 132)
+    tok[1, 17] = 0                                                     # interior padding
+    case = dict(extra=True, lengths=[140, 90, 129])
+    ref = helpers.oracle_encoder(case, cfg, state, tok, extra)
+    enc = _build_encoder(cfg, state, "fp16")
+    with torch.no_grad():
+        out = enc(tok.cuda(), extra.cuda()).cpu()
+    assert float((out - ref).abs().max()) <= ENC_TOL["fp16"][0] and not out[1, 17].any() and not out[1, 90:].any()
+
+
+def test_text_to_mel_chain_matches_oracle_chain():
+    """The whole front of ProDiffTeacher.forward (prodiff_teacher.py:103-167) on the CUDA path -- dur/lang embeddings (torch),
+    FastspeechEncoder (pd_encoder_forward), frame-level condition assembly (pd_cond_assemble), K-step sampler (pd_sample) --
+    against the same chain of the oracle restatements on identical x_T / noise: final mel L1 within the north-star 1e-2."""
+    import types
+    import prodiff_b200 as pb
+    from oracle import encoder_oracle as eo
+    from prodiff_b200 import synth
+    ecfg = synth.EncoderConfig(40, 256, 4, 9, 2)
+    estate = synth.make_encoder_state(ecfg, 141)
+    B, Tph, T, K = 2, 30, 200, 4
+    lens_ph = [30, 22]
+    tok, _ = synth.make_encoder_inputs(ecfg, lens_ph, Tph, 142)
+    rng = np.random.default_rng(143)
+    mel2ph = np.zeros((B, T), dtype=np.int64)
+    for b, n_fr in enumerate([200, 170]):
+        mel2ph[b, :n_fr] = np.sort(rng.integers(1, lens_ph[b] + 1, size=n_fr))
+    mel2ph = torch.from_numpy(mel2ph)
+    f0 = torch.from_numpy(rng.uniform(80, 800, size=(B, T)).astype(np.float32))
+    f32 = lambda a: torch.from_numpy(np.asarray(a, dtype=np.float32))
+    dur_w, dur_b = f32(rng.normal(size=(256, 1)) * 0.05), f32(rng.normal(size=(256,)) * 0.05)
+    pitch_w, pitch_b = f32(rng.normal(size=(256, 1)) * 0.3), f32(rng.normal(size=(256,)) * 0.1)
+    spk = f32(rng.normal(size=(B, 1, 256)) * 0.3)
+    cfg = synth.DiffNetConfig(128, 256, 6, 256, 2)
+    state = synth.make_state(cfg, 144, "trained")
+    case = dict(timesteps=4, schedule_type="vpsde", max_beta=40, infer_step=K)
+    _, x_T, noise = synth.make_inputs(cfg, B, T, K, 145)
+    # oracle chain
+    with torch.no_grad():
+        dur = eo.mel2ph_to_dur(mel2ph, Tph).float()
+        extra = torch.nn.functional.linear(dur[:, :, None], dur_w, dur_b)
+        enc_ref = eo.encoder_forward(estate, tok, extra, ecfg.num_heads)
+        cond_ref = oracle.assemble_condition(enc_ref, mel2ph, f0, pitch_w, pitch_b, spk, None, [])
+        mel_ref, _ = helpers.oracle_sample(case, cfg, state, cond_ref, x_T, noise)
+    # CUDA chain through the reference-facing entry points
+    enc = _build_encoder(ecfg, estate)
+    gd = _build(cfg, state, case)
+    dur_embed = torch.nn.Linear(1, 256)
+    with torch.no_grad():
+        dur_embed.weight.copy_(dur_w)
+        dur_embed.bias.copy_(dur_b)
+    dur_embed = dur_embed.cuda()
+    teacher = types.SimpleNamespace(
+        with_dur_embed=True, dur_embed=dur_embed, with_lang_embed=False, encoder=enc,
+        pitch_embed=types.SimpleNamespace(weight=pitch_w.cuda(), bias=pitch_b.cuda()), with_spk_embed=True, with_gender_embed=False,
+        add_spk_embed=lambda i, mix: mix, with_voicing_embed=False, with_breath_embed=False)
+    import sys
+    tm = types.ModuleType("modules.fastspeech.tts_modules")          # forward_condition borrows mel2ph_to_dur from the reference tree
+    tm.mel2ph_to_dur = lambda m2p, T_txt, max_dur=None: eo.mel2ph_to_dur(m2p.cpu(), T_txt).to(m2p.device)
+    saved = {k: sys.modules.get(k) for k in ("modules", "modules.fastspeech", "modules.fastspeech.tts_modules")}
+    sys.modules.setdefault("modules", types.ModuleType("modules"))
+    sys.modules.setdefault("modules.fastspeech", types.ModuleType("modules.fastspeech"))
+    sys.modules["modules.fastspeech.tts_modules"] = tm
+    try:
+        with torch.no_grad():
+            ac = pb.forward_condition(teacher, tok.cuda(), mel2ph.cuda(), f0.cuda(), spk_mix_embed=spk.cuda())
+            mel = gd(ac, infer_step=K, infer=True, x_T=x_T.cuda(), noise=noise.cuda()).cpu()
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    assert float((ac.encoder_out.cpu() - enc_ref).abs().max()) <= ENC_TOL["bf16"][0]
+    valid = (mel2ph > 0)[:, :, None].expand_as(mel_ref)
+    l1 = float((mel - mel_ref)[valid].abs().mean())
+    assert l1 <= MEL_L1_TOL, f"text -> mel L1 {l1:.4g}"
+
+
+def test_text_encoder_fails_loudly():
+    import prodiff_b200 as pb
+    with pytest.raises(NotImplementedError):
+        pb.FastspeechEncoder(30, 256, 1, 9, rel_pos=True)
+    enc = pb.FastspeechEncoder(30, 256, 1, 9).cuda()
+    tok = torch.ones(1, 4, dtype=torch.long).cuda()
+    with pytest.raises(RuntimeError, match="inference-only"):
+        enc(tok)                                                       # training mode
+    enc.eval()
+    with pytest.raises(RuntimeError, match="inference-only"):
+        enc(tok)                                                       # grad mode with trainable parameters
+    with torch.no_grad():
+        assert enc(tok).shape == (1, 4, 256)
+        with pytest.raises(ValueError):
+            enc(tok, torch.zeros(1, 5, 256).cuda())
+    with pytest.raises(RuntimeError, match="512"):
+        with torch.no_grad():
+            pb.FastspeechEncoder(30, 512, 1, 9).cuda().eval()(tok)
+
+
 SHAPE_SWEEP = [
     # (B, T, L, C, cycle, M, K, operand dtype, ragged)      what it stresses
     (1, 1, 2, 256, 1, 128, 1, "bf16", False),               # a single frame, a single step
