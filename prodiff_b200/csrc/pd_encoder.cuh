@@ -227,6 +227,160 @@ __global__ void __launch_bounds__(256) k_enc_attention(T* __restrict__ out16, co
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// The same attention on the tensor cores.  T_txt x T_txt x head_dim per (utterance, head) is far too small to feed a
+// tcgen05 pipeline (a 200 x 200 score matrix is 1.6 M MACs), so this uses warp-level mma.sync m16n8k8 with TF32 operands
+// (fp32 storage, 10-bit mantissa -- no 16-bit rounding of q, k, v or the probabilities) and fp32 accumulation: the CUDA-core
+// version above is bound by instruction issue (one FMA per MAC), this one issues one instruction per 2048 MACs.
+// CTA = 4 warps x 16 queries; per 64-key tile each warp computes S = q k^T (fragments of q live in registers for the whole
+// kernel), the online softmax on the accumulator fragments (a row is spread over the 4 lanes of a quad), P through a
+// per-warp shared-memory tile (accumulator layout -> A-operand layout), then O += P v.  Shared-memory row strides are
+// padded (+4 / +8 words) so that every fragment load is bank-conflict free.
+__device__ __forceinline__ uint32_t f2tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return r;
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+constexpr int kMmaQ = 64;   // queries per CTA (4 warps x 16)
+template <int HD> struct AttnMmaCfg {
+  static constexpr int QS = HD + 4, KS = HD + 4, VS = HD + 8, PS = kAttnK + 4;
+  static constexpr int kQWords = kMmaQ * QS, kPWords = 4 * 16 * PS;
+  static constexpr int kSmemBytes = (kAttnK * KS + kAttnK * VS + (kQWords > kPWords ? kQWords : kPWords)) * 4;
+};
+
+template <typename T, int HD>
+__global__ void __launch_bounds__(128, 2) k_enc_attention_mma(T* __restrict__ out16, const float* __restrict__ qkv,
+                                                              const uint8_t* __restrict__ keep, int Tn, float scale) {
+  using Cfg = AttnMmaCfg<HD>;
+  constexpr int QS = Cfg::QS, KS = Cfg::KS, VS = Cfg::VS, PS = Cfg::PS;
+  constexpr int KQ = HD / 8;                    // k-steps of q k^T = 8-wide output blocks of P v
+  extern __shared__ float sm[];
+  uint32_t* Ks = reinterpret_cast<uint32_t*>(sm);           // [64][HD + 4] tf32
+  uint32_t* Vs = Ks + kAttnK * KS;                           // [64][HD + 8] tf32
+  float* QPs = reinterpret_cast<float*>(Vs + kAttnK * VS);   // q tile [64][HD + 4] at start, then the per-warp P tiles
+  __shared__ uint8_t kvalid[kAttnK];
+  const int b = blockIdx.z, head = blockIdx.y, q0 = blockIdx.x * kMmaQ;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const long long row0 = (long long)b * Tn;
+  const int ld = 3 * kEncH;
+  if (!__syncthreads_or(tid < kMmaQ && q0 + tid < Tn && keep[row0 + q0 + tid] != 0)) return;   // padding-only query block
+  for (int i = tid; i < kMmaQ * (HD / 4); i += 128) {
+    const int r = i / (HD / 4), c4 = i - r * (HD / 4);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (q0 + r < Tn) v = *reinterpret_cast<const float4*>(qkv + (row0 + q0 + r) * ld + head * HD + 4 * c4);
+    *reinterpret_cast<float4*>(QPs + r * QS + 4 * c4) = make_float4(v.x * scale, v.y * scale, v.z * scale, v.w * scale);
+  }
+  __syncthreads();
+  uint32_t qa[KQ][4];
+  {
+    const float* qr = QPs + (warp * 16 + g) * QS + t;
+#pragma unroll
+    for (int ks = 0; ks < KQ; ++ks) {
+      qa[ks][0] = f2tf32(qr[ks * 8]);
+      qa[ks][1] = f2tf32(qr[8 * QS + ks * 8]);
+      qa[ks][2] = f2tf32(qr[ks * 8 + 4]);
+      qa[ks][3] = f2tf32(qr[8 * QS + ks * 8 + 4]);
+    }
+  }
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;   // rows g and g + 8 of this warp's 16 queries
+  float o[KQ][4];
+#pragma unroll
+  for (int nb = 0; nb < KQ; ++nb) o[nb][0] = o[nb][1] = o[nb][2] = o[nb][3] = 0.f;
+  float* Pw = QPs + warp * 16 * PS;
+  for (int k0 = 0; k0 < Tn; k0 += kAttnK) {
+    // (also orders the q-fragment reads / the previous tile's reads before the shared memory is overwritten)
+    if (!__syncthreads_or(tid < kAttnK && k0 + tid < Tn && keep[row0 + k0 + tid] != 0)) continue;
+    for (int i = tid; i < kAttnK * (HD / 4); i += 128) {
+      const int r = i / (HD / 4), c4 = i - r * (HD / 4);
+      float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
+      if (k0 + r < Tn) {
+        const float* src = qkv + (row0 + k0 + r) * ld + head * HD + 4 * c4;
+        kv = *reinterpret_cast<const float4*>(src + kEncH);
+        vv = *reinterpret_cast<const float4*>(src + 2 * kEncH);
+      }
+      *reinterpret_cast<uint4*>(Ks + r * KS + 4 * c4) = make_uint4(f2tf32(kv.x), f2tf32(kv.y), f2tf32(kv.z), f2tf32(kv.w));
+      *reinterpret_cast<uint4*>(Vs + r * VS + 4 * c4) = make_uint4(f2tf32(vv.x), f2tf32(vv.y), f2tf32(vv.z), f2tf32(vv.w));
+    }
+    if (tid < kAttnK) kvalid[tid] = (k0 + tid < Tn && keep[row0 + k0 + tid]) ? 1 : 0;
+    __syncthreads();
+    // S[16 x 64]: accumulator fragment sc[nb] holds keys nb*8 + 2t, +1 for rows g (.x .y) and g + 8 (.z .w)
+    float sc[kAttnK / 8][4];
+#pragma unroll
+    for (int nb = 0; nb < kAttnK / 8; ++nb) {
+      sc[nb][0] = sc[nb][1] = sc[nb][2] = sc[nb][3] = 0.f;
+      const uint32_t* kr = Ks + (nb * 8 + g) * KS + t;
+#pragma unroll
+      for (int ks = 0; ks < KQ; ++ks) mma_tf32(sc[nb], qa[ks], kr[ks * 8], kr[ks * 8 + 4]);
+    }
+    float t0 = -INFINITY, t1 = -INFINITY;
+#pragma unroll
+    for (int nb = 0; nb < kAttnK / 8; ++nb) {
+      const bool va = kvalid[nb * 8 + 2 * t] != 0, vb = kvalid[nb * 8 + 2 * t + 1] != 0;
+      if (!va) sc[nb][0] = sc[nb][2] = -INFINITY;
+      if (!vb) sc[nb][1] = sc[nb][3] = -INFINITY;
+      t0 = fmaxf(t0, fmaxf(sc[nb][0], sc[nb][1]));
+      t1 = fmaxf(t1, fmaxf(sc[nb][2], sc[nb][3]));
+    }
+    t0 = fmaxf(t0, __shfl_xor_sync(0xffffffffu, t0, 1));
+    t0 = fmaxf(t0, __shfl_xor_sync(0xffffffffu, t0, 2));
+    t1 = fmaxf(t1, __shfl_xor_sync(0xffffffffu, t1, 1));
+    t1 = fmaxf(t1, __shfl_xor_sync(0xffffffffu, t1, 2));
+    const float n0 = fmaxf(m0, t0), n1 = fmaxf(m1, t1);
+    const float c0 = m0 == -INFINITY ? 0.f : expf(m0 - n0), c1 = m1 == -INFINITY ? 0.f : expf(m1 - n1);
+    float s0 = 0.f, s1 = 0.f;
+    __syncwarp();                                   // the previous tile's P reads are done
+#pragma unroll
+    for (int nb = 0; nb < kAttnK / 8; ++nb) {
+      // exp(-inf - n) = 0 for masked keys; a row with no valid key so far has n = -inf: keep its probabilities at 0
+      const float p00 = n0 == -INFINITY ? 0.f : expf(sc[nb][0] - n0), p01 = n0 == -INFINITY ? 0.f : expf(sc[nb][1] - n0);
+      const float p10 = n1 == -INFINITY ? 0.f : expf(sc[nb][2] - n1), p11 = n1 == -INFINITY ? 0.f : expf(sc[nb][3] - n1);
+      s0 += p00 + p01;
+      s1 += p10 + p11;
+      *reinterpret_cast<float2*>(Pw + g * PS + nb * 8 + 2 * t) = make_float2(p00, p01);
+      *reinterpret_cast<float2*>(Pw + (g + 8) * PS + nb * 8 + 2 * t) = make_float2(p10, p11);
+    }
+    s0 += __shfl_xor_sync(0xffffffffu, s0, 1);
+    s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+    l0 = l0 * c0 + s0;
+    l1 = l1 * c1 + s1;
+    m0 = n0;
+    m1 = n1;
+#pragma unroll
+    for (int nb = 0; nb < KQ; ++nb) {
+      o[nb][0] *= c0; o[nb][1] *= c0; o[nb][2] *= c1; o[nb][3] *= c1;
+    }
+    __syncwarp();
+    // O[16 x HD] += P[16 x 64] V[64 x HD]
+#pragma unroll
+    for (int ks = 0; ks < kAttnK / 8; ++ks) {
+      uint32_t pa[4];
+      pa[0] = f2tf32(Pw[g * PS + ks * 8 + t]);
+      pa[1] = f2tf32(Pw[(g + 8) * PS + ks * 8 + t]);
+      pa[2] = f2tf32(Pw[g * PS + ks * 8 + t + 4]);
+      pa[3] = f2tf32(Pw[(g + 8) * PS + ks * 8 + t + 4]);
+      const uint32_t* vr = Vs + (ks * 8 + t) * VS + g;
+#pragma unroll
+      for (int nb = 0; nb < KQ; ++nb) mma_tf32(o[nb], pa, vr[nb * 8], vr[4 * VS + nb * 8]);
+    }
+  }
+  const float i0 = l0 > 0.f ? 1.f / l0 : 0.f, i1 = l1 > 0.f ? 1.f / l1 : 0.f;
+  const int qa0 = q0 + warp * 16 + g, qa1 = qa0 + 8;
+#pragma unroll
+  for (int nb = 0; nb < KQ; ++nb) {
+    const int col = head * HD + nb * 8 + 2 * t;
+    if (qa0 < Tn) *reinterpret_cast<uint32_t*>(out16 + (row0 + qa0) * kEncH + col) = Cvt<T>::pack(o[nb][0] * i0, o[nb][1] * i0);
+    if (qa1 < Tn) *reinterpret_cast<uint32_t*>(out16 + (row0 + qa1) * kEncH + col) = Cvt<T>::pack(o[nb][2] * i1, o[nb][3] * i1);
+  }
+}
+
 // ffn_1.weight [4H, H, k] fp32 -> [4H rows][K = tap * H + c] 16-bit (the implicit-GEMM K order of pd_gemm.cuh's tap mode).
 template <typename T>
 __global__ void k_pack_conv_taps(T* __restrict__ dst, const float* __restrict__ src, int rows, int C, int taps) {
