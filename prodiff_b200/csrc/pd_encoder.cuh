@@ -229,94 +229,103 @@ __global__ void __launch_bounds__(256) k_enc_attention(T* __restrict__ out16, co
 
 // ---------------------------------------------------------------------------------------------------------------------
 // The same attention on the tensor cores.  T_txt x T_txt x head_dim per (utterance, head) is far too small to feed a
-// tcgen05 pipeline (a 200 x 200 score matrix is 1.6 M MACs), so this uses warp-level mma.sync m16n8k8 with TF32 operands
-// (fp32 storage, 10-bit mantissa -- no 16-bit rounding of q, k, v or the probabilities) and fp32 accumulation: the CUDA-core
-// version above is bound by instruction issue (one FMA per MAC), this one issues one instruction per 2048 MACs.
-// CTA = 4 warps x 16 queries; per 64-key tile each warp computes S = q k^T (fragments of q live in registers for the whole
-// kernel), the online softmax on the accumulator fragments (a row is spread over the 4 lanes of a quad), P through a
-// per-warp shared-memory tile (accumulator layout -> A-operand layout), then O += P v.  Shared-memory row strides are
-// padded (+4 / +8 words) so that every fragment load is bank-conflict free.
-__device__ __forceinline__ uint32_t f2tf32(float v) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
-  return r;
+// tcgen05 pipeline (a 200 x 200 score matrix is 1.6 M MACs), so this uses warp-level mma.sync m16n8k16 with fp16 operands,
+// fp32 accumulation and an fp32 online softmax: the CUDA-core version above is bound by instruction issue (one FMA per MAC,
+// 128 us per launch at 64 x 200 tokens), this one takes 46 us.  fp16 has a 10-bit mantissa like TF32, and q / sqrt(d), k, v
+// (projections of a LayerNorm output) and the probabilities are far inside its range, so it is used whatever the encoder's
+// GEMM operand type is.  (A TF32 m16n8k8 version with P staged through shared memory measured 64-66 us, with synchronous
+// and with cp.async double-buffered tile fills alike: the legacy tensor path's TF32 rate bounds it.)  The probabilities
+// never touch shared memory: the accumulator fragments of two adjacent 8-key blocks ARE the A fragment of one 16-key k-step.
+// CTA = 4 warps x 16 queries, several CTAs per SM; K tile [64 keys][HD] and V^T tile [HD][64 keys] in fp16 with row
+// strides padded by 8 halves (every fragment load bank-conflict free).
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  __half2 v = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
 }
-__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+__device__ __forceinline__ void mma_f16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-constexpr int kMmaQ = 64;   // queries per CTA (4 warps x 16)
-template <int HD> struct AttnMmaCfg {
-  static constexpr int QS = HD + 4, KS = HD + 4, VS = HD + 8, PS = kAttnK + 4;
-  static constexpr int kQWords = kMmaQ * QS, kPWords = 4 * 16 * PS;
-  static constexpr int kSmemBytes = (kAttnK * KS + kAttnK * VS + (kQWords > kPWords ? kQWords : kPWords)) * 4;
-};
-
+constexpr int kHQ = 64;   // queries per CTA (4 warps x 16)
 template <typename T, int HD>
-__global__ void __launch_bounds__(128, 2) k_enc_attention_mma(T* __restrict__ out16, const float* __restrict__ qkv,
+__global__ void __launch_bounds__(128, 3) k_enc_attention_f16(T* __restrict__ out16, const float* __restrict__ qkv,
                                                               const uint8_t* __restrict__ keep, int Tn, float scale) {
-  using Cfg = AttnMmaCfg<HD>;
-  constexpr int QS = Cfg::QS, KS = Cfg::KS, VS = Cfg::VS, PS = Cfg::PS;
-  constexpr int KQ = HD / 8;                    // k-steps of q k^T = 8-wide output blocks of P v
-  extern __shared__ float sm[];
-  uint32_t* Ks = reinterpret_cast<uint32_t*>(sm);           // [64][HD + 4] tf32
-  uint32_t* Vs = Ks + kAttnK * KS;                           // [64][HD + 8] tf32
-  float* QPs = reinterpret_cast<float*>(Vs + kAttnK * VS);   // q tile [64][HD + 4] at start, then the per-warp P tiles
+  constexpr int KW = (HD + 8) / 2;              // words per K row (and per staged q row)
+  constexpr int VW = (kAttnK + 8) / 2;          // words per V^T row
+  constexpr int KQ = HD / 16;                   // k-steps of q k^T
+  constexpr int NO = HD / 8;                    // 8-wide output blocks of P v
+  __shared__ uint32_t Ks[kAttnK * KW];          // [64 keys][HD + 8] fp16 (first: the q tile)
+  __shared__ uint32_t Vt[HD * VW];              // [HD dims][64 + 8] fp16
   __shared__ uint8_t kvalid[kAttnK];
-  const int b = blockIdx.z, head = blockIdx.y, q0 = blockIdx.x * kMmaQ;
+  __shared__ int s_last;
+  const int b = blockIdx.z, head = blockIdx.y, q0 = blockIdx.x * kHQ;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const long long row0 = (long long)b * Tn;
   const int ld = 3 * kEncH;
-  if (!__syncthreads_or(tid < kMmaQ && q0 + tid < Tn && keep[row0 + q0 + tid] != 0)) return;   // padding-only query block
-  for (int i = tid; i < kMmaQ * (HD / 4); i += 128) {
+  if (!__syncthreads_or(tid < kHQ && q0 + tid < Tn && keep[row0 + q0 + tid] != 0)) return;   // padding-only query block
+  if (tid == 0) s_last = -1;
+  __syncthreads();
+  {
+    int last = -1;
+    for (int i = tid; i < Tn; i += 128)
+      if (keep[row0 + i]) last = i;
+    if (last >= 0) atomicMax(&s_last, last);
+  }
+  for (int i = tid; i < kHQ * (HD / 4); i += 128) {      // q tile, scaled, fp16, staged in the K buffer
     const int r = i / (HD / 4), c4 = i - r * (HD / 4);
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (q0 + r < Tn) v = *reinterpret_cast<const float4*>(qkv + (row0 + q0 + r) * ld + head * HD + 4 * c4);
-    *reinterpret_cast<float4*>(QPs + r * QS + 4 * c4) = make_float4(v.x * scale, v.y * scale, v.z * scale, v.w * scale);
+    *reinterpret_cast<uint2*>(Ks + r * KW + 2 * c4) = make_uint2(pack_h2(v.x * scale, v.y * scale), pack_h2(v.z * scale, v.w * scale));
   }
   __syncthreads();
+  const int n_tiles = (s_last + kAttnK) / kAttnK;   // keys past the last real token contribute nothing
   uint32_t qa[KQ][4];
   {
-    const float* qr = QPs + (warp * 16 + g) * QS + t;
+    const uint32_t* qr = Ks + (warp * 16 + g) * KW + t;
 #pragma unroll
     for (int ks = 0; ks < KQ; ++ks) {
-      qa[ks][0] = f2tf32(qr[ks * 8]);
-      qa[ks][1] = f2tf32(qr[8 * QS + ks * 8]);
-      qa[ks][2] = f2tf32(qr[ks * 8 + 4]);
-      qa[ks][3] = f2tf32(qr[8 * QS + ks * 8 + 4]);
+      qa[ks][0] = qr[ks * 8];
+      qa[ks][1] = qr[8 * KW + ks * 8];
+      qa[ks][2] = qr[ks * 8 + 4];
+      qa[ks][3] = qr[8 * KW + ks * 8 + 4];
     }
   }
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;   // rows g and g + 8 of this warp's 16 queries
-  float o[KQ][4];
+  float o[NO][4];
 #pragma unroll
-  for (int nb = 0; nb < KQ; ++nb) o[nb][0] = o[nb][1] = o[nb][2] = o[nb][3] = 0.f;
-  float* Pw = QPs + warp * 16 * PS;
-  for (int k0 = 0; k0 < Tn; k0 += kAttnK) {
-    // (also orders the q-fragment reads / the previous tile's reads before the shared memory is overwritten)
-    if (!__syncthreads_or(tid < kAttnK && k0 + tid < Tn && keep[row0 + k0 + tid] != 0)) continue;
-    for (int i = tid; i < kAttnK * (HD / 4); i += 128) {
+  for (int nb = 0; nb < NO; ++nb) o[nb][0] = o[nb][1] = o[nb][2] = o[nb][3] = 0.f;
+  __half* Vth = reinterpret_cast<__half*>(Vt);
+  for (int tile = 0; tile < n_tiles; ++tile) {
+    const int k0 = tile * kAttnK;
+    __syncthreads();                                   // q fragments / the previous tile's fragments have been read
+    for (int i = tid; i < kAttnK * (HD / 4); i += 128) {   // K: a warp covers one key row (256 contiguous bytes)
       const int r = i / (HD / 4), c4 = i - r * (HD / 4);
-      float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
-      if (k0 + r < Tn) {
-        const float* src = qkv + (row0 + k0 + r) * ld + head * HD + 4 * c4;
-        kv = *reinterpret_cast<const float4*>(src + kEncH);
-        vv = *reinterpret_cast<const float4*>(src + 2 * kEncH);
-      }
-      *reinterpret_cast<uint4*>(Ks + r * KS + 4 * c4) = make_uint4(f2tf32(kv.x), f2tf32(kv.y), f2tf32(kv.z), f2tf32(kv.w));
-      *reinterpret_cast<uint4*>(Vs + r * VS + 4 * c4) = make_uint4(f2tf32(vv.x), f2tf32(vv.y), f2tf32(vv.z), f2tf32(vv.w));
+      float4 kv = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k0 + r < Tn) kv = *reinterpret_cast<const float4*>(qkv + (row0 + k0 + r) * ld + kEncH + head * HD + 4 * c4);
+      *reinterpret_cast<uint2*>(Ks + r * KW + 2 * c4) = make_uint2(pack_h2(kv.x, kv.y), pack_h2(kv.z, kv.w));
+    }
+    for (int i = tid; i < kAttnK * (HD / 4); i += 128) {   // V^T: a warp covers 32 keys of one 4-dim chunk (conflict-free stores)
+      const int r = i % kAttnK, c4 = i / kAttnK;
+      float4 vv = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k0 + r < Tn) vv = *reinterpret_cast<const float4*>(qkv + (row0 + k0 + r) * ld + 2 * kEncH + head * HD + 4 * c4);
+      __half* d = Vth + (4 * c4) * (2 * VW) + r;
+      d[0] = __float2half_rn(vv.x);
+      d[2 * VW] = __float2half_rn(vv.y);
+      d[4 * VW] = __float2half_rn(vv.z);
+      d[6 * VW] = __float2half_rn(vv.w);
     }
     if (tid < kAttnK) kvalid[tid] = (k0 + tid < Tn && keep[row0 + k0 + tid]) ? 1 : 0;
     __syncthreads();
-    // S[16 x 64]: accumulator fragment sc[nb] holds keys nb*8 + 2t, +1 for rows g (.x .y) and g + 8 (.z .w)
+    // S[16 x 64]: sc[nb] holds keys nb*8 + 2t, +1 for rows g (.x .y) and g + 8 (.z .w)
     float sc[kAttnK / 8][4];
 #pragma unroll
     for (int nb = 0; nb < kAttnK / 8; ++nb) {
       sc[nb][0] = sc[nb][1] = sc[nb][2] = sc[nb][3] = 0.f;
-      const uint32_t* kr = Ks + (nb * 8 + g) * KS + t;
+      const uint32_t* kr = Ks + (nb * 8 + g) * KW + t;
 #pragma unroll
-      for (int ks = 0; ks < KQ; ++ks) mma_tf32(sc[nb], qa[ks], kr[ks * 8], kr[ks * 8 + 4]);
+      for (int ks = 0; ks < KQ; ++ks) mma_f16(sc[nb], qa[ks], kr[ks * 8], kr[ks * 8 + 4]);
     }
     float t0 = -INFINITY, t1 = -INFINITY;
 #pragma unroll
@@ -334,16 +343,15 @@ __global__ void __launch_bounds__(128, 2) k_enc_attention_mma(T* __restrict__ ou
     const float n0 = fmaxf(m0, t0), n1 = fmaxf(m1, t1);
     const float c0 = m0 == -INFINITY ? 0.f : expf(m0 - n0), c1 = m1 == -INFINITY ? 0.f : expf(m1 - n1);
     float s0 = 0.f, s1 = 0.f;
-    __syncwarp();                                   // the previous tile's P reads are done
 #pragma unroll
     for (int nb = 0; nb < kAttnK / 8; ++nb) {
       // exp(-inf - n) = 0 for masked keys; a row with no valid key so far has n = -inf: keep its probabilities at 0
-      const float p00 = n0 == -INFINITY ? 0.f : expf(sc[nb][0] - n0), p01 = n0 == -INFINITY ? 0.f : expf(sc[nb][1] - n0);
-      const float p10 = n1 == -INFINITY ? 0.f : expf(sc[nb][2] - n1), p11 = n1 == -INFINITY ? 0.f : expf(sc[nb][3] - n1);
-      s0 += p00 + p01;
-      s1 += p10 + p11;
-      *reinterpret_cast<float2*>(Pw + g * PS + nb * 8 + 2 * t) = make_float2(p00, p01);
-      *reinterpret_cast<float2*>(Pw + (g + 8) * PS + nb * 8 + 2 * t) = make_float2(p10, p11);
+      sc[nb][0] = n0 == -INFINITY ? 0.f : expf(sc[nb][0] - n0);
+      sc[nb][1] = n0 == -INFINITY ? 0.f : expf(sc[nb][1] - n0);
+      sc[nb][2] = n1 == -INFINITY ? 0.f : expf(sc[nb][2] - n1);
+      sc[nb][3] = n1 == -INFINITY ? 0.f : expf(sc[nb][3] - n1);
+      s0 += sc[nb][0] + sc[nb][1];
+      s1 += sc[nb][2] + sc[nb][3];
     }
     s0 += __shfl_xor_sync(0xffffffffu, s0, 1);
     s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
@@ -354,27 +362,26 @@ __global__ void __launch_bounds__(128, 2) k_enc_attention_mma(T* __restrict__ ou
     m0 = n0;
     m1 = n1;
 #pragma unroll
-    for (int nb = 0; nb < KQ; ++nb) {
+    for (int nb = 0; nb < NO; ++nb) {
       o[nb][0] *= c0; o[nb][1] *= c0; o[nb][2] *= c1; o[nb][3] *= c1;
     }
-    __syncwarp();
-    // O[16 x HD] += P[16 x 64] V[64 x HD]
+    // O[16 x HD] += P[16 x 64] V[64 x HD]: the accumulator fragments of key blocks 2ks, 2ks + 1 are the A fragment of k-step ks
 #pragma unroll
-    for (int ks = 0; ks < kAttnK / 8; ++ks) {
+    for (int ks = 0; ks < kAttnK / 16; ++ks) {
       uint32_t pa[4];
-      pa[0] = f2tf32(Pw[g * PS + ks * 8 + t]);
-      pa[1] = f2tf32(Pw[(g + 8) * PS + ks * 8 + t]);
-      pa[2] = f2tf32(Pw[g * PS + ks * 8 + t + 4]);
-      pa[3] = f2tf32(Pw[(g + 8) * PS + ks * 8 + t + 4]);
-      const uint32_t* vr = Vs + (ks * 8 + t) * VS + g;
+      pa[0] = pack_h2(sc[2 * ks][0], sc[2 * ks][1]);
+      pa[1] = pack_h2(sc[2 * ks][2], sc[2 * ks][3]);
+      pa[2] = pack_h2(sc[2 * ks + 1][0], sc[2 * ks + 1][1]);
+      pa[3] = pack_h2(sc[2 * ks + 1][2], sc[2 * ks + 1][3]);
+      const uint32_t* vr = Vt + g * VW + ks * 8 + t;
 #pragma unroll
-      for (int nb = 0; nb < KQ; ++nb) mma_tf32(o[nb], pa, vr[nb * 8], vr[4 * VS + nb * 8]);
+      for (int nb = 0; nb < NO; ++nb) mma_f16(o[nb], pa, vr[nb * 8 * VW], vr[nb * 8 * VW + 4]);
     }
   }
   const float i0 = l0 > 0.f ? 1.f / l0 : 0.f, i1 = l1 > 0.f ? 1.f / l1 : 0.f;
   const int qa0 = q0 + warp * 16 + g, qa1 = qa0 + 8;
 #pragma unroll
-  for (int nb = 0; nb < KQ; ++nb) {
+  for (int nb = 0; nb < NO; ++nb) {
     const int col = head * HD + nb * 8 + 2 * t;
     if (qa0 < Tn) *reinterpret_cast<uint32_t*>(out16 + (row0 + qa0) * kEncH + col) = Cvt<T>::pack(o[nb][0] * i0, o[nb][1] * i0);
     if (qa1 < Tn) *reinterpret_cast<uint32_t*>(out16 + (row0 + qa1) * kEncH + col) = Cvt<T>::pack(o[nb][2] * i1, o[nb][3] * i1);

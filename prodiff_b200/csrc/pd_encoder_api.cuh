@@ -155,26 +155,17 @@ static int launch_attention(T* out16, const float* qkv, const uint8_t* keep, int
   return 0;
 }
 template <typename T, int HD>
-static int launch_attention_mma(T* out16, const float* qkv, const uint8_t* keep, int B, int Tn, int heads, cudaStream_t s) {
-  auto kern = k_enc_attention_mma<T, HD>;
-  const int smem = AttnMmaCfg<HD>::kSmemBytes;
-  static bool configured[64] = {false};
-  int dev = 0;
-  PD_CUDA(cudaGetDevice(&dev));
-  if (!configured[dev & 63]) {
-    PD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured[dev & 63] = true;
-  }
-  kern<<<dim3((Tn + kMmaQ - 1) / kMmaQ, heads, B), 128, smem, s>>>(out16, qkv, keep, Tn, sqrtf(1.0f / (float)HD));
-  PD_LAUNCH_CHECK("k_enc_attention_mma");
+static int launch_attention_f16(T* out16, const float* qkv, const uint8_t* keep, int B, int Tn, int heads, cudaStream_t s) {
+  k_enc_attention_f16<T, HD><<<dim3((Tn + kHQ - 1) / kHQ, heads, B), 128, 0, s>>>(out16, qkv, keep, Tn, sqrtf(1.0f / (float)HD));
+  PD_LAUNCH_CHECK("k_enc_attention_f16");
   return 0;
 }
 template <typename T>
 static int enc_attention(T* out16, const float* qkv, const uint8_t* keep, int B, int Tn, int heads, cudaStream_t s) {
-  static int simt = -1;   // PD_ENC_ATTN=simt: the CUDA-core kernel (A/B and fallback for head_dim 256)
+  static int simt = -1;   // PD_ENC_ATTN=simt: the CUDA-core kernel (A/B; always used for head_dim 256)
   if (simt < 0) { const char* e = getenv("PD_ENC_ATTN"); simt = (e && e[0] == 's') ? 1 : 0; }
-  if (!simt && kEncH / heads == 128) return launch_attention_mma<T, 128>(out16, qkv, keep, B, Tn, heads, s);
-  if (!simt && kEncH / heads == 64) return launch_attention_mma<T, 64>(out16, qkv, keep, B, Tn, heads, s);
+  if (!simt && kEncH / heads == 128) return launch_attention_f16<T, 128>(out16, qkv, keep, B, Tn, heads, s);
+  if (!simt && kEncH / heads == 64) return launch_attention_f16<T, 64>(out16, qkv, keep, B, Tn, heads, s);
   switch (kEncH / heads) {
     case 64: return launch_attention<T, 64>(out16, qkv, keep, B, Tn, heads, s);
     case 128: return launch_attention<T, 128>(out16, qkv, keep, B, Tn, heads, s);
@@ -244,7 +235,7 @@ static int enc_forward_t(pd_encoder* e, const long long* tok, const float* extra
       ep.scale = 1.0f / sqrtf((float)k);
       ep.gelu = 1;
       // (cta_group::2 pairs measured slower here: 0.913 vs 0.885 ms per forward -- 100 frame tiles leave half the pairs idle)
-      if (launch_gemm<EPI_STORE_X, 256>(dt, tm_xn, e->tm_w_f1, sh, ep, sms, s, "gemm(enc ffn_1)", 7)) return 1;
+      if (launch_gemm<EPI_STORE_XH, 256>(dt, tm_xn, e->tm_w_f1, sh, ep, sms, s, "gemm(enc ffn_1)", 7)) return 1;
     }
     {  // ffn_2 + bias + residual, then the padding mask (common_layers.py:582, 669-672)
       GemmShape sh = base_shape(B, Tn, H / 256, 4 * H / 64);

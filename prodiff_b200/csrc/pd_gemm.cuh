@@ -21,7 +21,8 @@
 //   EPI_RES   : (x + acc + bias) / sqrt(2)                      (ResidualBlock residual path)
 //   EPI_OUT   : x0 = acc + bias, then the q-posterior update x_{t-1} = c1*x0 + c2*x_t + sigma*noise
 //   EPI_STORE_X : EPI_STORE plus what the text encoder's GEMMs need (pd_encoder.cuh): erf-GELU, an fp32 residual added
-//               after the activation, and a per-row keep mask (padding tokens come out as zeros)
+//               after the activation, and a per-row keep mask (padding tokens come out as zeros); EPI_STORE_XH = the same
+//               for 16-bit outputs without a residual (smaller staging tiles, one more ring stage for the K = 2304 FFN conv)
 #pragma once
 #include "pd_ptx.cuh"
 
@@ -33,7 +34,7 @@ constexpr int kEpiWarps = 8;
 constexpr int kGemmThreads = 32 * (2 + kEpiWarps);
 constexpr uint32_t kTmemCols = 512;
 
-enum EpiKind { EPI_STORE = 0, EPI_GATE = 1, EPI_RES = 2, EPI_OUT = 3, EPI_STORE_BLK = 4, EPI_STORE_X = 5 };
+enum EpiKind { EPI_STORE = 0, EPI_GATE = 1, EPI_RES = 2, EPI_OUT = 3, EPI_STORE_BLK = 4, EPI_STORE_X = 5, EPI_STORE_XH = 6 };
 enum OutType { OUT_T = 0, OUT_F16 = 1, OUT_F32 = 2 };
 
 struct GemmShape {
@@ -185,7 +186,9 @@ template <int EPI, int BN, bool kPair = false> struct GemmCfg {
   static constexpr uint32_t kBBytes = (kPair ? BN / 2 : BN) * kBlockK * 2;
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;
   static constexpr uint32_t kStagingBytes = (EPI == EPI_STORE_BLK) ? 65536 : 0;   // blocked-output tile staged for a bulk store
-  static constexpr uint32_t kExtraBytes = ((EPI == EPI_GATE) ? 2 * 16384 : (EPI == EPI_RES ? 4 * 16384 : 0)) + kStagingBytes;
+  static constexpr uint32_t kXRowWords = (EPI == EPI_STORE_XH) ? 20 : 36;                        // 16-bit only / fp32 rows (padded)
+  static constexpr uint32_t kXStageBytes = (EPI == EPI_STORE_X || EPI == EPI_STORE_XH) ? kEpiWarps * 32 * kXRowWords * 4 : 0;    // per-warp 32 x 32 transposition tiles
+  static constexpr uint32_t kExtraBytes = ((EPI == EPI_GATE) ? 2 * 16384 : (EPI == EPI_RES ? 4 * 16384 : 0)) + kStagingBytes + kXStageBytes;
   // smem ring depth: as many stages as fit next to the epilogue's operand/output tile (cap 8)
   static constexpr int kStagesFit = (int)((227u * 1024u - 1024u - 256u - kExtraBytes) / kStageBytes);
   static constexpr int kStagesWant = kPair ? 8 : ((EPI == EPI_RES) ? 3 : (BN == 256 ? 4 : 6));
@@ -440,7 +443,92 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           bulk_store(static_cast<uint16_t*>(ep.out) + blocked_off(tile_b, ep.ld >> 3, within0 >> 3, 0), stg, 32768);
           tma_store_commit();
         }
-      } else if constexpr (EPI == EPI_STORE || EPI == EPI_STORE_X) {
+      } else if constexpr (EPI == EPI_STORE_X || EPI == EPI_STORE_XH) {
+        // (acc + bias) * scale [-> GELU] [+ residual] [-> keep mask], fp32 or 16-bit row-major output.  One thread owns one
+        // accumulator row, so direct global access would touch 32 lines per warp instruction (the in_proj GEMM wrote its
+        // 39 MB at 1.1 TB/s that way): every 32-row x 32-column block goes through a per-warp shared-memory tile instead and
+        // moves to / from global memory as full 128-byte (fp32) or 64-byte (16-bit) row segments.
+        const long long nfr = (long long)sh.B * sh.T;
+        float* stg = reinterpret_cast<float*>(extra) + (warp - 2) * (32 * Cfg::kXRowWords);   // [32 rows][36] floats (16-bit: [32][20] words)
+        const int rows_left = (m_tile < num_m_tiles) ? sh.T - (t0 + q * 32) : 0;      // rows of this warp's slab inside the utterance
+        const long long nrow0 = (long long)b * sh.T + t0 + q * 32;                   // global row of slab row 0
+        const bool kp = ep.keep == nullptr || (valid && ep.keep[n] != 0);
+        uint32_t rr[2][32];
+        tmem_ld_x32(trow + h * (BN / 2), rr[0]);
+#pragma unroll
+        for (int ci = 0; ci < (BN / 2) / 32; ++ci) {
+          const int c = h * (BN / 2) + ci * 32;
+          tmem_ld_wait();
+          if (ci + 1 < (BN / 2) / 32) tmem_ld_x32(trow + c + 32, rr[(ci + 1) & 1]);
+          const uint32_t (&r)[32] = rr[ci & 1];
+          const int gcol = n_tile * BN + c;            // first output column of this chunk (ld = full row width)
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 bv = __ldg(reinterpret_cast<const float4*>(ep.bias + gcol + j));
+            v[j + 0] = (__uint_as_float(r[j + 0]) + bv.x) * ep.scale;
+            v[j + 1] = (__uint_as_float(r[j + 1]) + bv.y) * ep.scale;
+            v[j + 2] = (__uint_as_float(r[j + 2]) + bv.z) * ep.scale;
+            v[j + 3] = (__uint_as_float(r[j + 3]) + bv.w) * ep.scale;
+          }
+          if (ep.gelu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0.5f * v[j] * (1.f + erff(v[j] * 0.70710678118654752f));
+          }
+          if (EPI == EPI_STORE_X && ep.resid != nullptr) {
+            // the residual block, loaded as full row segments (4 rows per warp instruction), read back one row per thread
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int rrow = i * 4 + (lane >> 3), c4 = lane & 7;
+              float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (rrow < rows_left) rv = *reinterpret_cast<const float4*>(ep.resid + (nrow0 + rrow) * ep.ld + gcol + 4 * c4);
+              *reinterpret_cast<float4*>(stg + rrow * 36 + 4 * c4) = rv;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 rv = *reinterpret_cast<const float4*>(stg + lane * 36 + j);
+              v[j] += rv.x; v[j + 1] += rv.y; v[j + 2] += rv.z; v[j + 3] += rv.w;
+            }
+            __syncwarp();
+          }
+          if (!kp) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0.f;
+          }
+          if (EPI == EPI_STORE_X && ep.out_type == OUT_F32) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(stg + lane * 36 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int rrow = i * 4 + (lane >> 3), c4 = lane & 7;
+              if (rrow < rows_left)
+                *reinterpret_cast<float4*>(static_cast<float*>(ep.out) + (nrow0 + rrow) * ep.ld + gcol + 4 * c4) =
+                    *reinterpret_cast<const float4*>(stg + rrow * 36 + 4 * c4);
+            }
+          } else {
+            uint32_t* sw = reinterpret_cast<uint32_t*>(stg);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<uint4*>(sw + lane * 20 + 4 * j) =
+                  ep.out_type == OUT_F16
+                      ? make_uint4(Cvt<__half>::pack(v[8 * j], v[8 * j + 1]), Cvt<__half>::pack(v[8 * j + 2], v[8 * j + 3]),
+                                   Cvt<__half>::pack(v[8 * j + 4], v[8 * j + 5]), Cvt<__half>::pack(v[8 * j + 6], v[8 * j + 7]))
+                      : make_uint4(Cvt<T>::pack(v[8 * j], v[8 * j + 1]), Cvt<T>::pack(v[8 * j + 2], v[8 * j + 3]),
+                                   Cvt<T>::pack(v[8 * j + 4], v[8 * j + 5]), Cvt<T>::pack(v[8 * j + 6], v[8 * j + 7]));
+            __syncwarp();
+            uint16_t* ob = static_cast<uint16_t*>(ep.out);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int rrow = i * 8 + (lane >> 2), c4 = lane & 3;
+              if (rrow < rows_left)
+                *reinterpret_cast<uint4*>(ob + (nrow0 + rrow) * ep.ld + gcol + 8 * c4) = *reinterpret_cast<const uint4*>(sw + rrow * 20 + 4 * c4);
+            }
+          }
+          __syncwarp();   // the staging tile is reused by the next chunk
+        }
+      } else if constexpr (EPI == EPI_STORE) {
         const long long nfr = (long long)sh.B * sh.T;
         // two register buffers: the TMEM load of chunk i+1 is in flight while chunk i is converted and stored
         uint32_t rr[2][32];
@@ -470,24 +558,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             if (ep.lens != nullptr && t >= __ldg(ep.lens + b)) {   // ragged batch: frames past this utterance's end stay zero
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = 0.f;
-            }
-            if constexpr (EPI == EPI_STORE_X) {
-              if (ep.gelu) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = 0.5f * v[j] * (1.f + erff(v[j] * 0.70710678118654752f));
-              }
-              if (ep.resid != nullptr) {
-                const float4* rs = reinterpret_cast<const float4*>(ep.resid + ((long long)slab * nfr + n) * ep.ld + within);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  const float4 rv = rs[j];
-                  v[4 * j] += rv.x; v[4 * j + 1] += rv.y; v[4 * j + 2] += rv.z; v[4 * j + 3] += rv.w;
-                }
-              }
-              if (ep.keep != nullptr && !ep.keep[n]) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = 0.f;
-              }
             }
             if (ep.out_type == OUT_F32) {
               float4* dst = reinterpret_cast<float4*>(static_cast<float*>(ep.out) + ((long long)slab * nfr + n) * ep.ld + within);
