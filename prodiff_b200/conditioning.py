@@ -25,7 +25,7 @@ class AssembledCondition:
     """
 
     def __init__(self, encoder_out, mel2ph, f0, pitch_w, pitch_b, utt: Sequence[torch.Tensor] = (), frame=None,
-                 variances: Sequence[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]] = ()):
+                 variances: Sequence[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]] = (), validate: bool = True):
         dev = encoder_out.device
         f = lambda t: t.detach().to(device=dev, dtype=torch.float32).contiguous()
         self.encoder_out = f(encoder_out)
@@ -35,7 +35,9 @@ class AssembledCondition:
         T = self.mel2ph.shape[1]
         if self.mel2ph.shape != (B, T) or self.f0.shape != (B, T):
             raise ValueError("mel2ph and f0 must both be [B, T]")
-        if int(self.mel2ph.max()) > self.encoder_out.shape[1] or int(self.mel2ph.min()) < 0:
+        # (a device -> host read: it makes the host wait for the encoder before it can queue the sampler's launches;
+        # validate=False skips it -- the kernel itself treats an out-of-range index as padding and never reads through it)
+        if validate and (int(self.mel2ph.max()) > self.encoder_out.shape[1] or int(self.mel2ph.min()) < 0):
             raise ValueError("mel2ph indexes outside the encoder output")
         self.pitch_w, self.pitch_b = f(pitch_w).reshape(H), f(pitch_b).reshape(H)
         self.utt = [f(u).reshape(B, H) for u in utt]
@@ -69,7 +71,8 @@ class AssembledCondition:
 
 
 def forward_condition(teacher, txt_tokens, mel2ph, f0, lang_seq=None, spk_embed_id=None, spk_mix_embed=None,
-                      gender_embed_id=None, gender_mix_embed=None, voicing=None, breath=None) -> AssembledCondition:
+                      gender_embed_id=None, gender_mix_embed=None, voicing=None, breath=None, *,
+                      validate: bool = True) -> AssembledCondition:
     """Same arguments as ``ProDiffTeacher.forward_condition`` (prodiff_teacher.py:103-110), ``teacher`` being the reference
     module (or anything with its attributes).  Token-level part as in :111-126, frame-level part deferred to the kernel."""
     extra_embed = None
@@ -102,7 +105,8 @@ def forward_condition(teacher, txt_tokens, mel2ph, f0, lang_seq=None, spk_embed_
         variances.append((voicing, teacher.voicing_embed.weight, teacher.voicing_embed.bias))
     if teacher.with_breath_embed:
         variances.append((breath, teacher.breath_embed.weight, teacher.breath_embed.bias))
-    return AssembledCondition(encoder_out, mel2ph, f0, teacher.pitch_embed.weight, teacher.pitch_embed.bias, utt, frame, variances)
+    return AssembledCondition(encoder_out, mel2ph, f0, teacher.pitch_embed.weight, teacher.pitch_embed.bias, utt, frame, variances,
+                              validate=validate)
 
 
 __all__ = ["AssembledCondition", "forward_condition"]

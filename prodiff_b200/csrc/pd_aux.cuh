@@ -165,7 +165,8 @@ __global__ void k_assemble_cond(T* __restrict__ cond16, float* __restrict__ cond
     const long long n = i / H4;            // frame index b * T + t
     const int h = (int)(i - n * H4) * 4;
     const int b = (int)(n / a.T);
-    const long long tok = a.mel2ph[n];
+    long long tok = a.mel2ph[n];
+    if (tok > a.Tph) tok = 0;              // out of range (the reference's gather would raise): handled as padding, never read
     float v[4] = {0.f, 0.f, 0.f, 0.f};
     if (tok > 0) {
       const float4 e = __ldg(reinterpret_cast<const float4*>(a.enc + ((long long)b * a.Tph + (tok - 1)) * a.H + h));

@@ -5,8 +5,9 @@
 //   MultiheadAttention.forward     common_layers.py:242-287 -> F.multi_head_attention_forward  (bias-free, key padding mask)
 // The dense contractions (packed q/k/v projection, out_proj, the kernel-9 FFN convolution, ffn_2) run on the generic
 // tcgen05 GEMM kernel (pd_gemm.cuh, EPI_STORE_X epilogue: GELU, residual, keep mask).  What is left is per-token work on
-// ~10^4 tokens: fp32 throughout, one warp per token, and a tiled fp32 attention with an online softmax (T_txt x T_txt x
-// head_dim per head is a few GFLOP per batch -- small against the 9-tap FFN GEMM, so it stays on the CUDA cores for now).
+// ~10^4 tokens: the embedding and LayerNorm kernels (fp32, one warp per token) and the attention (warp-level fp16 mma.sync
+// with an fp32 online softmax, k_enc_attention_f16; k_enc_attention is the fp32 CUDA-core version kept for head_dim 256 and
+// for A/B runs).
 #pragma once
 #include "pd_aux.cuh"
 

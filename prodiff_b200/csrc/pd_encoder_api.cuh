@@ -205,7 +205,7 @@ static int enc_forward_t(pd_encoder* e, const long long* tok, const float* extra
       ep.bias = reinterpret_cast<const float*>(pk + e->lay.zeros);
       ep.ld = 3 * H;
       ep.out_type = OUT_F32;
-      if (launch_gemm<EPI_STORE_X, 256>(dt, tm_xn, e->tm_w_qkv, sh, ep, sms, s, "gemm(enc in_proj)", 7)) return 1;
+      if (launch_gemm<EPI_STORE_X, 256>(dt, tm_xn, e->tm_w_qkv, sh, ep, sms, s, "gemm(enc in_proj)", 11)) return 1;
     }
     if (enc_attention<T>(att, qkv, keep, B, Tn, c.num_heads, s)) return 1;
     {  // out_proj (bias-free) + residual, then the padding mask (common_layers.py:665-667)
@@ -218,7 +218,7 @@ static int enc_forward_t(pd_encoder* e, const long long* tok, const float* extra
       ep.out_type = OUT_F32;
       ep.resid = x;
       ep.keep = keep;
-      if (launch_gemm<EPI_STORE_X, 256>(dt, tm_att, e->tm_w_out, sh, ep, sms, s, "gemm(enc out_proj)", 7)) return 1;
+      if (launch_gemm<EPI_STORE_X, 256>(dt, tm_att, e->tm_w_out, sh, ep, sms, s, "gemm(enc out_proj)", 11)) return 1;
     }
     k_enc_layernorm<T><<<ln_blocks, 256, 0, s>>>(xn, nullptr, x, lnl + 2 * H, lnl + 3 * H, nullptr, N);
     PD_LAUNCH_CHECK("k_enc_layernorm(2)");
@@ -234,8 +234,11 @@ static int enc_forward_t(pd_encoder* e, const long long* tok, const float* extra
       ep.ld = 4 * H;
       ep.scale = 1.0f / sqrtf((float)k);
       ep.gelu = 1;
-      // (cta_group::2 pairs measured slower here: 0.913 vs 0.885 ms per forward -- 100 frame tiles leave half the pairs idle)
-      if (launch_gemm<EPI_STORE_XH, 256>(dt, tm_xn, e->tm_w_f1, sh, ep, sms, s, "gemm(enc ffn_1)", 7)) return 1;
+      // In-kernel timeline (tools/encoder_trace.py): 630 cycles per K block against 256 of MMA -- the 48 KB of operands per
+      // K block arrive at ~76 B/clk per SM with every SM streaming; the erf-GELU epilogue (11-15 k cycles per tile) hides
+      // behind the next tile's K loop.  cta_group::2 pairs measured no faster (0.740 vs 0.738 ms per forward); serving the
+      // 9 taps from one resident haloed A tile (as pd_layer.cuh does for 3) is the next step, DESIGN.md section 9.
+      if (launch_gemm<EPI_STORE_XH, 256>(dt, tm_xn, e->tm_w_f1, sh, ep, sms, s, "gemm(enc ffn_1)", 12)) return 1;
     }
     {  // ffn_2 + bias + residual, then the padding mask (common_layers.py:582, 669-672)
       GemmShape sh = base_shape(B, Tn, H / 256, 4 * H / 64);
@@ -247,7 +250,7 @@ static int enc_forward_t(pd_encoder* e, const long long* tok, const float* extra
       ep.out_type = OUT_F32;
       ep.resid = x;
       ep.keep = keep;
-      if (launch_gemm<EPI_STORE_X, 256>(dt, tm_h1, e->tm_w_f2, sh, ep, sms, s, "gemm(enc ffn_2)", 7)) return 1;
+      if (launch_gemm<EPI_STORE_X, 256>(dt, tm_h1, e->tm_w_f2, sh, ep, sms, s, "gemm(enc ffn_2)", 11)) return 1;
     }
   }
   const float* lnf = ln + (size_t)L * 4 * H;

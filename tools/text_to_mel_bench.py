@@ -60,7 +60,7 @@ def main():
                                     with_voicing_embed=False, with_breath_embed=False)
     tk, m2p, f0d = tok.cuda(), mel2ph.cuda(), f0.cuda()
     with torch.no_grad():
-        cond = lambda: pb.forward_condition(teacher, tk, m2p, f0d, spk_mix_embed=spk)
+        cond = lambda: pb.forward_condition(teacher, tk, m2p, f0d, spk_mix_embed=spk, validate=False)   # no host sync in the chain
         ac = cond()
         res = dict(workload=f"{B} utt x {Tph} tokens -> {B} x {T} frames x 128 mel, K={K}, DiffNet 20x256, encoder 4x256",
                    encoder_ms=cuda_ms(lambda: enc(tk, None)),
