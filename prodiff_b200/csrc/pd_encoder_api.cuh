@@ -234,10 +234,12 @@ static int enc_forward_t(pd_encoder* e, const long long* tok, const float* extra
       ep.ld = 4 * H;
       ep.scale = 1.0f / sqrtf((float)k);
       ep.gelu = 1;
-      // In-kernel timeline (tools/encoder_trace.py): 630 cycles per K block against 256 of MMA -- the 48 KB of operands per
-      // K block arrive at ~76 B/clk per SM with every SM streaming; the erf-GELU epilogue (11-15 k cycles per tile) hides
-      // behind the next tile's K loop.  cta_group::2 pairs measured no faster (0.740 vs 0.738 ms per forward); serving the
-      // 9 taps from one resident haloed A tile (as pd_layer.cuh does for 3) is the next step, DESIGN.md section 9.
+      // In-kernel timeline (tools/encoder_trace.py): 630 cycles per K block (4 MMAs of M = 128, N = 256, K = 16) against 256
+      // at the tensor core's nominal rate; the erf-GELU epilogue (11-15 k cycles per tile) hides behind the next tile's K
+      // loop.  Not the L2 -> SM operand stream: serving the 9 taps from one resident haloed A tile (a third fewer TMA bytes)
+      // left the K block at 621 cycles (and cost a ring stage: 0.765 vs 0.737 ms per forward), and cta_group::2 pairs
+      // measured 0.740.  What remains is the MMA's own shared-memory operand fetch: 12 KB per single-CTA MMA at the ~64-80
+      // B/clk the layer kernel also sees is ~155 cycles per MMA.
       if (launch_gemm<EPI_STORE_XH, 256>(dt, tm_xn, e->tm_w_f1, sh, ep, sms, s, "gemm(enc ffn_1)", 12)) return 1;
     }
     {  // ffn_2 + bias + residual, then the padding mask (common_layers.py:582, 669-672)
