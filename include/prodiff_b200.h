@@ -158,7 +158,7 @@ typedef struct pd_encoder_config {
   int32_t hidden_size; /* 256 */
   int32_t num_layers;
   int32_t kernel_size; /* odd; the FFN's Conv1d (enc_ffn_kernel_size, 9) */
-  int32_t num_heads;   /* 1, 2 or 4 */
+  int32_t num_heads;   /* 2 or 4 */
   int32_t dtype;       /* PD_BF16 / PD_FP16 tensor-core operands; LayerNorm, softmax, residual stream in fp32 */
 } pd_encoder_config;
 typedef struct pd_encoder pd_encoder;

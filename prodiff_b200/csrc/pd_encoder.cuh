@@ -14,7 +14,6 @@
 namespace pd {
 
 constexpr int kEncH = 256;        // hidden size the encoder kernels are specialised for (base_config.yaml:112)
-constexpr int kAttnQ = 32;        // queries per CTA (8 warps x 4)
 constexpr int kAttnK = 64;        // keys per shared-memory tile
 
 // x[b,t,:] = (sqrt(H) * E[tok] + extra + pos(t)) * keep  (tts_modules.py:314-325, :269-275) and keep[b,t] = tok != 0.
@@ -101,144 +100,19 @@ __global__ void __launch_bounds__(256) k_enc_layernorm(T* __restrict__ out16, fl
   }
 }
 
-// Self-attention of one (utterance, head, 32-query block): softmax(q k^T / sqrt(HD) + key padding mask) v, fp32, with an
-// online softmax over 64-key tiles.  qkv [B*T, 3H] fp32 = the packed in-projection output (q | k | v, head h at columns
-// h*HD of each part); out16 [B*T, H] 16-bit = the A operand of out_proj.  Each warp owns 4 queries: a lane scores keys
-// (lane, lane + 32) of the tile for all 4, then accumulates output dims [4*lane', ...) over the tile's probabilities
-// read back from shared memory.  A row whose keys are ALL padding yields zeros (the reference yields NaN there).
-template <typename T, int HD>
-__global__ void __launch_bounds__(256) k_enc_attention(T* __restrict__ out16, const float* __restrict__ qkv,
-                                                       const uint8_t* __restrict__ keep, int Tn, float scale) {
-  constexpr int KS = HD + 4;                    // padded key row: conflict-free 128-bit reads with one key per lane
-  constexpr int DL = HD / 32;                   // output dims per lane
-  extern __shared__ float sm[];
-  float* Ks = sm;                               // [64][HD + 4]
-  float* Vs = Ks + kAttnK * KS;                 // [64][HD]
-  float* Qs = Vs + kAttnK * HD;                 // [32][HD], pre-scaled
-  float* Ps = Qs + kAttnQ * HD;                 // [8 warps][4 queries][64]
-  __shared__ uint8_t kvalid[kAttnK];
-  const int b = blockIdx.z, head = blockIdx.y, q0 = blockIdx.x * kAttnQ;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const long long row0 = (long long)b * Tn;
-  const int ld = 3 * kEncH;
-  // a query block of padding tokens only: its rows are zeroed by the keep mask after out_proj, nothing to compute
-  if (!__syncthreads_or(tid < kAttnQ && q0 + tid < Tn && keep[row0 + q0 + tid] != 0)) return;
-  for (int i = tid; i < kAttnQ * (HD / 4); i += 256) {
-    const int r = i / (HD / 4), c4 = i - r * (HD / 4);
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (q0 + r < Tn) v = *reinterpret_cast<const float4*>(qkv + (row0 + q0 + r) * ld + head * HD + 4 * c4);
-    *reinterpret_cast<float4*>(Qs + r * HD + 4 * c4) = make_float4(v.x * scale, v.y * scale, v.z * scale, v.w * scale);
-  }
-  float m[4], l[4], o[4][DL];
-#pragma unroll
-  for (int qi = 0; qi < 4; ++qi) {
-    m[qi] = -INFINITY;
-    l[qi] = 0.f;
-#pragma unroll
-    for (int d = 0; d < DL; ++d) o[qi][d] = 0.f;
-  }
-  float* Pw = Ps + warp * 4 * kAttnK;
-  for (int k0 = 0; k0 < Tn; k0 += kAttnK) {
-    // previous tile fully consumed (and Qs written, first time round); a tile of padded keys only contributes nothing
-    if (!__syncthreads_or(tid < kAttnK && k0 + tid < Tn && keep[row0 + k0 + tid] != 0)) continue;
-    for (int i = tid; i < kAttnK * (HD / 4); i += 256) {
-      const int r = i / (HD / 4), c4 = i - r * (HD / 4);
-      float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
-      if (k0 + r < Tn) {
-        const float* src = qkv + (row0 + k0 + r) * ld + head * HD + 4 * c4;
-        kv = *reinterpret_cast<const float4*>(src + kEncH);
-        vv = *reinterpret_cast<const float4*>(src + 2 * kEncH);
-      }
-      *reinterpret_cast<float4*>(Ks + r * KS + 4 * c4) = kv;
-      *reinterpret_cast<float4*>(Vs + r * HD + 4 * c4) = vv;
-    }
-    if (tid < kAttnK) kvalid[tid] = (k0 + tid < Tn && keep[row0 + k0 + tid]) ? 1 : 0;
-    __syncthreads();
-    // scores of keys (lane, lane + 32) for this warp's 4 queries
-    float s[4][2];
-#pragma unroll
-    for (int qi = 0; qi < 4; ++qi) s[qi][0] = s[qi][1] = 0.f;
-    const float* ka = Ks + lane * KS;
-    const float* kb = Ks + (lane + 32) * KS;
-    const float* qa = Qs + (warp * 4) * HD;
-#pragma unroll 4
-    for (int d = 0; d < HD; d += 4) {
-      const float4 a = *reinterpret_cast<const float4*>(ka + d), c = *reinterpret_cast<const float4*>(kb + d);
-#pragma unroll
-      for (int qi = 0; qi < 4; ++qi) {
-        const float4 qv = *reinterpret_cast<const float4*>(qa + qi * HD + d);
-        s[qi][0] += qv.x * a.x + qv.y * a.y + qv.z * a.z + qv.w * a.w;
-        s[qi][1] += qv.x * c.x + qv.y * c.y + qv.z * c.z + qv.w * c.w;
-      }
-    }
-    const bool v0 = kvalid[lane] != 0, v1 = kvalid[lane + 32] != 0;
-#pragma unroll
-    for (int qi = 0; qi < 4; ++qi) {
-      float tm = fmaxf(v0 ? s[qi][0] : -INFINITY, v1 ? s[qi][1] : -INFINITY);
-#pragma unroll
-      for (int off = 16; off > 0; off >>= 1) tm = fmaxf(tm, __shfl_xor_sync(0xffffffffu, tm, off));
-      const float mn = fmaxf(m[qi], tm);
-      const float corr = (m[qi] == -INFINITY) ? 0.f : expf(m[qi] - mn);
-      const float p0 = (v0 && mn != -INFINITY) ? expf(s[qi][0] - mn) : 0.f;
-      const float p1 = (v1 && mn != -INFINITY) ? expf(s[qi][1] - mn) : 0.f;
-      float ps = p0 + p1;
-#pragma unroll
-      for (int off = 16; off > 0; off >>= 1) ps += __shfl_xor_sync(0xffffffffu, ps, off);
-      l[qi] = l[qi] * corr + ps;
-      m[qi] = mn;
-#pragma unroll
-      for (int d = 0; d < DL; ++d) o[qi][d] *= corr;
-      Pw[qi * kAttnK + lane] = p0;
-      Pw[qi * kAttnK + lane + 32] = p1;
-    }
-    __syncwarp();
-    // o[qi][dims of this lane] += sum over the tile's keys of p * v
-    for (int k = 0; k < kAttnK; k += 4) {
-      float4 pq[4];
-#pragma unroll
-      for (int qi = 0; qi < 4; ++qi) pq[qi] = *reinterpret_cast<const float4*>(Pw + qi * kAttnK + k);
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
-        float vv[DL];
-        if constexpr (DL == 4) {
-          const float4 t4 = *reinterpret_cast<const float4*>(Vs + (k + kk) * HD + 4 * lane);
-          vv[0] = t4.x; vv[1] = t4.y; vv[2] = t4.z; vv[3] = t4.w;
-        } else {
-#pragma unroll
-          for (int d = 0; d < DL; ++d) vv[d] = Vs[(k + kk) * HD + DL * lane + d];
-        }
-#pragma unroll
-        for (int qi = 0; qi < 4; ++qi) {
-          const float p = kk == 0 ? pq[qi].x : (kk == 1 ? pq[qi].y : (kk == 2 ? pq[qi].z : pq[qi].w));
-#pragma unroll
-          for (int d = 0; d < DL; ++d) o[qi][d] += p * vv[d];
-        }
-      }
-    }
-    __syncwarp();
-  }
-#pragma unroll
-  for (int qi = 0; qi < 4; ++qi) {
-    const int q = q0 + warp * 4 + qi;
-    if (q >= Tn) continue;
-    const float inv = l[qi] > 0.f ? 1.f / l[qi] : 0.f;
-    T* dst = out16 + (row0 + q) * kEncH + head * HD + DL * lane;
-#pragma unroll
-    for (int d = 0; d < DL; d += 2) *reinterpret_cast<uint32_t*>(dst + d) = Cvt<T>::pack(o[qi][d] * inv, o[qi][d + 1] * inv);
-  }
-}
-
 // ---------------------------------------------------------------------------------------------------------------------
-// The same attention on the tensor cores.  T_txt x T_txt x head_dim per (utterance, head) is far too small to feed a
-// tcgen05 pipeline (a 200 x 200 score matrix is 1.6 M MACs), so this uses warp-level mma.sync m16n8k16 with fp16 operands,
-// fp32 accumulation and an fp32 online softmax: the CUDA-core version above is bound by instruction issue (one FMA per MAC,
-// 128 us per launch at 64 x 200 tokens), this one takes 46 us.  fp16 has a 10-bit mantissa like TF32, and q / sqrt(d), k, v
-// (projections of a LayerNorm output) and the probabilities are far inside its range, so it is used whatever the encoder's
-// GEMM operand type is.  (A TF32 m16n8k8 version with P staged through shared memory measured 64-66 us, with synchronous
-// and with cp.async double-buffered tile fills alike: the legacy tensor path's TF32 rate bounds it.)  The probabilities
-// never touch shared memory: the accumulator fragments of two adjacent 8-key blocks ARE the A fragment of one 16-key k-step.
-// CTA = 4 warps x 16 queries, several CTAs per SM; K tile [64 keys][HD] and V^T tile [HD][64 keys] in fp16 with row
-// strides padded by 8 halves (every fragment load bank-conflict free).
+// Self-attention of one (utterance, head, 64-query block): softmax(q k^T / sqrt(HD) + key padding mask) v with an online
+// softmax over 64-key tiles.  T_txt x T_txt x head_dim per (utterance, head) is far too small to feed a tcgen05 pipeline (a
+// 200 x 200 score matrix is 1.6 M MACs), so this uses warp-level mma.sync m16n8k16 with fp16 operands, fp32 accumulation
+// and fp32 softmax.  fp16 has a 10-bit mantissa like TF32, and q, k, v (projections of a LayerNorm output) and the
+// probabilities are far inside its range, so it is used whatever the encoder's GEMM operand type is.  History, all at
+// 64 x 200 tokens: fp32 on the CUDA cores 128 us per launch (issue-bound: one FMA per MAC); TF32 m16n8k8 with P staged
+// through shared memory 64-66 us (the legacy path's TF32 rate); this fp16 form with fp32 q|k|v converted while filling the
+// tiles 46 us; with the in-projection GEMM storing fp16 and the tiles arriving by cp.async, see the numbers in DESIGN.md 3.8.
+// The probabilities never touch shared memory: the accumulator fragments of two adjacent 8-key blocks ARE the A fragment
+// of one 16-key k-step.  CTA = 4 warps x 16 queries, three CTAs per SM; q, K and V tiles row-major [token][HD] in fp16 with
+// rows padded by 8 halves (every fragment load and ldmatrix bank-conflict free).  A row whose keys are ALL padding yields
+// zeros (the reference yields NaN there).
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   __half2 v = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
@@ -250,16 +124,37 @@ __device__ __forceinline__ void mma_f16(float (&d)[4], const uint32_t (&a)[4], u
 }
 
 constexpr int kHQ = 64;   // queries per CTA (4 warps x 16)
+template <int HD> struct AttnCfg {
+  static constexpr int RW = (HD + 8) / 2;                  // words per staged row (q, K and V rows alike)
+  static constexpr int kStageWords = 2 * kAttnK * RW;      // one K tile + one V tile
+  static constexpr int kSmemBytes = 2 * kStageWords * 4;   // two stages; the q tile is staged through stage 1
+};
+__device__ __forceinline__ void cp_async16(void* dst, const void* src, bool pred) {
+  const int n = pred ? 16 : 0;   // src-size 0: the 16 bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// four 8x8 fp16 matrices, transposed: with lane l pointing at row (l & 7) + 8 * ((l >> 3) & 1) of a row-major [key][dim]
+// tile (dims n0 .. n0 + 7 for l < 16, n0 + 8 .. n0 + 15 above), r0/r1 are the B fragment (keys 0-7 / 8-15) of output
+// block n0 and r2/r3 that of block n0 + 8.
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(p)));
+}
+
+// qkv16 [B*T, 3H] fp16: the packed in-projection output as its GEMM epilogue stores it (q | k | v).  q, K and V tiles are
+// plain cp.async copies (two-stage ring over the 64-key tiles: the fill of tile i + 1 overlaps the MMAs of tile i); the
+// 1 / sqrt(head_dim) factor is applied to the fp32 scores.
 template <typename T, int HD>
-__global__ void __launch_bounds__(128, 3) k_enc_attention_f16(T* __restrict__ out16, const float* __restrict__ qkv,
+__global__ void __launch_bounds__(128, 3) k_enc_attention_f16(T* __restrict__ out16, const __half* __restrict__ qkv16,
                                                               const uint8_t* __restrict__ keep, int Tn, float scale) {
-  constexpr int KW = (HD + 8) / 2;              // words per K row (and per staged q row)
-  constexpr int VW = (kAttnK + 8) / 2;          // words per V^T row
+  using Cfg = AttnCfg<HD>;
+  constexpr int RW = Cfg::RW;
   constexpr int KQ = HD / 16;                   // k-steps of q k^T
   constexpr int NO = HD / 8;                    // 8-wide output blocks of P v
-  __shared__ uint32_t Ks[kAttnK * KW];          // [64 keys][HD + 8] fp16 (first: the q tile)
-  __shared__ uint32_t Vt[HD * VW];              // [HD dims][64 + 8] fp16
-  __shared__ uint8_t kvalid[kAttnK];
+  extern __shared__ uint32_t smw[];
+  __shared__ uint8_t kvalid[2][kAttnK];
   __shared__ int s_last;
   const int b = blockIdx.z, head = blockIdx.y, q0 = blockIdx.x * kHQ;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
@@ -274,66 +169,74 @@ __global__ void __launch_bounds__(128, 3) k_enc_attention_f16(T* __restrict__ ou
       if (keep[row0 + i]) last = i;
     if (last >= 0) atomicMax(&s_last, last);
   }
-  for (int i = tid; i < kHQ * (HD / 4); i += 128) {      // q tile, scaled, fp16, staged in the K buffer
-    const int r = i / (HD / 4), c4 = i - r * (HD / 4);
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (q0 + r < Tn) v = *reinterpret_cast<const float4*>(qkv + (row0 + q0 + r) * ld + head * HD + 4 * c4);
-    *reinterpret_cast<uint2*>(Ks + r * KW + 2 * c4) = make_uint2(pack_h2(v.x * scale, v.y * scale), pack_h2(v.z * scale, v.w * scale));
+  auto load_tile = [&](int tile, int stage) {     // K and V rows of 64 keys -> stage, 16 bytes (8 dims) per copy
+    uint32_t* Kd = smw + stage * Cfg::kStageWords;
+    uint32_t* Vd = Kd + kAttnK * RW;
+    const int k0 = tile * kAttnK;
+    for (int i = tid; i < kAttnK * (HD / 8); i += 128) {
+      const int r = i / (HD / 8), c8 = i - r * (HD / 8);
+      const bool in = k0 + r < Tn;
+      const __half* src = qkv16 + (row0 + (in ? k0 + r : 0)) * ld + head * HD + 8 * c8;
+      cp_async16(Kd + r * RW + 4 * c8, src + kEncH, in);
+      cp_async16(Vd + r * RW + 4 * c8, src + 2 * kEncH, in);
+    }
+    if (tid < kAttnK) kvalid[stage][tid] = (k0 + tid < Tn && keep[row0 + k0 + tid]) ? 1 : 0;
+  };
+  load_tile(0, 0);
+  cp_async_commit();
+  uint32_t* Qs = smw + Cfg::kStageWords;            // q tile [64][HD + 8] through stage 1
+  for (int i = tid; i < kHQ * (HD / 8); i += 128) {
+    const int r = i / (HD / 8), c8 = i - r * (HD / 8);
+    const bool in = q0 + r < Tn;
+    cp_async16(Qs + r * RW + 4 * c8, qkv16 + (row0 + (in ? q0 + r : 0)) * ld + head * HD + 8 * c8, in);
   }
+  cp_async_commit();
+  cp_async_wait<0>();
   __syncthreads();
   const int n_tiles = (s_last + kAttnK) / kAttnK;   // keys past the last real token contribute nothing
   uint32_t qa[KQ][4];
   {
-    const uint32_t* qr = Ks + (warp * 16 + g) * KW + t;
+    const uint32_t* qr = Qs + (warp * 16 + g) * RW + t;
 #pragma unroll
     for (int ks = 0; ks < KQ; ++ks) {
       qa[ks][0] = qr[ks * 8];
-      qa[ks][1] = qr[8 * KW + ks * 8];
+      qa[ks][1] = qr[8 * RW + ks * 8];
       qa[ks][2] = qr[ks * 8 + 4];
-      qa[ks][3] = qr[8 * KW + ks * 8 + 4];
+      qa[ks][3] = qr[8 * RW + ks * 8 + 4];
     }
   }
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;   // rows g and g + 8 of this warp's 16 queries
   float o[NO][4];
 #pragma unroll
   for (int nb = 0; nb < NO; ++nb) o[nb][0] = o[nb][1] = o[nb][2] = o[nb][3] = 0.f;
-  __half* Vth = reinterpret_cast<__half*>(Vt);
   for (int tile = 0; tile < n_tiles; ++tile) {
-    const int k0 = tile * kAttnK;
-    __syncthreads();                                   // q fragments / the previous tile's fragments have been read
-    for (int i = tid; i < kAttnK * (HD / 4); i += 128) {   // K: a warp covers one key row (256 contiguous bytes)
-      const int r = i / (HD / 4), c4 = i - r * (HD / 4);
-      float4 kv = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (k0 + r < Tn) kv = *reinterpret_cast<const float4*>(qkv + (row0 + k0 + r) * ld + kEncH + head * HD + 4 * c4);
-      *reinterpret_cast<uint2*>(Ks + r * KW + 2 * c4) = make_uint2(pack_h2(kv.x, kv.y), pack_h2(kv.z, kv.w));
-    }
-    for (int i = tid; i < kAttnK * (HD / 4); i += 128) {   // V^T: a warp covers 32 keys of one 4-dim chunk (conflict-free stores)
-      const int r = i % kAttnK, c4 = i / kAttnK;
-      float4 vv = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (k0 + r < Tn) vv = *reinterpret_cast<const float4*>(qkv + (row0 + k0 + r) * ld + 2 * kEncH + head * HD + 4 * c4);
-      __half* d = Vth + (4 * c4) * (2 * VW) + r;
-      d[0] = __float2half_rn(vv.x);
-      d[2 * VW] = __float2half_rn(vv.y);
-      d[4 * VW] = __float2half_rn(vv.z);
-      d[6 * VW] = __float2half_rn(vv.w);
-    }
-    if (tid < kAttnK) kvalid[tid] = (k0 + tid < Tn && keep[row0 + k0 + tid]) ? 1 : 0;
+    const int stage = tile & 1;
+    // everyone is done with the other stage (tile - 1's fragments, or the q tile): prefetch tile + 1 into it, then wait for
+    // this tile's copies only
     __syncthreads();
+    if (tile + 1 < n_tiles) load_tile(tile + 1, stage ^ 1);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    const uint32_t* Ks = smw + stage * Cfg::kStageWords;
+    const uint32_t* Vs = Ks + kAttnK * RW;
     // S[16 x 64]: sc[nb] holds keys nb*8 + 2t, +1 for rows g (.x .y) and g + 8 (.z .w)
     float sc[kAttnK / 8][4];
 #pragma unroll
     for (int nb = 0; nb < kAttnK / 8; ++nb) {
       sc[nb][0] = sc[nb][1] = sc[nb][2] = sc[nb][3] = 0.f;
-      const uint32_t* kr = Ks + (nb * 8 + g) * KW + t;
+      const uint32_t* kr = Ks + (nb * 8 + g) * RW + t;
 #pragma unroll
       for (int ks = 0; ks < KQ; ++ks) mma_f16(sc[nb], qa[ks], kr[ks * 8], kr[ks * 8 + 4]);
     }
     float t0 = -INFINITY, t1 = -INFINITY;
 #pragma unroll
     for (int nb = 0; nb < kAttnK / 8; ++nb) {
-      const bool va = kvalid[nb * 8 + 2 * t] != 0, vb = kvalid[nb * 8 + 2 * t + 1] != 0;
-      if (!va) sc[nb][0] = sc[nb][2] = -INFINITY;
-      if (!vb) sc[nb][1] = sc[nb][3] = -INFINITY;
+      const bool va = kvalid[stage][nb * 8 + 2 * t] != 0, vb = kvalid[stage][nb * 8 + 2 * t + 1] != 0;
+      sc[nb][0] = va ? sc[nb][0] * scale : -INFINITY;
+      sc[nb][2] = va ? sc[nb][2] * scale : -INFINITY;
+      sc[nb][1] = vb ? sc[nb][1] * scale : -INFINITY;
+      sc[nb][3] = vb ? sc[nb][3] * scale : -INFINITY;
       t0 = fmaxf(t0, fmaxf(sc[nb][0], sc[nb][1]));
       t1 = fmaxf(t1, fmaxf(sc[nb][2], sc[nb][3]));
     }
@@ -366,7 +269,8 @@ __global__ void __launch_bounds__(128, 3) k_enc_attention_f16(T* __restrict__ ou
     for (int nb = 0; nb < NO; ++nb) {
       o[nb][0] *= c0; o[nb][1] *= c0; o[nb][2] *= c1; o[nb][3] *= c1;
     }
-    // O[16 x HD] += P[16 x 64] V[64 x HD]: the accumulator fragments of key blocks 2ks, 2ks + 1 are the A fragment of k-step ks
+    // O[16 x HD] += P[16 x 64] V[64 x HD]: the accumulator fragments of key blocks 2ks, 2ks + 1 are the A fragment of k-step
+    // ks; the B fragments come from the row-major V tile through ldmatrix.trans (two 8-dim output blocks per instruction)
 #pragma unroll
     for (int ks = 0; ks < kAttnK / 16; ++ks) {
       uint32_t pa[4];
@@ -374,9 +278,14 @@ __global__ void __launch_bounds__(128, 3) k_enc_attention_f16(T* __restrict__ ou
       pa[1] = pack_h2(sc[2 * ks][2], sc[2 * ks][3]);
       pa[2] = pack_h2(sc[2 * ks + 1][0], sc[2 * ks + 1][1]);
       pa[3] = pack_h2(sc[2 * ks + 1][2], sc[2 * ks + 1][3]);
-      const uint32_t* vr = Vt + g * VW + ks * 8 + t;
+      const uint32_t* vrow = Vs + (ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * RW + (lane >> 4) * 4;
 #pragma unroll
-      for (int nb = 0; nb < NO; ++nb) mma_f16(o[nb], pa, vr[nb * 8 * VW], vr[nb * 8 * VW + 4]);
+      for (int nb = 0; nb < NO; nb += 2) {
+        uint32_t vb[4];
+        ldmatrix_x4_trans(vb, vrow + nb * 4);
+        mma_f16(o[nb], pa, vb[0], vb[1]);
+        mma_f16(o[nb + 1], pa, vb[2], vb[3]);
+      }
     }
   }
   const float i0 = l0 > 0.f ? 1.f / l0 : 0.f, i1 = l1 > 0.f ? 1.f / l1 : 0.f;

@@ -32,7 +32,7 @@ static EncLayout enc_layout(const pd_encoder_config& c) {
 static int check_enc_config(const pd_encoder_config* c) {
   if (!c) return fail("null encoder config");
   if (c->hidden_size != kEncH) return fail("encoder hidden_size must be %d (got %d)", kEncH, c->hidden_size);
-  if (c->num_heads != 1 && c->num_heads != 2 && c->num_heads != 4) return fail("encoder num_heads must be 1, 2 or 4 (got %d)", c->num_heads);
+  if (c->num_heads != 2 && c->num_heads != 4) return fail("encoder num_heads must be 2 or 4 (got %d)", c->num_heads);
   if (c->num_layers < 1) return fail("encoder num_layers must be >= 1");
   if (c->kernel_size < 1 || c->kernel_size % 2 == 0 || c->kernel_size > 31) return fail("encoder kernel_size must be odd and <= 31 (got %d)", c->kernel_size);
   if (c->vocab_size < 2) return fail("encoder vocab_size must be >= 2");
@@ -127,7 +127,7 @@ static EncScratch enc_scratch(int H, long long N) {
   auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 1024); return r; };
   w.x = take((size_t)N * H * 4);
   w.xn = take((size_t)N * H * 2);
-  w.qkv = take((size_t)N * 3 * H * 4);
+  w.qkv = take((size_t)N * 3 * H * 2);
   w.att = take((size_t)N * H * 2);
   w.h1 = take((size_t)N * 4 * H * 2);
   w.keep = take((size_t)N);
@@ -140,9 +140,9 @@ extern "C" size_t pd_encoder_workspace_bytes(const pd_encoder* e, int B, int T) 
 }
 
 template <typename T, int HD>
-static int launch_attention(T* out16, const float* qkv, const uint8_t* keep, int B, int Tn, int heads, cudaStream_t s) {
-  auto kern = k_enc_attention<T, HD>;
-  const int smem = (kAttnK * (HD + 4) + kAttnK * HD + kAttnQ * HD + 8 * 4 * kAttnK) * 4;
+static int launch_attention_f16(T* out16, const __half* qkv16, const uint8_t* keep, int B, int Tn, int heads, cudaStream_t s) {
+  auto kern = k_enc_attention_f16<T, HD>;
+  const int smem = AttnCfg<HD>::kSmemBytes;
   static bool configured[64] = {false};
   int dev = 0;
   PD_CUDA(cudaGetDevice(&dev));
@@ -150,27 +150,14 @@ static int launch_attention(T* out16, const float* qkv, const uint8_t* keep, int
     PD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured[dev & 63] = true;
   }
-  kern<<<dim3((Tn + kAttnQ - 1) / kAttnQ, heads, B), 256, smem, s>>>(out16, qkv, keep, Tn, sqrtf(1.0f / (float)HD));
-  PD_LAUNCH_CHECK("k_enc_attention");
-  return 0;
-}
-template <typename T, int HD>
-static int launch_attention_f16(T* out16, const float* qkv, const uint8_t* keep, int B, int Tn, int heads, cudaStream_t s) {
-  k_enc_attention_f16<T, HD><<<dim3((Tn + kHQ - 1) / kHQ, heads, B), 128, 0, s>>>(out16, qkv, keep, Tn, sqrtf(1.0f / (float)HD));
+  kern<<<dim3((Tn + kHQ - 1) / kHQ, heads, B), 128, smem, s>>>(out16, qkv16, keep, Tn, sqrtf(1.0f / (float)HD));
   PD_LAUNCH_CHECK("k_enc_attention_f16");
   return 0;
 }
 template <typename T>
-static int enc_attention(T* out16, const float* qkv, const uint8_t* keep, int B, int Tn, int heads, cudaStream_t s) {
-  static int simt = -1;   // PD_ENC_ATTN=simt: the CUDA-core kernel (A/B; always used for head_dim 256)
-  if (simt < 0) { const char* e = getenv("PD_ENC_ATTN"); simt = (e && e[0] == 's') ? 1 : 0; }
-  if (!simt && kEncH / heads == 128) return launch_attention_f16<T, 128>(out16, qkv, keep, B, Tn, heads, s);
-  if (!simt && kEncH / heads == 64) return launch_attention_f16<T, 64>(out16, qkv, keep, B, Tn, heads, s);
-  switch (kEncH / heads) {
-    case 64: return launch_attention<T, 64>(out16, qkv, keep, B, Tn, heads, s);
-    case 128: return launch_attention<T, 128>(out16, qkv, keep, B, Tn, heads, s);
-    default: return launch_attention<T, 256>(out16, qkv, keep, B, Tn, heads, s);
-  }
+static int enc_attention(T* out16, const __half* qkv16, const uint8_t* keep, int B, int Tn, int heads, cudaStream_t s) {
+  return kEncH / heads == 128 ? launch_attention_f16<T, 128>(out16, qkv16, keep, B, Tn, heads, s)
+                              : launch_attention_f16<T, 64>(out16, qkv16, keep, B, Tn, heads, s);
 }
 
 template <typename T>
@@ -181,7 +168,7 @@ static int enc_forward_t(pd_encoder* e, const long long* tok, const float* extra
   const EncScratch w = enc_scratch(H, N);
   float* x = reinterpret_cast<float*>(ws + w.x);
   T* xn = reinterpret_cast<T*>(ws + w.xn);
-  float* qkv = reinterpret_cast<float*>(ws + w.qkv);
+  __half* qkv = reinterpret_cast<__half*>(ws + w.qkv);   // fp16 whatever the GEMM operand type (see k_enc_attention_f16)
   T* att = reinterpret_cast<T*>(ws + w.att);
   T* h1 = reinterpret_cast<T*>(ws + w.h1);
   uint8_t* keep = ws + w.keep;
@@ -197,14 +184,14 @@ static int enc_forward_t(pd_encoder* e, const long long* tok, const float* extra
     const float* lnl = ln + (size_t)l * 4 * H;
     k_enc_layernorm<T><<<ln_blocks, 256, 0, s>>>(xn, nullptr, x, lnl, lnl + H, nullptr, N);
     PD_LAUNCH_CHECK("k_enc_layernorm(1)");
-    {  // packed in-projection, bias-free (common_layers.py:195,640-641) -> fp32 q | k | v
+    {  // packed in-projection, bias-free (common_layers.py:195,640-641) -> fp16 q | k | v
       GemmShape sh = base_shape(B, Tn, 3 * H / 256, H / 64);
       sh.b_row0 = l * 3 * H;
       EpiArgs ep = base_epi();
       ep.out = qkv;
       ep.bias = reinterpret_cast<const float*>(pk + e->lay.zeros);
       ep.ld = 3 * H;
-      ep.out_type = OUT_F32;
+      ep.out_type = OUT_F16;
       if (launch_gemm<EPI_STORE_X, 256>(dt, tm_xn, e->tm_w_qkv, sh, ep, sms, s, "gemm(enc in_proj)", 11)) return 1;
     }
     if (enc_attention<T>(att, qkv, keep, B, Tn, c.num_heads, s)) return 1;

@@ -573,6 +573,18 @@ def test_text_encoder_ragged_rows_and_interior_padding():
     assert float((out - ref).abs().max()) <= ENC_TOL["fp16"][0] and not out[1, 17].any() and not out[1, 90:].any()
 
 
+def test_text_encoder_four_heads():
+    """head_dim 64 instantiation of the attention kernel (the configured encoder has 2 heads of 128)."""
+    from prodiff_b200 import synth
+    cfg = synth.EncoderConfig(40, 256, 2, 5, 4)                        # 4 heads, FFN kernel 5
+    state = synth.make_encoder_state(cfg, 151)
+    tok, extra = synth.make_encoder_inputs(cfg, [70, 33], 70, 152)
+    ref = helpers.oracle_encoder(dict(extra=True), cfg, state, tok, extra)
+    with torch.no_grad():
+        out = _build_encoder(cfg, state, "bf16")(tok.cuda(), extra.cuda()).cpu()
+    assert float((out - ref).abs().max()) <= ENC_TOL["bf16"][0] and float((out - ref).abs().mean()) <= ENC_TOL["bf16"][1]
+
+
 def test_text_to_mel_chain_matches_oracle_chain():
     """The whole front of ProDiffTeacher.forward (prodiff_teacher.py:103-167) on the CUDA path -- dur/lang embeddings (torch),
     FastspeechEncoder (pd_encoder_forward), frame-level condition assembly (pd_cond_assemble), K-step sampler (pd_sample) --

@@ -49,7 +49,7 @@ def main():
         o_x = 0
         o_xn = al(o_x + N * H * 4)
         o_qkv = al(o_xn + N * H * 2)
-        o_att = al(o_qkv + N * 3 * H * 4)
+        o_att = al(o_qkv + N * 3 * H * 2)
         o_h1 = al(o_att + N * H * 2)
         view = lambda o, n, d: ws[off0 + o: off0 + o + n * d.itemsize].view(d)
         x_gpu = view(o_x, N * H, torch.float32).view(B, T, H).cpu()
@@ -59,7 +59,7 @@ def main():
             x0 = tr["embed"]
             ln1 = F.layer_norm(x0, (H,), state[p + "layer_norm1.weight"], state[p + "layer_norm1.bias"], 1e-5)
             qkv_ref = F.linear(ln1, state[p + "self_attn.in_proj_weight"])
-            qkv_gpu = view(o_qkv, N * 3 * H, torch.float32).view(B, T, 3 * H).cpu()
+            qkv_gpu = view(o_qkv, N * 3 * H, torch.float16).view(B, T, 3 * H).float().cpu()
             r["qkv_max"] = float((qkv_gpu - qkv_ref).abs().max())
             x1 = tr["attn0"]
             d16 = torch.float16 if dt == "fp16" else torch.bfloat16
