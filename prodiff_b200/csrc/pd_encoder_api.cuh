@@ -221,12 +221,12 @@ static int enc_forward_t(pd_encoder* e, const long long* tok, const float* extra
       ep.ld = 4 * H;
       ep.scale = 1.0f / sqrtf((float)k);
       ep.gelu = 1;
-      // In-kernel timeline (tools/encoder_trace.py): 630 cycles per K block (4 MMAs of M = 128, N = 256, K = 16) against 256
-      // at the tensor core's nominal rate; the erf-GELU epilogue (11-15 k cycles per tile) hides behind the next tile's K
-      // loop.  Not the L2 -> SM operand stream: serving the 9 taps from one resident haloed A tile (a third fewer TMA bytes)
-      // left the K block at 621 cycles (and cost a ring stage: 0.765 vs 0.737 ms per forward), and cta_group::2 pairs
-      // measured 0.740.  What remains is the MMA's own shared-memory operand fetch: 12 KB per single-CTA MMA at the ~64-80
-      // B/clk the layer kernel also sees is ~155 cycles per MMA.
+      // In-kernel timeline (tools/encoder_trace.py): 630 cycles per K block = 4 MMAs of M = 128, N = 256, K = 16, whose
+      // issue floor is 128 cycles each (4096 MAC/clk/SM), so the K loop runs at ~81 % of the tensor peak; the erf-GELU
+      // epilogue (11-15 k cycles per tile) hides behind the next tile's K loop.  What the launch loses is at tile granularity:
+      // 512 tiles on 148 CTAs are 3.46 waves (4 tiles on the busiest CTAs) and the last tile's epilogue is exposed -- 0.85
+      // PFLOP/s per launch.  Measured and not adopted: the 9 taps from one resident haloed A tile (a third fewer TMA bytes:
+      // K block 621 cycles, one ring stage less, 0.765 vs 0.737 ms per forward) and cta_group::2 pairs (654 cycles, 0.740 ms).
       if (launch_gemm<EPI_STORE_XH, 256>(dt, tm_xn, e->tm_w_f1, sh, ep, sms, s, "gemm(enc ffn_1)", 12)) return 1;
     }
     {  // ffn_2 + bias + residual, then the padding mask (common_layers.py:582, 669-672)
