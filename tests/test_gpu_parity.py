@@ -573,6 +573,22 @@ def test_text_encoder_ragged_rows_and_interior_padding():
     assert float((out - ref).abs().max()) <= ENC_TOL["fp16"][0] and not out[1, 17].any() and not out[1, 90:].any()
 
 
+def test_text_encoder_edge_rows():
+    """A one-token utterance, an utterance with no real token at all (the reference's softmax over an all-masked row is NaN;
+    here that row is defined as zeros and must not disturb its neighbours) and a long row (700 tokens: 11 key tiles)."""
+    from prodiff_b200 import synth
+    cfg = synth.EncoderConfig(50, 256, 2, 9, 2)
+    state = synth.make_encoder_state(cfg, 161)
+    tok, extra = synth.make_encoder_inputs(cfg, [1, 0, 700], 700, 162)
+    enc = _build_encoder(cfg, state, "fp16")
+    with torch.no_grad():
+        out = enc(tok.cuda(), extra.cuda()).cpu()
+    assert torch.isfinite(out).all() and not out[1].any() and not out[0, 1:].any()
+    for b in (0, 2):                                                    # each real row against the oracle run on it alone
+        ref = helpers.oracle_encoder(dict(extra=True), cfg, state, tok[b:b + 1], extra[b:b + 1])
+        assert float((out[b:b + 1] - ref).abs().max()) <= ENC_TOL["fp16"][0]
+
+
 def test_text_encoder_four_heads():
     """head_dim 64 instantiation of the attention kernel (the configured encoder has 2 heads of 128)."""
     from prodiff_b200 import synth
