@@ -89,6 +89,26 @@ def test_model_create_rejects_bad_arguments_without_gpu(lib):
     assert not h.value
 
 
+def test_encoder_config_validation_without_gpu(lib):
+    """pd_encoder_* argument checks that run before anything touches a device (include/prodiff_b200.h, text encoder)."""
+    from prodiff_b200 import _lib
+    ok = _lib.pd_encoder_config(64, 256, 4, 9, 2, 0)
+    assert lib.pd_encoder_state_count(C.byref(ok)) == 3 + 10 * 4
+    n = lib.pd_encoder_packed_bytes(C.byref(ok))
+    # 4 layers x (3 + 1 + 36 + 4) x 65536 16-bit weights + fp32 LayerNorm / bias / embedding tables
+    assert 4 * 44 * 65536 * 2 < n < 4 * 44 * 65536 * 2 + 1e6
+    for bad, word in ((_lib.pd_encoder_config(64, 512, 4, 9, 2, 0), b"hidden_size"), (_lib.pd_encoder_config(64, 256, 4, 9, 3, 0), b"num_heads"),
+                      (_lib.pd_encoder_config(64, 256, 4, 8, 2, 0), b"kernel_size"), (_lib.pd_encoder_config(64, 256, 0, 9, 2, 0), b"num_layers"),
+                      (_lib.pd_encoder_config(1, 256, 4, 9, 2, 0), b"vocab_size"), (_lib.pd_encoder_config(64, 256, 4, 9, 2, 7), b"dtype")):
+        assert lib.pd_encoder_packed_bytes(C.byref(bad)) == 0 and word in lib.pd_last_error(), word
+    h = C.c_void_p()
+    ptrs = (C.c_void_p * 3)()
+    assert lib.pd_encoder_create(C.byref(ok), ptrs, 3, None, 0, None, C.byref(h)) != 0
+    assert b"expected 43 encoder state tensors" in lib.pd_last_error() and not h.value
+    assert lib.pd_encoder_workspace_bytes(None, 1, 1) == 0
+    assert lib.pd_encoder_forward(None, None, None, None, 1, 1, None, 0, None) != 0 and b"null argument" in lib.pd_last_error()
+
+
 def test_missing_library_fails_loudly(monkeypatch):
     from prodiff_b200 import _lib
     monkeypatch.setattr(_lib, "_lib", None)

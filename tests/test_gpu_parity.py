@@ -589,6 +589,30 @@ def test_text_encoder_edge_rows():
         assert float((out[b:b + 1] - ref).abs().max()) <= ENC_TOL["fp16"][0]
 
 
+def test_text_encoder_random_shape_sweep():
+    """Seeded sweep over batch size, token count (tile boundaries of the 128-row GEMM tiles and the 64-key attention tiles),
+    depth, FFN kernel size, head count, operand type and padding patterns, each against the oracle."""
+    from prodiff_b200 import synth
+    rng = np.random.default_rng(171)
+    sizes = [1, 2, 63, 64, 65, 127, 128, 129, 191, 192, 193, 257, 300]
+    for i in range(12):
+        heads = int(rng.choice([2, 4]))
+        cfg = synth.EncoderConfig(int(rng.integers(5, 80)), 256, int(rng.integers(1, 4)), int(rng.choice([1, 3, 5, 9])), heads)
+        Tph = int(rng.choice(sizes))
+        B = int(rng.integers(1, 6))
+        lengths = [Tph] + [int(rng.integers(1, Tph + 1)) for _ in range(B - 1)]
+        state = synth.make_encoder_state(cfg, 200 + i)
+        tok, extra = synth.make_encoder_inputs(cfg, lengths, Tph, 300 + i)
+        use_extra = bool(i % 3)
+        dt = "fp16" if i % 2 else "bf16"
+        ref = helpers.oracle_encoder(dict(extra=use_extra), cfg, state, tok, extra)
+        with torch.no_grad():
+            out = _build_encoder(cfg, state, dt)(tok.cuda(), extra.cuda() if use_extra else None).cpu()
+        err = float((out - ref).abs().max())
+        assert err <= ENC_TOL[dt][0], (i, cfg, B, Tph, lengths, dt, err)
+        assert float((out - ref).abs().mean()) <= ENC_TOL[dt][1]
+
+
 def test_text_encoder_four_heads():
     """head_dim 64 instantiation of the attention kernel (the configured encoder has 2 heads of 128)."""
     from prodiff_b200 import synth
