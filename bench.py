@@ -190,9 +190,19 @@ def main():
     device = torch.device("cuda", local_rank)
     torch.cuda.set_device(device)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
-        dist.init_process_group("nccl", device_id=device)
+        # NCCL writes its version banner (and any NCCL_DEBUG output) to stdout when the first communicator is created.
+        # Rank 0 must print exactly one JSON line there, so file descriptor 1 points at stderr until that has happened.
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=device)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     w = WORKLOAD
     B, T, K, M, H = w["B"], w["T"], w["K"], w["in_dims"], w["hidden"]
     gd, cfg, _ = build_model(device, args.dtype)
