@@ -12,7 +12,9 @@ utterances are independent, every rank samples its own 64 x 1000 shard, no colle
 Printed JSON (rank 0, one line): see the keys below.  `value` is timed with CUDA events with the inputs resident in
 HBM; `e2e` goes through the public module API from pinned HOST buffers with the H2D/D2H copies inside the timed
 region; `roofline` is the dominant kernel (dilated conv + gate GEMM) timed with per-launch CUDA events in a second
-pass over the same steps; `cpu_baseline` is the CPU oracle port (the reference's algorithm in PyTorch fp32) on the host.
+pass over the same steps; `cpu_baseline` is the CPU oracle port (the reference's algorithm in PyTorch fp32) on the host;
+`text_front` (N = 1, unscored, outside every timed region above) times the step in front of the path on the same batch:
+the text encoder and the whole tokens -> mel chain.
 """
 from __future__ import annotations
 
@@ -164,6 +166,48 @@ def run_reference(args, rank):
     }))
 
 
+def text_front(gd, device, B, T, K):
+    """Not part of the metric: the step in front of the hot path on the same batch -- FastspeechEncoder
+    (pd_encoder_forward) on B x 200 tokens and the whole tokens -> mel chain (encoder + condition assembly + sampler),
+    CUDA-event timed.  Mirrors tools/text_to_mel_bench.py; reported so that the widening is measured by the same run."""
+    import types
+    import numpy as np
+    import prodiff_b200 as pb
+    from prodiff_b200 import synth
+    Tph = 200
+    ecfg = synth.EncoderConfig(64, 256, 4, 9, 2)
+    enc = pb.FastspeechEncoder(ecfg.vocab_size, 256, 4, 9, num_heads=2)
+    enc.load_state_dict(synth.make_encoder_state(ecfg, 1234), strict=False)
+    enc = enc.to(device).eval()
+    rng = np.random.default_rng(7)
+    tok, _ = synth.make_encoder_inputs(ecfg, [Tph] * B, Tph, 4321)
+    tk = tok.to(device)
+    m2p = torch.from_numpy(np.sort(rng.integers(1, Tph + 1, size=(B, T)), axis=1)).to(device)
+    f0 = torch.from_numpy(rng.uniform(80, 800, size=(B, T)).astype(np.float32)).to(device)
+    pitch = torch.nn.Linear(1, 256).to(device)
+    teacher = types.SimpleNamespace(with_dur_embed=False, with_lang_embed=False, encoder=enc, pitch_embed=pitch, with_spk_embed=False,
+                                    with_gender_embed=False, with_voicing_embed=False, with_breath_embed=False)
+
+    def ms(fn, n=10, warm=3):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / n
+    with torch.no_grad():
+        cond = lambda: pb.forward_condition(teacher, tk, m2p, f0, validate=False)
+        enc_ms = ms(lambda: enc(tk, None))
+        t2m_ms = ms(lambda: gd(cond(), infer_step=K, infer=True, seed=1))
+    return {"workload": f"{B} utt x {Tph} tokens -> {B} x {T} frames, encoder 4 layers x 256, 2 heads, kernel 9",
+            "encoder_ms": enc_ms, "encoder_tokens_per_s": B * Tph / enc_ms * 1e3,
+            "text_to_mel_ms": t2m_ms, "text_to_mel_frames_per_s": B * T / t2m_ms * 1e3}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -172,6 +216,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-text-front", action="store_true", help="skip the (unscored) encoder / text -> mel timing")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -375,6 +420,11 @@ def main():
             "flops_per_frame": F,
             "rtf_x_realtime": value / FRAME_RATE,
         }
+        if not args.no_text_front and world == 1:
+            try:
+                out["text_front"] = text_front(gd, device, B, T, K)
+            except Exception as e:  # never let the unscored extra break the bench line
+                out["text_front"] = {"error": f"{type(e).__name__}: {e}"}
         if not args.no_cpu_baseline and world == 1:
             out["cpu_baseline"] = cpu_baseline()
         print(json.dumps(out))
