@@ -63,6 +63,39 @@ def test_wavenet_from_reference_like_module():
         assert torch.equal(v, new.state_dict()[k])
 
 
+def test_encoder_dropin_state_dict_and_loud_failures():
+    """prodiff_b200.FastspeechEncoder: the reference's state_dict keys / shapes / init (tts_modules.py:291-303), the order the
+    C ABI expects, and no CPU path."""
+    import os
+    import sys
+    import types
+    import prodiff_b200 as pb
+    from prodiff_b200.encoder import encoder_state_key_order
+    cfg = synth.EncoderConfig(37, 256, 3, 9, 2)
+    enc = pb.FastspeechEncoder(cfg.vocab_size, 256, 3, 9, dropout=0.1, num_heads=2)
+    sd = enc.state_dict()
+    keys = encoder_state_key_order(3)
+    assert len(keys) == 3 + 10 * 3 and sorted(keys + ["embed_positions._float_tensor"]) == sorted(sd)
+    st = synth.make_encoder_state(cfg, 3)
+    assert sorted(st) == sorted(keys) and all(st[k].shape == sd[k].shape for k in keys)
+    assert not sd["embed_tokens.weight"][0].any() and abs(float(sd["embed_tokens.weight"][1:].std()) - 256 ** -0.5) < 5e-3
+    assert not sd["layers.0.op.ffn.ffn_2.bias"].any() and sd["layers.1.op.self_attn.in_proj_weight"].shape == (768, 256)
+    enc.eval()
+    with torch.no_grad(), pytest.raises(RuntimeError, match="no CPU fallback"):
+        enc(torch.ones(1, 3, dtype=torch.long))
+    if os.path.isdir("/root/reference/modules/fastspeech"):
+        sys.path.insert(0, "/root/reference")
+        sys.modules.setdefault("chardet", types.ModuleType("chardet"))
+        try:
+            from modules.fastspeech.tts_modules import FastspeechEncoder as Ref
+            ref = Ref(cfg.vocab_size, 256, 3, 9, dropout=0.1, num_heads=2)
+            assert {k: tuple(v.shape) for k, v in ref.state_dict().items()} == {k: tuple(v.shape) for k, v in sd.items()}
+            new = pb.FastspeechEncoder.from_reference(ref, "fp16")
+            assert new.cfg == enc.cfg and all(torch.equal(v, new.state_dict()[k]) for k, v in ref.state_dict().items())
+        finally:
+            sys.path.remove("/root/reference")
+
+
 def test_shard_bounds():
     assert sharding.shard_bounds(64, 8) == [(8 * i, 8 * i + 8) for i in range(8)]
     assert sharding.shard_bounds(10, 4) == [(0, 3), (3, 6), (6, 8), (8, 10)]
