@@ -6,8 +6,7 @@
 // The dense contractions (packed q/k/v projection, out_proj, the kernel-9 FFN convolution, ffn_2) run on the generic
 // tcgen05 GEMM kernel (pd_gemm.cuh, EPI_STORE_X epilogue: GELU, residual, keep mask).  What is left is per-token work on
 // ~10^4 tokens: the embedding and LayerNorm kernels (fp32, one warp per token) and the attention (warp-level fp16 mma.sync
-// with an fp32 online softmax, k_enc_attention_f16; k_enc_attention is the fp32 CUDA-core version kept for head_dim 256 and
-// for A/B runs).
+// with an fp32 online softmax, k_enc_attention_f16).
 #pragma once
 #include "pd_aux.cuh"
 
@@ -108,7 +107,7 @@ __global__ void __launch_bounds__(256) k_enc_layernorm(T* __restrict__ out16, fl
 // probabilities are far inside its range, so it is used whatever the encoder's GEMM operand type is.  History, all at
 // 64 x 200 tokens: fp32 on the CUDA cores 128 us per launch (issue-bound: one FMA per MAC); TF32 m16n8k8 with P staged
 // through shared memory 64-66 us (the legacy path's TF32 rate); this fp16 form with fp32 q|k|v converted while filling the
-// tiles 46 us; with the in-projection GEMM storing fp16 and the tiles arriving by cp.async, see the numbers in DESIGN.md 3.8.
+// tiles 46 us; this version (the in-projection GEMM stores fp16, tiles arrive by cp.async, V through ldmatrix.trans) 24 us.
 // The probabilities never touch shared memory: the accumulator fragments of two adjacent 8-key blocks ARE the A fragment
 // of one 16-key k-step.  CTA = 4 warps x 16 queries, three CTAs per SM; q, K and V tiles row-major [token][HD] in fp16 with
 // rows padded by 8 halves (every fragment load and ldmatrix bank-conflict free).  A row whose keys are ALL padding yields
