@@ -218,7 +218,7 @@ def test_fused_sampler_tail_equals_separate_kernels(mode):
     assert float((res[0][2][K - 1] - x0s[K - 1]).abs().max()) <= STEP_TOL * 4   # last step: errors of K - 1 updates ride along
 
 
-@pytest.mark.parametrize("path", ["tail", "separate", "unfused512", "reflow"])
+@pytest.mark.parametrize("path", ["tail", "sumtail", "separate", "unfused512", "reflow"])
 def test_vocoder_handoff_scale_is_fused_and_bit_identical(path):
     """SURVEY 8f N3 (first sub-step): with ``vocoder_scale`` the last posterior update (denorm_spec kernel for rectified
     flow) stores fl(2.30259 * x), so the call returns the contiguous [B,M,T] generator input of nsf_hifigan.py:50-52 --
@@ -233,6 +233,7 @@ def test_vocoder_handoff_scale_is_fused_and_bit_identical(path):
     B, T, K = 2, 300, 3
     cond, x_T, noise = synth.make_inputs(cfg, B, T, K, 32)
     prev = lib.pd_set_tail(0 if path == "separate" else 1)
+    prev_st = lib.pd_set_sumtail(1 if path == "sumtail" else 0)
     try:
         if path == "reflow":
             rf = pb.RectifiedFlow(128, _build(cfg, state), time_scale=1000, sampling_algorithm="rk2",
@@ -253,6 +254,7 @@ def test_vocoder_handoff_scale_is_fused_and_bit_identical(path):
                 assert float(c.abs().max()) > 0
     finally:
         lib.pd_set_tail(1 if prev != 0 else 0)
+        lib.pd_set_sumtail(1 if prev_st != 0 else 0)
 
 
 @pytest.mark.parametrize("name", ["euler", "rk2", "rk4", "rk5", "pitch64"])
