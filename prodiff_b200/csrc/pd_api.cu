@@ -454,6 +454,7 @@ static bool pair_enabled() {
   return g_pair == 1;
 }
 
+static thread_local bool g_enc_pdl = false;   // set by the text encoder's launch sequence (pd_encoder_api.cuh)
 template <int EPI, int BN, typename T, bool kPair>
 static int launch_gemm_t(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, const CUtensorMap& x,
                          const GemmShape& sh, const EpiArgs& ep, int sms, cudaStream_t s, const char* name, int kind) {
@@ -475,13 +476,15 @@ static int launch_gemm_t(const CUtensorMap& a, const CUtensorMap& b, const CUten
   cfg.blockDim = dim3(kGemmThreads);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = s;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = kPair ? 2 : 1;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // encoder chain only (pd_encoder_api.cuh)
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = (g_enc_pdl && (EPI == EPI_STORE_X || EPI == EPI_STORE_XH)) ? 2 : 1;
   prof_before(kind, s);
   PD_CUDA(cudaLaunchKernelEx(&cfg, kern, a, b, o, x, sh, ep));
   prof_after(s);

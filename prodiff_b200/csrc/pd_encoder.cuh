@@ -24,6 +24,7 @@ __global__ void __launch_bounds__(256) k_enc_embed(float* __restrict__ x, uint8_
                                                    const float* __restrict__ extra, int Tn, int vocab) {
   const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t = blockIdx.x * 8 + warp;
+  griddep_launch();   // (first kernel of the call: launched normally, but the LayerNorm behind it may start early)
   if (t >= Tn) return;
   const long long* tk = tok + (long long)b * Tn;
   const long long id = tk[t];
@@ -66,6 +67,8 @@ __global__ void __launch_bounds__(256) k_enc_layernorm(T* __restrict__ out16, fl
                                                        const uint8_t* __restrict__ keep, long long n_tok) {
   const int lane = threadIdx.x & 31;
   const long long n = blockIdx.x * 8ll + (threadIdx.x >> 5);
+  griddep_launch();
+  griddep_wait();
   if (n >= n_tok) return;
   const float4* xr = reinterpret_cast<const float4*>(x + n * kEncH);
   float4 v[2] = {xr[lane], xr[lane + 32]};   // channels 4*lane..+3 and 128 + 4*lane..+3
@@ -159,6 +162,8 @@ __global__ void __launch_bounds__(128, 3) k_enc_attention_f16(T* __restrict__ ou
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const long long row0 = (long long)b * Tn;
   const int ld = 3 * kEncH;
+  griddep_launch();
+  griddep_wait();
   if (!__syncthreads_or(tid < kHQ && q0 + tid < Tn && keep[row0 + q0 + tid] != 0)) return;   // padding-only query block
   if (tid == 0) s_last = -1;
   __syncthreads();

@@ -118,6 +118,24 @@ extern "C" int pd_encoder_create(const pd_encoder_config* cfg, const float* cons
 }
 extern "C" void pd_encoder_destroy(pd_encoder* e) { delete e; }
 
+// Launch with the programmatic-dependent-launch attribute (pd_ptx.cuh): every encoder kernel but the first (g_enc_pdl is
+// declared next to launch_gemm_t in pd_api.cu).
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_dep(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_enc_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 struct EncScratch {
   size_t x, xn, qkv, att, h1, keep, total;
 };
@@ -150,7 +168,7 @@ static int launch_attention_f16(T* out16, const __half* qkv16, const uint8_t* ke
     PD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured[dev & 63] = true;
   }
-  kern<<<dim3((Tn + kHQ - 1) / kHQ, heads, B), 128, smem, s>>>(out16, qkv16, keep, Tn, sqrtf(1.0f / (float)HD));
+  PD_CUDA(launch_dep(kern, dim3((Tn + kHQ - 1) / kHQ, heads, B), dim3(128), (size_t)smem, s, out16, qkv16, keep, Tn, sqrtf(1.0f / (float)HD)));
   PD_LAUNCH_CHECK("k_enc_attention_f16");
   return 0;
 }
@@ -177,12 +195,16 @@ static int enc_forward_t(pd_encoder* e, const long long* tok, const float* extra
   CUtensorMap tm_xn, tm_att, tm_h1;
   if (make_act_map(&tm_xn, dt, xn, H, Tn, B, 1) || make_act_map(&tm_att, dt, att, H, Tn, B, 1) || make_act_map(&tm_h1, dt, h1, 4 * H, Tn, B, 1))
     return 1;
+  g_enc_pdl = false;
   k_enc_embed<<<dim3((Tn + 7) / 8, B), 256, 0, s>>>(x, keep, tok, reinterpret_cast<const float*>(pk + e->lay.emb), extra, Tn, c.vocab_size);
   PD_LAUNCH_CHECK("k_enc_embed");
+  static int pdl = -1;   // PD_ENC_PDL=0: ordinary stream-ordered launches (A/B)
+  if (pdl < 0) { const char* ev = getenv("PD_ENC_PDL"); pdl = (ev && ev[0] == '0') ? 0 : 1; }
+  g_enc_pdl = pdl != 0;
   const int ln_blocks = (int)((N + 7) / 8);
   for (int l = 0; l < L; ++l) {
     const float* lnl = ln + (size_t)l * 4 * H;
-    k_enc_layernorm<T><<<ln_blocks, 256, 0, s>>>(xn, nullptr, x, lnl, lnl + H, nullptr, N);
+    PD_CUDA(launch_dep(k_enc_layernorm<T>, dim3(ln_blocks), dim3(256), 0, s, xn, (float*)nullptr, (const float*)x, lnl, lnl + H, (const uint8_t*)nullptr, N));
     PD_LAUNCH_CHECK("k_enc_layernorm(1)");
     {  // packed in-projection, bias-free (common_layers.py:195,640-641) -> fp16 q | k | v
       GemmShape sh = base_shape(B, Tn, 3 * H / 256, H / 64);
@@ -207,7 +229,7 @@ static int enc_forward_t(pd_encoder* e, const long long* tok, const float* extra
       ep.keep = keep;
       if (launch_gemm<EPI_STORE_X, 256>(dt, tm_att, e->tm_w_out, sh, ep, sms, s, "gemm(enc out_proj)", 11)) return 1;
     }
-    k_enc_layernorm<T><<<ln_blocks, 256, 0, s>>>(xn, nullptr, x, lnl + 2 * H, lnl + 3 * H, nullptr, N);
+    PD_CUDA(launch_dep(k_enc_layernorm<T>, dim3(ln_blocks), dim3(256), 0, s, xn, (float*)nullptr, (const float*)x, lnl + 2 * H, lnl + 3 * H, (const uint8_t*)nullptr, N));
     PD_LAUNCH_CHECK("k_enc_layernorm(2)");
     {  // ffn_1: Conv1d(H, 4H, k, padding = k // 2) as an implicit GEMM over k taps, * k^-0.5, GELU (common_layers.py:570-576)
       GemmShape sh = base_shape(B, Tn, 4 * H / 256, H / 64);
@@ -243,8 +265,9 @@ static int enc_forward_t(pd_encoder* e, const long long* tok, const float* extra
     }
   }
   const float* lnf = ln + (size_t)L * 4 * H;
-  k_enc_layernorm<T><<<ln_blocks, 256, 0, s>>>(nullptr, out, x, lnf, lnf + H, keep, N);
+  PD_CUDA(launch_dep(k_enc_layernorm<T>, dim3(ln_blocks), dim3(256), 0, s, (T*)nullptr, out, (const float*)x, lnf, lnf + H, (const uint8_t*)keep, N));
   PD_LAUNCH_CHECK("k_enc_layernorm(last)");
+  g_enc_pdl = false;
   return 0;
 }
 

@@ -281,6 +281,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   }
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if constexpr (EPI == EPI_STORE_X || EPI == EPI_STORE_XH) {
+    // the encoder chains ~30 short launches: let the next one run its prologue while this grid drains, and do not touch the
+    // previous kernel's output before it has completed (pd_ptx.cuh, programmatic dependent launch)
+    griddep_launch();
+    griddep_wait();
+  }
 
   const int num_m_tiles = sh.B * sh.m_tiles_per_row;
   // work items: (m-tile, n-tile), or (pair of adjacent m-tiles, n-tile) with this CTA taking m-tile 2 * pair + rank

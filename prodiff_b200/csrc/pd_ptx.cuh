@@ -311,6 +311,12 @@ __device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr) {
   const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
   return (static_cast<uint64_t>(hi) << 32) | lo;
 }
+// Programmatic dependent launch: a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start (run its
+// prologue) once every CTA of its predecessor has called griddep_launch() or exited; griddep_wait() then blocks until the
+// predecessor grid has completed and its memory is visible.  Both are no-ops for ordinary launches.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // Advancing along K inside the 128-byte swizzle atom: +32 bytes per UMMA_K=16 step => +2 in the address field.
 __device__ __forceinline__ uint64_t desc_advance_k(uint64_t desc, uint32_t k16) { return desc + (uint64_t)(k16 * 2u); }
 
