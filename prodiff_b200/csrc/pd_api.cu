@@ -469,8 +469,7 @@ static int launch_gemm_t(const CUtensorMap& a, const CUtensorMap& b, const CUten
   }
   const int m_tiles = sh.B * sh.m_tiles_per_row;
   const int items = (kPair ? (m_tiles + 1) / 2 : m_tiles) * sh.n_tiles;
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchConfig_t cfg = {};
   const int ctas = kPair ? 2 * (items < sms / 2 ? items : sms / 2) : (items < sms ? items : sms);
   cfg.gridDim = dim3(ctas);
   cfg.blockDim = dim3(kGemmThreads);
@@ -576,8 +575,7 @@ static int launch_layer_t(const LayerMaps& mp, const LayerParams& lp, int sms, c
   }
   const int num_pairs = (lp.B * lp.m_tiles_per_row + 1) / 2;
   const int clusters = num_pairs < sms / 2 ? num_pairs : sms / 2;
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * clusters);
   cfg.blockDim = dim3(kLayerThreads);
   cfg.dynamicSmemBytes = layer_smem_bytes(lp.xsub, lp.ident_resident);
@@ -669,8 +667,7 @@ static int launch_sumtail_t(const CUtensorMap& y, const CUtensorMap& wskip, cons
     configured[dev & 63] = true;
   }
   const int pairs = (sp.tp.B * sp.tp.m_tiles_per_row + 1) / 2;
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * (pairs < sms / 2 ? pairs : sms / 2));
   cfg.blockDim = dim3(kSumTailThreads);
   cfg.dynamicSmemBytes = kSumTailSmemBytes;

@@ -122,8 +122,7 @@ extern "C" void pd_encoder_destroy(pd_encoder* e) { delete e; }
 // declared next to launch_gemm_t in pd_api.cu).
 template <typename... KArgs, typename... Args>
 static cudaError_t launch_dep(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;

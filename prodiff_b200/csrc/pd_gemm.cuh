@@ -468,7 +468,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         // accumulator row, so direct global access would touch 32 lines per warp instruction (the in_proj GEMM wrote its
         // 39 MB at 1.1 TB/s that way): every 32-row x 32-column block goes through a per-warp shared-memory tile instead and
         // moves to / from global memory as full 128-byte (fp32) or 64-byte (16-bit) row segments.
-        const long long nfr = (long long)sh.B * sh.T;
         float* stg = reinterpret_cast<float*>(extra) + (warp - 2) * (32 * Cfg::kXRowWords);   // [32 rows][36] floats (16-bit: [32][20] words)
         const int rows_left = (m_tile < num_m_tiles) ? sh.T - (t0 + q * 32) : 0;      // rows of this warp's slab inside the utterance
         const long long nrow0 = (long long)b * sh.T + t0 + q * 32;                   // global row of slab row 0
