@@ -70,6 +70,12 @@ class AssembledCondition:
         return out
 
 
+def mel2ph_to_dur(mel2ph: torch.Tensor, T_txt: int) -> torch.Tensor:
+    """Frames per token: tts_modules.py:223-229 with max_dur=None (an integer histogram of mel2ph, index 0 = padding dropped)."""
+    dur = mel2ph.new_zeros(mel2ph.shape[0], T_txt + 1).scatter_add(1, mel2ph, torch.ones_like(mel2ph))
+    return dur[:, 1:]
+
+
 def forward_condition(teacher, txt_tokens, mel2ph, f0, lang_seq=None, spk_embed_id=None, spk_mix_embed=None,
                       gender_embed_id=None, gender_mix_embed=None, voicing=None, breath=None, *,
                       validate: bool = True) -> AssembledCondition:
@@ -77,9 +83,7 @@ def forward_condition(teacher, txt_tokens, mel2ph, f0, lang_seq=None, spk_embed_
     module (or anything with its attributes).  Token-level part as in :111-126, frame-level part deferred to the kernel."""
     extra_embed = None
     if teacher.with_dur_embed:
-        import importlib
-        from_ref = importlib.import_module("modules.fastspeech.tts_modules")   # the reference's own helper (:113)
-        dur = from_ref.mel2ph_to_dur(mel2ph, txt_tokens.shape[1]).float()
+        dur = mel2ph_to_dur(mel2ph, txt_tokens.shape[1]).float()                # :113
         extra_embed = teacher.dur_embed(dur[:, :, None])
     if teacher.with_lang_embed:
         assert lang_seq is not None, "use_lang_embed is True, lang_seq is required"
@@ -109,4 +113,4 @@ def forward_condition(teacher, txt_tokens, mel2ph, f0, lang_seq=None, spk_embed_
                               validate=validate)
 
 
-__all__ = ["AssembledCondition", "forward_condition"]
+__all__ = ["AssembledCondition", "forward_condition", "mel2ph_to_dur"]

@@ -673,23 +673,9 @@ def test_text_to_mel_chain_matches_oracle_chain():
         with_dur_embed=True, dur_embed=dur_embed, with_lang_embed=False, encoder=enc,
         pitch_embed=types.SimpleNamespace(weight=pitch_w.cuda(), bias=pitch_b.cuda()), with_spk_embed=True, with_gender_embed=False,
         add_spk_embed=lambda i, mix: mix, with_voicing_embed=False, with_breath_embed=False)
-    import sys
-    tm = types.ModuleType("modules.fastspeech.tts_modules")          # forward_condition borrows mel2ph_to_dur from the reference tree
-    tm.mel2ph_to_dur = lambda m2p, T_txt, max_dur=None: eo.mel2ph_to_dur(m2p.cpu(), T_txt).to(m2p.device)
-    saved = {k: sys.modules.get(k) for k in ("modules", "modules.fastspeech", "modules.fastspeech.tts_modules")}
-    sys.modules.setdefault("modules", types.ModuleType("modules"))
-    sys.modules.setdefault("modules.fastspeech", types.ModuleType("modules.fastspeech"))
-    sys.modules["modules.fastspeech.tts_modules"] = tm
-    try:
-        with torch.no_grad():
-            ac = pb.forward_condition(teacher, tok.cuda(), mel2ph.cuda(), f0.cuda(), spk_mix_embed=spk.cuda())
-            mel = gd(ac, infer_step=K, infer=True, x_T=x_T.cuda(), noise=noise.cuda()).cpu()
-    finally:
-        for k, v in saved.items():
-            if v is None:
-                sys.modules.pop(k, None)
-            else:
-                sys.modules[k] = v
+    with torch.no_grad():
+        ac = pb.forward_condition(teacher, tok.cuda(), mel2ph.cuda(), f0.cuda(), spk_mix_embed=spk.cuda())
+        mel = gd(ac, infer_step=K, infer=True, x_T=x_T.cuda(), noise=noise.cuda()).cpu()
     assert float((ac.encoder_out.cpu() - enc_ref).abs().max()) <= ENC_TOL["bf16"][0]
     valid = (mel2ph > 0)[:, :, None].expand_as(mel_ref)
     l1 = float((mel - mel_ref)[valid].abs().mean())

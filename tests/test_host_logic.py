@@ -91,7 +91,9 @@ def test_encoder_dropin_state_dict_and_loud_failures():
             ref = Ref(cfg.vocab_size, 256, 3, 9, dropout=0.1, num_heads=2)
             assert {k: tuple(v.shape) for k, v in ref.state_dict().items()} == {k: tuple(v.shape) for k, v in sd.items()}
             new = pb.FastspeechEncoder.from_reference(ref, "fp16")
-            assert new.cfg == enc.cfg and all(torch.equal(v, new.state_dict()[k]) for k, v in ref.state_dict().items())
+            # (embed_positions._float_tensor is torch.FloatTensor(1): uninitialised memory, possibly NaN -- a device marker only)
+            assert new.cfg == enc.cfg and all(torch.equal(v, new.state_dict()[k]) for k, v in ref.state_dict().items()
+                                              if not k.endswith("_float_tensor"))
         finally:
             sys.path.remove("/root/reference")
 

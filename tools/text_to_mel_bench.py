@@ -47,14 +47,6 @@ def main():
     dur_embed = torch.nn.Linear(1, 256).cuda()
     pitch = torch.nn.Linear(1, 256).cuda()
     spk = torch.randn(B, 1, 256).cuda()
-    tm = types.ModuleType("modules.fastspeech.tts_modules")      # forward_condition borrows mel2ph_to_dur from the reference tree
-
-    def mel2ph_to_dur(m2p, T_txt, max_dur=None):
-        return m2p.new_zeros(m2p.shape[0], T_txt + 1).scatter_add(1, m2p, torch.ones_like(m2p))[:, 1:]
-    tm.mel2ph_to_dur = mel2ph_to_dur
-    sys.modules.setdefault("modules", types.ModuleType("modules"))
-    sys.modules.setdefault("modules.fastspeech", types.ModuleType("modules.fastspeech"))
-    sys.modules["modules.fastspeech.tts_modules"] = tm
     teacher = types.SimpleNamespace(with_dur_embed=True, dur_embed=dur_embed, with_lang_embed=False, encoder=enc, pitch_embed=pitch,
                                     with_spk_embed=True, with_gender_embed=False, add_spk_embed=lambda i, mix: mix,
                                     with_voicing_embed=False, with_breath_embed=False)
