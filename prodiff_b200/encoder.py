@@ -27,7 +27,7 @@ class _Positions(nn.Module):
 
     def __init__(self):
         super().__init__()
-        self.register_buffer("_float_tensor", torch.FloatTensor(1))
+        self.register_buffer("_float_tensor", torch.zeros(1))   # (the reference leaves it uninitialised: torch.FloatTensor(1))
 
 
 class _SelfAttention(nn.Module):
