@@ -191,9 +191,10 @@ long long pd_launch_count(int reset);
  * bracketed by a CUDA-event pair on its stream.  pd_profile_end synchronises and returns, per kernel kind, the summed
  * milliseconds and the launch count.  Kinds: 0 cond_proj, 1 input_proj, 2 dilated_conv+gate, 3 res_proj, 4 skip_sum,
  * 5 skip_proj, 6 output_proj+posterior, 7 debug. */
-#define PD_N_KINDS 11  /* kind 8 = fused ResidualBlock layer kernel (2-CTA); kind 9 = fused sampler tail (skip_projection +
+#define PD_N_KINDS 13  /* kind 8 = fused ResidualBlock layer kernel (2-CTA); kind 9 = fused sampler tail (skip_projection +
                           output_projection + q-posterior + next step's input_projection, pd_sample only); kind 10 = skip sum +
-                          that tail as one kernel */
+                          that tail as one kernel; kind 11 = text-encoder GEMMs with an fp32 / residual epilogue (in_proj,
+                          out_proj, ffn_2); kind 12 = text-encoder FFN conv (ffn_1) */
 int pd_profile_begin(void);
 int pd_profile_end(float* ms_by_kind, int* count_by_kind, int n_kinds);
 
@@ -212,11 +213,12 @@ int pd_debug_gemm(int dtype, const void* a, int B, int T, int Cin, int taps, int
 int pd_set_fused(int on);
 /* With the fused kernel: run all layers of a denoiser call in ONE persistent launch whose tiles synchronise through
  * per-tile flags (1, default; env PD_STACK=0 also disables) or launch one kernel per layer (0). Returns the previous value.
- * The persistent form needs all its clusters resident at once: the library checks that against an otherwise idle GPU, so
- * run ONE sampling call at a time per GPU (what the reference does, handler/infer/handler.py:373-378; one process per GPU
- * for multi-GPU).  Two such launches racing for the same SMs from different streams or processes can each end up holding
- * SMs the other's unscheduled clusters need; the in-kernel watchdog then traps (an error, not a hang).  A host that
- * must overlap several calls on one GPU selects the per-layer form (0), which has no inter-cluster waits. */
+ * The persistent form needs all its clusters resident at once.  The library (a) checks with the occupancy query that the
+ * grid fits the device and (b) launches it COOPERATIVELY (cudaLaunchAttributeCooperative), so the driver schedules the
+ * grid as a whole: kernels of other streams or processes that hold SMs delay the launch but cannot leave it half
+ * resident.  If the cooperative launch is refused the call silently uses one launch per layer (no inter-cluster waits).
+ * Different plans may therefore run on different streams of one GPU; they serialise at the persistent kernel (each one
+ * fills the device anyway).  Every in-kernel wait still has a clock watchdog that traps instead of hanging. */
 int pd_set_stack(int on);
 
 /* pd_sample only: run skip_projection (wavenet.py:120-121), output_projection (:122), the q-posterior update
@@ -231,7 +233,7 @@ int pd_set_tail(int on);
  * bit-identical but measured no faster).  Returns the previous value. */
 int pd_set_sumtail(int on);
 
-/* Debug: when set to a device buffer of 12 x 1024 int64, CTA 0 of every GEMM launch writes clock64() stamps of its
+/* Debug: when set to a device buffer of PD_N_KINDS x 1024 int64 (a kind outside [0, PD_N_KINDS) is never traced), CTA 0 of every GEMM launch writes clock64() stamps of its
  * pipeline events at [kind * 1024 + tile * 16 + slot] (slots: 0/1 first/last TMA issue, 2 accumulator free, 3/4 first/
  * last operand stage landed, 5/6 epilogue before/after accumulator wait, 7 epilogue done, 14 exit, 15 entry). */
 int pd_debug_set_trace(long long* device_buf);

@@ -95,7 +95,8 @@ def load() -> C.CDLL:
 
 
 KIND_NAMES = ["cond_proj", "input_proj", "dilated_conv+gate", "res_proj", "skip_sum", "skip_proj", "output_proj+posterior",
-              "debug", "residual_layer(fused)", "sampler_tail(fused)", "skip_sum+tail(fused)"]
+              "debug", "residual_layer(fused)", "sampler_tail(fused)", "skip_sum+tail(fused)", "encoder_gemm", "encoder_ffn_conv"]
+N_KINDS = len(KIND_NAMES)   # == PD_N_KINDS (include/prodiff_b200.h); debug trace buffers hold N_KINDS x 1024 int64
 
 
 def profile_begin() -> None:
@@ -104,10 +105,10 @@ def profile_begin() -> None:
 
 def profile_end() -> dict:
     """{kind name: (total ms, launches)} for every GEMM launched since profile_begin()."""
-    ms = (C.c_float * 11)()
-    cnt = (C.c_int * 11)()
-    check(load().pd_profile_end(ms, cnt, 11), "pd_profile_end")
-    return {KIND_NAMES[i]: (float(ms[i]), int(cnt[i])) for i in range(11) if cnt[i]}
+    ms = (C.c_float * N_KINDS)()
+    cnt = (C.c_int * N_KINDS)()
+    check(load().pd_profile_end(ms, cnt, N_KINDS), "pd_profile_end")
+    return {KIND_NAMES[i]: (float(ms[i]), int(cnt[i])) for i in range(N_KINDS) if cnt[i]}
 
 
 def check(rc: int, what: str) -> None:

@@ -76,8 +76,8 @@ static void prof_after(cudaStream_t s) {
   cudaEventRecord((*g_prof)[g_prof_used].e1, s);
   ++g_prof_used;
 }
-// debug: device buffer of 8 kinds x 1024 slots; CTA 0 of every GEMM launch records clock64() at pipeline events
-static thread_local long long* g_trace = nullptr;  // 9 kinds x 1024 slots
+// debug: device buffer of PD_N_KINDS x 1024 slots; CTA 0 of every GEMM launch records clock64() at pipeline events
+static thread_local long long* g_trace = nullptr;
 extern "C" int pd_debug_set_trace(long long* device_buf) {
   g_trace = device_buf;
   return 0;
@@ -496,7 +496,7 @@ template <int EPI, int BN>
 static int launch_gemm(int dtype, const CUtensorMap& a, const CUtensorMap& b, GemmShape sh, const EpiArgs& ep, int sms,
                        cudaStream_t s, const char* name, int kind, const CUtensorMap* o = nullptr,
                        const CUtensorMap* x = nullptr, const CUtensorMap* bh = nullptr) {
-  sh.trace = g_trace ? g_trace + kind * 1024 : nullptr;
+  sh.trace = (g_trace && kind >= 0 && kind < PD_N_KINDS) ? g_trace + kind * 1024 : nullptr;   // the buffer holds PD_N_KINDS x 1024 slots
   const CUtensorMap& om = o ? *o : a;  // unused maps alias the A map
   const CUtensorMap& xm = x ? *x : a;
   if (bh != nullptr && pair_enabled() && sh.B * sh.m_tiles_per_row >= 2) {
@@ -580,7 +580,7 @@ static int launch_layer_t(const LayerMaps& mp, const LayerParams& lp, int sms, c
   cfg.blockDim = dim3(kLayerThreads);
   cfg.dynamicSmemBytes = layer_smem_bytes(lp.xsub, lp.ident_resident);
   cfg.stream = s;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
@@ -593,9 +593,28 @@ static int launch_layer_t(const LayerMaps& mp, const LayerParams& lp, int sms, c
     *ok_multi = (e == cudaSuccess) && max_clusters >= clusters;
     if (e != cudaSuccess) cudaGetLastError();
     if (!*ok_multi) return 0;
+    // The clusters of a multi-layer launch wait on one another through global flags, so ALL of them must be resident at
+    // once.  The occupancy query above only says the grid fits an idle GPU; a COOPERATIVE launch makes the driver schedule
+    // the grid as a whole (or not at all), so another stream's or process's kernels holding SMs can delay this launch but
+    // cannot leave it half-resident and spinning.  PD_COOP=0 drops the attribute (A/B only).
+    static int coop = -1;
+    if (coop < 0) { const char* ev = getenv("PD_COOP"); coop = (ev && ev[0] == '0') ? 0 : 1; }
+    if (coop) {
+      attr[1].id = cudaLaunchAttributeCooperative;
+      attr[1].val.cooperative = 1;
+      cfg.numAttrs = 2;
+    }
   }
   prof_before(8, s);
-  PD_CUDA(cudaLaunchKernelEx(&cfg, kern, mp, lp));
+  const cudaError_t le = cudaLaunchKernelEx(&cfg, kern, mp, lp);
+  if (le != cudaSuccess && ok_multi && cfg.numAttrs == 2) {
+    // the cooperative form was refused (grid larger than what can be co-resident right now, or not supported together
+    // with clusters by this driver): nothing was launched; the caller runs one launch per layer instead
+    cudaGetLastError();   // (the profiling slot opened by prof_before is simply reused by the next launch)
+    *ok_multi = false;
+    return 0;
+  }
+  if (le != cudaSuccess) return fail("cudaLaunchKernelEx(layer_kernel) failed: %s", cudaGetErrorString(le));
   prof_after(s);
   PD_LAUNCH_CHECK("layer_kernel");
   return 0;

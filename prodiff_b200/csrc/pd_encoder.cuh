@@ -164,7 +164,15 @@ __global__ void __launch_bounds__(128, 3) k_enc_attention_f16(T* __restrict__ ou
   const int ld = 3 * kEncH;
   griddep_launch();
   griddep_wait();
-  if (!__syncthreads_or(tid < kHQ && q0 + tid < Tn && keep[row0 + q0 + tid] != 0)) return;   // padding-only query block
+  if (!__syncthreads_or(tid < kHQ && q0 + tid < Tn && keep[row0 + q0 + tid] != 0)) {
+    // padding-only query block: no attention to compute, but out_proj's A operand must not be uninitialised memory (its
+    // keep mask is a select today; zeros keep it safe if that ever becomes a multiply)
+    for (int i = tid; i < kHQ * (HD / 8); i += 128) {
+      const int r = i / (HD / 8), c8 = i - r * (HD / 8);
+      if (q0 + r < Tn) *reinterpret_cast<uint4*>(out16 + (row0 + q0 + r) * kEncH + head * HD + 8 * c8) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    return;
+  }
   if (tid == 0) s_last = -1;
   __syncthreads();
   {

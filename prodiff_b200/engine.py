@@ -63,6 +63,15 @@ def row_chunks(B: int, T: int, frames_per_call: int):
     return out
 
 
+def workspace_bucket(nbytes: int) -> int:
+    """Allocation size for a plan workspace of ``nbytes``: the next of eight steps per power of two (<= 12.5 % slack), at
+    least 1 MiB.  Plans of nearby shapes (online inference: every new T) then share a handful of block sizes, so an evicted
+    plan's block fits the next plan and the caching allocator is not left with multi-GB holes of slightly different sizes."""
+    n = max(int(nbytes), 1 << 20)
+    step = 1 << max(n.bit_length() - 4, 0)
+    return -(-n // step) * step
+
+
 class Plan:
     def __init__(self, engine: "Engine", B: int, T: int, entries: int):
         lib = engine.lib
@@ -70,7 +79,9 @@ class Plan:
         nbytes = lib.pd_workspace_bytes(engine.handle, B, T, entries)
         if nbytes == 0:
             raise RuntimeError(f"prodiff_b200: bad plan shape B={B} T={T} entries={entries}")
-        self.workspace = _aligned_bytes(nbytes, engine.device)
+        self.block = engine.take_block(nbytes)        # uint8 tensor of a bucketed size, returned to the pool on eviction
+        off = (-self.block.data_ptr()) % 1024
+        self.workspace = self.block[off:off + nbytes]
         h = C.c_void_p()
         _lib.check(lib.pd_plan_create(engine.handle, B, T, entries, self.workspace.data_ptr(), nbytes, C.byref(h)),
                    "pd_plan_create")
@@ -94,7 +105,7 @@ class Plan:
 class Engine:
     """Packed weights of one DiffNet on one device + a small cache of plans."""
 
-    MAX_PLANS = 4
+    MAX_PLANS = 8
     FRAMES_PER_CALL = 65536   # see row_chunks
 
     def __init__(self, cfg: dict, state: Dict[str, torch.Tensor], device: torch.device, operand_dtype: str = "bf16"):
@@ -120,17 +131,35 @@ class Engine:
             # the pack kernels read `tensors` asynchronously: keep them alive until the stream has run them
             torch.cuda.current_stream(device).synchronize()
         self.handle = h
-        self.plans: Dict[Tuple[int, int, int], Plan] = {}
+        self.plans: Dict[Tuple[int, int, int], Plan] = {}   # insertion order = recency (LRU first)
+        self.pool: list = []                                # workspace blocks of evicted plans
+
+    def take_block(self, nbytes: int) -> torch.Tensor:
+        """A workspace block of at least nbytes + 1024 bytes: the smallest pooled one that fits, else a new allocation of
+        the bucketed size.  Reuse is stream-ordered like every other use of the plan (the engine launches on the caller's
+        current stream)."""
+        need = workspace_bucket(nbytes + 1024)
+        fit = [i for i, b in enumerate(self.pool) if b.numel() >= need]
+        if fit:
+            return self.pool.pop(min(fit, key=lambda i: self.pool[i].numel()))
+        self.pool.clear()   # nothing pooled fits: let the allocator reuse those bytes for the new block
+        return torch.empty(need, dtype=torch.uint8, device=self.device)
 
     def plan(self, B: int, T: int, entries: int) -> Plan:
+        """Least-recently-used cache of MAX_PLANS plans keyed by (B, T, entries); an evicted plan hands its workspace
+        block to the pool, so a new shape usually costs only the ~30 tensor-map encodes of pd_plan_create."""
         key = (B, T, entries)
-        p = self.plans.get(key)
+        p = self.plans.pop(key, None)
         if p is None:
-            if len(self.plans) >= self.MAX_PLANS:
-                self.plans.pop(next(iter(self.plans)))
+            while len(self.plans) >= self.MAX_PLANS:
+                old = self.plans.pop(next(iter(self.plans)))    # first key = least recently used
+                self.lib.pd_plan_destroy(old.handle)
+                old.handle = None
+                self.pool.append(old.block)
+                old.block = old.workspace = None
             with torch.cuda.device(self.device):
                 p = Plan(self, B, T, entries)
-            self.plans[key] = p
+        self.plans[key] = p   # (re)insert at the most-recently-used end
         return p
 
     def _stream(self):

@@ -183,6 +183,33 @@ def test_fused_layer_kernel_equals_unfused_pair():
     assert float((outs[0] - ref).abs().max()) <= STEP_TOL and float((outs[1] - ref).abs().max()) <= STEP_TOL
 
 
+def test_plan_cache_is_lru_and_reuses_workspace_blocks():
+    """Engine.plan: least-recently-used eviction (a plan in constant use survives), bucketed workspace blocks handed from an
+    evicted plan to the next shape, and results unaffected by the reuse."""
+    from prodiff_b200 import synth
+    from prodiff_b200.engine import workspace_bucket
+    cfg = synth.DiffNetConfig(128, 256, 2, 256, 1)
+    state = synth.make_state(cfg, 51, "trained")
+    wn = _build(cfg, state)
+    eng = wn.engine()
+    eng.MAX_PLANS = 3
+    hot = eng.plan(2, 256, 4)
+    ptrs = set()
+    for T in (250, 251, 252, 253, 254, 255):
+        assert eng.plan(2, 256, 4) is hot                      # touched between every miss: never the LRU entry
+        p = eng.plan(2, T, 4)
+        ptrs.add(p.block.data_ptr())
+        assert p.block.numel() == workspace_bucket(p.workspace.numel() + 1024)
+    assert (2, 256, 4) in eng.plans and len(eng.plans) == 3
+    assert len(ptrs) <= 3                                       # evicted blocks were reused, not reallocated
+    cond, x_T, _ = synth.make_inputs(cfg, 2, 255, 1, 52)
+    steps = torch.tensor([1.0, 3.0])
+    with torch.no_grad():
+        out = wn(x_T.cuda(), steps.cuda(), cond.cuda().transpose(1, 2)).cpu()
+        ref = oracle.wavenet_forward(state, x_T, steps, cond.transpose(1, 2), cfg.dilation_cycle_length)
+    assert float((out - ref).abs().max()) <= STEP_TOL
+
+
 @pytest.mark.parametrize("mode", ["sumtail", "tail"])
 def test_fused_sampler_tail_equals_separate_kernels(mode):
     """(mode "sumtail": the skip sum runs in the same kernel as well, pd_sumtail.cuh.)

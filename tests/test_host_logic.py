@@ -243,3 +243,12 @@ def test_bucket_by_length_properties():
     assert offline.my_batches(10, rank=1, world=4) == [1, 5, 9] and offline.my_batches(3, rank=0, world=1) == [0, 1, 2]
     with pytest.raises(ValueError):
         offline.bucket_by_length([10, 0, 5])
+
+
+def test_workspace_bucket_bounds_slack_and_collapses_nearby_sizes():
+    from prodiff_b200.engine import workspace_bucket
+    for n in (1, 1 << 20, (1 << 20) + 1, 123_456_789, 2_200_000_000, 2_205_000_000, 21 << 30):
+        b = workspace_bucket(n)
+        assert b >= n and b >= 1 << 20 and b <= max(1 << 20, int(n * 1.125) + 1)
+    assert workspace_bucket(2_200_000_000) == workspace_bucket(2_205_000_000)   # T = 1000 vs 1002 land in one bucket
+    assert len({workspace_bucket(n) for n in range((1 << 30) + 1, (2 << 30) + 1, 1 << 22)}) == 8

@@ -128,7 +128,7 @@ def check_trace():
     cond = cond.cuda()
     with torch.no_grad():
         gd(cond, infer_step=4, infer=True, seed=1)
-        buf = torch.zeros(12 * 1024, dtype=torch.int64, device="cuda")
+        buf = torch.zeros(_lib.N_KINDS * 1024, dtype=torch.int64, device="cuda")
         lib.pd_debug_set_trace(buf.data_ptr())
         gd(cond, infer_step=4, infer=True, seed=1)
         torch.cuda.synchronize()
