@@ -184,6 +184,52 @@ size_t pd_encoder_workspace_bytes(const pd_encoder* e, int B, int T);
 int pd_encoder_forward(pd_encoder* e, const long long* txt_tokens, const float* extra_embed, float* out, int B, int T,
                        void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * NSF-HiFiGAN generator: the step right after the sampler.  Replaces Generator.forward(x, f0)
+ * (modules/nsf_hifigan/models.py:269-290, with ResBlock1 :39-76, SineGen :103-188 and SourceModuleHnNSF :191-216) as
+ * called by NsfHifiGAN.spec2wav_torch (component/vocoder/nsf_hifigan.py:49-58).  Every convolution runs as an implicit
+ * GEMM on tcgen05 (prodiff_b200/csrc/pd_voc.cuh), fp16 operands, fp32 accumulation; no cuDNN, no fallback. */
+typedef struct pd_vocoder_config {
+  int32_t num_mels;                  /* h.num_mels: 128 */
+  int32_t upsample_initial_channel;  /* h.upsample_initial_channel: 512 */
+  int32_t n_upsamples;               /* len(h.upsample_rates) <= 8 */
+  int32_t upsample_rates[8];         /* e.g. 8 8 2 2 2 */
+  int32_t upsample_kernel_sizes[8];  /* must be 2 * rate (e.g. 16 16 4 4 4) */
+  int32_t n_resblock_kernels;        /* len(h.resblock_kernel_sizes) <= 4 */
+  int32_t resblock_kernel_sizes[4];  /* e.g. 3 7 11 */
+  int32_t resblock_dilation_sizes[4][3]; /* e.g. 1 3 5 each */
+  int32_t resblock_type;             /* 1 = ResBlock1 (h.resblock == '1'); the only one implemented */
+  int32_t sampling_rate;             /* h.sampling_rate: 44100 */
+} pd_vocoder_config;
+typedef struct pd_vocoder pd_vocoder;
+
+/* State tensors (fp32, device, contiguous; weight norm already folded, i.e. what Generator.remove_weight_norm() leaves,
+ * models.py:292-297), in this order:
+ *   conv_pre.weight [C0, num_mels, 7], conv_pre.bias;
+ *   for each up-sampling stage i: ups.i.weight [Cin, Cin/2, k], ups.i.bias, noise_convs.i.weight [Cin/2, 1, k'], noise_convs.i.bias,
+ *     then for each resblock kernel j (resblocks.{i * n_kernels + j}): convs1.{0,1,2}.weight, .bias interleaved (6 tensors),
+ *     convs2.{0,1,2}.weight, .bias interleaved (6 tensors);
+ *   conv_post.weight [1, C_last, 7], conv_post.bias; m_source.l_linear.weight [1, 9], m_source.l_linear.bias [1]. */
+int pd_vocoder_state_count(const pd_vocoder_config* cfg);
+size_t pd_vocoder_packed_bytes(const pd_vocoder_config* cfg);   /* 0 = unsupported config, see pd_last_error() */
+int pd_vocoder_create(const pd_vocoder_config* cfg, const float* const* state, int n_state, void* packed, size_t packed_bytes,
+                      void* stream, pd_vocoder** out);
+void pd_vocoder_destroy(pd_vocoder* v);
+int pd_vocoder_upp(const pd_vocoder* v);                         /* samples per mel frame (prod of the rates, models.py:267) */
+size_t pd_vocoder_workspace_bytes(const pd_vocoder* v, int B, int T);
+/* c [B, num_mels, T] fp32 device: the generator input (2.30259 * mel.transpose(2, 1), nsf_hifigan.py:50-52 -- what
+ * pd_plan_set_output_scale makes the sampler write); f0 [B, T] fp32 device; rand_ini [9] fp32 device: SineGen's random
+ * initial phases (models.py:143-145; entry 0 must be 0); noise: optional [B, T * upp, 9] fp32 device N(0,1) draws standing
+ * in for torch.randn_like (:186), NULL = in-kernel Philox keyed by `seed`; wave [B, T * upp] fp32 device (the reference
+ * returns it as [B, 1, T * upp]).  workspace: pd_vocoder_workspace_bytes(v, B, T) bytes, 1024-aligned, used during the call. */
+int pd_vocoder_forward(pd_vocoder* v, const float* c, const float* f0, const float* rand_ini, const float* noise, uint64_t seed,
+                       float* wave, int B, int T, void* workspace, size_t workspace_bytes, void* stream);
+/* Test hook: one convolution through the generator's kernel (fp16 operands): out [B, Cout, T] = conv1d(x [B, Cin, T],
+ * w [Cout, Cin, k], bias, dilation = dil, padding = (k - 1) / 2 * dil), all fp32 device tensors. */
+size_t pd_voc_debug_conv_scratch(int B, int T, int Cin, int Cout, int k);
+int pd_voc_debug_conv(const float* x, int B, int T, int Cin, const float* w, const float* bias, int Cout, int k, int dil, float* out,
+                      void* scratch, size_t scratch_bytes, void* stream);
+
 /* Number of kernels of this library launched by the calling thread since the last reset (bench evidence). */
 long long pd_launch_count(int reset);
 
@@ -191,10 +237,10 @@ long long pd_launch_count(int reset);
  * bracketed by a CUDA-event pair on its stream.  pd_profile_end synchronises and returns, per kernel kind, the summed
  * milliseconds and the launch count.  Kinds: 0 cond_proj, 1 input_proj, 2 dilated_conv+gate, 3 res_proj, 4 skip_sum,
  * 5 skip_proj, 6 output_proj+posterior, 7 debug. */
-#define PD_N_KINDS 13  /* kind 8 = fused ResidualBlock layer kernel (2-CTA); kind 9 = fused sampler tail (skip_projection +
+#define PD_N_KINDS 14  /* kind 8 = fused ResidualBlock layer kernel (2-CTA); kind 9 = fused sampler tail (skip_projection +
                           output_projection + q-posterior + next step's input_projection, pd_sample only); kind 10 = skip sum +
                           that tail as one kernel; kind 11 = text-encoder GEMMs with an fp32 / residual epilogue (in_proj,
-                          out_proj, ffn_2); kind 12 = text-encoder FFN conv (ffn_1) */
+                          out_proj, ffn_2); kind 12 = text-encoder FFN conv (ffn_1); kind 13 = vocoder convolutions (pd_vocoder_forward) */
 int pd_profile_begin(void);
 int pd_profile_end(float* ms_by_kind, int* count_by_kind, int n_kinds);
 

@@ -22,7 +22,16 @@ SYMBOLS = [
     "pd_plan_set_output_scale",
     "pd_encoder_state_count", "pd_encoder_packed_bytes", "pd_encoder_create", "pd_encoder_destroy",
     "pd_encoder_workspace_bytes", "pd_encoder_forward",
+    "pd_vocoder_state_count", "pd_vocoder_packed_bytes", "pd_vocoder_create", "pd_vocoder_destroy", "pd_vocoder_upp",
+    "pd_vocoder_workspace_bytes", "pd_vocoder_forward", "pd_voc_debug_conv_scratch", "pd_voc_debug_conv",
 ]
+
+
+class pd_vocoder_config(C.Structure):
+    _fields_ = [("num_mels", C.c_int32), ("upsample_initial_channel", C.c_int32), ("n_upsamples", C.c_int32),
+                ("upsample_rates", C.c_int32 * 8), ("upsample_kernel_sizes", C.c_int32 * 8),
+                ("n_resblock_kernels", C.c_int32), ("resblock_kernel_sizes", C.c_int32 * 4),
+                ("resblock_dilation_sizes", (C.c_int32 * 3) * 4), ("resblock_type", C.c_int32), ("sampling_rate", C.c_int32)]
 
 
 class pd_encoder_config(C.Structure):
@@ -76,6 +85,16 @@ def load() -> C.CDLL:
     lib.pd_encoder_destroy.argtypes = [vp]; lib.pd_encoder_destroy.restype = None
     lib.pd_encoder_workspace_bytes.argtypes = [vp, C.c_int, C.c_int]; lib.pd_encoder_workspace_bytes.restype = sz
     lib.pd_encoder_forward.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, vp, sz, vp]; lib.pd_encoder_forward.restype = C.c_int
+    lib.pd_vocoder_state_count.argtypes = [P(pd_vocoder_config)]; lib.pd_vocoder_state_count.restype = C.c_int
+    lib.pd_vocoder_packed_bytes.argtypes = [P(pd_vocoder_config)]; lib.pd_vocoder_packed_bytes.restype = sz
+    lib.pd_vocoder_create.argtypes = [P(pd_vocoder_config), P(vp), C.c_int, vp, sz, vp, P(vp)]; lib.pd_vocoder_create.restype = C.c_int
+    lib.pd_vocoder_destroy.argtypes = [vp]; lib.pd_vocoder_destroy.restype = None
+    lib.pd_vocoder_upp.argtypes = [vp]; lib.pd_vocoder_upp.restype = C.c_int
+    lib.pd_vocoder_workspace_bytes.argtypes = [vp, C.c_int, C.c_int]; lib.pd_vocoder_workspace_bytes.restype = sz
+    lib.pd_vocoder_forward.argtypes = [vp, vp, vp, vp, vp, u64, vp, C.c_int, C.c_int, vp, sz, vp]; lib.pd_vocoder_forward.restype = C.c_int
+    lib.pd_voc_debug_conv_scratch.argtypes = [C.c_int] * 5; lib.pd_voc_debug_conv_scratch.restype = sz
+    lib.pd_voc_debug_conv.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, sz, vp]
+    lib.pd_voc_debug_conv.restype = C.c_int
     lib.pd_launch_count.argtypes = [C.c_int]; lib.pd_launch_count.restype = C.c_longlong
     lib.pd_plan_buffer.argtypes = [vp, cp, P(sz), P(sz)]; lib.pd_plan_buffer.restype = C.c_int
     lib.pd_debug_gemm.argtypes = [C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp, vp, vp]
@@ -95,7 +114,7 @@ def load() -> C.CDLL:
 
 
 KIND_NAMES = ["cond_proj", "input_proj", "dilated_conv+gate", "res_proj", "skip_sum", "skip_proj", "output_proj+posterior",
-              "debug", "residual_layer(fused)", "sampler_tail(fused)", "skip_sum+tail(fused)", "encoder_gemm", "encoder_ffn_conv"]
+              "debug", "residual_layer(fused)", "sampler_tail(fused)", "skip_sum+tail(fused)", "encoder_gemm", "encoder_ffn_conv", "vocoder_conv"]
 N_KINDS = len(KIND_NAMES)   # == PD_N_KINDS (include/prodiff_b200.h); debug trace buffers hold N_KINDS x 1024 int64
 
 

@@ -5,7 +5,9 @@
 #include "pd_layer.cuh"
 #include "pd_tail.cuh"
 #include "pd_sumtail.cuh"
+#include "pd_voc.cuh"
 
+#include <algorithm>
 #include <math.h>
 #include <stdarg.h>
 #include <string.h>
@@ -1319,3 +1321,6 @@ extern "C" int pd_debug_shift(int dtype, const void* a, int R, const void* w, in
 
 // ------------------------------------------------------------------ FastSpeech text encoder
 #include "pd_encoder_api.cuh"
+
+// ------------------------------------------------------------------ NSF-HiFiGAN generator
+#include "pd_voc_api.cuh"

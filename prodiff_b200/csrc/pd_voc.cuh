@@ -1,0 +1,467 @@
+// Conv1d as an implicit GEMM on tcgen05 for the NSF-HiFiGAN generator (modules/nsf_hifigan/models.py:39-290):
+// every convolution of the generator -- conv_pre, the transposed up-sampling convs, the 90 ResBlock convs with 16..256
+// channels, kernel sizes 3/7/11 and dilations 1/3/5, conv_post -- is one instance of this kernel,
+//
+//   D[128 positions, BN out-channels] = sum over K blocks of  A_kb[128 positions, 64] * W_kb[BN, 64]^T      (fp32 in TMEM)
+//
+// * Activations are fp16, channels-last, one utterance after the other with GUARD rows of zeros in front of and behind
+//   each utterance: [B][G + T + G][C].  The guard rows ARE the convolution's zero padding, so a tap that reaches outside
+//   the utterance simply reads zeros from memory and every conv input is stored exactly once.
+// * The A operand is read through a 4-D tensor map (channel, tap, position, utterance) with strides
+//   (2, dil * C * 2, C * 2, (T + 2G) * C * 2) bytes -- overlapping on purpose: element (c, tap, t) is x[t + tap * dil][c].
+//   A K block is 64 channels of one tap (box 64 x 1 x 128), landing as the usual 128-byte-swizzled K-major tile.
+// * For C = 16 / 32 (the late stages: 256-512 samples per mel frame) a K block is all channels of 4 / 2 consecutive taps.
+//   TMA cannot build that tile (with the 128-byte swizzle every box row shorter than 128 bytes is padded to a full
+//   swizzle row -- measured, tools/voc_probe.py), so four extra producer warps gather it: one thread per position copies
+//   its g pieces of C channels with 16-byte cp.async straight into the swizzled rows (chunk j of row r at (j ^ (r & 7))),
+//   completion signalled on the stage's mbarrier (cp.async.mbarrier.arrive.noinc); the MMA issuer adds the generic ->
+//   async proxy fence.  Consecutive lanes read consecutive positions, i.e. contiguous memory.  That keeps the narrow
+//   stages on the tensor cores without padding their channels to 64; taps past the kernel size are zero-filled.
+// * The weights are packed [N][K] with K = tap * C + c (taps padded to a multiple of g with zeros), 2-D map, (64, BN) box.
+// * A transposed convolution with kernel 2s and stride s is a 3-tap convolution with N = s * C_out whose output row of
+//   s * C_out values IS s consecutive rows of the up-sampled channels-last tensor (no shuffle kernel); taps a phase does
+//   not use carry zero weights.
+// * warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..9 = epilogue: (acc + bias [+ residual] [+ addend]) * scale ->
+//   LeakyReLU / tanh -> fp16 (or fp32 for the waveform), every global access as full row segments through a per-warp
+//   shared-memory tile.  Tensors that feed a next convolution are stored ALREADY activated (LeakyReLU is invertible, so
+//   the residual path recovers the raw value with one multiply): each activation tensor exists once in HBM.
+#pragma once
+#include "pd_gemm.cuh"
+
+namespace pd {
+
+struct VocShape {
+  int B, T;              // utterances, positions per utterance (the conv's output length = its input length)
+  int m_tiles_per_row;   // ceil(T / 128)
+  int n_tiles;           // N_total / BN
+  int cc_blocks;         // 64-channel chunks per tap group (C >= 64: C / 64, else 1)
+  int tap_groups;        // ceil(taps / g)
+  int g;                 // taps per K block (C >= 64: 1, else 64 / C)
+  uint32_t idesc;
+  // gather path (C < 64): the guarded activation buffer itself
+  const __half* a_ptr;   // first element of the buffer (front guard of utterance 0)
+  int a_C, a_taps, a_dil, a_G;
+};
+
+struct VocEpi {
+  __half* out16;           // fp16 output, element (b, t, col) at out16[b * out_bstride + t * out_ld + col]
+  float* out32;            // fp32 output of column 0 only (conv_post: the waveform), element (b, t) at out32[b * T + t]
+  long long out_bstride;
+  int out_ld;
+  const float* bias;       // [N_total]
+  const __half* res16;     // optional residual, stored LeakyReLU-activated: raw = r >= 0 ? r : r * res_inv_slope
+  long long res_bstride;
+  int res_ld;
+  float res_inv_slope;
+  const __half* add16;     // optional raw addend (harmonic source branch / running sum over the ResBlocks); may alias out16
+  long long add_bstride;
+  int add_ld;
+  float scale;             // applied after the sums
+  int act;                 // 0 none, 1 LeakyReLU(slope), 2 tanh
+  float slope;
+};
+
+constexpr int kVocGatherThreads = 128;   // one per position of a 128-row tile
+
+__device__ __forceinline__ void voc_cp_async16(uint32_t dst_smem, const void* src, bool pred) {
+  const int n = pred ? 16 : 0;   // src-size 0: the 16 bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(n) : "memory");
+}
+// the mbarrier receives one arrival from this thread once all its earlier cp.async have landed (not counted as pending)
+__device__ __forceinline__ void voc_cp_async_arrive(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int BN> struct VocCfg {
+  static constexpr int kCW = BN >= 64 ? 32 : BN;                  // columns per epilogue chunk
+  static constexpr int kRowWords = kCW / 2 + 4;                   // staging row: kCW halves + 16 bytes of padding
+  static constexpr uint32_t kABytes = kBlockM * kBlockK * 2;
+  static constexpr uint32_t kBBytes = BN * kBlockK * 2;
+  static constexpr uint32_t kStageBytes = kABytes + kBBytes;
+  static constexpr uint32_t kStagingBytes = kEpiWarps * 32 * kRowWords * 4;
+  static constexpr int kStagesFit = (int)((200u * 1024u - kStagingBytes) / kStageBytes);
+  static constexpr int kStages = kStagesFit < 8 ? kStagesFit : 8;
+  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 + 256;
+};
+
+template <int BN, bool kGather>
+__global__ void __launch_bounds__(kGemmThreads + (kGather ? kVocGatherThreads : 0), 1)
+voc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const VocShape sh, const VocEpi ep) {
+  using Cfg = VocCfg<BN>;
+  constexpr int kStages = Cfg::kStages;
+  constexpr int CW = Cfg::kCW;
+  constexpr int RW = Cfg::kRowWords;
+  static_assert(BN == 16 || BN == 32 || BN == 64 || BN == 128 || BN == 256, "tile width");
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint32_t* staging = reinterpret_cast<uint32_t*>(smem + kStages * Cfg::kStageBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(staging) + Cfg::kStagingBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kStages;
+  uint64_t* tfull_bar = bars + 2 * kStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], kGather ? 1 + kVocGatherThreads : 1);   // B by TMA (+ one arrival per gathering thread)
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], kEpiWarps);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  // the generator is a chain of ~100 short launches: overlap this grid's prologue with the previous grid's tail
+  griddep_launch();
+  griddep_wait();
+
+  const int num_tiles = sh.B * sh.m_tiles_per_row * sh.n_tiles;
+  const int k_blocks = sh.tap_groups * sh.cc_blocks;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int n_tile = tile % sh.n_tiles, m_tile = tile / sh.n_tiles;
+        const int b = m_tile / sh.m_tiles_per_row;
+        const int t0 = (m_tile - b * sh.m_tiles_per_row) * kBlockM;
+        for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+          const uint32_t stage = it % kStages, parity = (it / kStages) & 1u;
+          mbar_wait(&empty_bar[stage], parity ^ 1u, 1);
+          uint8_t* sa = smem + stage * Cfg::kStageBytes;
+          const int tg = kb / sh.cc_blocks, cc = kb - tg * sh.cc_blocks;
+          if constexpr (kGather) {
+            mbar_arrive_expect_tx(&full_bar[stage], Cfg::kBBytes);
+          } else {
+            mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+            tma_load_4d(sa, &tmA, &full_bar[stage], cc * kBlockK, tg * sh.g, t0, b);
+          }
+          tma_load_2d(sa + Cfg::kABytes, &tmB, &full_bar[stage], kb * kBlockK, n_tile * BN);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      uint32_t it = 0, ti = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
+        const uint32_t as = ti & 1u, aph = (ti >> 1) & 1u;
+        mbar_wait(&tempty_bar[as], aph ^ 1u, 2);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+          const uint32_t stage = it % kStages, parity = (it / kStages) & 1u;
+          mbar_wait(&full_bar[stage], parity, 3);
+          if constexpr (kGather) fence_proxy_async_smem();   // the A tile was written through the generic proxy (cp.async)
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint64_t adesc = make_sw128_kmajor_desc(sa);
+          const uint64_t bdesc = make_sw128_kmajor_desc(sa + Cfg::kABytes);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k)
+            umma_f16(d_tmem, desc_advance_k(adesc, k), desc_advance_k(bdesc, k), sh.idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit(&empty_bar[stage]);
+        }
+        umma_commit(&tfull_bar[as]);
+      }
+    }
+  } else if (warp >= 2 + kEpiWarps) {
+    // ===================== gather producers (C < 64): thread tau builds row tau of every A tile =====================
+    if constexpr (kGather) {
+      const int tau = (int)threadIdx.x - kGemmThreads;
+      const int C = sh.a_C, half = (sh.a_taps - 1) / 2;
+      const int cshift = C == 16 ? 1 : 2;                 // 16-byte chunks per tap piece: C / 8
+      const long long pitch = (long long)(sh.T + 2 * sh.a_G) * C;
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_tile = tile / sh.n_tiles;
+        const int b = m_tile / sh.m_tiles_per_row;
+        const int pos = (m_tile - b * sh.m_tiles_per_row) * kBlockM + tau;
+        const bool in_utt = pos < sh.T;
+        const __half* rowp = sh.a_ptr + (long long)b * pitch + (long long)(sh.a_G + pos) * C;
+        for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+          const uint32_t stage = it % kStages, parity = (it / kStages) & 1u;
+          mbar_wait(&empty_bar[stage], parity ^ 1u, 5);
+          const uint32_t dst_row = smem_u32(smem + stage * Cfg::kStageBytes) + (uint32_t)tau * 128u;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int tap = kb * sh.g + (j >> cshift);
+            const bool ok = in_utt && tap < sh.a_taps;
+            const __half* src = rowp + (long long)(tap - half) * sh.a_dil * C + ((j & ((1 << cshift) - 1)) << 3);
+            voc_cp_async16(dst_row + (uint32_t)((j ^ (tau & 7)) << 4), ok ? (const void*)src : (const void*)sh.a_ptr, ok);
+          }
+          voc_cp_async_arrive(&full_bar[stage]);
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const int q = warp & 3, h = (warp - 2) >> 2;
+    uint32_t* stg = staging + (warp - 2) * (32 * RW);
+    constexpr int LPR = CW / 8;            // lanes per row segment (16 bytes each)
+    constexpr int RPI = 32 / LPR;          // rows per warp-wide access
+    constexpr int kChunks = BN >= 64 ? (BN / 2) / 32 : 1;
+    const bool works = BN >= 64 || h == 0;  // narrow tiles: one warp per lane quadrant takes all BN columns
+    uint32_t ti = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
+      const int n_tile = tile % sh.n_tiles, m_tile = tile / sh.n_tiles;
+      const int b = m_tile / sh.m_tiles_per_row;
+      const int t0 = (m_tile - b * sh.m_tiles_per_row) * kBlockM;
+      const int t = t0 + q * 32 + lane;                       // this thread's position (accumulator row)
+      const int rows_left = sh.T - (t0 + q * 32);            // rows of this warp's 32-row slab inside the utterance
+      const uint32_t as = ti & 1u, aph = (ti >> 1) & 1u;
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
+      mbar_wait(&tfull_bar[as], aph, 4);
+      tc_fence_after();
+      if (works) {
+#pragma unroll
+        for (int ci = 0; ci < kChunks; ++ci) {
+          const int c = (BN >= 64 ? h * (BN / 2) : 0) + ci * CW;   // first column of this chunk inside the tile
+          const int gcol = n_tile * BN + c;
+          uint32_t r[CW];
+          if constexpr (CW == 32) tmem_ld_x32(trow + c, r);
+          else tmem_ld_x16(trow + c, reinterpret_cast<uint32_t (&)[16]>(r));
+          tmem_ld_wait();
+          float v[CW];
+#pragma unroll
+          for (int j = 0; j < CW; j += 4) {
+            const float4 bv = __ldg(reinterpret_cast<const float4*>(ep.bias + gcol + j));
+            v[j] = __uint_as_float(r[j]) + bv.x;
+            v[j + 1] = __uint_as_float(r[j + 1]) + bv.y;
+            v[j + 2] = __uint_as_float(r[j + 2]) + bv.z;
+            v[j + 3] = __uint_as_float(r[j + 3]) + bv.w;
+          }
+          // 16-bit side inputs: the [32 rows x CW] block arrives as full row segments and is read back one row per thread
+          auto add_side = [&](const __half* src, long long bstride, int ld, bool unact) {
+            const __half* base = src + (long long)b * bstride + (long long)(t0 + q * 32) * ld + gcol;
+#pragma unroll
+            for (int i = 0; i < 32 / RPI; ++i) {
+              const int rrow = i * RPI + lane / LPR, c8 = lane % LPR;
+              uint4 w = make_uint4(0u, 0u, 0u, 0u);
+              if (rrow < rows_left) w = *reinterpret_cast<const uint4*>(base + (long long)rrow * ld + 8 * c8);
+              *reinterpret_cast<uint4*>(stg + rrow * RW + 4 * c8) = w;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < CW; j += 8) {
+              const uint4 w = *reinterpret_cast<const uint4*>(stg + lane * RW + j / 2);
+              const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                float2 f = Cvt<__half>::unpack(ww[u]);
+                if (unact) {
+                  f.x = f.x >= 0.f ? f.x : f.x * ep.res_inv_slope;
+                  f.y = f.y >= 0.f ? f.y : f.y * ep.res_inv_slope;
+                }
+                v[j + 2 * u] += f.x;
+                v[j + 2 * u + 1] += f.y;
+              }
+            }
+            __syncwarp();
+          };
+          if (ep.res16 != nullptr) add_side(ep.res16, ep.res_bstride, ep.res_ld, true);
+          if (ep.add16 != nullptr) add_side(ep.add16, ep.add_bstride, ep.add_ld, false);
+#pragma unroll
+          for (int j = 0; j < CW; ++j) {
+            float x = v[j] * ep.scale;
+            if (ep.act == 1) x = x >= 0.f ? x : x * ep.slope;
+            else if (ep.act == 2) x = tanhf(x);
+            v[j] = x;
+          }
+          if (ep.out32 != nullptr) {
+            if (gcol == 0 && t < sh.T) ep.out32[(long long)b * sh.T + t] = v[0];
+          } else {
+#pragma unroll
+            for (int j = 0; j < CW; j += 8)
+              *reinterpret_cast<uint4*>(stg + lane * RW + j / 2) =
+                  make_uint4(Cvt<__half>::pack(v[j], v[j + 1]), Cvt<__half>::pack(v[j + 2], v[j + 3]),
+                             Cvt<__half>::pack(v[j + 4], v[j + 5]), Cvt<__half>::pack(v[j + 6], v[j + 7]));
+            __syncwarp();
+            __half* base = ep.out16 + (long long)b * ep.out_bstride + (long long)(t0 + q * 32) * ep.out_ld + gcol;
+#pragma unroll
+            for (int i = 0; i < 32 / RPI; ++i) {
+              const int rrow = i * RPI + lane / LPR, c8 = lane % LPR;
+              if (rrow < rows_left)
+                *reinterpret_cast<uint4*>(base + (long long)rrow * ep.out_ld + 8 * c8) = *reinterpret_cast<const uint4*>(stg + rrow * RW + 4 * c8);
+            }
+            __syncwarp();
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------ weight packing
+// Conv1d weight [Cout, Cin, k] fp32 -> [Cout rows (zero rows up to n_pad)][K = tap * Cin + c, taps padded to taps_pad] fp16.
+__global__ void k_voc_pack_conv(__half* __restrict__ dst, const float* __restrict__ src, int Cout, int Cin, int k, int n_pad, int taps_pad) {
+  const long long total = (long long)n_pad * taps_pad * Cin;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / ((long long)taps_pad * Cin));
+    const int rem = (int)(i - (long long)r * taps_pad * Cin);
+    const int tap = rem / Cin, c = rem - tap * Cin;
+    const float v = (r < Cout && tap < k) ? src[((long long)r * Cin + c) * k + tap] : 0.f;
+    dst[i] = __float2half_rn(v);
+  }
+}
+// ConvTranspose1d weight [Cin, Cout, k = 2s] (stride s, padding s / 2) -> the equivalent 3-tap convolution with
+// N = s * Cout rows: row (phase r, co), tap j in {0, 1, 2} = input position q - 1 + j for output position q * s + r:
+//   out[q * s + r] = sum over i, kk with i * s - s/2 + kk = q * s + r  of  x[i] . W[:, :, kk]   ->  kk = r + s/2 - (j - 1) * s.
+__global__ void k_voc_pack_convT(__half* __restrict__ dst, const float* __restrict__ src, int Cin, int Cout, int s, int taps_pad) {
+  const int k = 2 * s;
+  const long long total = (long long)s * Cout * taps_pad * Cin;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int row = (int)(i / ((long long)taps_pad * Cin));
+    const int rem = (int)(i - (long long)row * taps_pad * Cin);
+    const int j = rem / Cin, c = rem - j * Cin;
+    const int r = row / Cout, co = row - r * Cout;
+    const int kk = r + s / 2 - (j - 1) * s;
+    const float v = (j < 3 && kk >= 0 && kk < k) ? src[((long long)c * Cout + co) * k + kk] : 0.f;
+    dst[i] = __float2half_rn(v);
+  }
+}
+// the bias of a transposed conv repeated per phase: [s * Cout]
+__global__ void k_voc_tile_bias(float* __restrict__ dst, const float* __restrict__ src, int Cout, int n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = src[i % Cout];
+}
+__global__ void k_voc_pad_bias(float* __restrict__ dst, const float* __restrict__ src, int n_src, int n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = i < n_src ? src[i] : 0.f;
+}
+
+// ------------------------------------------------------------------ generator input / harmonic source
+// c [B, M, T] fp32 (the sampler's hand-off tensor, nsf_hifigan.py:50-52) -> guarded channels-last fp16 [B][G + T + G][M]
+__global__ void k_voc_mel_in(__half* __restrict__ dst, const float* __restrict__ c, int M, int Tn, int G) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, m0 = blockIdx.y * 32, t0 = blockIdx.x * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+  for (int i = ty; i < 32; i += 8) {
+    const int m = m0 + i, t = t0 + tx;
+    tile[i][tx] = (m < M && t < Tn) ? c[((long long)b * M + m) * Tn + t] : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int t = t0 + i, m = m0 + tx;
+    if (t < Tn && m < M) dst[((long long)b * (Tn + 2 * G) + G + t) * M + m] = __float2half_rn(tile[tx][i]);
+  }
+}
+
+constexpr int kVocHarm = 9;   // fundamental + 8 overtones (models.py:219, harmonic_num = 8)
+
+// SineGen phase bookkeeping (models.py:138-170).  The reference integrates the per-sample phase increment
+// rad = frac(f0 * (h + 1) / sr) -- constant over the `upp` samples of a frame, plus rand_ini on the whole first frame --
+// with a float64 cumsum over samples and adds whole turns wherever a wrapped copy of the phase steps back; whole turns do
+// not change sin(2 pi phase), so the phase of sample j of frame f is  P[f] + (j + 1) * rad[f]  with the frame-level
+// exclusive sum P[f] = upp * sum_{f' < f} rad[f'] (float64, reduced mod 1).  One thread per (utterance, harmonic).
+__global__ void k_voc_phase(double* __restrict__ P, float* __restrict__ rad_out, const float* __restrict__ f0, const float* __restrict__ rand_ini,
+                            int B, int Tn, int upp, float sr) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * kVocHarm) return;
+  const int b = idx / kVocHarm, h = idx - b * kVocHarm;
+  double acc = 0.0;
+  for (int f = 0; f < Tn; ++f) {
+    const float fn = f0[(long long)b * Tn + f] * (float)(h + 1);
+    float rad = fmodf(fn / sr, 1.f);
+    if (f == 0) rad += rand_ini[h];
+    P[((long long)b * Tn + f) * kVocHarm + h] = acc;
+    rad_out[((long long)b * Tn + f) * kVocHarm + h] = rad;
+    acc += (double)upp * (double)rad;
+    acc -= floor(acc);
+  }
+}
+
+// har_source[b, n] = tanh(l_linear(sine_waves * uv + noise)) (models.py:171-216): sine = sin(2 pi phase) * sine_amp,
+// uv = f0 > 0, noise = (uv * noise_std + (1 - uv) * sine_amp / 3) * randn.  noise_in: optional injected N(0,1) draws
+// [B, T * upp, 9] (parity tests); nullptr = in-kernel Philox.  One thread per sample.
+__global__ void k_voc_source(float* __restrict__ har, const double* __restrict__ P, const float* __restrict__ rad, const float* __restrict__ f0,
+                             const float* __restrict__ noise_in, const float* __restrict__ w_lin, const float* __restrict__ b_lin,
+                             int Tn, int upp, long long total, float sine_amp, float noise_std, unsigned long long seed) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long fr = i / upp;               // b * T + f
+    const int j = (int)(i - fr * upp);
+    const float uv = f0[fr] > 0.f ? 1.f : 0.f;
+    const float namp = uv * noise_std + (1.f - uv) * sine_amp / 3.f;
+    float nz[12];
+    if (noise_in != nullptr) {
+#pragma unroll
+      for (int h = 0; h < kVocHarm; ++h) nz[h] = noise_in[i * kVocHarm + h];
+    } else {
+#pragma unroll
+      for (int g4 = 0; g4 < 3; ++g4) {
+        const float4 n4 = philox_normal4(seed, 0x564f43u + g4, (uint32_t)i, (uint32_t)(i >> 32));
+        nz[4 * g4] = n4.x; nz[4 * g4 + 1] = n4.y; nz[4 * g4 + 2] = n4.z; nz[4 * g4 + 3] = n4.w;
+      }
+    }
+    float acc = b_lin[0];
+#pragma unroll
+    for (int h = 0; h < kVocHarm; ++h) {
+      double ph = P[fr * kVocHarm + h] + (double)(j + 1) * (double)rad[fr * kVocHarm + h];
+      ph -= floor(ph);
+      const float s = sinf((float)(ph * 6.283185307179586476925)) * sine_amp;
+      acc = fmaf(w_lin[h], s * uv + namp * nz[h], acc);
+    }
+    har[i] = tanhf(acc);
+  }
+}
+
+// noise_convs[i] (models.py:233-238, :276): x_source[b, o, c] = bias[c] + sum_kk W[c, kk] * har[b, o * stride - pad + kk], zero
+// padded, written raw as fp16 in the up-sampled tensor's guarded layout (it is the `add16` input of the transposed conv's
+// epilogue).  Block: 64 output positions x all C channels; the har window sits in shared memory.
+__global__ void k_voc_srcconv(__half* __restrict__ dst, const float* __restrict__ har, const float* __restrict__ w, const float* __restrict__ bias,
+                              int C, int k, int stride, int pad, int To, long long Lh, int G) {
+  extern __shared__ float s_h[];   // 63 * stride + k samples
+  const int b = blockIdx.y, o0 = blockIdx.x * 64;
+  const int win = 63 * stride + k;
+  const long long h0 = (long long)o0 * stride - pad;
+  for (int i = threadIdx.x; i < win; i += blockDim.x) {
+    const long long n = h0 + i;
+    s_h[i] = (n >= 0 && n < Lh) ? har[(long long)b * Lh + n] : 0.f;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < 64 * C; e += blockDim.x) {
+    const int o = e / C, c = e - o * C;
+    if (o0 + o >= To) continue;
+    float acc = bias[c];
+    const float* wr = w + (long long)c * k;
+    const float* hp = s_h + o * stride;
+    for (int kk = 0; kk < k; ++kk) acc = fmaf(__ldg(wr + kk), hp[kk], acc);
+    dst[((long long)b * (To + 2 * G) + G + o0 + o) * C + c] = __float2half_rn(acc);
+  }
+}
+
+// zero a guarded activation buffer's guard rows ([B][G + T + G][C]): front and back G rows of every utterance
+__global__ void k_voc_zero_guards(__half* __restrict__ buf, int Tn, int C, int G, int B) {
+  const long long per = 2ll * G * C;
+  const long long total = per * B;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / per);
+    const long long r = i - (long long)b * per;
+    const long long row = r / C, c = r - row * C;
+    const long long prow = row < G ? row : (long long)Tn + row;   // rows [0, G) and [G + T, G + T + G)
+    buf[((long long)b * (Tn + 2 * G) + prow) * C + c] = __float2half_rn(0.f);
+  }
+}
+
+}  // namespace pd
