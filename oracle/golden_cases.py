@@ -109,3 +109,23 @@ ENCODER_CASES = {
     # shorter than the conv kernel
     "tiny": dict(cfg=EncoderConfig(30, 256, 1, 9, 2), Tph=5, lengths=[5, 3], extra=True, wseed=125, iseed=126),
 }
+
+
+# NSF-HiFiGAN generator (modules/nsf_hifigan/models.py:269-290).  ``h`` = the config.json fields the reference
+# constructor reads; rand_ini and the SineGen noise are injected in place of torch.rand / torch.randn_like (models.py:143,186).
+# B = 1 everywhere: the reference's SineGen only takes one utterance per call (models.py:163).
+VOCODER_CASES = {
+    # every tile width of the conv kernel: stages of 128 / 64 / 32 / 16 channels, rate-2 up-sampling (kernel 4)
+    "ladder": dict(h=dict(resblock="1", num_mels=128, sampling_rate=44100, upsample_rates=[2, 2, 2, 2],
+                          upsample_kernel_sizes=[4, 4, 4, 4], upsample_initial_channel=256, resblock_kernel_sizes=[3, 7, 11],
+                          resblock_dilation_sizes=[[1, 3, 5], [1, 3, 5], [1, 3, 5]]), B=1, T=150, wseed=201, iseed=202),
+    # rate-8 up-sampling (kernel 16) into 64 and 32 channels, two resblock kernels, 64 mel bins
+    "rate8": dict(h=dict(resblock="1", num_mels=64, sampling_rate=22050, upsample_rates=[8, 2], upsample_kernel_sizes=[16, 4],
+                         upsample_initial_channel=128, resblock_kernel_sizes=[3, 11],
+                         resblock_dilation_sizes=[[1, 3, 5], [1, 2, 4]]), B=1, T=70, wseed=203, iseed=204),
+    # the 44.1 kHz configuration (512 samples per frame), one short utterance; a single resblock kernel exercises the
+    # no-running-sum path
+    "full44k_short": dict(h=dict(resblock="1", num_mels=128, sampling_rate=44100, upsample_rates=[8, 8, 2, 2, 2],
+                                 upsample_kernel_sizes=[16, 16, 4, 4, 4], upsample_initial_channel=512,
+                                 resblock_kernel_sizes=[7], resblock_dilation_sizes=[[1, 3, 5]]), B=1, T=9, wseed=205, iseed=206),
+}

@@ -193,10 +193,75 @@ def run_reference_encoder(case):
     return dict(out=out.contiguous().numpy(), digest=np.array(synth.digest(state, tok.float(), extra)))
 
 
+def load_reference_generator():
+    """The reference's NSF-HiFiGAN ``Generator`` class (models.py:209).  nsf_hifigan/utils.py imports matplotlib at module
+    level (absent here, unused by the generator): stub it."""
+    import types
+    load_reference()
+    if "matplotlib" not in sys.modules:
+        mpl = types.ModuleType("matplotlib")
+        mpl.use = lambda *a, **k: None
+        sys.modules["matplotlib"] = mpl
+    from modules.nsf_hifigan.models import Generator      # noqa
+    from modules.nsf_hifigan.env import AttrDict           # noqa
+    return Generator, AttrDict
+
+
+def build_reference_generator(h, state):
+    """Construct the unmodified reference generator, fold its weight norm (what load_model does, models.py:33) and load the
+    seeded plain weights."""
+    Generator, AttrDict = load_reference_generator()
+    _print = __builtins__["print"] if isinstance(__builtins__, dict) else __builtins__.print
+    gen = Generator(AttrDict(h)).eval()
+    gen.remove_weight_norm()
+    missing = gen.load_state_dict(state, strict=True)
+    for p in gen.parameters():
+        p.requires_grad_(False)
+    return gen
+
+
+class injected_sinegen_randomness:
+    """Patch torch.rand / torch.randn_like for one Generator.forward: SineGen draws rand_ini with torch.rand(1, dim, device=...)
+    (models.py:143) and the additive noise with torch.randn_like(sine_waves) (:186)."""
+
+    def __init__(self, rand_ini, noise):
+        self.rand_ini, self.noise = rand_ini, noise
+
+    def __enter__(self):
+        self._rand, self._randn_like = torch.rand, torch.randn_like
+
+        def rand(*shape, **kw):
+            assert tuple(shape) == tuple(self.rand_ini.shape), shape
+            return self.rand_ini.clone()
+
+        def randn_like(t, **kw):
+            assert tuple(t.shape) == tuple(self.noise.shape), (t.shape, self.noise.shape)
+            return self.noise.clone()
+
+        torch.rand, torch.randn_like = rand, randn_like
+        return self
+
+    def __exit__(self, *a):
+        torch.rand, torch.randn_like = self._rand, self._randn_like
+
+
+def run_reference_vocoder(case):
+    from prodiff_b200 import synth
+    h = case["h"]
+    state = synth.make_vocoder_state(h, case["wseed"])
+    c, f0, rand_ini, noise = synth.make_vocoder_inputs(h, case["B"], case["T"], case["iseed"])
+    gen = build_reference_generator(h, state)
+    with torch.no_grad(), injected_sinegen_randomness(rand_ini, noise):
+        wav = gen(c, f0)
+    return dict(wav=wav.contiguous().numpy(), digest=np.array(synth.digest(state, c, f0, rand_ini, noise)))
+
+
 def main():
-    from oracle.golden_cases import SAMPLE_CASES, DENOISE_CASES, REFLOW_CASES, CONDITION_CASES, ENCODER_CASES
+    from oracle.golden_cases import SAMPLE_CASES, DENOISE_CASES, REFLOW_CASES, CONDITION_CASES, ENCODER_CASES, VOCODER_CASES
+    if "--vocoder-only" in sys.argv:
+        SAMPLE_CASES, DENOISE_CASES, REFLOW_CASES, CONDITION_CASES, ENCODER_CASES = {}, {}, {}, {}, {}
     if "--encoder-only" in sys.argv:
-        SAMPLE_CASES, DENOISE_CASES, REFLOW_CASES, CONDITION_CASES = {}, {}, {}, {}
+        SAMPLE_CASES, DENOISE_CASES, REFLOW_CASES, CONDITION_CASES, VOCODER_CASES = {}, {}, {}, {}, {}
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     out_dir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
@@ -220,6 +285,10 @@ def main():
         r = run_reference_encoder(case)
         np.savez(os.path.join(out_dir, f"encoder_{name}.npz"), **r)
         print(f"encoder_{name}: out {r['out'].shape} |out|max {np.abs(r['out']).max():.3f}")
+    for name, case in VOCODER_CASES.items():
+        r = run_reference_vocoder(case)
+        np.savez_compressed(os.path.join(out_dir, f"vocoder_{name}.npz"), **r)
+        print(f"vocoder_{name}: wav {r['wav'].shape} |wav|max {np.abs(r['wav']).max():.3f} std {r['wav'].std():.3f}")
 
 
 if __name__ == "__main__":

@@ -9,6 +9,7 @@ Public surface (mirrors the reference's module API for this path, SURVEY.md sect
         .forward(cond, gt_spec=None, infer_step=20, infer=True)          (PitchRectifiedFlow likewise)
     FastspeechEncoder(vocab_size, hidden_size, num_layers, kernel_size, dropout, num_heads, rel_pos)
         .forward(txt_tokens, extra_embed=None)                           (the step before the sampler)
+    Generator(h).forward(x, f0)                                          (the NSF-HiFiGAN generator after it)
 
 ``install()`` swaps these classes into the reference's own modules so that ``ProDiffTeacher``, the SVS inferer
 (``handler/infer/handler.py``), ``main.py infer`` and the vocoder hand-off run unchanged on top of them.
@@ -18,6 +19,7 @@ from .diffusion import GaussianDiffusion
 from .reflow import RectifiedFlow, PitchRectifiedFlow
 from .conditioning import AssembledCondition, forward_condition
 from .encoder import FastspeechEncoder
+from .vocoder import Generator
 from .synth import DiffNetConfig
 
 __version__ = "0.1.0"
@@ -35,8 +37,13 @@ def install():
     rf.PitchRectifiedFlow = PitchRectifiedFlow
     tm = importlib.import_module("modules.fastspeech.tts_modules")   # prodiff_teacher.py:8 imports the name from here
     tm.FastspeechEncoder = FastspeechEncoder
+    try:   # load_model (models.py:21-36) then builds, loads (weight-normed keys) and "un-norms" the replacement class
+        voc = importlib.import_module("modules.nsf_hifigan.models")
+        voc.Generator = Generator
+    except ImportError:   # the reference's nsf_hifigan package needs matplotlib at import time (utils.py:1-3)
+        pass
     return wn, gd
 
 
-__all__ = ["WaveNet", "GaussianDiffusion", "RectifiedFlow", "PitchRectifiedFlow", "FastspeechEncoder", "AssembledCondition", "forward_condition",
+__all__ = ["WaveNet", "GaussianDiffusion", "RectifiedFlow", "PitchRectifiedFlow", "FastspeechEncoder", "Generator", "AssembledCondition", "forward_condition",
            "DiffNetConfig", "install"]

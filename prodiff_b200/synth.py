@@ -156,3 +156,58 @@ def make_encoder_inputs(cfg: EncoderConfig, lengths, Tph: int, seed: int = 4321)
         tok[b, :n] = rng.integers(1, cfg.vocab_size, size=n)
     extra = (0.3 * rng.standard_normal((B, Tph, cfg.hidden_size))).astype(np.float32)
     return torch.from_numpy(tok), torch.from_numpy(extra)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# NSF-HiFiGAN generator: the fields of the checkpoint's config.json that ``Generator.__init__`` reads
+# (`/root/reference/modules/nsf_hifigan/models.py:210-267`) and seeded weights under the reference's ``state_dict`` keys
+# after ``remove_weight_norm()``.  The reference initialises its convs with N(0, 0.01) (`nsf_hifigan/utils.py:6-9`), which
+# leaves a freshly built generator with activations ~1e-3 and a waveform that is all bias; the synthetic state uses
+# fan-in-scaled weights instead so that every stage carries O(1) signal and the output tanh is driven over its range.
+VOCODER_44K = dict(resblock="1", num_mels=128, sampling_rate=44100, upsample_rates=[8, 8, 2, 2, 2],
+                   upsample_kernel_sizes=[16, 16, 4, 4, 4], upsample_initial_channel=512,
+                   resblock_kernel_sizes=[3, 7, 11], resblock_dilation_sizes=[[1, 3, 5], [1, 3, 5], [1, 3, 5]])
+
+
+def make_vocoder_state(h: dict, seed: int = 1234) -> Dict[str, torch.Tensor]:
+    rng = np.random.default_rng(seed)
+    st: Dict[str, np.ndarray] = {}
+    nrm = lambda shape, std: (rng.standard_normal(shape) * std).astype(np.float32)
+    c0, rates, ksz = h["upsample_initial_channel"], h["upsample_rates"], h["upsample_kernel_sizes"]
+    st["conv_pre.weight"] = nrm((c0, h["num_mels"], 7), 1.0 / np.sqrt(h["num_mels"] * 7))
+    st["conv_pre.bias"] = nrm((c0,), 0.1)
+    ch = c0
+    for i, (u, k) in enumerate(zip(rates, ksz)):
+        st[f"ups.{i}.weight"] = nrm((ch, ch // 2, k), 1.0 / np.sqrt(ch * k / u))      # k / u taps reach each output sample
+        st[f"ups.{i}.bias"] = nrm((ch // 2,), 0.1)
+        ch //= 2
+        sk = 2 * int(np.prod(rates[i + 1:])) if i + 1 < len(rates) else 1
+        st[f"noise_convs.{i}.weight"] = nrm((ch, 1, sk), 1.0 / np.sqrt(sk))
+        st[f"noise_convs.{i}.bias"] = nrm((ch,), 0.1)
+        for j, rk in enumerate(h["resblock_kernel_sizes"]):
+            p = f"resblocks.{i * len(h['resblock_kernel_sizes']) + j}"
+            for d in range(3):
+                for cv in ("convs1", "convs2"):
+                    st[f"{p}.{cv}.{d}.weight"] = nrm((ch, ch, rk), 0.6 / np.sqrt(ch * rk))
+                    st[f"{p}.{cv}.{d}.bias"] = nrm((ch,), 0.05)
+    st["conv_post.weight"] = nrm((1, ch, 7), 1.0 / np.sqrt(ch * 7))
+    st["conv_post.bias"] = nrm((1,), 0.1)
+    st["m_source.l_linear.weight"] = nrm((1, 9), 1.0 / 3.0 / 0.1)     # sine amplitudes are 0.1: keep the tanh input O(1)
+    st["m_source.l_linear.bias"] = nrm((1,), 0.1)
+    return {k_: torch.from_numpy(v) for k_, v in st.items()}
+
+
+def make_vocoder_inputs(h: dict, lengths_or_B, T: int, seed: int = 4321):
+    """c [B, num_mels, T] (the hand-off tensor: natural-log mel, roughly N(-5, 2)), f0 [B, T] Hz with unvoiced (0) stretches,
+    rand_ini [1, 9] (entry 0 zero, models.py:143-144) and noise [B, T * upp, 9] ~ N(0,1)."""
+    rng = np.random.default_rng(seed)
+    B = int(lengths_or_B)
+    upp = int(np.prod(h["upsample_rates"]))
+    c = (rng.standard_normal((B, h["num_mels"], T)) * 2.0 - 5.0).astype(np.float32)
+    f0 = (220.0 * 2.0 ** (rng.uniform(-1.0, 1.5, size=(B, 1)) + 0.3 * np.sin(np.arange(T)[None, :] / 9.0 + rng.uniform(0, 6, size=(B, 1))))).astype(np.float32)
+    voiced = (np.sin(np.arange(T)[None, :] / 5.0 + rng.uniform(0, 6, size=(B, 1))) > -0.4)
+    f0 = np.where(voiced, f0, 0.0).astype(np.float32)
+    rand_ini = rng.uniform(0, 1, size=(1, 9)).astype(np.float32)
+    rand_ini[:, 0] = 0
+    noise = rng.standard_normal((B, T * upp, 9)).astype(np.float32)
+    return torch.from_numpy(c), torch.from_numpy(f0), torch.from_numpy(rand_ini), torch.from_numpy(noise)
