@@ -14,8 +14,8 @@
 //   TMA cannot build that tile (with the 128-byte swizzle every box row shorter than 128 bytes is padded to a full
 //   swizzle row -- measured, tools/voc_probe.py), so four extra producer warps gather it: one thread per position copies
 //   its g pieces of C channels with 16-byte cp.async straight into the swizzled rows (chunk j of row r at (j ^ (r & 7))),
-//   completion signalled on the stage's mbarrier (cp.async.mbarrier.arrive.noinc); the MMA issuer adds the generic ->
-//   async proxy fence.  Consecutive lanes read consecutive positions, i.e. contiguous memory.  That keeps the narrow
+//   then -- a few K blocks later, so the copies stay in flight -- waits for its own copies, issues the generic -> async
+//   proxy fence and arrives on the stage's mbarrier.  Consecutive lanes read consecutive positions, i.e. contiguous memory.  That keeps the narrow
 //   stages on the tensor cores without padding their channels to 64; taps past the kernel size are zero-filled.
 // * The weights are packed [N][K] with K = tap * C + c (taps padded to a multiple of g with zeros), 2-D map, (64, BN) box.
 // * A transposed convolution with kernel 2s and stride s is a 3-tap convolution with N = s * C_out whose output row of
@@ -67,11 +67,6 @@ __device__ __forceinline__ void voc_cp_async16(uint32_t dst_smem, const void* sr
   const int n = pred ? 16 : 0;   // src-size 0: the 16 bytes are zero-filled
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(n) : "memory");
 }
-// the mbarrier receives one arrival from this thread once all its earlier cp.async have landed (not counted as pending)
-__device__ __forceinline__ void voc_cp_async_arrive(uint64_t* bar) {
-  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
 template <int BN> struct VocCfg {
   static constexpr int kCW = BN >= 64 ? 32 : BN;                  // columns per epilogue chunk
   static constexpr int kRowWords = kCW / 2 + 4;                   // staging row: kCW halves + 16 bytes of padding
@@ -116,7 +111,7 @@ voc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], kEpiWarps);
+      mbar_init(&tempty_bar[i], BN >= 64 ? kEpiWarps : kEpiWarps / 2);   // narrow tiles: one warp group per accumulator stage
     }
     fence_mbar_init();
   }
@@ -165,7 +160,6 @@ voc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int kb = 0; kb < k_blocks; ++kb, ++it) {
           const uint32_t stage = it % kStages, parity = (it / kStages) & 1u;
           mbar_wait(&full_bar[stage], parity, 3);
-          if constexpr (kGather) fence_proxy_async_smem();   // the A tile was written through the generic proxy (cp.async)
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
           const uint64_t adesc = make_sw128_kmajor_desc(sa);
@@ -185,6 +179,11 @@ voc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int C = sh.a_C, half = (sh.a_taps - 1) / 2;
       const int cshift = C == 16 ? 1 : 2;                 // 16-byte chunks per tap piece: C / 8
       const long long pitch = (long long)(sh.T + 2 * sh.a_G) * C;
+      // Completion protocol: a thread's copies of K block i are known to have landed when cp.async.wait_group leaves at most
+      // kLag younger groups pending; it then makes them visible to the async proxy (the tensor core reads shared memory
+      // through it) and arrives on that stage's barrier.  Doing the wait + fence HERE, kLag blocks late and spread over 128
+      // threads, keeps it off the single MMA-issuing thread (where a per-block proxy fence cost ~1000 cycles per K block).
+      constexpr int kLag = kStages >= 6 ? 4 : (kStages >= 4 ? 2 : 1);
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m_tile = tile / sh.n_tiles;
@@ -203,13 +202,112 @@ voc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const __half* src = rowp + (long long)(tap - half) * sh.a_dil * C + ((j & ((1 << cshift) - 1)) << 3);
             voc_cp_async16(dst_row + (uint32_t)((j ^ (tau & 7)) << 4), ok ? (const void*)src : (const void*)sh.a_ptr, ok);
           }
-          voc_cp_async_arrive(&full_bar[stage]);
+          asm volatile("cp.async.commit_group;" ::: "memory");
+          if (it >= (uint32_t)kLag) {
+            asm volatile("cp.async.wait_group %0;" ::"n"(kLag) : "memory");
+            fence_proxy_async_smem();
+            mbar_arrive(&full_bar[(it - kLag) % kStages]);
+          }
         }
       }
+      // drain: the last min(it, kLag) blocks
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      fence_proxy_async_smem();
+      for (uint32_t i = it > (uint32_t)kLag ? it - kLag : 0u; i < it; ++i) mbar_arrive(&full_bar[i % kStages]);
     }
   } else {
     // ===================== epilogue warps =====================
     const int q = warp & 3, h = (warp - 2) >> 2;
+    if constexpr (BN <= 32) {
+      // Narrow tiles (16 / 32 channels): a tile is 128 x BN values and its epilogue is one chain of dependent latencies
+      // (side-input loads -> math -> stores), so the two warp groups each own ONE accumulator stage and work on alternate
+      // tiles, and the side inputs -- which do not depend on the accumulator -- are fetched before the MMA wait.  A row is
+      // BN * 2 <= 64 contiguous bytes and consecutive rows are adjacent, so row-per-thread vector access is coalesced as is.
+      constexpr int NV = BN / 8;                       // uint4 per row
+      uint32_t ti = (uint32_t)h;
+      for (int tile = blockIdx.x + h * (int)gridDim.x; tile < num_tiles; tile += 2 * (int)gridDim.x, ti += 2) {
+        const int n_tile = tile % sh.n_tiles, m_tile = tile / sh.n_tiles;
+        const int b = m_tile / sh.m_tiles_per_row;
+        const int t = (m_tile - b * sh.m_tiles_per_row) * kBlockM + q * 32 + lane;
+        const bool live = t < sh.T;
+        const int gcol = n_tile * BN;
+        const uint32_t as = ti & 1u, aph = (ti >> 1) & 1u;
+        uint4 rs[NV], ad[NV];
+        if (live && ep.res16 != nullptr) {
+          const uint4* p = reinterpret_cast<const uint4*>(ep.res16 + (long long)b * ep.res_bstride + (long long)t * ep.res_ld + gcol);
+#pragma unroll
+          for (int j = 0; j < NV; ++j) rs[j] = p[j];
+        }
+        if (live && ep.add16 != nullptr) {
+          const uint4* p = reinterpret_cast<const uint4*>(ep.add16 + (long long)b * ep.add_bstride + (long long)t * ep.add_ld + gcol);
+#pragma unroll
+          for (int j = 0; j < NV; ++j) ad[j] = p[j];
+        }
+        mbar_wait(&tfull_bar[as], aph, 4);
+        tc_fence_after();
+        uint32_t r[BN];
+        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
+        if constexpr (BN == 32) tmem_ld_x32(trow, r);
+        else tmem_ld_x16(trow, r);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[as]);    // the accumulator is in registers: hand the stage back early
+        if (live) {
+          float v[BN];
+#pragma unroll
+          for (int j = 0; j < BN; j += 4) {
+            const float4 bv = __ldg(reinterpret_cast<const float4*>(ep.bias + gcol + j));
+            v[j] = __uint_as_float(r[j]) + bv.x;
+            v[j + 1] = __uint_as_float(r[j + 1]) + bv.y;
+            v[j + 2] = __uint_as_float(r[j + 2]) + bv.z;
+            v[j + 3] = __uint_as_float(r[j + 3]) + bv.w;
+          }
+          if (ep.res16 != nullptr) {
+#pragma unroll
+            for (int j = 0; j < NV; ++j) {
+              const uint32_t ww[4] = {rs[j].x, rs[j].y, rs[j].z, rs[j].w};
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                float2 f = Cvt<__half>::unpack(ww[u]);
+                f.x = f.x >= 0.f ? f.x : f.x * ep.res_inv_slope;
+                f.y = f.y >= 0.f ? f.y : f.y * ep.res_inv_slope;
+                v[8 * j + 2 * u] += f.x;
+                v[8 * j + 2 * u + 1] += f.y;
+              }
+            }
+          }
+          if (ep.add16 != nullptr) {
+#pragma unroll
+            for (int j = 0; j < NV; ++j) {
+              const uint32_t ww[4] = {ad[j].x, ad[j].y, ad[j].z, ad[j].w};
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const float2 f = Cvt<__half>::unpack(ww[u]);
+                v[8 * j + 2 * u] += f.x;
+                v[8 * j + 2 * u + 1] += f.y;
+              }
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < BN; ++j) {
+            float x = v[j] * ep.scale;
+            if (ep.act == 1) x = x >= 0.f ? x : x * ep.slope;
+            else if (ep.act == 2) x = tanhf(x);
+            v[j] = x;
+          }
+          if (ep.out32 != nullptr) {
+            if (gcol == 0) ep.out32[(long long)b * sh.T + t] = v[0];
+          } else {
+            uint4* p = reinterpret_cast<uint4*>(ep.out16 + (long long)b * ep.out_bstride + (long long)t * ep.out_ld + gcol);
+#pragma unroll
+            for (int j = 0; j < NV; ++j)
+              p[j] = make_uint4(Cvt<__half>::pack(v[8 * j], v[8 * j + 1]), Cvt<__half>::pack(v[8 * j + 2], v[8 * j + 3]),
+                                Cvt<__half>::pack(v[8 * j + 4], v[8 * j + 5]), Cvt<__half>::pack(v[8 * j + 6], v[8 * j + 7]));
+          }
+        }
+      }
+    } else {
     uint32_t* stg = staging + (warp - 2) * (32 * RW);
     constexpr int LPR = CW / 8;            // lanes per row segment (16 bytes each)
     constexpr int RPI = 32 / LPR;          // rows per warp-wide access
@@ -304,6 +402,7 @@ voc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[as]);
+    }
     }
   }
 
@@ -428,26 +527,46 @@ __global__ void k_voc_source(float* __restrict__ har, const double* __restrict__
 
 // noise_convs[i] (models.py:233-238, :276): x_source[b, o, c] = bias[c] + sum_kk W[c, kk] * har[b, o * stride - pad + kk], zero
 // padded, written raw as fp16 in the up-sampled tensor's guarded layout (it is the `add16` input of the transposed conv's
-// epilogue).  Block: 64 output positions x all C channels; the har window sits in shared memory.
-__global__ void k_voc_srcconv(__half* __restrict__ dst, const float* __restrict__ har, const float* __restrict__ w, const float* __restrict__ bias,
-                              int C, int k, int stride, int pad, int To, long long Lh, int G) {
-  extern __shared__ float s_h[];   // 63 * stride + k samples
-  const int b = blockIdx.y, o0 = blockIdx.x * 64;
-  const int win = 63 * stride + k;
+// epilogue).  wt is the weight TRANSPOSED to [k][C] (k_voc_transpose_src at pack time), so the threads of a warp -- consecutive
+// channels -- read consecutive words, and the har sample is a shared-memory broadcast.  Block: 64 output positions x all C
+// channels, 8 positions per thread at a time (one weight load per 8 FMAs).
+constexpr int kSrcPos = 64;
+__global__ void __launch_bounds__(256)
+k_voc_srcconv(__half* __restrict__ dst, const float* __restrict__ har, const float* __restrict__ wt, const float* __restrict__ bias,
+              int C, int k, int stride, int pad, int To, long long Lh, int G) {
+  extern __shared__ float s_h[];   // (kSrcPos - 1) * stride + k samples
+  const int b = blockIdx.y, o0 = blockIdx.x * kSrcPos;
+  const int win = (kSrcPos - 1) * stride + k;
   const long long h0 = (long long)o0 * stride - pad;
   for (int i = threadIdx.x; i < win; i += blockDim.x) {
     const long long n = h0 + i;
     s_h[i] = (n >= 0 && n < Lh) ? har[(long long)b * Lh + n] : 0.f;
   }
   __syncthreads();
-  for (int e = threadIdx.x; e < 64 * C; e += blockDim.x) {
-    const int o = e / C, c = e - o * C;
-    if (o0 + o >= To) continue;
-    float acc = bias[c];
-    const float* wr = w + (long long)c * k;
-    const float* hp = s_h + o * stride;
-    for (int kk = 0; kk < k; ++kk) acc = fmaf(__ldg(wr + kk), hp[kk], acc);
-    dst[((long long)b * (To + 2 * G) + G + o0 + o) * C + c] = __float2half_rn(acc);
+  const int c = threadIdx.x % C, pg = threadIdx.x / C, n_pg = blockDim.x / C;   // C divides 256
+  const float bc = bias[c];
+  for (int p0 = pg * 8; p0 < kSrcPos; p0 += n_pg * 8) {
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = bc;
+    const float* hp = s_h + p0 * stride;
+    for (int kk = 0; kk < k; ++kk) {
+      const float w = __ldg(wt + (long long)kk * C + c);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = fmaf(w, hp[i * stride + kk], acc[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int o = o0 + p0 + i;
+      if (o < To) dst[((long long)b * (To + 2 * G) + G + o) * C + c] = __float2half_rn(acc[i]);
+    }
+  }
+}
+// noise_convs weight [C, 1, k] -> [k][C]
+__global__ void k_voc_transpose_src(float* __restrict__ dst, const float* __restrict__ src, int C, int k) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < C * k; i += gridDim.x * blockDim.x) {
+    const int kk = i / C, c = i - kk * C;
+    dst[i] = src[c * k + kk];
   }
 }
 

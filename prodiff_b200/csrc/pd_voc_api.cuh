@@ -116,7 +116,7 @@ struct pd_vocoder {
   VocConv conv_pre, conv_post;
   VocConv ups[kVocMaxUps];
   VocConv res[kVocMaxUps][kVocMaxRes][6];    // [stage][kernel][c1_0, c2_0, c1_1, c2_1, c1_2, c2_2]
-  size_t src_w[kVocMaxUps], src_b[kVocMaxUps];   // fp32 noise_convs weights [C, k] / bias [C]
+  size_t src_w[kVocMaxUps], src_b[kVocMaxUps];   // fp32 noise_convs weights, transposed to [k][C] / bias [C]
   int src_k[kVocMaxUps], src_stride[kVocMaxUps], src_pad[kVocMaxUps];
   size_t lin_w, lin_b;                       // m_source.l_linear
 };
@@ -242,7 +242,8 @@ extern "C" int pd_vocoder_create(const pd_vocoder_config* cfg, const float* cons
     PD_LAUNCH_CHECK("k_voc_pack_convT");
     rc |= make_w_map(&up.tm_w, PD_FP16, pk + up.w_off, up.taps_pad * up.cin, up.n_total, up.bn);
     ch /= 2;
-    PD_CUDA(cudaMemcpyAsync(pk + v->src_w[i], state[si + 2], (size_t)ch * v->src_k[i] * 4, cudaMemcpyDeviceToDevice, s));
+    k_voc_transpose_src<<<blocks((long long)ch * v->src_k[i]), TB, 0, s>>>((float*)(pk + v->src_w[i]), state[si + 2], ch, v->src_k[i]);
+    PD_LAUNCH_CHECK("k_voc_transpose_src");
     PD_CUDA(cudaMemcpyAsync(pk + v->src_b[i], state[si + 3], (size_t)ch * 4, cudaMemcpyDeviceToDevice, s));
     si += 4;
     for (int j = 0; j < cfg->n_resblock_kernels && !rc; ++j) {
@@ -368,8 +369,8 @@ extern "C" int pd_vocoder_forward(pd_vocoder* v, const float* c, const float* f0
     // noise_convs[i](har_source) (:276)
     {
       const int k = v->src_k[i], st = v->src_stride[i];
-      const dim3 grid((unsigned)((To + 63) / 64), B);
-      k_voc_srcconv<<<grid, 256, (63 * st + k) * sizeof(float), s>>>(SRC, har, (const float*)(pk + v->src_w[i]), (const float*)(pk + v->src_b[i]), co, k,
+      const dim3 grid((unsigned)((To + kSrcPos - 1) / kSrcPos), B);
+      k_voc_srcconv<<<grid, 256, ((kSrcPos - 1) * st + k) * sizeof(float), s>>>(SRC, har, (const float*)(pk + v->src_w[i]), (const float*)(pk + v->src_b[i]), co, k,
                                                                        st, v->src_pad[i], (int)To, Lh, G);
       PD_LAUNCH_CHECK("k_voc_srcconv");
     }

@@ -91,10 +91,14 @@ class Generator(nn.Module):
             raise NotImplementedError("prodiff_b200.Generator implements resblock '1' (ResBlock1, models.py:39) only")
         self.num_kernels = len(g("resblock_kernel_sizes"))
         self.num_upsamples = len(g("upsample_rates"))
+        # attribute order = the reference's registration order (models.py:215-262), so state_dict() lists the same keys in
+        # the same order
         self.m_source = _Source()
+        self.noise_convs = nn.ModuleList()
         c0 = g("upsample_initial_channel")
         self.conv_pre = nn.Conv1d(g("num_mels"), c0, 7, 1, padding=3)
-        self.ups, self.noise_convs, self.resblocks = nn.ModuleList(), nn.ModuleList(), nn.ModuleList()
+        self.ups = nn.ModuleList()
+        resblocks = []
         rates = list(g("upsample_rates"))
         ch = c0
         for i, (u, k) in enumerate(zip(rates, g("upsample_kernel_sizes"))):
@@ -106,7 +110,8 @@ class Generator(nn.Module):
             else:
                 self.noise_convs.append(nn.Conv1d(1, ch, kernel_size=1))
             for k2, d in zip(g("resblock_kernel_sizes"), g("resblock_dilation_sizes")):
-                self.resblocks.append(_ResBlock1(ch, k2, d))
+                resblocks.append(_ResBlock1(ch, k2, d))
+        self.resblocks = nn.ModuleList(resblocks)
         self.conv_post = nn.Conv1d(ch, 1, 7, 1, padding=3)
         for m in list(self.ups) + [self.conv_post]:
             m.weight.data.normal_(0.0, 0.01)             # init_weights (nsf_hifigan/utils.py:6-9), as models.py:264-265

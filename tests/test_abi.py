@@ -109,6 +109,38 @@ def test_encoder_config_validation_without_gpu(lib):
     assert lib.pd_encoder_forward(None, None, None, None, 1, 1, None, 0, None) != 0 and b"null argument" in lib.pd_last_error()
 
 
+def test_vocoder_config_validation_without_gpu(lib):
+    """pd_vocoder_* argument checks that run before anything touches a device (include/prodiff_b200.h, NSF-HiFiGAN generator)."""
+    from prodiff_b200 import _lib
+
+    def cfg(rates=(8, 8, 2, 2, 2), ks=(16, 16, 4, 4, 4), c0=512, mels=128, rk=(3, 7, 11), rd=((1, 3, 5),) * 3, rb=1):
+        c = _lib.pd_vocoder_config()
+        c.num_mels, c.upsample_initial_channel, c.n_upsamples, c.n_resblock_kernels = mels, c0, len(rates), len(rk)
+        for i, (u, k) in enumerate(zip(rates, ks)):
+            c.upsample_rates[i], c.upsample_kernel_sizes[i] = u, k
+        for j, (k, d) in enumerate(zip(rk, rd)):
+            c.resblock_kernel_sizes[j] = k
+            for q in range(3):
+                c.resblock_dilation_sizes[j][q] = d[q]
+        c.resblock_type, c.sampling_rate = rb, 44100
+        return c
+
+    ok = cfg()
+    assert lib.pd_vocoder_state_count(C.byref(ok)) == 2 + 5 * (4 + 3 * 12) + 4
+    n = lib.pd_vocoder_packed_bytes(C.byref(ok))
+    assert 20e6 < n < 40e6        # ~14 M weights as fp16 (transposed convs carry one third zeros) + biases
+    for bad, word in ((cfg(ks=(15, 16, 4, 4, 4)), b"kernel"), (cfg(c0=500), b"upsample_initial_channel"), (cfg(mels=80), b"num_mels"),
+                      (cfg(rb=2), b"resblock"), (cfg(rk=(3, 8, 11)), b"kernel size"), (cfg(rd=((1, 3, 5), (1, 3, 12), (1, 3, 5))), b"guard"),
+                      (cfg(rates=(8, 8, 2, 2, 2, 2), ks=(16, 16, 4, 4, 4, 4)), b"channels")):
+        assert lib.pd_vocoder_packed_bytes(C.byref(bad)) == 0 and word in lib.pd_last_error(), (word, lib.pd_last_error())
+    h = C.c_void_p()
+    ptrs = (C.c_void_p * 3)()
+    assert lib.pd_vocoder_create(C.byref(ok), ptrs, 3, None, 0, None, C.byref(h)) != 0
+    assert b"expected 206 state tensors" in lib.pd_last_error() and not h.value
+    assert lib.pd_vocoder_workspace_bytes(None, 1, 1) == 0 and lib.pd_vocoder_upp(None) == 0
+    assert lib.pd_vocoder_forward(None, None, None, None, None, 0, None, 1, 1, None, 0, None) != 0 and b"null argument" in lib.pd_last_error()
+
+
 def test_missing_library_fails_loudly(monkeypatch):
     from prodiff_b200 import _lib
     monkeypatch.setattr(_lib, "_lib", None)

@@ -31,7 +31,7 @@ def test_product_forward_has_no_torch_compute_fallback():
     """wavenet.py / diffusion.py may not call conv / linear / activation ops: all compute is in the CUDA library."""
     banned = ("F.conv1d", "F.linear", "torch.sigmoid", "torch.tanh", "F.relu", "softplus", "torch.matmul", "@ ",
               "self.input_projection(", "self.mlp(", "layer(x", "self.skip_projection(", "self.output_projection(")
-    for name in ("wavenet.py", "engine.py", "encoder.py"):
+    for name in ("wavenet.py", "engine.py", "encoder.py", "vocoder.py"):
         src = open(os.path.join(PKG, name)).read()
         for b in banned:
             assert b not in src, f"{name} contains {b}"

@@ -133,3 +133,40 @@ def test_encoder_positions_and_durations():
     assert not tab[0].any() and torch.allclose(tab[1, :3], torch.sin(torch.tensor([1.0, 1e-2, 1e-4])), atol=1e-6)
     mel2ph = torch.tensor([[1, 1, 2, 4, 4, 4, 0, 0]])
     assert eo.mel2ph_to_dur(mel2ph, 4).tolist() == [[2, 1, 0, 3]]
+
+
+@pytest.mark.parametrize("name", ["ladder", "rate8", "full44k_short"])
+def test_vocoder_matches_reference_fixture(name):
+    """oracle/vocoder_oracle.py against what the unmodified reference Generator produced (tests/golden/vocoder_*.npz)."""
+    from oracle import vocoder_oracle as vo
+    from oracle.golden_cases import VOCODER_CASES
+    from prodiff_b200 import synth
+    case = VOCODER_CASES[name]
+    h = case["h"]
+    state = synth.make_vocoder_state(h, case["wseed"])
+    c, f0, ri, nz = synth.make_vocoder_inputs(h, case["B"], case["T"], case["iseed"])
+    g = helpers.load_golden("vocoder", name)
+    assert str(g["digest"]) == synth.digest(state, c, f0, ri, nz)
+    with torch.no_grad():
+        wav = vo.generator_forward(state, h, c, f0, ri, nz)
+    assert np.array_equal(wav.numpy(), g["wav"])
+
+
+def test_vocoder_source_phase_is_invariant_to_whole_turns():
+    """The CUDA path computes SineGen's phase as P[f] + (j + 1) * rad[f] mod 1 (pd_voc.cuh, k_voc_phase) instead of the
+    reference's sample-level float64 cumsum with whole-turn corrections (models.py:146-165).  Check that closed form
+    against the oracle's op-for-op restatement on the CPU, including unvoiced stretches and the rand_ini quirk of frame 0."""
+    from oracle import vocoder_oracle as vo
+    from prodiff_b200 import synth
+    h = synth.VOCODER_44K
+    _, f0, ri, _ = synth.make_vocoder_inputs(h, 2, 60, 77)
+    upp, sr = vo.upp_of(h), float(h["sampling_rate"])
+    fn = f0.unsqueeze(-1) * torch.arange(1, 10).reshape(1, 1, -1)
+    ref = vo.f02sine(fn.clone(), upp, sr, ri)
+    rad = (fn / sr).fmod(1.)
+    rad[:, 0, :] += ri
+    P = torch.cumsum(rad.double() * upp, 1) - rad.double() * upp            # exclusive frame-level sum
+    j = torch.arange(1, upp + 1, dtype=torch.double).reshape(1, 1, upp, 1)
+    ph = (P.unsqueeze(2) + j * rad.double().unsqueeze(2)).reshape(2, 60 * upp, 9)
+    mine = torch.sin((ph - ph.floor()) * 2 * np.pi).float()
+    assert float((mine - ref).abs().max()) < 1e-5

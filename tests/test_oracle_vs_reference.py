@@ -87,3 +87,44 @@ def test_reference_init_distribution_matches_synth(mg):
         assert ref[k].shape == mine[k].shape, k
         if ref[k].numel() >= 4096:
             assert abs(float(ref[k].std()) - float(mine[k].std())) <= 0.08 * float(ref[k].std()) + 1e-8, k
+
+
+@pytest.mark.parametrize("name", ["ladder", "rate8", "full44k_short"])
+def test_vocoder_bit_exact(mg, name):
+    """oracle/vocoder_oracle.py against the live reference Generator (models.py:209-297), weight norm folded as load_model does."""
+    from oracle import vocoder_oracle as vo
+    from oracle.golden_cases import VOCODER_CASES
+    from prodiff_b200 import synth
+    case = VOCODER_CASES[name]
+    h = case["h"]
+    ref = mg.run_reference_vocoder(case)
+    state = synth.make_vocoder_state(h, case["wseed"])
+    c, f0, ri, nz = synth.make_vocoder_inputs(h, case["B"], case["T"], case["iseed"])
+    with torch.no_grad():
+        wav = vo.generator_forward(state, h, c, f0, ri, nz)
+    assert np.array_equal(wav.numpy(), ref["wav"])
+
+
+def test_vocoder_dropin_loads_a_weight_normed_reference_checkpoint(mg):
+    """load_model (models.py:21-36) builds Generator(h), loads the checkpoint's weight-normed state and removes the norm.  The
+    drop-in class must accept that very state dict (weight_g / weight_v keys), end up with the reference's plain weights and
+    expose the reference's parameter names."""
+    import prodiff_b200 as pb
+    from oracle.golden_cases import VOCODER_CASES
+    h = VOCODER_CASES["rate8"]["h"]
+    Generator, AttrDict = mg.load_reference_generator()
+    torch.manual_seed(5)
+    ref = Generator(AttrDict(h))
+    for p_ in ref.parameters():
+        p_.data.normal_(0, 0.3)
+    ckpt = {k: v.clone() for k, v in ref.state_dict().items()}          # weight_g / weight_v form
+    assert any(k.endswith("weight_g") for k in ckpt)
+    ours = pb.Generator(AttrDict(h))
+    ours.load_state_dict(ckpt)
+    ours.remove_weight_norm()
+    ref.remove_weight_norm()
+    plain = ref.state_dict()
+    assert sorted(ours.state_dict().keys()) == sorted(plain.keys())   # (remove_weight_norm re-registers weight after bias)
+    for k, v in plain.items():
+        assert torch.allclose(ours.state_dict()[k], v, rtol=1e-6, atol=1e-7), k
+    assert ours.upp == ref.upp
