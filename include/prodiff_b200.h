@@ -229,6 +229,12 @@ int pd_vocoder_forward(pd_vocoder* v, const float* c, const float* f0, const flo
 size_t pd_voc_debug_conv_scratch(int B, int T, int Cin, int Cout, int k);
 int pd_voc_debug_conv(const float* x, int B, int T, int Cin, const float* w, const float* bias, int Cout, int k, int dil, float* out,
                       void* scratch, size_t scratch_bytes, void* stream);
+/* Test hook: one fused ResBlock1 round (models.py:62-69) through the resident-tile kernel used for the 16 / 32 / 64-channel
+ * stages: out [B, C, T] = c2(leaky_relu(c1(leaky_relu(x, 0.1)), 0.1)) + x, c1 with dilation `dil`, all fp32 device tensors
+ * (fp16 operands and storage inside). */
+size_t pd_voc_debug_pair_scratch(int B, int T, int C, int k);
+int pd_voc_debug_pair(const float* x, int B, int T, int C, const float* w1, const float* b1, const float* w2, const float* b2, int k,
+                      int dil, float* out, void* scratch, size_t scratch_bytes, void* stream);
 
 /* Number of kernels of this library launched by the calling thread since the last reset (bench evidence). */
 long long pd_launch_count(int reset);
@@ -278,6 +284,10 @@ int pd_set_tail(int on);
  * cta_group::2 pairs and at least two frame tiles) or keep skip_sum a separate GEMM launch (0, default: the fused form is
  * bit-identical but measured no faster).  Returns the previous value. */
 int pd_set_sumtail(int on);
+/* NSF-HiFiGAN generator: run every ResBlock1 round (models.py:62-69) of the stages with <= 64 channels as one resident-tile
+ * kernel (1, default; env PD_VOC_FUSED=0 disables) or as two convolution launches like the wider stages (0).  Returns the
+ * previous value (-1 = not yet set). */
+int pd_set_voc_fused(int on);
 
 /* Debug: when set to a device buffer of PD_N_KINDS x 1024 int64 (a kind outside [0, PD_N_KINDS) is never traced), CTA 0 of every GEMM launch writes clock64() stamps of its
  * pipeline events at [kind * 1024 + tile * 16 + slot] (slots: 0/1 first/last TMA issue, 2 accumulator free, 3/4 first/

@@ -18,12 +18,13 @@ PD_BF16, PD_FP16 = 0, 1
 SYMBOLS = [
     "pd_state_count", "pd_last_error", "pd_abi_version", "pd_packed_bytes", "pd_model_create", "pd_model_destroy",
     "pd_workspace_bytes", "pd_plan_create", "pd_plan_destroy", "pd_cond_project", "pd_denoise", "pd_sample",
-    "pd_launch_count", "pd_plan_buffer", "pd_debug_gemm", "pd_profile_begin", "pd_profile_end", "pd_debug_shift", "pd_debug_set_trace", "pd_set_fused", "pd_set_stack", "pd_set_tail", "pd_set_sumtail", "pd_reflow_sample", "pd_plan_set_lengths", "pd_cond_assemble",
+    "pd_launch_count", "pd_plan_buffer", "pd_debug_gemm", "pd_profile_begin", "pd_profile_end", "pd_debug_shift", "pd_debug_set_trace", "pd_set_fused", "pd_set_stack", "pd_set_tail", "pd_set_sumtail", "pd_set_voc_fused", "pd_reflow_sample", "pd_plan_set_lengths", "pd_cond_assemble",
     "pd_plan_set_output_scale",
     "pd_encoder_state_count", "pd_encoder_packed_bytes", "pd_encoder_create", "pd_encoder_destroy",
     "pd_encoder_workspace_bytes", "pd_encoder_forward",
     "pd_vocoder_state_count", "pd_vocoder_packed_bytes", "pd_vocoder_create", "pd_vocoder_destroy", "pd_vocoder_upp",
     "pd_vocoder_workspace_bytes", "pd_vocoder_forward", "pd_voc_debug_conv_scratch", "pd_voc_debug_conv",
+    "pd_voc_debug_pair_scratch", "pd_voc_debug_pair",
 ]
 
 
@@ -95,6 +96,9 @@ def load() -> C.CDLL:
     lib.pd_voc_debug_conv_scratch.argtypes = [C.c_int] * 5; lib.pd_voc_debug_conv_scratch.restype = sz
     lib.pd_voc_debug_conv.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, sz, vp]
     lib.pd_voc_debug_conv.restype = C.c_int
+    lib.pd_voc_debug_pair_scratch.argtypes = [C.c_int] * 4; lib.pd_voc_debug_pair_scratch.restype = sz
+    lib.pd_voc_debug_pair.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, C.c_int, C.c_int, vp, vp, sz, vp]
+    lib.pd_voc_debug_pair.restype = C.c_int
     lib.pd_launch_count.argtypes = [C.c_int]; lib.pd_launch_count.restype = C.c_longlong
     lib.pd_plan_buffer.argtypes = [vp, cp, P(sz), P(sz)]; lib.pd_plan_buffer.restype = C.c_int
     lib.pd_debug_gemm.argtypes = [C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp, vp, vp]
@@ -105,6 +109,7 @@ def load() -> C.CDLL:
     lib.pd_set_stack.argtypes = [C.c_int]; lib.pd_set_stack.restype = C.c_int
     lib.pd_set_tail.argtypes = [C.c_int]; lib.pd_set_tail.restype = C.c_int
     lib.pd_set_sumtail.argtypes = [C.c_int]; lib.pd_set_sumtail.restype = C.c_int
+    lib.pd_set_voc_fused.argtypes = [C.c_int]; lib.pd_set_voc_fused.restype = C.c_int
     lib.pd_profile_begin.argtypes = []; lib.pd_profile_begin.restype = C.c_int
     lib.pd_profile_end.argtypes = [P(C.c_float), P(C.c_int), C.c_int]; lib.pd_profile_end.restype = C.c_int
     if lib.pd_abi_version() != 1:

@@ -6,6 +6,7 @@
 #include "pd_tail.cuh"
 #include "pd_sumtail.cuh"
 #include "pd_voc.cuh"
+#include "pd_voc_pair.cuh"
 
 #include <algorithm>
 #include <math.h>

@@ -105,6 +105,82 @@ VocEpi voc_epi() {
 
 bool voc_pow2_ch(int c) { return c == 16 || c == 32 || c == 64 || c == 128 || c == 256 || c == 512 || c == 1024; }
 
+// ---- fused ResBlock rounds (pd_voc_pair.cuh): stages with <= 64 channels
+int g_voc_fused = -1;      // -1: read PD_VOC_FUSED from the environment on first use (default on)
+bool voc_fused_enabled() {
+  if (g_voc_fused < 0) {
+    const char* e = getenv("PD_VOC_FUSED");
+    g_voc_fused = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_voc_fused == 1;
+}
+}  // namespace
+extern "C" int pd_set_voc_fused(int on) {
+  const int prev = g_voc_fused;
+  g_voc_fused = on ? 1 : 0;
+  return prev;
+}
+namespace {
+bool voc_pair_ok(int C, int k) { return (C == 16 || C == 32 || C == 64) && k % 2 == 1 && k <= 15; }
+
+template <int C, int NB, bool kRes, int kXB, int EW, int kMinCtas>
+int launch_voc_pair_t(VocPairArgs a, int sms, cudaStream_t s) {
+  auto kern = voc_pair_kernel<C, NB, kRes, kXB, EW, kMinCtas>;
+  constexpr int kPairThreads = (EW + 2) * 32;
+  const VocPairSmem L = voc_pair_smem<C, NB, kRes, kXB>(a.k, a.dil);
+  static int configured[64] = {0};
+  int dev = 0;
+  PD_CUDA(cudaGetDevice(&dev));
+  if (configured[dev & 63] < (int)L.total) {
+    PD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+    PD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+    configured[dev & 63] = (int)L.total;
+  }
+  // co-resident CTAs per SM: shared memory (227 KB per SM, 1 KB reserved per CTA), registers, TMEM columns
+  cudaFuncAttributes fa;
+  PD_CUDA(cudaFuncGetAttributes(&fa, kern));
+  const int cols = NB * C < 32 ? 32 : NB * C;
+  int occ = (int)((227u * 1024u) / (L.total + 1024u));
+  const int regs_per_cta = ((fa.numRegs * 32 + 511) / 512 * 512) * (kPairThreads / 32);   // allocation unit: 512 registers per warp
+  occ = std::min(occ, 65536 / regs_per_cta);
+  occ = std::min(occ, 512 / cols);
+  occ = std::min(occ, 8);
+  if (occ < 1) return fail("voc_pair_kernel<%d>: %u bytes of shared memory do not fit", C, L.total);
+  if (getenv("PD_VOC_DEBUG")) {
+    int api = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&api, kern, kPairThreads, L.total);
+    fprintf(stderr, "[voc_pair C=%d k=%d dil=%d] smem %u regs %d occ %d (api %d)\n", C, a.k, a.dil, L.total, fa.numRegs, occ, api);
+  }
+  const int P = NB * 128 - (a.k - 1);
+  a.tiles_per_row = (a.T + P - 1) / P;
+  a.idesc = make_idesc(PD_FP16, C);
+  a.trace = g_trace ? g_trace + 13 * 1024 : nullptr;
+  const long long tiles = (long long)a.B * a.tiles_per_row;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)std::min<long long>(tiles, (long long)sms * occ));
+  cfg.blockDim = dim3(kPairThreads);
+  cfg.dynamicSmemBytes = L.total;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  prof_before(13, s);
+  PD_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
+  prof_after(s);
+  PD_LAUNCH_CHECK("voc_pair_kernel");
+  return 0;
+}
+int launch_voc_pair(int C, const VocPairArgs& a, int sms, cudaStream_t s) {
+  switch (C) {
+    case 16: return launch_voc_pair_t<16, 2, true, 2, 4, 4>(a, sms, s);
+    case 32: return launch_voc_pair_t<32, 2, true, 2, 8, 2>(a, sms, s);
+    case 64: return launch_voc_pair_t<64, 2, false, 1, 8, 2>(a, sms, s);
+    default: return fail("voc_pair_kernel: %d channels not supported", C);
+  }
+}
+
 }  // namespace
 
 struct pd_vocoder {
@@ -116,6 +192,7 @@ struct pd_vocoder {
   VocConv conv_pre, conv_post;
   VocConv ups[kVocMaxUps];
   VocConv res[kVocMaxUps][kVocMaxRes][6];    // [stage][kernel][c1_0, c2_0, c1_1, c2_1, c1_2, c2_2]
+  size_t pair_w[kVocMaxUps][kVocMaxRes][3];  // fused-round weight images (pd_voc_pair.cuh) where voc_pair_ok(), else 0
   size_t src_w[kVocMaxUps], src_b[kVocMaxUps];   // fp32 noise_convs weights, transposed to [k][C] / bias [C]
   int src_k[kVocMaxUps], src_stride[kVocMaxUps], src_pad[kVocMaxUps];
   size_t lin_w, lin_b;                       // m_source.l_linear
@@ -180,6 +257,12 @@ static size_t voc_layout(const pd_vocoder_config& c, pd_vocoder* v) {
       for (int d = 0; d < 3; ++d) {
         conv(v ? &v->res[i][j][2 * d] : nullptr, ch, ch, c.resblock_kernel_sizes[j], c.resblock_dilation_sizes[j][d]);
         conv(v ? &v->res[i][j][2 * d + 1] : nullptr, ch, ch, c.resblock_kernel_sizes[j], 1);
+        if (voc_pair_ok(ch, c.resblock_kernel_sizes[j])) {
+          const size_t pw = take((size_t)2 * c.resblock_kernel_sizes[j] * ch * ch * 2);
+          if (v) v->pair_w[i][j][d] = pw;
+        } else if (v) {
+          v->pair_w[i][j][d] = 0;
+        }
       }
   }
   conv(v ? &v->conv_post : nullptr, ch, 1, 7, 1);
@@ -251,6 +334,11 @@ extern "C" int pd_vocoder_create(const pd_vocoder_config* cfg, const float* cons
       for (int d = 0; d < 3 && !rc; ++d) {
         rc |= pack_conv(v->res[i][j][2 * d], state[si + 2 * d], state[si + 2 * d + 1], ch);
         rc |= pack_conv(v->res[i][j][2 * d + 1], state[si + 6 + 2 * d], state[si + 6 + 2 * d + 1], ch);
+        const int kk = cfg->resblock_kernel_sizes[j];
+        if (voc_pair_ok(ch, kk)) {
+          k_voc_pack_pair<<<blocks(2ll * kk * ch * ch), TB, 0, s>>>((__half*)(pk + v->pair_w[i][j][d]), state[si + 2 * d], state[si + 6 + 2 * d], ch, kk);
+          PD_LAUNCH_CHECK("k_voc_pack_pair");
+        }
       }
       si += 12;
     }
@@ -392,11 +480,55 @@ extern "C" int pd_vocoder_forward(pd_vocoder* v, const float* c, const float* f0
     }
     // xs = sum over the ResBlocks (:278-284); each ResBlock1 is three (conv dil d -> conv dil 1 -> + x) rounds (:62-69)
     const bool last_stage = i + 1 == cf.n_upsamples;
+    const bool fused = voc_fused_enabled();
     for (int j = 0; j < cf.n_resblock_kernels; ++j) {
       for (int d = 0; d < 3; ++d) {
         const VocConv& c1 = v->res[i][j][2 * d];
         const VocConv& c2 = v->res[i][j][2 * d + 1];
-        const __half* xin = d == 0 ? XL : CUR;
+        const bool pair = fused && voc_pair_ok(co, c1.taps);
+        // unfused: x lives in XL (d = 0) then CUR, updated in place through TMP; fused: XL -> CUR -> TMP -> result (a tile reads
+        // its neighbours' rows, so a round never writes the tensor it reads)
+        const __half* xin = d == 0 ? XL : (pair && d == 2 ? TMP : CUR);
+        __half* xout = pair && d == 1 ? TMP : CUR;
+        __half* dst = nullptr;
+        const __half* add = nullptr;
+        float scale = 1.f, slope = 0.1f;
+        int act = 1;
+        if (d < 2) {                                  // x = xt + x, kept activated for the next round's first conv
+          dst = xout;
+        } else if (j + 1 < cf.n_resblock_kernels) {   // this ResBlock's result joins the running sum (raw)
+          dst = XS;
+          if (j > 0) add = XS;
+          act = 0;
+        } else {                                      // last ResBlock: x = xs / num_kernels (:285), then the next consumer's LeakyReLU
+          dst = OUT;
+          if (j > 0) add = XS;
+          scale = 1.f / (float)cf.n_resblock_kernels;
+          slope = last_stage ? 0.01f : 0.1f;          // F.leaky_relu(x) before conv_post uses the default slope (:286)
+        }
+        if (pair) {
+          VocPairArgs pa;
+          memset(&pa, 0, sizeof(pa));
+          pa.x = xin;
+          pa.add = add;
+          pa.out = dst;
+          pa.w = (const __half*)(pk + v->pair_w[i][j][d]);
+          pa.b1 = (const float*)(pk + c1.b_off);
+          pa.b2 = (const float*)(pk + c2.b_off);
+          pa.bstride = obs;
+          pa.B = B;
+          pa.T = (int)To;
+          pa.G = G;
+          pa.k = c1.taps;
+          pa.dil = c1.dil;
+          pa.slope1 = 0.1f;
+          pa.in_inv_slope = 10.f;
+          pa.scale = scale;
+          pa.act = act;
+          pa.slope = slope;
+          if (launch_voc_pair(co, pa, sms, s)) return 1;
+          continue;
+        }
         {
           if (make_voc_a_map(&tmA, xin, co, c1.taps, c1.dil, (int)To, B)) return 1;
           VocEpi ep = voc_epi();
@@ -417,20 +549,11 @@ extern "C" int pd_vocoder_forward(pd_vocoder* v, const float* c, const float* f0
           ep.res_ld = co;
           ep.out_bstride = obs;
           ep.out_ld = co;
-          if (d < 2) {                       // x = xt + x, kept activated for the next round's first conv
-            ep.out16 = CUR + (size_t)G * co;
-            ep.act = 1;
-            ep.slope = 0.1f;
-          } else if (j + 1 < cf.n_resblock_kernels) {   // this ResBlock's result joins the running sum (raw)
-            ep.out16 = XS + (size_t)G * co;
-            if (j > 0) { ep.add16 = XS + (size_t)G * co; ep.add_bstride = obs; ep.add_ld = co; }
-          } else {                           // last ResBlock: x = xs / num_kernels (:285), then the next consumer's LeakyReLU
-            ep.out16 = OUT + (size_t)G * co;
-            if (j > 0) { ep.add16 = XS + (size_t)G * co; ep.add_bstride = obs; ep.add_ld = co; }
-            ep.scale = 1.f / (float)cf.n_resblock_kernels;
-            ep.act = 1;
-            ep.slope = last_stage ? 0.01f : 0.1f;    // F.leaky_relu(x) before conv_post uses the default slope (:286)
-          }
+          ep.out16 = dst + (size_t)G * co;
+          if (add) { ep.add16 = add + (size_t)G * co; ep.add_bstride = obs; ep.add_ld = co; }
+          ep.scale = scale;
+          ep.act = act;
+          ep.slope = slope;
           if (launch_voc(c2, tmA, TMP, B, (int)To, ep, sms, s)) return 1;
         }
       }
@@ -509,6 +632,70 @@ extern "C" int pd_voc_debug_conv(const float* x, int B, int T, int Cin, const fl
   ep.bias = b32;
   if (launch_voc(cv, tmA, xin, B, T, ep, sms, s)) return 1;
   k_voc_dbg_out<<<(int)std::min<long long>((nout + 255) / 256, 4096), 256, 0, s>>>(out, o16, Cout, n_pad, T, kVocG, nout);
+  PD_LAUNCH_CHECK("k_voc_dbg_out");
+  return 0;
+}
+
+// Test hook: one fused ResBlock round (pd_voc_pair.cuh).  x [B, C, T] fp32 (the raw x), w1 / w2 [C, C, k], b1 / b2 [C] ->
+// out [B, C, T] fp32 = c2(leaky_relu(c1(leaky_relu(x, 0.1)), 0.1)) + x with c1 dilated by `dil`, fp16 operands and storage.
+extern "C" size_t pd_voc_debug_pair_scratch(int B, int T, int C, int k) {
+  return 2 * align_up((size_t)B * (T + 2 * kVocG) * C * 2, 1024) + align_up((size_t)2 * k * C * C * 2, 1024) + 2 * align_up((size_t)C * 4, 1024);
+}
+__global__ void k_voc_dbg_in_act(__half* __restrict__ dst, const float* __restrict__ x, int C, int Tn, int G, long long total, float slope) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const long long bt = i / C;
+    const int t = (int)(bt % Tn), b = (int)(bt / Tn);
+    const float v = x[((long long)b * C + c) * Tn + t];
+    dst[((long long)b * (Tn + 2 * G) + G + t) * C + c] = __float2half_rn(v >= 0.f ? v : v * slope);
+  }
+}
+extern "C" int pd_voc_debug_pair(const float* x, int B, int T, int C, const float* w1, const float* b1, const float* w2, const float* b2, int k,
+                                 int dil, float* out, void* scratch, size_t scratch_bytes, void* stream) {
+  if (!x || !w1 || !b1 || !w2 || !b2 || !out || !scratch) return fail("null argument");
+  if (!voc_pair_ok(C, k) || dil < 1 || (k - 1) / 2 * (dil + 1) > kVocG) return fail("unsupported debug pair shape");
+  if (scratch_bytes < pd_voc_debug_pair_scratch(B, T, C, k) || reinterpret_cast<uintptr_t>(scratch) % 1024) return fail("scratch too small or misaligned");
+  int device = 0, sms = 0;
+  if (check_device(&device, &sms)) return 1;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  uint8_t* p = static_cast<uint8_t*>(scratch);
+  const size_t act_bytes = align_up((size_t)B * (T + 2 * kVocG) * C * 2, 1024);
+  __half* xin = reinterpret_cast<__half*>(p);
+  p += act_bytes;
+  __half* o16 = reinterpret_cast<__half*>(p);
+  p += act_bytes;
+  __half* w16 = reinterpret_cast<__half*>(p);
+  p += align_up((size_t)2 * k * C * C * 2, 1024);
+  float* b1d = reinterpret_cast<float*>(p);
+  p += align_up((size_t)C * 4, 1024);
+  float* b2d = reinterpret_cast<float*>(p);
+  PD_CUDA(cudaMemsetAsync(xin, 0, act_bytes, s));
+  PD_CUDA(cudaMemsetAsync(o16, 0, act_bytes, s));
+  const long long n = (long long)B * T * C;
+  k_voc_dbg_in_act<<<(int)std::min<long long>((n + 255) / 256, 4096), 256, 0, s>>>(xin, x, C, T, kVocG, n, 0.1f);
+  k_voc_pack_pair<<<(int)std::min<long long>((2ll * k * C * C + 255) / 256, 4096), 256, 0, s>>>(w16, w1, w2, C, k);
+  PD_CUDA(cudaMemcpyAsync(b1d, b1, (size_t)C * 4, cudaMemcpyDeviceToDevice, s));
+  PD_CUDA(cudaMemcpyAsync(b2d, b2, (size_t)C * 4, cudaMemcpyDeviceToDevice, s));
+  PD_LAUNCH_CHECK("k_voc_dbg_in_act");
+  VocPairArgs pa;
+  memset(&pa, 0, sizeof(pa));
+  pa.x = xin;
+  pa.out = o16;
+  pa.w = w16;
+  pa.b1 = b1d;
+  pa.b2 = b2d;
+  pa.bstride = (long long)(T + 2 * kVocG) * C;
+  pa.B = B;
+  pa.T = T;
+  pa.G = kVocG;
+  pa.k = k;
+  pa.dil = dil;
+  pa.slope1 = 0.1f;
+  pa.in_inv_slope = 10.f;
+  pa.scale = 1.f;
+  const int rc = launch_voc_pair(C, pa, sms, s);
+  if (rc) return 1;
+  k_voc_dbg_out<<<(int)std::min<long long>((n + 255) / 256, 4096), 256, 0, s>>>(out, o16, C, C, T, kVocG, n);
   PD_LAUNCH_CHECK("k_voc_dbg_out");
   return 0;
 }

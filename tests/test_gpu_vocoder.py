@@ -85,6 +85,64 @@ def test_conv_kernel_vs_fp32_conv(shape):
     assert float(err.max()) <= 2e-3 * max(1.0, float(ref.abs().max())), float(err.max())
 
 
+PAIR_SHAPES = [  # C, k, dil, B, T: the three fused widths, every kernel size / dilation of the generator, single- and many-tile runs
+    (16, 3, 1, 2, 900), (16, 7, 5, 1, 2048), (16, 11, 3, 2, 1111), (16, 11, 5, 1, 3), (32, 3, 1, 2, 777), (32, 7, 3, 1, 1500),
+    (32, 11, 5, 2, 640), (64, 3, 1, 2, 400), (64, 7, 3, 1, 1000), (64, 11, 5, 1, 1000), (64, 3, 1, 1, 5), (64, 11, 1, 3, 246),
+    (16, 7, 1, 3, 250), (32, 11, 1, 40, 4000), (64, 7, 1, 30, 3000), (16, 3, 1, 64, 8000),
+]
+
+
+@pytest.mark.parametrize("shape", PAIR_SHAPES, ids=lambda s: "c%d_k%d_d%d_B%d_T%d" % s)
+def test_fused_resblock_round_vs_fp64_convs(shape):
+    """One ResBlock1 round (models.py:62-69: x + c2(leaky_relu(c1(leaky_relu(x))))) through the resident-tile kernel
+    (pd_voc_debug_pair) against float64 convolutions over the same fp16-rounded operands and fp16-rounded intermediate: only
+    the fp16 rounding of the result separates them.  Covers tiles at both utterance edges (zero padding of BOTH convolutions),
+    utterances shorter than the halo, and persistent CTAs walking many tiles."""
+    import torch.nn.functional as F
+    from prodiff_b200 import _lib
+    lib = _lib.load()
+    Cc, k, dil, B, T = shape
+    h = (k - 1) // 2
+    g = torch.Generator().manual_seed(Cc * 1000 + k + dil + T)
+    x = torch.randn(B, Cc, T, generator=g)
+    w1 = torch.randn(Cc, Cc, k, generator=g) / (Cc * k) ** 0.5
+    w2 = torch.randn(Cc, Cc, k, generator=g) / (Cc * k) ** 0.5
+    b1 = torch.randn(Cc, generator=g) * 0.1
+    b2 = torch.randn(Cc, generator=g) * 0.1
+    xa = F.leaky_relu(x, 0.1).half().double()
+    y1 = F.leaky_relu(F.conv1d(xa, w1.half().double(), b1.double(), dilation=dil, padding=h * dil), 0.1).half().double()
+    ref = (F.conv1d(y1, w2.half().double(), b2.double(), padding=h) + torch.where(xa >= 0, xa, xa * 10.0)).float()
+    d = [t.cuda().contiguous() for t in (x, w1, b1, w2, b2)]
+    y = torch.full((B, Cc, T), float("nan"), device="cuda")
+    n = lib.pd_voc_debug_pair_scratch(B, T, Cc, k)
+    scratch = torch.empty(n + 1024, dtype=torch.uint8, device="cuda")
+    off = (-scratch.data_ptr()) % 1024
+    _lib.check(lib.pd_voc_debug_pair(d[0].data_ptr(), B, T, Cc, d[1].data_ptr(), d[2].data_ptr(), d[3].data_ptr(), d[4].data_ptr(), k, dil,
+                                     y.data_ptr(), scratch.data_ptr() + off, n, torch.cuda.current_stream().cuda_stream), "pd_voc_debug_pair")
+    torch.cuda.synchronize()
+    err = (y.cpu() - ref).abs()
+    assert float(err.max()) <= 2e-3 * max(1.0, float(ref.abs().max())), float(err.max())
+
+
+def test_fused_rounds_match_the_two_launch_form():
+    """The generator with fused ResBlock rounds (default) against the same generator running every round as two convolution
+    launches: same operands, same fp16 intermediates, fp32 accumulation in the same tap order."""
+    from prodiff_b200 import _lib, synth
+    lib = _lib.load()
+    h, state, c, f0, ri, nz = _case("full44k_short")
+    gen = _build(h, state)
+    args = dict(rand_ini=ri.cuda(), noise=nz.cuda())
+    prev = lib.pd_set_voc_fused(1)
+    try:
+        with torch.no_grad():
+            fused = gen(c.cuda(), f0.cuda(), **args).cpu()
+            lib.pd_set_voc_fused(0)
+            plain = gen(c.cuda(), f0.cuda(), **args).cpu()
+    finally:
+        lib.pd_set_voc_fused(1 if prev != 0 else 0)
+    assert float((fused - plain).abs().max()) <= 1e-3, float((fused - plain).abs().max())
+
+
 def test_batch_rows_equal_single_utterance_runs():
     """Batching the vocoder (what N3 asks for; the reference's SineGen takes one utterance per call, models.py:163): every
     row of a batch must come out exactly as that utterance alone -- tiles never span utterances and the guard rows carry
