@@ -527,39 +527,77 @@ __global__ void k_voc_source(float* __restrict__ har, const double* __restrict__
 
 // noise_convs[i] (models.py:233-238, :276): x_source[b, o, c] = bias[c] + sum_kk W[c, kk] * har[b, o * stride - pad + kk], zero
 // padded, written raw as fp16 in the up-sampled tensor's guarded layout (it is the `add16` input of the transposed conv's
-// epilogue).  wt is the weight TRANSPOSED to [k][C] (k_voc_transpose_src at pack time), so the threads of a warp -- consecutive
-// channels -- read consecutive words, and the har sample is a shared-memory broadcast.  Block: 64 output positions x all C
-// channels, 8 positions per thread at a time (one weight load per 8 FMAs).
-constexpr int kSrcPos = 64;
-__global__ void __launch_bounds__(256)
+// epilogue).  wt is the weight TRANSPOSED to [k][C] (k_voc_transpose_src at pack time).  A block covers 16384 / C output
+// positions x all C channels; a thread owns 8 channels x 8 positions (64 accumulators: per tap two float4 weight loads and 8
+// shared-memory har samples feed 64 FMAs), its positions interleaved with the other threads' so that every store
+// instruction of a warp writes whole 16-byte channel groups of adjacent positions -- contiguous memory.
+constexpr int kSrcThreads = 256;
+// ppt = positions per thread (8, fewer when the har window of a block would not fit in shared memory)
+__host__ __device__ inline int voc_src_positions(int C, int ppt) { return ppt * (kSrcThreads / (C / 8)); }
+template <bool kVec4>
+__global__ void __launch_bounds__(kSrcThreads, 2)
 k_voc_srcconv(__half* __restrict__ dst, const float* __restrict__ har, const float* __restrict__ wt, const float* __restrict__ bias,
-              int C, int k, int stride, int pad, int To, long long Lh, int G) {
-  extern __shared__ float s_h[];   // (kSrcPos - 1) * stride + k samples
-  const int b = blockIdx.y, o0 = blockIdx.x * kSrcPos;
-  const int win = (kSrcPos - 1) * stride + k;
+              int C, int k, int stride, int pad, int To, long long Lh, int G, int ppt) {
+  extern __shared__ __align__(16) float s_h[];   // (positions - 1) * stride + k samples
+  const int n_cg = C / 8, n_ps = kSrcThreads / n_cg, n_pos = ppt * n_ps;
+  const int b = blockIdx.y, o0 = blockIdx.x * n_pos;
+  const int win = (n_pos - 1) * stride + k;
   const long long h0 = (long long)o0 * stride - pad;
-  for (int i = threadIdx.x; i < win; i += blockDim.x) {
+  for (int i = threadIdx.x; i < win; i += kSrcThreads) {
     const long long n = h0 + i;
     s_h[i] = (n >= 0 && n < Lh) ? har[(long long)b * Lh + n] : 0.f;
   }
   __syncthreads();
-  const int c = threadIdx.x % C, pg = threadIdx.x / C, n_pg = blockDim.x / C;   // C divides 256
-  const float bc = bias[c];
-  for (int p0 = pg * 8; p0 < kSrcPos; p0 += n_pg * 8) {
-    float acc[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = bc;
-    const float* hp = s_h + p0 * stride;
-    for (int kk = 0; kk < k; ++kk) {
-      const float w = __ldg(wt + (long long)kk * C + c);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] = fmaf(w, hp[i * stride + kk], acc[i]);
-    }
+  const int cg = threadIdx.x % n_cg, ps = threadIdx.x / n_cg;   // positions ps, ps + n_ps, ..., ps + 7 * n_ps of the block
+  float acc[8][8];
+  {
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + cg * 8)), b1 = __ldg(reinterpret_cast<const float4*>(bias + cg * 8 + 4));
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const int o = o0 + p0 + i;
-      if (o < To) dst[((long long)b * (To + 2 * G) + G + o) * C + c] = __float2half_rn(acc[i]);
+      acc[i][0] = b0.x; acc[i][1] = b0.y; acc[i][2] = b0.z; acc[i][3] = b0.w;
+      acc[i][4] = b1.x; acc[i][5] = b1.y; acc[i][6] = b1.z; acc[i][7] = b1.w;
     }
+  }
+  const float* hp = s_h + ps * stride;
+  const int pstep = n_ps * stride;
+  if (kVec4) {   // stride % 4 == 0 and k % 4 == 0: four taps per 16-byte shared-memory load (the scalar form is LSU-bound)
+    for (int kk = 0; kk < k; kk += 4) {
+      float4 hv[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) hv[i] = i < ppt ? *reinterpret_cast<const float4*>(hp + i * pstep + kk) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(wt + (long long)(kk + t) * C + cg * 8));
+        const float4 w1 = __ldg(reinterpret_cast<const float4*>(wt + (long long)(kk + t) * C + cg * 8 + 4));
+        const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float h1 = t == 0 ? hv[i].x : (t == 1 ? hv[i].y : (t == 2 ? hv[i].z : hv[i].w));
+#pragma unroll
+          for (int u = 0; u < 8; ++u) acc[i][u] = fmaf(w[u], h1, acc[i][u]);
+        }
+      }
+    }
+  } else {
+    for (int kk = 0; kk < k; ++kk) {
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(wt + (long long)kk * C + cg * 8));
+      const float4 w1 = __ldg(reinterpret_cast<const float4*>(wt + (long long)kk * C + cg * 8 + 4));
+      const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float hv = i < ppt ? hp[i * pstep + kk] : 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc[i][u] = fmaf(w[u], hv, acc[i][u]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int o = o0 + ps + i * n_ps;
+    if (i < ppt && o < To)
+      *reinterpret_cast<uint4*>(dst + ((long long)b * (To + 2 * G) + G + o) * C + cg * 8) =
+          make_uint4(Cvt<__half>::pack(acc[i][0], acc[i][1]), Cvt<__half>::pack(acc[i][2], acc[i][3]), Cvt<__half>::pack(acc[i][4], acc[i][5]),
+                     Cvt<__half>::pack(acc[i][6], acc[i][7]));
   }
 }
 // noise_convs weight [C, 1, k] -> [k][C]

@@ -127,7 +127,7 @@ template <int C, int NB, bool kRes, int kXB, int EW, int kMinCtas>
 int launch_voc_pair_t(VocPairArgs a, int sms, cudaStream_t s) {
   auto kern = voc_pair_kernel<C, NB, kRes, kXB, EW, kMinCtas>;
   constexpr int kPairThreads = (EW + 2) * 32;
-  const VocPairSmem L = voc_pair_smem<C, NB, kRes, kXB>(a.k, a.dil);
+  const VocPairSmem L = voc_pair_smem<C, NB, kRes, kXB, kMinCtas>(a.k, a.dil);
   static int configured[64] = {0};
   int dev = 0;
   PD_CUDA(cudaGetDevice(&dev));
@@ -139,7 +139,7 @@ int launch_voc_pair_t(VocPairArgs a, int sms, cudaStream_t s) {
   // co-resident CTAs per SM: shared memory (227 KB per SM, 1 KB reserved per CTA), registers, TMEM columns
   cudaFuncAttributes fa;
   PD_CUDA(cudaFuncGetAttributes(&fa, kern));
-  const int cols = NB * C < 32 ? 32 : NB * C;
+  const int cols = std::max(32, (kXB == 2 ? 2 : 1) * NB * C);
   int occ = (int)((227u * 1024u) / (L.total + 1024u));
   const int regs_per_cta = ((fa.numRegs * 32 + 511) / 512 * 512) * (kPairThreads / 32);   // allocation unit: 512 registers per warp
   occ = std::min(occ, 65536 / regs_per_cta);
@@ -172,6 +172,10 @@ int launch_voc_pair_t(VocPairArgs a, int sms, cudaStream_t s) {
   PD_LAUNCH_CHECK("voc_pair_kernel");
   return 0;
 }
+// Tile shapes (measured on B200, gpurun_out/voc_ab*.log): 16 / 32 channels keep both convolutions' weights resident, double-buffer
+// the x tile and run 4 / 2 CTAs per SM; 64 channels stream one tap per ring stage (a round's weights are 48 - 176 KB) with 2 CTAs
+// per SM.  Measured no faster: resident weights with one CTA per SM for 64 channels (k <= 7), 512-row tiles, 5 - 6 CTAs per SM for
+// 16 channels, 3 - 4 for 32.
 int launch_voc_pair(int C, const VocPairArgs& a, int sms, cudaStream_t s) {
   switch (C) {
     case 16: return launch_voc_pair_t<16, 2, true, 2, 4, 4>(a, sms, s);
@@ -457,9 +461,19 @@ extern "C" int pd_vocoder_forward(pd_vocoder* v, const float* c, const float* f0
     // noise_convs[i](har_source) (:276)
     {
       const int k = v->src_k[i], st = v->src_stride[i];
-      const dim3 grid((unsigned)((To + kSrcPos - 1) / kSrcPos), B);
-      k_voc_srcconv<<<grid, 256, ((kSrcPos - 1) * st + k) * sizeof(float), s>>>(SRC, har, (const float*)(pk + v->src_w[i]), (const float*)(pk + v->src_b[i]), co, k,
-                                                                       st, v->src_pad[i], (int)To, Lh, G);
+      int ppt = 8;
+      auto shm_of = [&](int p) { return ((size_t)(voc_src_positions(co, p) - 1) * st + k) * sizeof(float); };
+      while (ppt > 1 && shm_of(ppt) > 48 * 1024) ppt /= 2;
+      const size_t shm = shm_of(ppt);
+      if (shm > 48 * 1024) return fail("noise_convs[%d]: %zu bytes of shared memory (stride %d, kernel %d) not supported", i, shm, st, k);
+      const int npos = voc_src_positions(co, ppt);
+      const dim3 grid((unsigned)((To + npos - 1) / npos), B);
+      if (st % 4 == 0 && k % 4 == 0 && k >= 32)   // long kernels are FMA-bound once four taps come per shared-memory load; short ones are store-bound
+        k_voc_srcconv<true><<<grid, kSrcThreads, shm, s>>>(SRC, har, (const float*)(pk + v->src_w[i]), (const float*)(pk + v->src_b[i]), co, k, st, v->src_pad[i],
+                                                           (int)To, Lh, G, ppt);
+      else
+        k_voc_srcconv<false><<<grid, kSrcThreads, shm, s>>>(SRC, har, (const float*)(pk + v->src_w[i]), (const float*)(pk + v->src_b[i]), co, k, st, v->src_pad[i],
+                                                            (int)To, Lh, G, ppt);
       PD_LAUNCH_CHECK("k_voc_srcconv");
     }
     // x = ups[i](leaky_relu(x)) + x_source (:274-277), stored activated for the ResBlocks' first convs

@@ -49,7 +49,10 @@ struct VocPairArgs {
 };
 
 #define PD_PAIR_TRACE(slot) do { if (a.trace != nullptr && blockIdx.x == 0 && it < 64u) a.trace[it * 16u + (slot)] = clock64(); } while (0)
-constexpr int kPairRingMax = 8;   // most weight ring stages (C = 64): one tap each
+#ifndef PD_PAIR_SLEEP_NS
+#define PD_PAIR_SLEEP_NS 40   // back-off between polls of the per-tile barriers (a third of all issued instructions were polls)
+#endif
+constexpr int kPairRingMax = 10;   // most weight ring stages (C = 64): one tap each
 
 // K-major operand without swizzle: start address, LBO (stride between the two 8-channel halves of a K = 16 step), SBO (stride
 // between 8-row groups); descriptor version 1, layout type 0.
@@ -95,9 +98,9 @@ struct VocPairSmem {
   uint32_t x_off[2], y_off, w_off, bar_off, total;
   uint32_t ring;          // weight ring stages (streamed weights)
 };
-constexpr uint32_t kPairSmemPerCta2 = (227u * 1024u) / 2u - 1024u;   // budget that leaves room for two CTAs per SM
-template <int C, int NB, bool kRes, int kXB>
+template <int C, int NB, bool kRes, int kXB, int kMinCtas>
 __host__ __device__ inline VocPairSmem voc_pair_smem(int k, int dil) {
+  constexpr uint32_t kBudget = (227u * 1024u) / (uint32_t)kMinCtas - 1024u;   // leaves room for kMinCtas CTAs per SM
   VocPairSmem s;
   const int h = (k - 1) / 2;
   s.xr = (uint32_t)(NB * 128 + 2 * h * dil) | 1u;
@@ -113,9 +116,9 @@ __host__ __device__ inline VocPairSmem voc_pair_smem(int k, int dil) {
   s.ring = 0;
   if (kRes) {
     o += (uint32_t)(2 * k * C * C * 2);
-  } else {   // as many one-tap stages as fit beside a second CTA on the SM (2 .. kPairRingMax)
+  } else {   // as many one-tap stages as fit beside the other CTAs on the SM (2 .. kPairRingMax)
     const uint32_t tap = C * C * 2, fixed = o + 256u + 128u;
-    uint32_t n = fixed + 2 * tap < kPairSmemPerCta2 ? (kPairSmemPerCta2 - fixed) / tap : 2u;
+    uint32_t n = fixed + 2 * tap < kBudget ? (kBudget - fixed) / tap : 2u;
     if (n > (uint32_t)kPairRingMax) n = kPairRingMax;
     if (n > (uint32_t)(2 * k)) n = 2 * k;
     s.ring = n;
@@ -133,7 +136,9 @@ __global__ void __launch_bounds__((EW + 2) * 32, kMinCtas) voc_pair_kernel(const
   constexpr int CW = C < 32 ? C : 32;            // accumulator columns per tcgen05.ld
   constexpr int NT = EW * 32;                    // gather / epilogue threads
   constexpr int MSTEP = EW / 4;                  // row blocks are dealt round-robin to the warp groups
-  constexpr uint32_t kCols = NB * C < 32 ? 32 : NB * C;
+  constexpr bool kAhead = kXB == 2;              // conv1 of tile i+1 is issued behind conv2 of tile i (own accumulator columns)
+  constexpr uint32_t kAcc2 = kAhead ? NB * C : 0;   // column offset of the conv2 accumulators
+  constexpr uint32_t kCols = (kAhead ? 2 : 1) * NB * C < 32 ? 32 : (kAhead ? 2 : 1) * NB * C;
   static_assert((kCols & (kCols - 1)) == 0 && kCols <= 512, "TMEM columns");
   static_assert(EW == 4 || EW == 4 * NB, "epilogue warps");
   constexpr uint32_t kTapBytes = C * C * 2;
@@ -141,7 +146,7 @@ __global__ void __launch_bounds__((EW + 2) * 32, kMinCtas) voc_pair_kernel(const
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((128u - (raw_addr & 127u)) & 127u);
-  const VocPairSmem L = voc_pair_smem<C, NB, kRes, kXB>(a.k, a.dil);
+  const VocPairSmem L = voc_pair_smem<C, NB, kRes, kXB, kMinCtas>(a.k, a.dil);
   const uint32_t XPS = L.xr * 16, YPS = L.yr * 16;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar_off);
   uint64_t* xfull = bars;             // [2]   NT arrivals: a gathered x tile is visible to the tensor core
@@ -209,7 +214,7 @@ __global__ void __launch_bounds__((EW + 2) * 32, kMinCtas) voc_pair_kernel(const
     const uint32_t dil_u = (uint32_t)a.dil, idesc = a.idesc;
     uint32_t it = 0, wstage = 0, wparity = 0;
     // one convolution: k taps x NB row blocks x C/16 K steps; a_lo walks one tap (a_step rows) per iteration
-    auto issue_conv = [&](uint32_t a_lo, const uint32_t a_ps, const uint32_t a_step, uint32_t b_lo) {
+    auto issue_conv = [&](uint32_t d_tm, uint32_t a_lo, const uint32_t a_ps, const uint32_t a_step, uint32_t b_lo) {
 #pragma unroll 1
       for (int tp = 0; tp < k; ++tp) {
         uint32_t bt = b_lo;
@@ -223,7 +228,7 @@ __global__ void __launch_bounds__((EW + 2) * 32, kMinCtas) voc_pair_kernel(const
         for (int m = 0; m < NB; ++m)
 #pragma unroll
           for (int s = 0; s < C / 16; ++s)
-            umma_f16_lohi(tm + (uint32_t)(m * C), a_lo + (uint32_t)(2 * s) * a_ps + (uint32_t)(m * 128), kDescHi, bt + (uint32_t)(2 * s * C), kDescHi, idesc,
+            umma_f16_lohi(d_tm + (uint32_t)(m * C), a_lo + (uint32_t)(2 * s) * a_ps + (uint32_t)(m * 128), kDescHi, bt + (uint32_t)(2 * s * C), kDescHi, idesc,
                           s != 0 ? 1u : acc);
         if constexpr (!kRes) {
           umma_commit_elect(&wempty[wstage]);
@@ -234,23 +239,28 @@ __global__ void __launch_bounds__((EW + 2) * 32, kMinCtas) voc_pair_kernel(const
         a_lo += a_step;
       }
     };
-    if constexpr (kRes) mbar_wait(&wfull[0], 0, 22);
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const uint32_t buf = kXB == 2 ? (it & 1u) : 0u;
-      mbar_wait(&xfull[buf], kXB == 2 ? ((it >> 1) & 1u) : (it & 1u), 23);
+    auto conv1 = [&](uint32_t itx) {   // tile iteration itx: wait for its x tile, issue, commit
+      const uint32_t buf = kXB == 2 ? (itx & 1u) : 0u;
+      mbar_wait(&xfull[buf], kXB == 2 ? ((itx >> 1) & 1u) : (itx & 1u), 23, PD_PAIR_SLEEP_NS);
       tc_fence_after();
-      if (lane == 0) PD_PAIR_TRACE(8);
-      issue_conv(buf != 0u ? x_lo1 : x_lo0, L.xr, dil_u, w_lo);
+      issue_conv(tm, buf != 0u ? x_lo1 : x_lo0, L.xr, dil_u, w_lo);
       umma_commit_elect(acc1);
-      if (lane == 0) PD_PAIR_TRACE(9);
       __syncwarp();
-      mbar_wait(yfull, it & 1u, 24);
+    };
+    if constexpr (kRes) mbar_wait(&wfull[0], 0, 22);
+    if (kAhead && (int)blockIdx.x < num_tiles) conv1(0);
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      if (lane == 0) PD_PAIR_TRACE(8);
+      if (!kAhead) conv1(it);
+      if (lane == 0) PD_PAIR_TRACE(9);
+      mbar_wait(yfull, it & 1u, 24, PD_PAIR_SLEEP_NS);
       tc_fence_after();
       if (lane == 0) PD_PAIR_TRACE(10);
-      issue_conv(y_lo, L.yr, 1u, w_lo + (kRes ? (uint32_t)k * kTapUnits : 0u));
+      issue_conv(tm + kAcc2, y_lo, L.yr, 1u, w_lo + (kRes ? (uint32_t)k * kTapUnits : 0u));
       umma_commit_elect(acc2);
       if (lane == 0) PD_PAIR_TRACE(11);
       __syncwarp();
+      if (kAhead && tile + (int)gridDim.x < num_tiles) conv1(it + 1);   // overlaps this tile's second epilogue
     }
   } else {
     // ===================== gather + epilogues: a thread owns one row of a 128-row block (= its TMEM lane) =====================
@@ -283,20 +293,28 @@ __global__ void __launch_bounds__((EW + 2) * 32, kMinCtas) voc_pair_kernel(const
     const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
     const bool has_add = a.add != nullptr;
     uint32_t it = 0;
-    if (kXB == 2 && (int)blockIdx.x < num_tiles) gather(blockIdx.x, 0);
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const uint32_t buf = kXB == 2 ? (it & 1u) : 0u;
-      if (kXB == 1) gather(tile, 0);
+    auto publish_x = [&](uint32_t buf) {   // this thread's share of a gathered tile has landed: make it visible to the tensor core
       asm volatile("cp.async.wait_group 0;" ::: "memory");
       fence_proxy_async_smem();
-      if (tid == 0) PD_PAIR_TRACE(0);
       mbar_arrive(&xfull[buf]);
-      if (kXB == 2 && tile + (int)gridDim.x < num_tiles) gather(tile + gridDim.x, buf ^ 1u);
+    };
+    if (kAhead && (int)blockIdx.x < num_tiles) {
+      gather(blockIdx.x, 0);
+      publish_x(0);
+      if ((int)(blockIdx.x + gridDim.x) < num_tiles) gather(blockIdx.x + gridDim.x, 1);
+    }
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const uint32_t buf = kXB == 2 ? (it & 1u) : 0u;
+      if (!kAhead) {
+        gather(tile, 0);
+        publish_x(0);
+      }
+      if (tid == 0) PD_PAIR_TRACE(0);
       if (tid == 0) PD_PAIR_TRACE(1);
       const int b = tile / a.tiles_per_row;
       const int p0 = (tile - b * a.tiles_per_row) * P;
       // ---- epilogue 1: intermediate tile row i <-> position p0 - h + i; rows outside the utterance are conv2's zero padding
-      mbar_wait(acc1, it & 1u, 26);
+      mbar_wait(acc1, it & 1u, 26, PD_PAIR_SLEEP_NS);
       tc_fence_after();
       if (tid == 0) PD_PAIR_TRACE(2);
       {
@@ -338,9 +356,10 @@ __global__ void __launch_bounds__((EW + 2) * 32, kMinCtas) voc_pair_kernel(const
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(yfull);
+      if (kAhead && tile + (int)gridDim.x < num_tiles) publish_x(buf ^ 1u);   // the next tile, gathered during the previous iteration
       if (tid == 0) PD_PAIR_TRACE(4);
       // ---- epilogue 2: output row r <-> position p0 + r; raw x from tile row r + h + hd
-      mbar_wait(acc2, it & 1u, 27);
+      mbar_wait(acc2, it & 1u, 27, PD_PAIR_SLEEP_NS);
       tc_fence_after();
       if (tid == 0) PD_PAIR_TRACE(5);
       {
@@ -355,8 +374,8 @@ __global__ void __launch_bounds__((EW + 2) * 32, kMinCtas) voc_pair_kernel(const
 #pragma unroll
           for (int cc = 0; cc < C / CW; ++cc) {
             uint32_t r[CW];
-            if constexpr (CW == 32) tmem_ld_x32(tlane + (uint32_t)(m * C + cc * CW), r);
-            else tmem_ld_x16(tlane + (uint32_t)(m * C + cc * CW), r);
+            if constexpr (CW == 32) tmem_ld_x32(tlane + kAcc2 + (uint32_t)(m * C + cc * CW), r);
+            else tmem_ld_x16(tlane + kAcc2 + (uint32_t)(m * C + cc * CW), r);
             tmem_ld_wait();
             if (live || C >= 64) {
 #pragma unroll
@@ -419,6 +438,7 @@ __global__ void __launch_bounds__((EW + 2) * 32, kMinCtas) voc_pair_kernel(const
       if (tid == 0) PD_PAIR_TRACE(6);
       tc_fence_before();
       named_bar_sync(1, NT);   // every reader of this x tile / every TMEM drain is done before the buffers are reused
+      if (kAhead && tile + 2 * (int)gridDim.x < num_tiles) gather(tile + 2 * gridDim.x, buf);
       if (tid == 0) PD_PAIR_TRACE(7);
     }
   }
