@@ -14,7 +14,8 @@ HBM; `e2e` goes through the public module API from pinned HOST buffers with the 
 region; `roofline` is the dominant kernel (dilated conv + gate GEMM) timed with per-launch CUDA events in a second
 pass over the same steps; `cpu_baseline` is the CPU oracle port (the reference's algorithm in PyTorch fp32) on the host;
 `text_front` (N = 1, unscored, outside every timed region above) times the step in front of the path on the same batch:
-the text encoder and the whole tokens -> mel chain.
+the text encoder and the whole tokens -> mel chain; `wave_back` (same conditions) times the step behind it:
+the NSF-HiFiGAN generator on the batch the sampler hands over, and the chain condition -> mel -> waveform.
 """
 from __future__ import annotations
 
@@ -208,6 +209,43 @@ def text_front(gd, device, B, T, K):
             "text_to_mel_ms": t2m_ms, "text_to_mel_frames_per_s": B * T / t2m_ms * 1e3}
 
 
+def wave_back(gd, device, B, T, K):
+    """Not part of the metric: the step behind the hot path on the same batch -- the NSF-HiFiGAN generator
+    (pd_vocoder_forward, 44.1 kHz config, 512 samples per frame) on the [B, 128, T] tensor the sampler hands over, and the chain
+    condition -> 4-step sampler (vocoder_scale fused into its last write) -> waveform.  CUDA-event timed, 3 warm-up + 5 timed calls."""
+    import prodiff_b200 as pb
+    from prodiff_b200 import handoff, synth
+    h = synth.VOCODER_44K
+    gen = pb.Generator(h)
+    gen.load_state_dict(synth.make_vocoder_state(h, 7))
+    gen = gen.to(device).eval()
+    cfg = synth.DiffNetConfig()
+    cond, _, _ = synth.make_inputs(cfg, B, T, 1, 5)
+    cond = cond.to(device)
+    f0 = torch.full((B, T), 220.0, device=device)
+
+    def ms(fn, n=5, warm=3):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / n
+    with torch.no_grad():
+        c = gd(cond, infer_step=K, infer=True, seed=1, vocoder_scale=handoff.LOG10_TO_LN)
+        voc_ms = ms(lambda: gen(c, f0, seed=1))
+        chain_ms = ms(lambda: gen(gd(cond, infer_step=K, infer=True, seed=1, vocoder_scale=handoff.LOG10_TO_LN), f0, seed=1))
+    upp = gen.upp
+    return {"workload": f"{B} utt x {T} frames x 128 mel -> {B} x {T * upp} samples, NSF-HiFiGAN 44.1 kHz config (512 initial channels, rates 8-8-2-2-2)",
+            "vocoder_ms": voc_ms, "vocoder_frames_per_s": B * T / voc_ms * 1e3, "vocoder_x_realtime": B * T / voc_ms * 1e3 / FRAME_RATE,
+            "vocoder_tflops": B * T * 648e6 / (voc_ms * 1e-3) / 1e12,
+            "cond_to_wave_ms": chain_ms, "cond_to_wave_frames_per_s": B * T / chain_ms * 1e3}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -217,6 +255,7 @@ def main():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-text-front", action="store_true", help="skip the (unscored) encoder / text -> mel timing")
+    ap.add_argument("--no-wave-back", action="store_true", help="skip the (unscored) vocoder / condition -> waveform timing")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -428,6 +467,11 @@ def main():
                 out["text_front"] = text_front(gd, device, B, T, K)
             except Exception as e:  # never let the unscored extra break the bench line
                 out["text_front"] = {"error": f"{type(e).__name__}: {e}"}
+        if not args.no_wave_back and world == 1:
+            try:
+                out["wave_back"] = wave_back(gd, device, B, T, K)
+            except Exception as e:
+                out["wave_back"] = {"error": f"{type(e).__name__}: {e}"}
         if not args.no_cpu_baseline and world == 1:
             out["cpu_baseline"] = cpu_baseline()
         print(json.dumps(out))
