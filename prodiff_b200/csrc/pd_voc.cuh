@@ -67,11 +67,14 @@ __device__ __forceinline__ void voc_cp_async16(uint32_t dst_smem, const void* sr
   const int n = pred ? 16 : 0;   // src-size 0: the 16 bytes are zero-filled
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(n) : "memory");
 }
-template <int BN> struct VocCfg {
+// kPair: two CTAs of a cluster take two adjacent 128-position tiles as ONE tcgen05.mma.cta_group::2 (M = 256); each CTA stages its
+// own A tile and HALF of every weight block, so an MMA fetches 4 KB + BN * 16 B of operands per SM instead of 4 KB + BN * 32 B --
+// the wide convolutions (BN = 128 / 256) run at the shared-memory operand rate, not at the tensor rate.
+template <int BN, bool kPair = false> struct VocCfg {
   static constexpr int kCW = BN >= 64 ? 32 : BN;                  // columns per epilogue chunk
   static constexpr int kRowWords = kCW / 2 + 4;                   // staging row: kCW halves + 16 bytes of padding
   static constexpr uint32_t kABytes = kBlockM * kBlockK * 2;
-  static constexpr uint32_t kBBytes = BN * kBlockK * 2;
+  static constexpr uint32_t kBBytes = (kPair ? BN / 2 : BN) * kBlockK * 2;
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;
   static constexpr uint32_t kStagingBytes = kEpiWarps * 32 * kRowWords * 4;
   static constexpr int kStagesFit = (int)((200u * 1024u - kStagingBytes) / kStageBytes);
@@ -79,10 +82,11 @@ template <int BN> struct VocCfg {
   static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 + 256;
 };
 
-template <int BN, bool kGather>
+template <int BN, bool kGather, bool kPair = false>
 __global__ void __launch_bounds__(kGemmThreads + (kGather ? kVocGatherThreads : 0), 1)
 voc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const VocShape sh, const VocEpi ep) {
-  using Cfg = VocCfg<BN>;
+  using Cfg = VocCfg<BN, kPair>;
+  static_assert(!(kPair && kGather) && (!kPair || BN >= 128), "pairs: TMA-fed wide tiles only");
   constexpr int kStages = Cfg::kStages;
   constexpr int CW = Cfg::kCW;
   constexpr int RW = Cfg::kRowWords;
@@ -100,38 +104,52 @@ voc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = kPair ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kStages; ++i) {
-      mbar_init(&full_bar[i], kGather ? 1 + kVocGatherThreads : 1);   // B by TMA (+ one arrival per gathering thread)
+      mbar_init(&full_bar[i], kPair ? 2 : (kGather ? 1 + kVocGatherThreads : 1));   // B by TMA (+ one arrival per gathering thread)
       mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], BN >= 64 ? kEpiWarps : kEpiWarps / 2);   // narrow tiles: one warp group per accumulator stage
+      mbar_init(&tempty_bar[i], (kPair ? 2 : 1) * (BN >= 64 ? kEpiWarps : kEpiWarps / 2));   // narrow tiles: one warp group per accumulator stage
     }
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc<kTmemCols>(tmem_slot);
-  tc_fence_before();
-  __syncthreads();
+  if constexpr (kPair) {
+    cluster_sync_all();   // both CTAs alive + barriers initialised before any remote arrive / paired allocation
+    if (warp == 2) tmem_alloc_2sm<kTmemCols>(tmem_slot);
+    tc_fence_before();
+    cluster_sync_all();
+  } else {
+    if (warp == 2) tmem_alloc<kTmemCols>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+  }
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // the generator is a chain of ~100 short launches: overlap this grid's prologue with the previous grid's tail
   griddep_launch();
   griddep_wait();
 
-  const int num_tiles = sh.B * sh.m_tiles_per_row * sh.n_tiles;
+  // work items: (m-tile, n-tile), or (pair of adjacent m-tiles, n-tile) with this CTA taking m-tile 2 * pair + rank (a
+  // trailing odd tile's partner has b == B: its loads are zero-filled and its epilogue stores nothing)
+  const int num_m_tiles = sh.B * sh.m_tiles_per_row;
+  const int num_tiles = (kPair ? (num_m_tiles + 1) / 2 : num_m_tiles) * sh.n_tiles;
+  const int tile_first = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, tile_step = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const int k_blocks = sh.tap_groups * sh.cc_blocks;
+  auto m_tile_of = [&](int tile) { return kPair ? 2 * (tile / sh.n_tiles) + (int)rank : tile / sh.n_tiles; };
 
   if (warp == 0) {
     if (lane == 0) {
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int n_tile = tile % sh.n_tiles, m_tile = tile / sh.n_tiles;
+      for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
+        const int n_tile = tile % sh.n_tiles, m_tile = m_tile_of(tile);
         const int b = m_tile / sh.m_tiles_per_row;
         const int t0 = (m_tile - b * sh.m_tiles_per_row) * kBlockM;
         for (int kb = 0; kb < k_blocks; ++kb, ++it) {
@@ -139,20 +157,27 @@ voc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           mbar_wait(&empty_bar[stage], parity ^ 1u, 1);
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           const int tg = kb / sh.cc_blocks, cc = kb - tg * sh.cc_blocks;
-          if constexpr (kGather) {
-            mbar_arrive_expect_tx(&full_bar[stage], Cfg::kBBytes);
+          if constexpr (kPair) {
+            if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+            else mbar_arrive_leader(&full_bar[stage]);
+            tma_load_4d_2sm(sa, &tmA, &full_bar[stage], cc * kBlockK, tg * sh.g, t0, b);
+            tma_load_2d_2sm(sa + Cfg::kABytes, &tmB, &full_bar[stage], kb * kBlockK, n_tile * BN + (int)rank * (BN / 2));
           } else {
-            mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-            tma_load_4d(sa, &tmA, &full_bar[stage], cc * kBlockK, tg * sh.g, t0, b);
+            if constexpr (kGather) {
+              mbar_arrive_expect_tx(&full_bar[stage], Cfg::kBBytes);
+            } else {
+              mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+              tma_load_4d(sa, &tmA, &full_bar[stage], cc * kBlockK, tg * sh.g, t0, b);
+            }
+            tma_load_2d(sa + Cfg::kABytes, &tmB, &full_bar[stage], kb * kBlockK, n_tile * BN);
           }
-          tma_load_2d(sa + Cfg::kABytes, &tmB, &full_bar[stage], kb * kBlockK, n_tile * BN);
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (lane == 0 && leader) {
       uint32_t it = 0, ti = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
+      for (int tile = tile_first; tile < num_tiles; tile += tile_step, ++ti) {
         const uint32_t as = ti & 1u, aph = (ti >> 1) & 1u;
         mbar_wait(&tempty_bar[as], aph ^ 1u, 2);
         tc_fence_after();
@@ -165,11 +190,15 @@ voc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           const uint64_t adesc = make_sw128_kmajor_desc(sa);
           const uint64_t bdesc = make_sw128_kmajor_desc(sa + Cfg::kABytes);
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k)
-            umma_f16(d_tmem, desc_advance_k(adesc, k), desc_advance_k(bdesc, k), sh.idesc, (kb | k) != 0 ? 1u : 0u);
-          umma_commit(&empty_bar[stage]);
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            if constexpr (kPair) umma_f16_2sm(d_tmem, desc_advance_k(adesc, k), desc_advance_k(bdesc, k), sh.idesc, (kb | k) != 0 ? 1u : 0u);
+            else umma_f16(d_tmem, desc_advance_k(adesc, k), desc_advance_k(bdesc, k), sh.idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          if constexpr (kPair) umma_commit_2sm(&empty_bar[stage]);
+          else umma_commit(&empty_bar[stage]);
         }
-        umma_commit(&tfull_bar[as]);
+        if constexpr (kPair) umma_commit_2sm(&tfull_bar[as]);
+        else umma_commit(&tfull_bar[as]);
       }
     }
   } else if (warp >= 2 + kEpiWarps) {
@@ -185,8 +214,8 @@ voc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       // threads, keeps it off the single MMA-issuing thread (where a per-block proxy fence cost ~1000 cycles per K block).
       constexpr int kLag = kStages >= 6 ? 4 : (kStages >= 4 ? 2 : 1);
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_tile = tile / sh.n_tiles;
+      for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
+        const int m_tile = m_tile_of(tile);
         const int b = m_tile / sh.m_tiles_per_row;
         const int pos = (m_tile - b * sh.m_tiles_per_row) * kBlockM + tau;
         const bool in_utt = pos < sh.T;
@@ -314,12 +343,12 @@ voc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     constexpr int kChunks = BN >= 64 ? (BN / 2) / 32 : 1;
     const bool works = BN >= 64 || h == 0;  // narrow tiles: one warp per lane quadrant takes all BN columns
     uint32_t ti = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
-      const int n_tile = tile % sh.n_tiles, m_tile = tile / sh.n_tiles;
+    for (int tile = tile_first; tile < num_tiles; tile += tile_step, ++ti) {
+      const int n_tile = tile % sh.n_tiles, m_tile = m_tile_of(tile);
       const int b = m_tile / sh.m_tiles_per_row;
       const int t0 = (m_tile - b * sh.m_tiles_per_row) * kBlockM;
       const int t = t0 + q * 32 + lane;                       // this thread's position (accumulator row)
-      const int rows_left = sh.T - (t0 + q * 32);            // rows of this warp's 32-row slab inside the utterance
+      const int rows_left = b < sh.B ? sh.T - (t0 + q * 32) : 0;   // rows of this warp's 32-row slab inside the utterance (0: a pair's phantom tile)
       const uint32_t as = ti & 1u, aph = (ti >> 1) & 1u;
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
       mbar_wait(&tfull_bar[as], aph, 4);
@@ -380,7 +409,7 @@ voc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             v[j] = x;
           }
           if (ep.out32 != nullptr) {
-            if (gcol == 0 && t < sh.T) ep.out32[(long long)b * sh.T + t] = v[0];
+            if (gcol == 0 && t < sh.T && b < sh.B) ep.out32[(long long)b * sh.T + t] = v[0];
           } else {
 #pragma unroll
             for (int j = 0; j < CW; j += 8)
@@ -401,16 +430,21 @@ voc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      if (lane == 0) {
+        if constexpr (kPair) mbar_arrive_leader(&tempty_bar[as]);
+        else mbar_arrive(&tempty_bar[as]);
+      }
     }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (kPair) cluster_sync_all();   // the leader's MMAs read the peer's shared memory and write its TMEM
+  else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc<kTmemCols>(tmem_base);
+    if constexpr (kPair) tmem_dealloc_2sm<kTmemCols>(tmem_base);
+    else tmem_dealloc<kTmemCols>(tmem_base);
   }
 }
 

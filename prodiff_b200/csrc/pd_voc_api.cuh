@@ -14,6 +14,7 @@ struct VocConv {        // one packed convolution
   size_t w_off, b_off;  // byte offsets in the packed block (fp16 weights [n_total][k_total], fp32 bias [n_total])
   int cin, n_total, taps, taps_pad, dil, bn;
   CUtensorMap tm_w;
+  CUtensorMap tm_w_half;   // half-height boxes (bn / 2 rows) for the cta_group::2 form; valid when bn >= 128
 };
 
 // 4-D activation map over a guarded channels-last buffer (see pd_voc.cuh): dims (C, taps, T, B), overlapping strides.
@@ -38,10 +39,10 @@ int make_voc_a_map(CUtensorMap* m, const void* buf, int C, int taps, int dil, in
   return 0;
 }
 
-template <int BN, bool kGather>
+template <int BN, bool kGather, bool kPair = false>
 int launch_voc_t(const CUtensorMap& a, const CUtensorMap& w, const VocShape& sh, const VocEpi& ep, int sms, cudaStream_t s) {
-  auto kern = voc_conv_kernel<BN, kGather>;
-  using Cfg = VocCfg<BN>;
+  auto kern = voc_conv_kernel<BN, kGather, kPair>;
+  using Cfg = VocCfg<BN, kPair>;
   static bool configured[64] = {false};
   int dev = 0;
   PD_CUDA(cudaGetDevice(&dev));
@@ -49,17 +50,22 @@ int launch_voc_t(const CUtensorMap& a, const CUtensorMap& w, const VocShape& sh,
     PD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes));
     configured[dev & 63] = true;
   }
-  const int items = sh.B * sh.m_tiles_per_row * sh.n_tiles;
+  const int m_tiles = sh.B * sh.m_tiles_per_row;
+  const int items = (kPair ? (m_tiles + 1) / 2 : m_tiles) * sh.n_tiles;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(items < sms ? items : sms);
+  cfg.gridDim = dim3(kPair ? 2 * (items < sms / 2 ? items : sms / 2) : (items < sms ? items : sms));
   cfg.blockDim = dim3(kGemmThreads + (kGather ? kVocGatherThreads : 0));
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = s;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
+  attr[1].id = cudaLaunchAttributeClusterDimension;
+  attr[1].val.clusterDim.x = 2;
+  attr[1].val.clusterDim.y = 1;
+  attr[1].val.clusterDim.z = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = kPair ? 2 : 1;
   prof_before(13, s);
   PD_CUDA(cudaLaunchKernelEx(&cfg, kern, a, w, sh, ep));
   prof_after(s);
@@ -67,8 +73,18 @@ int launch_voc_t(const CUtensorMap& a, const CUtensorMap& w, const VocShape& sh,
   return 0;
 }
 
+int g_voc_pair = -1;       // -1: read PD_VOC_PAIR from the environment on first use (default on)
+bool voc_pair_mode() {
+  if (g_voc_pair < 0) {
+    const char* e = getenv("PD_VOC_PAIR");
+    g_voc_pair = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_voc_pair == 1;
+}
+
 // `abuf`: the guarded activation buffer the convolution reads (its first element).  C >= 64: read through the 4-D map `a`;
-// C < 64: gathered by the kernel's extra producer warps (the map is unused).
+// C < 64: gathered by the kernel's extra producer warps (the map is unused).  Tiles of 128 / 256 output channels with at
+// least two position tiles run as cta_group::2 pairs.
 int launch_voc(const VocConv& cv, const CUtensorMap& a, const __half* abuf, int B, int T, VocEpi ep, int sms, cudaStream_t s) {
   VocShape sh;
   memset(&sh, 0, sizeof(sh));
@@ -86,6 +102,10 @@ int launch_voc(const VocConv& cv, const CUtensorMap& a, const __half* abuf, int 
   sh.a_dil = cv.dil;
   sh.a_G = kVocG;
   const bool gather = cv.cin < 64;
+  if (!gather && cv.bn >= 128 && voc_pair_mode() && B * sh.m_tiles_per_row >= 2) {
+    sh.idesc = make_idesc(PD_FP16, cv.bn, 256);
+    return cv.bn == 128 ? launch_voc_t<128, false, true>(a, cv.tm_w_half, sh, ep, sms, s) : launch_voc_t<256, false, true>(a, cv.tm_w_half, sh, ep, sms, s);
+  }
   switch (cv.bn) {
     case 16: return gather ? launch_voc_t<16, true>(a, cv.tm_w, sh, ep, sms, s) : launch_voc_t<16, false>(a, cv.tm_w, sh, ep, sms, s);
     case 32: return gather ? launch_voc_t<32, true>(a, cv.tm_w, sh, ep, sms, s) : launch_voc_t<32, false>(a, cv.tm_w, sh, ep, sms, s);
@@ -315,7 +335,8 @@ extern "C" int pd_vocoder_create(const pd_vocoder_config* cfg, const float* cons
     k_voc_pack_conv<<<blocks((long long)cv.n_total * cv.taps_pad * cv.cin), TB, 0, s>>>((__half*)(pk + cv.w_off), w, cout, cv.cin, cv.taps, cv.n_total, cv.taps_pad);
     k_voc_pad_bias<<<blocks(cv.n_total), TB, 0, s>>>((float*)(pk + cv.b_off), b, cout, cv.n_total);
     PD_LAUNCH_CHECK("k_voc_pack_conv");
-    return make_w_map(&cv.tm_w, PD_FP16, pk + cv.w_off, cv.taps_pad * cv.cin, cv.n_total, cv.bn);
+    if (make_w_map(&cv.tm_w, PD_FP16, pk + cv.w_off, cv.taps_pad * cv.cin, cv.n_total, cv.bn)) return 1;
+    return cv.bn >= 128 ? make_w_map(&cv.tm_w_half, PD_FP16, pk + cv.w_off, cv.taps_pad * cv.cin, cv.n_total, cv.bn / 2) : 0;
   };
   int si = 0, rc = 0;
   rc |= pack_conv(v->conv_pre, state[si], state[si + 1], cfg->upsample_initial_channel);
@@ -328,6 +349,7 @@ extern "C" int pd_vocoder_create(const pd_vocoder_config* cfg, const float* cons
     k_voc_tile_bias<<<blocks(up.n_total), TB, 0, s>>>((float*)(pk + up.b_off), state[si + 1], ch / 2, up.n_total);
     PD_LAUNCH_CHECK("k_voc_pack_convT");
     rc |= make_w_map(&up.tm_w, PD_FP16, pk + up.w_off, up.taps_pad * up.cin, up.n_total, up.bn);
+    if (!rc && up.bn >= 128) rc |= make_w_map(&up.tm_w_half, PD_FP16, pk + up.w_off, up.taps_pad * up.cin, up.n_total, up.bn / 2);
     ch /= 2;
     k_voc_transpose_src<<<blocks((long long)ch * v->src_k[i]), TB, 0, s>>>((float*)(pk + v->src_w[i]), state[si + 2], ch, v->src_k[i]);
     PD_LAUNCH_CHECK("k_voc_transpose_src");
@@ -639,6 +661,7 @@ extern "C" int pd_voc_debug_conv(const float* x, int B, int T, int Cin, const fl
   PD_LAUNCH_CHECK("k_voc_dbg_in");
   CUtensorMap tmA;
   if (make_voc_a_map(&tmA, xin, Cin, k, dil, T, B) || make_w_map(&cv.tm_w, PD_FP16, w16, cv.taps_pad * Cin, n_pad, cv.bn)) return 1;
+  if (cv.bn >= 128 && make_w_map(&cv.tm_w_half, PD_FP16, w16, cv.taps_pad * Cin, n_pad, cv.bn / 2)) return 1;
   VocEpi ep = voc_epi();
   ep.out16 = o16 + (size_t)kVocG * n_pad;
   ep.out_bstride = (long long)(T + 2 * kVocG) * n_pad;
