@@ -221,9 +221,13 @@ size_t pd_vocoder_workspace_bytes(const pd_vocoder* v, int B, int T);
  * pd_plan_set_output_scale makes the sampler write); f0 [B, T] fp32 device; rand_ini [9] fp32 device: SineGen's random
  * initial phases (models.py:143-145; entry 0 must be 0); noise: optional [B, T * upp, 9] fp32 device N(0,1) draws standing
  * in for torch.randn_like (:186), NULL = in-kernel Philox keyed by `seed`; wave [B, T * upp] fp32 device (the reference
- * returns it as [B, 1, T * upp]).  workspace: pd_vocoder_workspace_bytes(v, B, T) bytes, 1024-aligned, used during the call. */
+ * returns it as [B, 1, T * upp]).  lengths: optional [B] int32 device, valid frames per utterance of a padded batch (NULL = all
+ * T): every activation past lengths[b] is kept at zero through the whole generator, so samples [0, lengths[b] * upp) of row b
+ * are exactly what a call on that utterance alone returns (the reference runs one utterance per call) and the rest of the row
+ * is zeros; whatever c and f0 hold past lengths[b] is ignored.  workspace: pd_vocoder_workspace_bytes(v, B, T) bytes,
+ * 1024-aligned, used during the call. */
 int pd_vocoder_forward(pd_vocoder* v, const float* c, const float* f0, const float* rand_ini, const float* noise, uint64_t seed,
-                       float* wave, int B, int T, void* workspace, size_t workspace_bytes, void* stream);
+                       const int* lengths, float* wave, int B, int T, void* workspace, size_t workspace_bytes, void* stream);
 /* Test hook: one convolution through the generator's kernel (fp16 operands): out [B, Cout, T] = conv1d(x [B, Cin, T],
  * w [Cout, Cin, k], bias, dilation = dil, padding = (k - 1) / 2 * dil), all fp32 device tensors. */
 size_t pd_voc_debug_conv_scratch(int B, int T, int Cin, int Cout, int k);

@@ -10,6 +10,7 @@ Public surface (mirrors the reference's module API for this path, SURVEY.md sect
     FastspeechEncoder(vocab_size, hidden_size, num_layers, kernel_size, dropout, num_heads, rel_pos)
         .forward(txt_tokens, extra_embed=None)                           (the step before the sampler)
     Generator(h).forward(x, f0)                                          (the NSF-HiFiGAN generator after it)
+    pipeline.Synthesizer(teacher, generator)(txt_tokens, mel2ph, f0)     (tokens -> waveforms for a padded batch of segments)
 
 ``install()`` swaps these classes into the reference's own modules so that ``ProDiffTeacher``, the SVS inferer
 (``handler/infer/handler.py``), ``main.py infer`` and the vocoder hand-off run unchanged on top of them.

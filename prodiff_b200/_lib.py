@@ -92,7 +92,7 @@ def load() -> C.CDLL:
     lib.pd_vocoder_destroy.argtypes = [vp]; lib.pd_vocoder_destroy.restype = None
     lib.pd_vocoder_upp.argtypes = [vp]; lib.pd_vocoder_upp.restype = C.c_int
     lib.pd_vocoder_workspace_bytes.argtypes = [vp, C.c_int, C.c_int]; lib.pd_vocoder_workspace_bytes.restype = sz
-    lib.pd_vocoder_forward.argtypes = [vp, vp, vp, vp, vp, u64, vp, C.c_int, C.c_int, vp, sz, vp]; lib.pd_vocoder_forward.restype = C.c_int
+    lib.pd_vocoder_forward.argtypes = [vp, vp, vp, vp, vp, u64, vp, vp, C.c_int, C.c_int, vp, sz, vp]; lib.pd_vocoder_forward.restype = C.c_int
     lib.pd_voc_debug_conv_scratch.argtypes = [C.c_int] * 5; lib.pd_voc_debug_conv_scratch.restype = sz
     lib.pd_voc_debug_conv.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, sz, vp]
     lib.pd_voc_debug_conv.restype = C.c_int

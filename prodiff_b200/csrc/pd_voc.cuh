@@ -59,6 +59,8 @@ struct VocEpi {
   float scale;             // applied after the sums
   int act;                 // 0 none, 1 LeakyReLU(slope), 2 tanh
   float slope;
+  const int* lengths;      // optional [B] valid mel frames per utterance (ragged batch): output rows >= lengths[b] * len_mul are
+  int len_mul;             // stored as zeros, so every later convolution sees the zero padding a run of that utterance alone sees
 };
 
 constexpr int kVocGatherThreads = 128;   // one per position of a 128-row tile
@@ -259,6 +261,7 @@ voc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int b = m_tile / sh.m_tiles_per_row;
         const int t = (m_tile - b * sh.m_tiles_per_row) * kBlockM + q * 32 + lane;
         const bool live = t < sh.T;
+        const bool valid = ep.lengths == nullptr || t < ep.lengths[b] * ep.len_mul;   // ragged batch: rows past the utterance's own end become zeros
         const int gcol = n_tile * BN;
         const uint32_t as = ti & 1u, aph = (ti >> 1) & 1u;
         uint4 rs[NV], ad[NV];
@@ -323,7 +326,7 @@ voc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             float x = v[j] * ep.scale;
             if (ep.act == 1) x = x >= 0.f ? x : x * ep.slope;
             else if (ep.act == 2) x = tanhf(x);
-            v[j] = x;
+            v[j] = valid ? x : 0.f;
           }
           if (ep.out32 != nullptr) {
             if (gcol == 0) ep.out32[(long long)b * sh.T + t] = v[0];
@@ -349,6 +352,7 @@ voc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int t0 = (m_tile - b * sh.m_tiles_per_row) * kBlockM;
       const int t = t0 + q * 32 + lane;                       // this thread's position (accumulator row)
       const int rows_left = b < sh.B ? sh.T - (t0 + q * 32) : 0;   // rows of this warp's 32-row slab inside the utterance (0: a pair's phantom tile)
+      const bool valid = ep.lengths == nullptr || b >= sh.B || t < ep.lengths[b] * ep.len_mul;   // ragged batch: rows past the utterance's own end become zeros
       const uint32_t as = ti & 1u, aph = (ti >> 1) & 1u;
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
       mbar_wait(&tfull_bar[as], aph, 4);
@@ -406,7 +410,7 @@ voc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             float x = v[j] * ep.scale;
             if (ep.act == 1) x = x >= 0.f ? x : x * ep.slope;
             else if (ep.act == 2) x = tanhf(x);
-            v[j] = x;
+            v[j] = valid ? x : 0.f;
           }
           if (ep.out32 != nullptr) {
             if (gcol == 0 && t < sh.T && b < sh.B) ep.out32[(long long)b * sh.T + t] = v[0];
@@ -486,13 +490,15 @@ __global__ void k_voc_pad_bias(float* __restrict__ dst, const float* __restrict_
 
 // ------------------------------------------------------------------ generator input / harmonic source
 // c [B, M, T] fp32 (the sampler's hand-off tensor, nsf_hifigan.py:50-52) -> guarded channels-last fp16 [B][G + T + G][M]
-__global__ void k_voc_mel_in(__half* __restrict__ dst, const float* __restrict__ c, int M, int Tn, int G) {
+// lengths: optional [B] valid frames per utterance; frames past it enter as zeros (whatever the caller's tensor holds there)
+__global__ void k_voc_mel_in(__half* __restrict__ dst, const float* __restrict__ c, int M, int Tn, int G, const int* __restrict__ lengths) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z, m0 = blockIdx.y * 32, t0 = blockIdx.x * 32;
   const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+  const int Tb = lengths != nullptr ? min(Tn, lengths[b]) : Tn;
   for (int i = ty; i < 32; i += 8) {
     const int m = m0 + i, t = t0 + tx;
-    tile[i][tx] = (m < M && t < Tn) ? c[((long long)b * M + m) * Tn + t] : 0.f;
+    tile[i][tx] = (m < M && t < Tb) ? c[((long long)b * M + m) * Tn + t] : 0.f;
   }
   __syncthreads();
   for (int i = ty; i < 32; i += 8) {
@@ -571,15 +577,16 @@ __host__ __device__ inline int voc_src_positions(int C, int ppt) { return ppt * 
 template <bool kVec4>
 __global__ void __launch_bounds__(kSrcThreads, 2)
 k_voc_srcconv(__half* __restrict__ dst, const float* __restrict__ har, const float* __restrict__ wt, const float* __restrict__ bias,
-              int C, int k, int stride, int pad, int To, long long Lh, int G, int ppt) {
+              int C, int k, int stride, int pad, int To, long long Lh, int G, int ppt, const int* __restrict__ lengths, int upp) {
   extern __shared__ __align__(16) float s_h[];   // (positions - 1) * stride + k samples
   const int n_cg = C / 8, n_ps = kSrcThreads / n_cg, n_pos = ppt * n_ps;
   const int b = blockIdx.y, o0 = blockIdx.x * n_pos;
   const int win = (n_pos - 1) * stride + k;
   const long long h0 = (long long)o0 * stride - pad;
+  const long long Lb = lengths != nullptr ? min(Lh, (long long)lengths[b] * upp) : Lh;   // ragged batch: the source ends with the utterance
   for (int i = threadIdx.x; i < win; i += kSrcThreads) {
     const long long n = h0 + i;
-    s_h[i] = (n >= 0 && n < Lh) ? har[(long long)b * Lh + n] : 0.f;
+    s_h[i] = (n >= 0 && n < Lb) ? har[(long long)b * Lh + n] : 0.f;
   }
   __syncthreads();
   const int cg = threadIdx.x % n_cg, ps = threadIdx.x / n_cg;   // positions ps, ps + n_ps, ..., ps + 7 * n_ps of the block

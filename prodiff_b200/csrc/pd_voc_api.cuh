@@ -419,7 +419,7 @@ extern "C" size_t pd_vocoder_workspace_bytes(const pd_vocoder* v, int B, int T) 
 }
 
 extern "C" int pd_vocoder_forward(pd_vocoder* v, const float* c, const float* f0, const float* rand_ini, const float* noise, uint64_t seed,
-                                  float* wave, int B, int T, void* workspace, size_t workspace_bytes, void* stream) {
+                                  const int* lengths, float* wave, int B, int T, void* workspace, size_t workspace_bytes, void* stream) {
   if (!v || !c || !f0 || !rand_ini || !wave) return fail("null argument");
   if (B < 1 || T < 1) return fail("B and T must be >= 1 (got %d, %d)", B, T);
   if ((long long)B * T * v->upp >= (1ll << 31)) return fail("B * T * upp too large for one call");
@@ -452,7 +452,7 @@ extern "C" int pd_vocoder_forward(pd_vocoder* v, const float* c, const float* f0
   if (zero_guards(mel, T, cf.num_mels)) return 1;
   {
     const dim3 grid((T + 31) / 32, cf.num_mels / 32, B), block(32, 8);
-    k_voc_mel_in<<<grid, block, 0, s>>>(mel, c, cf.num_mels, T, G);
+    k_voc_mel_in<<<grid, block, 0, s>>>(mel, c, cf.num_mels, T, G, lengths);
     PD_LAUNCH_CHECK("k_voc_mel_in");
   }
   __half* act[7];
@@ -471,6 +471,8 @@ extern "C" int pd_vocoder_forward(pd_vocoder* v, const float* c, const float* f0
     ep.bias = (const float*)(pk + v->conv_pre.b_off);
     ep.act = 1;
     ep.slope = 0.1f;
+    ep.lengths = lengths;
+    ep.len_mul = 1;
     if (launch_voc(v->conv_pre, tmA, mel, B, (int)Ti, ep, sms, s)) return 1;
   }
   for (int i = 0; i < cf.n_upsamples; ++i) {
@@ -492,10 +494,10 @@ extern "C" int pd_vocoder_forward(pd_vocoder* v, const float* c, const float* f0
       const dim3 grid((unsigned)((To + npos - 1) / npos), B);
       if (st % 4 == 0 && k % 4 == 0 && k >= 32)   // long kernels are FMA-bound once four taps come per shared-memory load; short ones are store-bound
         k_voc_srcconv<true><<<grid, kSrcThreads, shm, s>>>(SRC, har, (const float*)(pk + v->src_w[i]), (const float*)(pk + v->src_b[i]), co, k, st, v->src_pad[i],
-                                                           (int)To, Lh, G, ppt);
+                                                           (int)To, Lh, G, ppt, lengths, v->upp);
       else
         k_voc_srcconv<false><<<grid, kSrcThreads, shm, s>>>(SRC, har, (const float*)(pk + v->src_w[i]), (const float*)(pk + v->src_b[i]), co, k, st, v->src_pad[i],
-                                                            (int)To, Lh, G, ppt);
+                                                            (int)To, Lh, G, ppt, lengths, v->upp);
       PD_LAUNCH_CHECK("k_voc_srcconv");
     }
     // x = ups[i](leaky_relu(x)) + x_source (:274-277), stored activated for the ResBlocks' first convs
@@ -512,6 +514,8 @@ extern "C" int pd_vocoder_forward(pd_vocoder* v, const float* c, const float* f0
       ep.add_ld = u * co;
       ep.act = 1;
       ep.slope = 0.1f;
+      ep.lengths = lengths;
+      ep.len_mul = (int)(Ti / T);   // rows of a transposed conv are its INPUT positions
       if (launch_voc(v->ups[i], tmA, act[cur_in], B, (int)Ti, ep, sms, s)) return 1;
     }
     // xs = sum over the ResBlocks (:278-284); each ResBlock1 is three (conv dil d -> conv dil 1 -> + x) rounds (:62-69)
@@ -562,6 +566,8 @@ extern "C" int pd_vocoder_forward(pd_vocoder* v, const float* c, const float* f0
           pa.scale = scale;
           pa.act = act;
           pa.slope = slope;
+          pa.lengths = lengths;
+          pa.len_mul = (int)(To / T);
           if (launch_voc_pair(co, pa, sms, s)) return 1;
           continue;
         }
@@ -574,6 +580,8 @@ extern "C" int pd_vocoder_forward(pd_vocoder* v, const float* c, const float* f0
           ep.bias = (const float*)(pk + c1.b_off);
           ep.act = 1;
           ep.slope = 0.1f;
+          ep.lengths = lengths;
+          ep.len_mul = (int)(To / T);
           if (launch_voc(c1, tmA, xin, B, (int)To, ep, sms, s)) return 1;
         }
         {
@@ -590,6 +598,8 @@ extern "C" int pd_vocoder_forward(pd_vocoder* v, const float* c, const float* f0
           ep.scale = scale;
           ep.act = act;
           ep.slope = slope;
+          ep.lengths = lengths;
+          ep.len_mul = (int)(To / T);
           if (launch_voc(c2, tmA, TMP, B, (int)To, ep, sms, s)) return 1;
         }
       }
@@ -605,6 +615,8 @@ extern "C" int pd_vocoder_forward(pd_vocoder* v, const float* c, const float* f0
     ep.out32 = wave;
     ep.bias = (const float*)(pk + v->conv_post.b_off);
     ep.act = 2;
+    ep.lengths = lengths;
+    ep.len_mul = v->upp;
     if (launch_voc(v->conv_post, tmA, act[cur_in], B, (int)Ti, ep, sms, s)) return 1;
   }
   return 0;

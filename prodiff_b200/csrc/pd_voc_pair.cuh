@@ -45,6 +45,8 @@ struct VocPairArgs {
   int act;                 // 0 none, 1 LeakyReLU(slope)
   float slope;
   uint32_t idesc;
+  const int* lengths;      // optional [B] valid mel frames per utterance: positions >= lengths[b] * len_mul are zeros in both the
+  int len_mul;             // intermediate and the result (ragged batch = every utterance computed as if alone)
   long long* trace;        // debug: CTA 0 stamps clock64() at [tile iteration * 16 + slot] for its first 64 tiles (pd_debug_set_trace)
 };
 
@@ -313,18 +315,19 @@ __global__ void __launch_bounds__((EW + 2) * 32, kMinCtas) voc_pair_kernel(const
       if (tid == 0) PD_PAIR_TRACE(1);
       const int b = tile / a.tiles_per_row;
       const int p0 = (tile - b * a.tiles_per_row) * P;
+      const int Tb = a.lengths != nullptr ? min(a.T, a.lengths[b] * a.len_mul) : a.T;   // this utterance's own end
       // ---- epilogue 1: intermediate tile row i <-> position p0 - h + i; rows outside the utterance are conv2's zero padding
       mbar_wait(acc1, it & 1u, 26, PD_PAIR_SLEEP_NS);
       tc_fence_after();
       if (tid == 0) PD_PAIR_TRACE(2);
       {
         uint8_t* yb = smem + L.y_off;
-        const bool interior = p0 - h >= 0 && p0 - h + NB * 128 <= a.T;   // tile-uniform: no row needs zeroing
+        const bool interior = p0 - h >= 0 && p0 - h + NB * 128 <= Tb;   // tile-uniform: no row needs zeroing
 #pragma unroll
         for (int m = m0; m < NB; m += MSTEP) {
           const int i = m * 128 + trow;
           const int pos = p0 - h + i;
-          const float keep = (interior || (pos >= 0 && pos < a.T)) ? 1.f : 0.f;
+          const float keep = (interior || (pos >= 0 && pos < Tb)) ? 1.f : 0.f;
 #pragma unroll
           for (int cc = 0; cc < C / CW; ++cc) {
             uint32_t r[CW];
@@ -411,6 +414,10 @@ __global__ void __launch_bounds__((EW + 2) * 32, kMinCtas) voc_pair_kernel(const
                 if (a.act == 1) {
 #pragma unroll
                   for (int u = 0; u < 8; ++u) v[u] = fmaxf(v[u], v[u] * a.slope);
+                }
+                if (pos >= Tb) {                                    // ragged batch: past this utterance's end
+#pragma unroll
+                  for (int u = 0; u < 8; ++u) v[u] = 0.f;
                 }
                 const uint4 o = make_uint4(Cvt<__half>::pack(v[0], v[1]), Cvt<__half>::pack(v[2], v[3]), Cvt<__half>::pack(v[4], v[5]), Cvt<__half>::pack(v[6], v[7]));
                 if constexpr (C >= 64) *reinterpret_cast<uint4*>(yb + (uint32_t)(cc * CW / 8 + j / 8) * YPS + (uint32_t)r0 * 16u) = o;

@@ -41,13 +41,14 @@ def spec2wav_from_generator_input(vocoder, c: torch.Tensor, **kwargs) -> torch.T
 def spec2wav_torch(generator, mel: torch.Tensor = None, f0: torch.Tensor = None, *, c: torch.Tensor = None, lengths=None, **kwargs):
     """``NsfHifiGAN.spec2wav_torch`` (nsf_hifigan.py:49-58) over a batch with ``prodiff_b200.Generator``: either ``mel``
     [B,T,M] (log10; scaled and transposed here like :50-52) or ``c`` [B,M,T] (the sampler's ``vocoder_scale`` output).
-    Returns [B, T * upp] -- or, with ``lengths`` (frames per utterance of a padded batch), a list of 1-D waveforms cut to
-    ``lengths[b] * upp`` samples (the reference flattens its single utterance with ``.view(-1)``)."""
+    Returns [B, T * upp] -- or, with ``lengths`` (frames per utterance of a padded batch), a list of 1-D waveforms of
+    ``lengths[b] * upp`` samples, each exactly what the call on that utterance alone returns (the generator holds every
+    activation past an utterance's own end at zero; the reference flattens its single utterance with ``.view(-1)``)."""
     if (mel is None) == (c is None):
         raise ValueError("pass exactly one of mel [B,T,M] or c [B,M,T]")
     if c is None:
         c = LOG10_TO_LN * mel.transpose(2, 1)
-    wav = generator(c, f0, **kwargs)[:, 0]
+    wav = generator(c, f0, lengths=lengths, **kwargs)[:, 0]
     if lengths is None:
         return wav
     return [wav[b, :int(n) * generator.upp] for b, n in enumerate(lengths)]

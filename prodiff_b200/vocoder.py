@@ -201,8 +201,10 @@ class Generator(nn.Module):
 
     # ------------------------------------------------------------------ forward (models.py:269-290)
     def forward(self, x, f0, *, rand_ini: Optional[torch.Tensor] = None, noise: Optional[torch.Tensor] = None,
-                seed: Optional[int] = None):
-        """x [B, num_mels, T] fp32 (the hand-off tensor ``2.30259 * mel.transpose(2, 1)``), f0 [B, T] -> [B, 1, T * upp]."""
+                seed: Optional[int] = None, lengths=None):
+        """x [B, num_mels, T] fp32 (the hand-off tensor ``2.30259 * mel.transpose(2, 1)``), f0 [B, T] -> [B, 1, T * upp].
+        ``lengths`` (B ints <= T, keyword-only): a padded batch -- samples [0, lengths[b] * upp) of row b are exactly what the
+        call on that utterance alone gives (every activation past an utterance's own end is held at zero), the rest zeros."""
         if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
             raise RuntimeError("prodiff_b200.Generator is inference-only; call it under torch.no_grad()")
         B, M, T = x.shape
@@ -225,12 +227,19 @@ class Generator(nn.Module):
                 raise ValueError(f"noise must be {(B, T * self.upp, 9)}, got {tuple(noise.shape)}")
         if seed is None:
             seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if noise is None else 0
+        len_dev = None
+        if lengths is not None:
+            ln = [int(v) for v in lengths]
+            if len(ln) != B or any(v < 0 or v > T for v in ln):
+                raise ValueError(f"lengths must be {B} integers in [0, {T}]")
+            len_dev = torch.tensor(ln, dtype=torch.int32, device=device)
         wave = torch.empty(B, 1, T * self.upp, dtype=torch.float32, device=device)
         with torch.cuda.device(device):
             nbytes = lib.pd_vocoder_workspace_bytes(hnd, B, T)
             ws = self._workspace(nbytes, device)
             _lib.check(lib.pd_vocoder_forward(hnd, x.data_ptr(), f0.data_ptr(), rand_ini.data_ptr(),
-                                              noise.data_ptr() if noise is not None else None, C.c_uint64(seed), wave.data_ptr(), B, T,
+                                              noise.data_ptr() if noise is not None else None, C.c_uint64(seed),
+                                              len_dev.data_ptr() if len_dev is not None else None, wave.data_ptr(), B, T,
                                               ws.data_ptr(), nbytes, torch.cuda.current_stream(device).cuda_stream), "pd_vocoder_forward")
         return wave
 

@@ -138,7 +138,7 @@ def test_vocoder_config_validation_without_gpu(lib):
     assert lib.pd_vocoder_create(C.byref(ok), ptrs, 3, None, 0, None, C.byref(h)) != 0
     assert b"expected 206 state tensors" in lib.pd_last_error() and not h.value
     assert lib.pd_vocoder_workspace_bytes(None, 1, 1) == 0 and lib.pd_vocoder_upp(None) == 0
-    assert lib.pd_vocoder_forward(None, None, None, None, None, 0, None, 1, 1, None, 0, None) != 0 and b"null argument" in lib.pd_last_error()
+    assert lib.pd_vocoder_forward(None, None, None, None, None, 0, None, None, 1, 1, None, 0, None) != 0 and b"null argument" in lib.pd_last_error()
 
 
 def test_missing_library_fails_loudly(monkeypatch):

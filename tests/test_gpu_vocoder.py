@@ -161,6 +161,34 @@ def test_batch_rows_equal_single_utterance_runs():
     assert float((full - ref).abs().max()) <= WAV_MAX_TOL
 
 
+def test_ragged_batch_rows_equal_single_utterance_runs():
+    """A padded batch with per-utterance lengths (what batching the reference's one-segment-per-call inferer needs,
+    handler/infer/handler.py:373-378): the generator's receptive field (~13 frames per side) would let whatever lies past
+    an utterance's end leak into its last frames; with ``lengths`` every activation past the end is held at zero, so row b
+    equals the run on utterance b alone -- exactly -- and the tail of the row is zeros.  Garbage is planted in the padding."""
+    from prodiff_b200 import synth
+    h = VOCODER_CASES["full44k_short"]["h"]
+    state = synth.make_vocoder_state(h, 401)
+    B, T = 3, 48
+    lens = [48, 29, 7]
+    c, f0, ri, nz = synth.make_vocoder_inputs(h, B, T, 402)
+    for b, n in enumerate(lens):           # the padding holds junk, as a sampler's ragged output may
+        c[b, :, n:] = 37.0
+        f0[b, n:] = 555.0
+    gen = _build(h, state)
+    upp = gen.upp
+    with torch.no_grad():
+        full = gen(c.cuda(), f0.cuda(), rand_ini=ri.cuda(), noise=nz.cuda(), lengths=lens).cpu()
+        for b, n in enumerate(lens):
+            one = gen(c[b:b + 1, :, :n].contiguous().cuda(), f0[b:b + 1, :n].contiguous().cuda(), rand_ini=ri.cuda(),
+                      noise=nz[b:b + 1, :n * upp].contiguous().cuda()).cpu()
+            assert torch.equal(full[b, 0, :n * upp], one[0, 0]), (b, float((full[b, 0, :n * upp] - one[0, 0]).abs().max()))
+            assert float(full[b, 0, n * upp:].abs().max()) == 0.0 if n < T else True
+        # and without lengths the junk does reach the last frames (the test would be vacuous otherwise)
+        plain = gen(c.cuda(), f0.cuda(), rand_ini=ri.cuda(), noise=nz.cuda()).cpu()
+        assert not torch.equal(plain[1, 0, :lens[1] * upp], full[1, 0, :lens[1] * upp])
+
+
 def test_philox_noise_path_and_determinism():
     """Without injected noise the SineGen noise comes from in-kernel Philox: same seed -> same waveform, another seed ->
     another one, and both stay close to the noise-free... to the injected-noise result in the voiced-signal sense (the noise
@@ -204,7 +232,9 @@ def test_handoff_chain_sampler_to_waveform():
     with torch.no_grad():
         ref = vo.spec2wav(vstate, h, mel_ref, f0, ri, nz).view(B, -1)
     upp = int(np.prod(h["upsample_rates"]))
-    assert wav.shape == (B, T * upp) and cut[1].shape == (17 * upp,) and torch.equal(cut[1].cpu(), wav[1, :17 * upp])
+    # lengths: row 0 is full length (nothing changes); row 1 ends at frame 17 and is recomputed as that utterance alone
+    # (test_ragged_batch_rows_equal_single_utterance_runs)
+    assert wav.shape == (B, T * upp) and cut[1].shape == (17 * upp,) and torch.equal(cut[0].cpu(), wav[0])
     # the sampler's own bf16 error (mel L1 <= 1e-2) rides into the generator input, so the chain bound is looser
     assert float((wav - ref).abs().mean()) <= 2e-2
 
@@ -229,4 +259,4 @@ def test_loud_failures():
             bad.cuda()(torch.zeros(1, 64, 10, device="cuda"), torch.zeros(1, 10, device="cuda"))
     lib = _lib.load()
     assert lib.pd_vocoder_workspace_bytes(None, 1, 1) == 0
-    assert lib.pd_vocoder_forward(None, None, None, None, None, 0, None, 1, 1, None, 0, None) != 0
+    assert lib.pd_vocoder_forward(None, None, None, None, None, 0, None, None, 1, 1, None, 0, None) != 0

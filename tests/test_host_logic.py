@@ -252,3 +252,47 @@ def test_workspace_bucket_bounds_slack_and_collapses_nearby_sizes():
         assert b >= n and b >= 1 << 20 and b <= max(1 << 20, int(n * 1.125) + 1)
     assert workspace_bucket(2_200_000_000) == workspace_bucket(2_205_000_000)   # T = 1000 vs 1002 land in one bucket
     assert len({workspace_bucket(n) for n in range((1 << 30) + 1, (2 << 30) + 1, 1 << 22)}) == 8
+
+
+def test_synthesizer_routes_arguments_like_the_reference_inferer():
+    """pipeline.Synthesizer (handler/infer/handler.py:133-158 for a batch) with stand-ins for the CUDA pieces: conditioning
+    keywords reach forward_condition, sampler extras reach diffusion, lengths default to the non-padding frames of mel2ph and
+    go to BOTH the sampler and the generator, the generator input is asked for with the 2.30259 scale fused."""
+    import types
+    import prodiff_b200.pipeline as pl
+    seen = {}
+
+    class FakeCond:
+        shape = torch.Size((2, 6, 256))
+
+        def lengths(self):
+            return [6, 4]
+
+    def fake_forward_condition(teacher, txt, m2p, f0, validate=True, **kw):
+        seen["cond_kw"] = kw
+        return FakeCond()
+
+    def diffusion(cond, **kw):
+        seen["diff_kw"] = kw
+        return torch.zeros(2, 128, 6)
+
+    class Gen:
+        upp = 4
+
+        def __call__(self, c, f0, **kw):
+            seen["gen_kw"] = kw
+            return torch.arange(2 * 24, dtype=torch.float32).reshape(2, 1, 24)
+
+    orig = pl.forward_condition
+    pl.forward_condition = fake_forward_condition
+    try:
+        syn = pl.Synthesizer(types.SimpleNamespace(diffusion=diffusion), Gen(), infer_step=4)
+        wavs = syn(torch.zeros(2, 3, dtype=torch.long), torch.zeros(2, 6, dtype=torch.long), torch.zeros(2, 6), voicing="v", seed=5,
+                   rand_ini="ri", voc_seed=9)
+    finally:
+        pl.forward_condition = orig
+    assert seen["cond_kw"] == {"voicing": "v"}
+    assert seen["diff_kw"]["lengths"] == [6, 4] and seen["diff_kw"]["seed"] == 5 and seen["diff_kw"]["infer_step"] == 4
+    assert abs(seen["diff_kw"]["vocoder_scale"] - 2.30259) < 1e-9 and seen["diff_kw"]["infer"] is True
+    assert seen["gen_kw"] == {"lengths": [6, 4], "rand_ini": "ri", "seed": 9}
+    assert [tuple(w.shape) for w in wavs] == [(24,), (16,)] and float(wavs[1][-1]) == 24 + 15
