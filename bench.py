@@ -411,12 +411,12 @@ def main():
         name = (f"layer_kernel (fused ResidualBlock: dilated conv + gate + residual 1x1, cta_group::2; {layers_per_launch} layer(s) per persistent launch)" if dom.startswith("residual_layer")
                 else "gemm_kernel<EPI_GATE,256> (dilated conv + gate)")
         # DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum) of one launch of the dominant kernel at THIS workload,
-        # from the committed `ncu --set full` captures: the persistent 20-layer launch (profiles/r01v_ncu_stack_summary.txt:
-        # 1.378 GB + 1.161 GB) or a one-layer launch (profiles/r01p_ncu_layer_summary.txt: 99.5 MB + 27.4 MB).
+        # from the committed `ncu --set full` captures: the persistent 20-layer launch (profiles/r02f_stack_ncu_summary.txt:
+        # 1.373 GB + 1.161 GB; round 1: r01v_ncu_stack_summary.txt, 1.378 + 1.161) or a one-layer launch (profiles/r01p_ncu_layer_summary.txt: 99.5 MB + 27.4 MB).
         traffic, traffic_src = None, None
         if dom.startswith("residual_layer") and (B, T, C) == (64, 1000, 256):
             if layers_per_launch == L == 20:
-                traffic, traffic_src = 2.539e9, "profiles/r01v_ncu_stack_summary.txt (20-layer persistent launch; algorithmic = frames x 2560 B x 20 = 3.28 GB)"
+                traffic, traffic_src = 2.533e9, "profiles/r02f_stack_ncu_summary.txt (20-layer persistent launch; algorithmic = frames x 2560 B x 20 = 3.28 GB)"
             elif layers_per_launch == 1:
                 traffic, traffic_src = 126.9e6, "profiles/r01p_ncu_layer_summary.txt (one-layer launch; algorithmic = frames x 2560 B = 163.8 MB)"
         roofline = {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
