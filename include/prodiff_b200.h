@@ -274,7 +274,11 @@ int pd_set_fused(int on);
  * grid as a whole: kernels of other streams or processes that hold SMs delay the launch but cannot leave it half
  * resident.  If the cooperative launch is refused the call silently uses one launch per layer (no inter-cluster waits).
  * Different plans may therefore run on different streams of one GPU; they serialise at the persistent kernel (each one
- * fills the device anyway).  Every in-kernel wait still has a clock watchdog that traps instead of hanging. */
+ * fills the device anyway).  Every in-kernel wait still has a clock watchdog that traps instead of hanging.
+ * Under an injected tool (Nsight Compute, Nsight Systems, compute-sanitizer: recognised by the environment variables they set in
+ * the target process) the cooperative attribute is dropped
+ * -- ncu cannot replay a cooperative cluster launch and would shut the application down -- those tools serialise kernels.
+ * PD_COOP=0 / 1 forces it off / on. */
 int pd_set_stack(int on);
 
 /* pd_sample only: run skip_projection (wavenet.py:120-121), output_projection (:122), the q-posterior update

@@ -600,8 +600,19 @@ static int launch_layer_t(const LayerMaps& mp, const LayerParams& lp, int sms, c
     // once.  The occupancy query above only says the grid fits an idle GPU; a COOPERATIVE launch makes the driver schedule
     // the grid as a whole (or not at all), so another stream's or process's kernels holding SMs can delay this launch but
     // cannot leave it half-resident and spinning.  PD_COOP=0 drops the attribute (A/B only).
+    // Under an injected tool (Nsight Compute sets NV_COMPUTE_PROFILER_PERFWORKS_DIR / NV_NSIGHT_INJECTION_PORT_BASE in the target
+    // process, Nsight Systems and compute-sanitizer CUDA_INJECTION64_PATH) the attribute is dropped as well: ncu cannot replay a cooperative cluster launch, reports LaunchFailed and shuts the
+    // application down before the fallback below could run; such tools serialise kernels, so co-residency is not at risk.
     static int coop = -1;
-    if (coop < 0) { const char* ev = getenv("PD_COOP"); coop = (ev && ev[0] == '0') ? 0 : 1; }
+    if (coop < 0) {
+      const char* ev = getenv("PD_COOP");
+      bool tool = false;
+      for (const char* name : {"NV_COMPUTE_PROFILER_PERFWORKS_DIR", "NV_NSIGHT_INJECTION_PORT_BASE", "CUDA_INJECTION64_PATH"}) {
+        const char* v = getenv(name);
+        tool = tool || (v && v[0] != 0);
+      }
+      coop = ((ev && ev[0] == '0') || (tool && !(ev && ev[0] == '1'))) ? 0 : 1;
+    }
     if (coop) {
       attr[1].id = cudaLaunchAttributeCooperative;
       attr[1].val.cooperative = 1;
