@@ -1,6 +1,6 @@
 """Throughput of the other BASELINE.json configs on ONE B200 (device-resident inputs, CUDA events, in-kernel Philox noise):
 configs[2] (teacher 100-step DDPM, 64 x 1000), configs[3] per-GPU share (1 x 6000 frames, C = 512, K = 100, x_T supplied),
-configs[4] sweep (B in {1, 8, 64, 256} x 1000 frames, K in {2, 4, 100}) and the rectified-flow samplers (N2).
+configs[4] sweep (B in {1 ... 1024} x 1000 frames, K in {2, 4}; K = 100 at B in {1, 8, 64}) and the rectified-flow samplers (N2).
 Writes gpurun_out/config_sweep.json.  Usage on the GPU box:  python tools/config_sweep.py"""
 import json
 import os
@@ -60,9 +60,9 @@ def main():
     run("configs[1] 4-step ProDiff", gd4, 256, 64, 1000, 4)
     run("configs[2] teacher 100-step DDPM (per GPU: full batch)", gd100, 256, 64, 1000, 100)
     run("configs[2] 8-GPU share (8 x 1000)", gd100, 256, 8, 1000, 100)
-    for B in (1, 8, 64, 256):
+    for B in (1, 2, 4, 8, 16, 32, 64, 128, 256, 1024):
         for K, gd in ((2, gd4), (4, gd4), (100, gd100)):
-            if B == 256 and K == 100:
+            if K == 100 and B not in (1, 8, 64):
                 continue
             run("configs[4] sweep", gd, 256, B, 1000, K)
     del gd4, gd100
