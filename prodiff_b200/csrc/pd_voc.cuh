@@ -355,6 +355,25 @@ voc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const bool valid = ep.lengths == nullptr || b >= sh.B || t < ep.lengths[b] * ep.len_mul;   // ragged batch: rows past the utterance's own end become zeros
       const uint32_t as = ti & 1u, aph = (ti >> 1) & 1u;
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
+      // The residual does not depend on the accumulator: fetch this warp's blocks of it BEFORE waiting for the MMAs (tiles of
+      // <= 128 columns: 8 uint4 per lane).  Loaded inside the chunk loop its latency was exposed once per chunk -- the second
+      // convolution of a round took 10-50 % longer than the first for the same MMA work (profiles/r02g_voc_conv_residentA_off.csv).
+      constexpr bool kPrefetchRes = BN >= 64 && BN <= 128;
+      uint4 pre_res[kPrefetchRes ? kChunks : 1][32 / RPI];
+      if constexpr (kPrefetchRes) {
+        if (works && ep.res16 != nullptr) {
+#pragma unroll
+          for (int ci = 0; ci < kChunks; ++ci) {
+            const int gcol = n_tile * BN + h * (BN / 2) + ci * CW;
+            const __half* base = ep.res16 + (long long)b * ep.res_bstride + (long long)(t0 + q * 32) * ep.res_ld + gcol;
+#pragma unroll
+            for (int i = 0; i < 32 / RPI; ++i) {
+              const int rrow = i * RPI + lane / LPR, c8 = lane % LPR;
+              pre_res[ci][i] = rrow < rows_left ? *reinterpret_cast<const uint4*>(base + (long long)rrow * ep.res_ld + 8 * c8) : make_uint4(0u, 0u, 0u, 0u);
+            }
+          }
+        }
+      }
       mbar_wait(&tfull_bar[as], aph, 4);
       tc_fence_after();
       if (works) {
@@ -376,13 +395,14 @@ voc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             v[j + 3] = __uint_as_float(r[j + 3]) + bv.w;
           }
           // 16-bit side inputs: the [32 rows x CW] block arrives as full row segments and is read back one row per thread
-          auto add_side = [&](const __half* src, long long bstride, int ld, bool unact) {
+          auto add_side = [&](const __half* src, long long bstride, int ld, bool unact, const uint4* pre) {
             const __half* base = src + (long long)b * bstride + (long long)(t0 + q * 32) * ld + gcol;
 #pragma unroll
             for (int i = 0; i < 32 / RPI; ++i) {
               const int rrow = i * RPI + lane / LPR, c8 = lane % LPR;
               uint4 w = make_uint4(0u, 0u, 0u, 0u);
-              if (rrow < rows_left) w = *reinterpret_cast<const uint4*>(base + (long long)rrow * ld + 8 * c8);
+              if (pre != nullptr) w = pre[i];
+              else if (rrow < rows_left) w = *reinterpret_cast<const uint4*>(base + (long long)rrow * ld + 8 * c8);
               *reinterpret_cast<uint4*>(stg + rrow * RW + 4 * c8) = w;
             }
             __syncwarp();
@@ -403,8 +423,8 @@ voc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
             __syncwarp();
           };
-          if (ep.res16 != nullptr) add_side(ep.res16, ep.res_bstride, ep.res_ld, true);
-          if (ep.add16 != nullptr) add_side(ep.add16, ep.add_bstride, ep.add_ld, false);
+          if (ep.res16 != nullptr) add_side(ep.res16, ep.res_bstride, ep.res_ld, true, kPrefetchRes ? pre_res[ci] : nullptr);
+          if (ep.add16 != nullptr) add_side(ep.add16, ep.add_bstride, ep.add_ld, false, nullptr);
 #pragma unroll
           for (int j = 0; j < CW; ++j) {
             float x = v[j] * ep.scale;
