@@ -65,6 +65,15 @@ struct VocEpi {
 
 constexpr int kVocGatherThreads = 128;   // one per position of a 128-row tile
 
+// scale -> activation of one output value (act is launch-uniform: the compiler hoists the branch out of the unrolled loops);
+// LeakyReLU as max(x, slope * x), 0 <= slope <= 1: two instructions instead of compare / multiply / select
+__device__ __forceinline__ float voc_finish(float x, float scale, int act, float slope) {
+  x *= scale;
+  if (act == 1) return fmaxf(x, x * slope);
+  if (act == 2) return tanhf(x);
+  return x;
+}
+
 __device__ __forceinline__ void voc_cp_async16(uint32_t dst_smem, const void* src, bool pred) {
   const int n = pred ? 16 : 0;   // src-size 0: the 16 bytes are zero-filled
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(n) : "memory");
@@ -302,8 +311,8 @@ voc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
               for (int u = 0; u < 4; ++u) {
                 float2 f = Cvt<__half>::unpack(ww[u]);
-                f.x = f.x >= 0.f ? f.x : f.x * ep.res_inv_slope;
-                f.y = f.y >= 0.f ? f.y : f.y * ep.res_inv_slope;
+                f.x = fminf(f.x, f.x * ep.res_inv_slope);   // undo the stored LeakyReLU (inverse slope >= 1)
+                f.y = fminf(f.y, f.y * ep.res_inv_slope);
                 v[8 * j + 2 * u] += f.x;
                 v[8 * j + 2 * u + 1] += f.y;
               }
@@ -322,11 +331,10 @@ voc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
           }
 #pragma unroll
-          for (int j = 0; j < BN; ++j) {
-            float x = v[j] * ep.scale;
-            if (ep.act == 1) x = x >= 0.f ? x : x * ep.slope;
-            else if (ep.act == 2) x = tanhf(x);
-            v[j] = valid ? x : 0.f;
+          for (int j = 0; j < BN; ++j) v[j] = voc_finish(v[j], ep.scale, ep.act, ep.slope);
+          if (!valid) {
+#pragma unroll
+            for (int j = 0; j < BN; ++j) v[j] = 0.f;
           }
           if (ep.out32 != nullptr) {
             if (gcol == 0) ep.out32[(long long)b * sh.T + t] = v[0];
@@ -414,8 +422,8 @@ voc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               for (int u = 0; u < 4; ++u) {
                 float2 f = Cvt<__half>::unpack(ww[u]);
                 if (unact) {
-                  f.x = f.x >= 0.f ? f.x : f.x * ep.res_inv_slope;
-                  f.y = f.y >= 0.f ? f.y : f.y * ep.res_inv_slope;
+                  f.x = fminf(f.x, f.x * ep.res_inv_slope);   // undo the stored LeakyReLU (inverse slope >= 1)
+                  f.y = fminf(f.y, f.y * ep.res_inv_slope);
                 }
                 v[j + 2 * u] += f.x;
                 v[j + 2 * u + 1] += f.y;
@@ -426,11 +434,10 @@ voc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           if (ep.res16 != nullptr) add_side(ep.res16, ep.res_bstride, ep.res_ld, true, kPrefetchRes ? pre_res[ci] : nullptr);
           if (ep.add16 != nullptr) add_side(ep.add16, ep.add_bstride, ep.add_ld, false, nullptr);
 #pragma unroll
-          for (int j = 0; j < CW; ++j) {
-            float x = v[j] * ep.scale;
-            if (ep.act == 1) x = x >= 0.f ? x : x * ep.slope;
-            else if (ep.act == 2) x = tanhf(x);
-            v[j] = valid ? x : 0.f;
+          for (int j = 0; j < CW; ++j) v[j] = voc_finish(v[j], ep.scale, ep.act, ep.slope);
+          if (!valid) {
+#pragma unroll
+            for (int j = 0; j < CW; ++j) v[j] = 0.f;
           }
           if (ep.out32 != nullptr) {
             if (gcol == 0 && t < sh.T && b < sh.B) ep.out32[(long long)b * sh.T + t] = v[0];
