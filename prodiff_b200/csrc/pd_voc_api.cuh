@@ -143,11 +143,11 @@ extern "C" int pd_set_voc_fused(int on) {
 namespace {
 bool voc_pair_ok(int C, int k) { return (C == 16 || C == 32 || C == 64) && k % 2 == 1 && k <= 15; }
 
-template <int C, int NB, bool kRes, int kXB, int EW, int kMinCtas>
+template <int C, int NB, bool kRes, int kXB, int EW, int kMinCtas, bool kSingle = false>
 int launch_voc_pair_t(VocPairArgs a, int sms, cudaStream_t s) {
-  auto kern = voc_pair_kernel<C, NB, kRes, kXB, EW, kMinCtas>;
+  auto kern = voc_pair_kernel<C, NB, kRes, kXB, EW, kMinCtas, kSingle>;
   constexpr int kPairThreads = (EW + 2) * 32;
-  const VocPairSmem L = voc_pair_smem<C, NB, kRes, kXB, kMinCtas>(a.k, a.dil);
+  const VocPairSmem L = voc_pair_smem<C, NB, kRes, kXB, kMinCtas, kSingle>(a.k, a.dil);
   static int configured[64] = {0};
   int dev = 0;
   PD_CUDA(cudaGetDevice(&dev));
@@ -157,21 +157,20 @@ int launch_voc_pair_t(VocPairArgs a, int sms, cudaStream_t s) {
     configured[dev & 63] = (int)L.total;
   }
   // co-resident CTAs per SM: shared memory (227 KB per SM, 1 KB reserved per CTA), registers, TMEM columns
-  cudaFuncAttributes fa;
-  PD_CUDA(cudaFuncGetAttributes(&fa, kern));
+  static int num_regs[64] = {0};   // per instantiation, per device
+  if (num_regs[dev & 63] == 0) {
+    cudaFuncAttributes fa;
+    PD_CUDA(cudaFuncGetAttributes(&fa, kern));
+    num_regs[dev & 63] = fa.numRegs;
+  }
   const int cols = std::max(32, (kXB == 2 ? 2 : 1) * NB * C);
   int occ = (int)((227u * 1024u) / (L.total + 1024u));
-  const int regs_per_cta = ((fa.numRegs * 32 + 511) / 512 * 512) * (kPairThreads / 32);   // allocation unit: 512 registers per warp
+  const int regs_per_cta = ((num_regs[dev & 63] * 32 + 511) / 512 * 512) * (kPairThreads / 32);   // allocation unit: 512 registers per warp
   occ = std::min(occ, 65536 / regs_per_cta);
   occ = std::min(occ, 512 / cols);
   occ = std::min(occ, 8);
   if (occ < 1) return fail("voc_pair_kernel<%d>: %u bytes of shared memory do not fit", C, L.total);
-  if (getenv("PD_VOC_DEBUG")) {
-    int api = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&api, kern, kPairThreads, L.total);
-    fprintf(stderr, "[voc_pair C=%d k=%d dil=%d] smem %u regs %d occ %d (api %d)\n", C, a.k, a.dil, L.total, fa.numRegs, occ, api);
-  }
-  const int P = NB * 128 - (a.k - 1);
+  const int P = NB * 128 - (kSingle ? 0 : a.k - 1);
   a.tiles_per_row = (a.T + P - 1) / P;
   a.idesc = make_idesc(PD_FP16, C);
   a.trace = g_trace ? g_trace + 13 * 1024 : nullptr;
@@ -204,6 +203,14 @@ int launch_voc_pair(int C, const VocPairArgs& a, int sms, cudaStream_t s) {
     default: return fail("voc_pair_kernel: %d channels not supported", C);
   }
 }
+// the rate-2 transposed convolutions of the narrow stages (C_in = 2 * C_out = 32 or 64) as ONE 3-tap convolution over a resident tile
+bool voc_single_ok(int cin, int u) { return u == 2 && (cin == 32 || cin == 64); }
+int launch_voc_single(int C, const VocPairArgs& a, int sms, cudaStream_t s) {
+  // (measured: 4 epilogue warps for 64 channels 1.87 ms against 1.01 ms with 8; 3 instead of 4 CTAs per SM for 32 channels: no change)
+  if (C == 32) return launch_voc_pair_t<32, 2, true, 1, 4, 4, true>(a, sms, s);
+  if (C == 64) return launch_voc_pair_t<64, 2, true, 1, 8, 2, true>(a, sms, s);
+  return fail("voc_pair_kernel (single conv): %d channels not supported", C);
+}
 
 }  // namespace
 
@@ -217,6 +224,7 @@ struct pd_vocoder {
   VocConv ups[kVocMaxUps];
   VocConv res[kVocMaxUps][kVocMaxRes][6];    // [stage][kernel][c1_0, c2_0, c1_1, c2_1, c1_2, c2_2]
   size_t pair_w[kVocMaxUps][kVocMaxRes][3];  // fused-round weight images (pd_voc_pair.cuh) where voc_pair_ok(), else 0
+  size_t ups_w[kVocMaxUps];                  // resident-tile image of the transposed conv where voc_single_ok(), else 0
   size_t src_w[kVocMaxUps], src_b[kVocMaxUps];   // fp32 noise_convs weights, transposed to [k][C] / bias [C]
   int src_k[kVocMaxUps], src_stride[kVocMaxUps], src_pad[kVocMaxUps];
   size_t lin_w, lin_b;                       // m_source.l_linear
@@ -268,6 +276,10 @@ static size_t voc_layout(const pd_vocoder_config& c, pd_vocoder* v) {
   for (int i = 0; i < c.n_upsamples; ++i) {
     const int u = c.upsample_rates[i];
     conv(v ? &v->ups[i] : nullptr, ch, u * (ch / 2), 3, 1);
+    {
+      const size_t uw = voc_single_ok(ch, u) ? take((size_t)3 * ch * ch * 2) : 0;
+      if (v) v->ups_w[i] = uw;
+    }
     ch /= 2;
     stride_f0 /= u;
     const int sk = i + 1 < c.n_upsamples ? 2 * stride_f0 : 1;
@@ -350,6 +362,10 @@ extern "C" int pd_vocoder_create(const pd_vocoder_config* cfg, const float* cons
     PD_LAUNCH_CHECK("k_voc_pack_convT");
     rc |= make_w_map(&up.tm_w, PD_FP16, pk + up.w_off, up.taps_pad * up.cin, up.n_total, up.bn);
     if (!rc && up.bn >= 128) rc |= make_w_map(&up.tm_w_half, PD_FP16, pk + up.w_off, up.taps_pad * up.cin, up.n_total, up.bn / 2);
+    if (voc_single_ok(ch, u)) {
+      k_voc_pack_convT_planes<<<blocks(3ll * ch * ch), TB, 0, s>>>((__half*)(pk + v->ups_w[i]), state[si], ch, ch / 2, u);
+      PD_LAUNCH_CHECK("k_voc_pack_convT_planes");
+    }
     ch /= 2;
     k_voc_transpose_src<<<blocks((long long)ch * v->src_k[i]), TB, 0, s>>>((float*)(pk + v->src_w[i]), state[si + 2], ch, v->src_k[i]);
     PD_LAUNCH_CHECK("k_voc_transpose_src");
@@ -502,7 +518,31 @@ extern "C" int pd_vocoder_forward(pd_vocoder* v, const float* c, const float* f0
     }
     // x = ups[i](leaky_relu(x)) + x_source (:274-277), stored activated for the ResBlocks' first convs
     if (zero_guards(XL, To, co) || zero_guards(TMP, To, co) || zero_guards(CUR, To, co) || zero_guards(OUT, To, co)) return 1;
-    {
+    if (voc_fused_enabled() && voc_single_ok(ch, u)) {
+      VocPairArgs pa;
+      memset(&pa, 0, sizeof(pa));
+      pa.x = act[cur_in];
+      pa.add = SRC;
+      pa.out = XL;
+      pa.w = (const __half*)(pk + v->ups_w[i]);
+      pa.b1 = pa.b2 = (const float*)(pk + v->ups[i].b_off);
+      pa.bstride = (Ti + 2 * G) * ch;
+      pa.out_bstride = obs;
+      pa.out_goff = (long long)G * co;
+      pa.B = B;
+      pa.T = (int)Ti;
+      pa.G = G;
+      pa.k = 3;
+      pa.dil = 1;
+      pa.slope1 = 0.1f;
+      pa.in_inv_slope = 10.f;
+      pa.scale = 1.f;
+      pa.act = 1;
+      pa.slope = 0.1f;
+      pa.lengths = lengths;
+      pa.len_mul = (int)(Ti / T);
+      if (launch_voc_single(ch, pa, sms, s)) return 1;
+    } else {
       if (make_voc_a_map(&tmA, act[cur_in], ch, 3, 1, (int)Ti, B)) return 1;
       VocEpi ep = voc_epi();
       ep.out16 = XL + (size_t)G * co;
@@ -556,6 +596,8 @@ extern "C" int pd_vocoder_forward(pd_vocoder* v, const float* c, const float* f0
           pa.b1 = (const float*)(pk + c1.b_off);
           pa.b2 = (const float*)(pk + c2.b_off);
           pa.bstride = obs;
+          pa.out_bstride = obs;
+          pa.out_goff = (long long)G * co;
           pa.B = B;
           pa.T = (int)To;
           pa.G = G;
@@ -734,6 +776,8 @@ extern "C" int pd_voc_debug_pair(const float* x, int B, int T, int C, const floa
   pa.b1 = b1d;
   pa.b2 = b2d;
   pa.bstride = (long long)(T + 2 * kVocG) * C;
+  pa.out_bstride = pa.bstride;
+  pa.out_goff = (long long)kVocG * C;
   pa.B = B;
   pa.T = T;
   pa.G = kVocG;

@@ -36,6 +36,8 @@ struct VocPairArgs {
   const float* b1;
   const float* b2;
   long long bstride;       // (T + 2G) * C
+  long long out_bstride;   // utterance stride of out / add (= bstride for a ResBlock round) and the element offset of their
+  long long out_goff;      // position 0 (= G * C); the rate-2 transposed conv writes T rows of C = 2 positions x C/2 channels
   int B, T, G;
   int k, dil;
   int tiles_per_row;       // ceil(T / P), P = NB * 128 - (k - 1)
@@ -100,7 +102,7 @@ struct VocPairSmem {
   uint32_t x_off[2], y_off, w_off, bar_off, total;
   uint32_t ring;          // weight ring stages (streamed weights)
 };
-template <int C, int NB, bool kRes, int kXB, int kMinCtas>
+template <int C, int NB, bool kRes, int kXB, int kMinCtas, bool kSingle = false>
 __host__ __device__ inline VocPairSmem voc_pair_smem(int k, int dil) {
   constexpr uint32_t kBudget = (227u * 1024u) / (uint32_t)kMinCtas - 1024u;   // leaves room for kMinCtas CTAs per SM
   VocPairSmem s;
@@ -113,11 +115,11 @@ __host__ __device__ inline VocPairSmem voc_pair_smem(int k, int dil) {
     if (i < kXB) o += s.xr * C * 2;
   }
   s.y_off = o;
-  o += s.yr * C * 2;
+  o += (kSingle && C < 64) ? 0u : s.yr * C * 2;   // single conv: only the 64-channel store staging uses it
   s.w_off = o;
   s.ring = 0;
   if (kRes) {
-    o += (uint32_t)(2 * k * C * C * 2);
+    o += (uint32_t)((kSingle ? 1 : 2) * k * C * C * 2);
   } else {   // as many one-tap stages as fit beside the other CTAs on the SM (2 .. kPairRingMax)
     const uint32_t tap = C * C * 2, fixed = o + 256u + 128u;
     uint32_t n = fixed + 2 * tap < kBudget ? (kBudget - fixed) / tap : 2u;
@@ -132,8 +134,12 @@ __host__ __device__ inline VocPairSmem voc_pair_smem(int k, int dil) {
 }
 
 // EW = epilogue warps: 4 (each thread walks the NB row blocks of its TMEM lane quadrant) or 4 * NB (one row block per warp group)
-template <int C, int NB, bool kRes, int kXB, int EW, int kMinCtas>
+// kSingle: ONE convolution per tile (conv1's weights, resident, single-buffered x), epilogue = + bias [+ add] -> scale / LeakyReLU
+// -> store, no residual: the rate-2 transposed convolutions of the narrow stages (a 3-tap conv whose output row of C values is two
+// positions of the up-sampled tensor) read their input once from a resident tile instead of gathering every tap through L2.
+template <int C, int NB, bool kRes, int kXB, int EW, int kMinCtas, bool kSingle = false>
 __global__ void __launch_bounds__((EW + 2) * 32, kMinCtas) voc_pair_kernel(const VocPairArgs a) {
+  static_assert(!kSingle || (kRes && kXB == 1), "single-conv form: resident weights, serial tiles");
   constexpr int PL = C / 8;                      // planes = 16-byte chunks per row
   constexpr int CW = C < 32 ? C : 32;            // accumulator columns per tcgen05.ld
   constexpr int NT = EW * 32;                    // gather / epilogue threads
@@ -148,7 +154,7 @@ __global__ void __launch_bounds__((EW + 2) * 32, kMinCtas) voc_pair_kernel(const
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((128u - (raw_addr & 127u)) & 127u);
-  const VocPairSmem L = voc_pair_smem<C, NB, kRes, kXB, kMinCtas>(a.k, a.dil);
+  const VocPairSmem L = voc_pair_smem<C, NB, kRes, kXB, kMinCtas, kSingle>(a.k, a.dil);
   const uint32_t XPS = L.xr * 16, YPS = L.yr * 16;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar_off);
   uint64_t* xfull = bars;             // [2]   NT arrivals: a gathered x tile is visible to the tensor core
@@ -179,7 +185,8 @@ __global__ void __launch_bounds__((EW + 2) * 32, kMinCtas) voc_pair_kernel(const
   const uint32_t tmem_base = *tmem_slot;
   griddep_launch();
 
-  const int k = a.k, h = (k - 1) / 2, hd = h * a.dil;
+  const int k = a.k, hd = (k - 1) / 2 * a.dil;
+  const int h = kSingle ? 0 : (k - 1) / 2;          // rows a tile gives up to the second convolution's reach
   const int P = NB * 128 - 2 * h;
   const int num_tiles = a.B * a.tiles_per_row;
   const int rows_total = a.T + 2 * a.G;
@@ -188,8 +195,8 @@ __global__ void __launch_bounds__((EW + 2) * 32, kMinCtas) voc_pair_kernel(const
     // ===================== weights =====================
     if (lane == 0) {
       if constexpr (kRes) {
-        mbar_arrive_expect_tx(&wfull[0], 2u * k * kTapBytes);
-        bulk_load(smem + L.w_off, a.w, 2u * k * kTapBytes, &wfull[0]);
+        mbar_arrive_expect_tx(&wfull[0], (kSingle ? 1u : 2u) * k * kTapBytes);
+        bulk_load(smem + L.w_off, a.w, (kSingle ? 1u : 2u) * k * kTapBytes, &wfull[0]);
       } else {
         uint32_t stage = 0, parity = 1;   // first pass: the stages start out empty
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
@@ -255,13 +262,15 @@ __global__ void __launch_bounds__((EW + 2) * 32, kMinCtas) voc_pair_kernel(const
       if (lane == 0) PD_PAIR_TRACE(8);
       if (!kAhead) conv1(it);
       if (lane == 0) PD_PAIR_TRACE(9);
-      mbar_wait(yfull, it & 1u, 24, PD_PAIR_SLEEP_NS);
-      tc_fence_after();
-      if (lane == 0) PD_PAIR_TRACE(10);
-      issue_conv(tm + kAcc2, y_lo, L.yr, 1u, w_lo + (kRes ? (uint32_t)k * kTapUnits : 0u));
-      umma_commit_elect(acc2);
-      if (lane == 0) PD_PAIR_TRACE(11);
-      __syncwarp();
+      if constexpr (!kSingle) {
+        mbar_wait(yfull, it & 1u, 24, PD_PAIR_SLEEP_NS);
+        tc_fence_after();
+        if (lane == 0) PD_PAIR_TRACE(10);
+        issue_conv(tm + kAcc2, y_lo, L.yr, 1u, w_lo + (kRes ? (uint32_t)k * kTapUnits : 0u));
+        umma_commit_elect(acc2);
+        if (lane == 0) PD_PAIR_TRACE(11);
+        __syncwarp();
+      }
       if (kAhead && tile + (int)gridDim.x < num_tiles) conv1(it + 1);   // overlaps this tile's second epilogue
     }
   } else {
@@ -317,10 +326,12 @@ __global__ void __launch_bounds__((EW + 2) * 32, kMinCtas) voc_pair_kernel(const
       const int p0 = (tile - b * a.tiles_per_row) * P;
       const int Tb = a.lengths != nullptr ? min(a.T, a.lengths[b] * a.len_mul) : a.T;   // this utterance's own end
       // ---- epilogue 1: intermediate tile row i <-> position p0 - h + i; rows outside the utterance are conv2's zero padding
-      mbar_wait(acc1, it & 1u, 26, PD_PAIR_SLEEP_NS);
-      tc_fence_after();
-      if (tid == 0) PD_PAIR_TRACE(2);
-      {
+      if constexpr (!kSingle) {
+        mbar_wait(acc1, it & 1u, 26, PD_PAIR_SLEEP_NS);
+        tc_fence_after();
+        if (tid == 0) PD_PAIR_TRACE(2);
+      }
+      if constexpr (!kSingle) {
         uint8_t* yb = smem + L.y_off;
         const bool interior = p0 - h >= 0 && p0 - h + NB * 128 <= Tb;   // tile-uniform: no row needs zeroing
 #pragma unroll
@@ -355,16 +366,35 @@ __global__ void __launch_bounds__((EW + 2) * 32, kMinCtas) voc_pair_kernel(const
           }
         }
       }
-      if (tid == 0) PD_PAIR_TRACE(3);
-      fence_proxy_async_smem();
-      tc_fence_before();
-      mbar_arrive(yfull);
-      if (kAhead && tile + (int)gridDim.x < num_tiles) publish_x(buf ^ 1u);   // the next tile, gathered during the previous iteration
-      if (tid == 0) PD_PAIR_TRACE(4);
-      // ---- epilogue 2: output row r <-> position p0 + r; raw x from tile row r + h + hd
-      mbar_wait(acc2, it & 1u, 27, PD_PAIR_SLEEP_NS);
-      tc_fence_after();
-      if (tid == 0) PD_PAIR_TRACE(5);
+      // single conv: the addend (the source branch) does not depend on the accumulator -- fetch this thread's rows of it first
+      uint4 pre_add[kSingle ? (NB + MSTEP - 1) / MSTEP : 1][kSingle ? C / 8 : 1];
+      if constexpr (kSingle) {
+        if (has_add) {
+#pragma unroll
+          for (int m = m0, mi = 0; m < NB; m += MSTEP, ++mi) {
+            const int pos = p0 + m * 128 + trow;
+            const bool live = pos < a.T;
+            const uint4* ap = reinterpret_cast<const uint4*>(a.add + (long long)b * a.out_bstride + a.out_goff + (long long)pos * C);
+#pragma unroll
+            for (int j = 0; j < C / 8; ++j) pre_add[mi][j] = live ? ap[j] : make_uint4(0u, 0u, 0u, 0u);
+          }
+        }
+      }
+      if constexpr (!kSingle) {
+        if (tid == 0) PD_PAIR_TRACE(3);
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(yfull);
+        if (kAhead && tile + (int)gridDim.x < num_tiles) publish_x(buf ^ 1u);   // the next tile, gathered during the previous iteration
+        if (tid == 0) PD_PAIR_TRACE(4);
+        // ---- epilogue 2: output row r <-> position p0 + r; raw x from tile row r + h + hd
+        mbar_wait(acc2, it & 1u, 27, PD_PAIR_SLEEP_NS);
+        tc_fence_after();
+        if (tid == 0) PD_PAIR_TRACE(5);
+      } else {
+        mbar_wait(acc1, it & 1u, 26, PD_PAIR_SLEEP_NS);
+        tc_fence_after();
+      }
       {
         const uint8_t* xb = smem + L.x_off[buf];
         uint8_t* yb = smem + L.y_off;                               // free again: staging for the coalesced store (C >= 64)
@@ -373,7 +403,7 @@ __global__ void __launch_bounds__((EW + 2) * 32, kMinCtas) voc_pair_kernel(const
           const int r0 = m * 128 + trow;
           const int pos = p0 + r0;
           const bool live = r0 < P && pos < a.T;
-          const long long goff = (long long)b * a.bstride + (long long)(a.G + pos) * C;
+          const long long goff = (long long)b * a.out_bstride + a.out_goff + (long long)pos * C;   // out / add geometry
 #pragma unroll
           for (int cc = 0; cc < C / CW; ++cc) {
             uint32_t r[CW];
@@ -392,13 +422,13 @@ __global__ void __launch_bounds__((EW + 2) * 32, kMinCtas) voc_pair_kernel(const
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                   float2 f = Cvt<__half>::unpack(xw[u]);
-                  f.x = fminf(f.x, f.x * a.in_inv_slope);          // undo the stored LeakyReLU, inv_slope >= 1
-                  f.y = fminf(f.y, f.y * a.in_inv_slope);
+                  f.x = kSingle ? 0.f : fminf(f.x, f.x * a.in_inv_slope);   // undo the stored LeakyReLU, inv_slope >= 1
+                  f.y = kSingle ? 0.f : fminf(f.y, f.y * a.in_inv_slope);   // (single conv: no residual)
                   v[2 * u] = __uint_as_float(r[j + 2 * u]) + bv[2 * u] + f.x;
                   v[2 * u + 1] = __uint_as_float(r[j + 2 * u + 1]) + bv[2 * u + 1] + f.y;
                 }
                 if (has_add && live) {
-                  const uint4 ar = *reinterpret_cast<const uint4*>(a.add + goff + cc * CW + j);
+                  const uint4 ar = kSingle ? pre_add[(m - m0) / MSTEP][(cc * CW + j) / 8] : *reinterpret_cast<const uint4*>(a.add + goff + cc * CW + j);
                   const uint32_t aw[4] = {ar.x, ar.y, ar.z, ar.w};
 #pragma unroll
                   for (int u = 0; u < 4; ++u) {
@@ -431,7 +461,7 @@ __global__ void __launch_bounds__((EW + 2) * 32, kMinCtas) voc_pair_kernel(const
             const int wr0 = m * 128 + q * 32;                       // first row of this warp's slab
             int n_live = P - wr0;                                   // live rows form a prefix of the slab
             if (a.T - (p0 + wr0) < n_live) n_live = a.T - (p0 + wr0);
-            __half* gbase = a.out + (long long)b * a.bstride + (long long)(a.G + p0 + wr0) * C;
+            __half* gbase = a.out + (long long)b * a.out_bstride + a.out_goff + (long long)(p0 + wr0) * C;
 #pragma unroll
             for (int t = 0; t < PL; ++t) {
               const int idx = lane + 32 * t, row = idx / PL, pl = idx % PL;
@@ -468,6 +498,20 @@ __global__ void k_voc_pack_pair(__half* __restrict__ dst, const float* __restric
     const int tap = pk / (C / 8), c = (pk - tap * (C / 8)) * 8 + c8;
     const float* w = conv == 0 ? w1 : w2;
     dst[i] = __float2half_rn(w[((long long)n * C + c) * k + tap]);
+  }
+}
+
+// ConvTranspose1d weight [Cin, Cout, 2s] (stride s, padding s / 2) as the equivalent 3-tap convolution with N = s * Cout rows (see
+// k_voc_pack_convT), in the resident-tile image [tap j][Cin / 8][N][8]: row (phase r, co), tap j = input position q - 1 + j.
+__global__ void k_voc_pack_convT_planes(__half* __restrict__ dst, const float* __restrict__ src, int Cin, int Cout, int s) {
+  const int N = s * Cout, k = 2 * s;
+  const int total = 3 * Cin * N;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c8 = i & 7, n = (i >> 3) % N, pk = (i >> 3) / N;   // pk = tap * (Cin / 8) + plane
+    const int j = pk / (Cin / 8), c = (pk - j * (Cin / 8)) * 8 + c8;
+    const int r = n / Cout, co = n - r * Cout;
+    const int kk = r + s / 2 - (j - 1) * s;
+    dst[i] = __float2half_rn((kk >= 0 && kk < k) ? src[((long long)c * Cout + co) * k + kk] : 0.f);
   }
 }
 
