@@ -18,11 +18,16 @@
 // * Per tile of NB * 128 conv1 rows: gather x (16-byte cp.async, fully contiguous in global memory; double-buffered, the
 //   next tile's gather is in flight during this tile's arithmetic) -> conv1: NB x k x C/16 MMAs (M = 128, N = C) into TMEM
 //   -> epilogue 1: + bias, LeakyReLU, zero outside the utterance (conv2's zero padding), fp16, back to shared memory in the
-//   same plane layout -> conv2 on that tile (same TMEM columns) -> epilogue 2: + bias + raw x (from the resident tile)
-//   [+ running ResBlock sum] -> scale / LeakyReLU -> fp16 rows to global memory.  A tile yields NB * 128 - (k - 1) positions.
-// * The chain is serial inside a CTA; several CTAs per SM (2 - 4: 30 - 100 KB of shared memory, 32 - 128 TMEM columns each)
-//   overlap one CTA's loads and epilogues with another's MMAs.
-// * Warps 0-3: gather + epilogues (thread = TMEM lane = tile row); warp 4: MMA issue; warp 5: weight fetch.
+//   same plane layout -> conv2 on that tile -> epilogue 2: + bias + raw x (from the resident tile) [+ running ResBlock sum]
+//   -> scale / LeakyReLU -> fp16 rows to global memory (64 channels: through a warp-local staging pass, so every store
+//   instruction writes full 128-byte rows).  A tile yields NB * 128 - (k - 1) positions.
+// * The chain is serial inside a CTA; several CTAs per SM (2 - 4: 30 - 110 KB of shared memory, 64 - 128 TMEM columns each)
+//   overlap one CTA's loads and epilogues with another's MMAs.  With a double-buffered x tile (16 / 32 channels) conv1 of tile
+//   i + 1 is issued right behind conv2 of tile i into its own TMEM columns, so it runs under epilogue 2.
+// * Warps 0 .. EW-1: gather + epilogues (thread = TMEM lane = a row of a 128-row block; EW = 8: one block per warp group);
+//   warp EW: MMA issue (whole warp, uniform operands, one elected lane -- see umma_f16_lohi); warp EW + 1: weight fetch.
+// * kSingle: the same machinery for ONE convolution (the rate-2 transposed convs of the narrow stages).
+// * lengths: per-utterance ends of a padded batch -- both the intermediate and the result are zero past them.
 #pragma once
 #include "pd_voc.cuh"
 
@@ -366,9 +371,11 @@ __global__ void __launch_bounds__((EW + 2) * 32, kMinCtas) voc_pair_kernel(const
           }
         }
       }
-      // single conv: the addend (the source branch) does not depend on the accumulator -- fetch this thread's rows of it first
-      uint4 pre_add[kSingle ? (NB + MSTEP - 1) / MSTEP : 1][kSingle ? C / 8 : 1];
-      if constexpr (kSingle) {
+      // the addend (source branch / running ResBlock sum) does not depend on the accumulator: fetch this thread's rows of it before
+      // the wait (16 channels and the single-conv form; at 32 / 64 channels the extra registers spill and the round gets slower: measured)
+      constexpr bool kPreAdd = kSingle || C == 16;
+      uint4 pre_add[kPreAdd ? (NB + MSTEP - 1) / MSTEP : 1][kPreAdd ? C / 8 : 1];
+      if constexpr (kPreAdd) {
         if (has_add) {
 #pragma unroll
           for (int m = m0, mi = 0; m < NB; m += MSTEP, ++mi) {
@@ -428,7 +435,7 @@ __global__ void __launch_bounds__((EW + 2) * 32, kMinCtas) voc_pair_kernel(const
                   v[2 * u + 1] = __uint_as_float(r[j + 2 * u + 1]) + bv[2 * u + 1] + f.y;
                 }
                 if (has_add && live) {
-                  const uint4 ar = kSingle ? pre_add[(m - m0) / MSTEP][(cc * CW + j) / 8] : *reinterpret_cast<const uint4*>(a.add + goff + cc * CW + j);
+                  const uint4 ar = kPreAdd ? pre_add[(m - m0) / MSTEP][(cc * CW + j) / 8] : *reinterpret_cast<const uint4*>(a.add + goff + cc * CW + j);
                   const uint32_t aw[4] = {ar.x, ar.y, ar.z, ar.w};
 #pragma unroll
                   for (int u = 0; u < 4; ++u) {
