@@ -204,11 +204,14 @@ int launch_voc_pair(int C, const VocPairArgs& a, int sms, cudaStream_t s) {
   }
 }
 // the rate-2 transposed convolutions of the narrow stages (C_in = 2 * C_out = 32 or 64) as ONE 3-tap convolution over a resident tile
-bool voc_single_ok(int cin, int u) { return u == 2 && (cin == 32 || cin == 64); }
+// Measured at 64 x 1000 frames: 32 -> 16 channels 1.32 -> 1.01 ms; 64 -> 32 channels 0.88 ms through the TMA-fed kernel against
+// 1.02 ms here (not used); 3 instead of 4 CTAs per SM for 32 channels: no change.
+bool voc_single_ok(int cin, int u) { return u == 2 && cin == 32; }
+// conv_post (C -> 1, k taps) on a narrow last stage: the same form with one real output row and the fp32 / tanh epilogue
+bool voc_post_ok(int cin, int k) { return cin == 16 && k % 2 == 1 && k <= 15; }
 int launch_voc_single(int C, const VocPairArgs& a, int sms, cudaStream_t s) {
-  // (measured: 4 epilogue warps for 64 channels 1.87 ms against 1.01 ms with 8; 3 instead of 4 CTAs per SM for 32 channels: no change)
+  if (C == 16) return launch_voc_pair_t<16, 2, true, 1, 4, 4, true>(a, sms, s);
   if (C == 32) return launch_voc_pair_t<32, 2, true, 1, 4, 4, true>(a, sms, s);
-  if (C == 64) return launch_voc_pair_t<64, 2, true, 1, 8, 2, true>(a, sms, s);
   return fail("voc_pair_kernel (single conv): %d channels not supported", C);
 }
 
@@ -225,6 +228,7 @@ struct pd_vocoder {
   VocConv res[kVocMaxUps][kVocMaxRes][6];    // [stage][kernel][c1_0, c2_0, c1_1, c2_1, c1_2, c2_2]
   size_t pair_w[kVocMaxUps][kVocMaxRes][3];  // fused-round weight images (pd_voc_pair.cuh) where voc_pair_ok(), else 0
   size_t ups_w[kVocMaxUps];                  // resident-tile image of the transposed conv where voc_single_ok(), else 0
+  size_t post_w;                             // resident-tile image of conv_post where voc_post_ok(), else 0
   size_t src_w[kVocMaxUps], src_b[kVocMaxUps];   // fp32 noise_convs weights, transposed to [k][C] / bias [C]
   int src_k[kVocMaxUps], src_stride[kVocMaxUps], src_pad[kVocMaxUps];
   size_t lin_w, lin_b;                       // m_source.l_linear
@@ -302,6 +306,10 @@ static size_t voc_layout(const pd_vocoder_config& c, pd_vocoder* v) {
       }
   }
   conv(v ? &v->conv_post : nullptr, ch, 1, 7, 1);
+  {
+    const size_t pw = voc_post_ok(ch, 7) ? take((size_t)7 * ch * ch * 2) : 0;
+    if (v) v->post_w = pw;
+  }
   const size_t lw = take(kVocHarm * 4), lb = take(4);
   if (v) { v->lin_w = lw; v->lin_b = lb; }
   return o;
@@ -386,6 +394,10 @@ extern "C" int pd_vocoder_create(const pd_vocoder_config* cfg, const float* cons
     }
   }
   if (!rc) rc |= pack_conv(v->conv_post, state[si], state[si + 1], 1);
+  if (!rc && voc_post_ok(ch, 7)) {
+    k_voc_pack_single<<<blocks(7ll * ch * ch), TB, 0, s>>>((__half*)(pk + v->post_w), state[si], ch, 1, 7);
+    PD_LAUNCH_CHECK("k_voc_pack_single");
+  }
   si += 2;
   if (!rc) {
     PD_CUDA(cudaMemcpyAsync(pk + v->lin_w, state[si], kVocHarm * 4, cudaMemcpyDeviceToDevice, s));
@@ -651,7 +663,29 @@ extern "C" int pd_vocoder_forward(pd_vocoder* v, const float* c, const float* f0
     Ti = To;
   }
   // ---- conv_post + tanh (:287-288) -> waveform [B, 1, T * upp] fp32
-  {
+  if (voc_fused_enabled() && voc_post_ok(ch, v->conv_post.taps)) {
+    VocPairArgs pa;
+    memset(&pa, 0, sizeof(pa));
+    pa.x = act[cur_in];
+    pa.out32 = wave;
+    pa.w = (const __half*)(pk + v->post_w);
+    pa.b1 = pa.b2 = (const float*)(pk + v->conv_post.b_off);   // padded to 16 entries
+    pa.bstride = (Ti + 2 * G) * ch;
+    pa.out_bstride = pa.bstride;
+    pa.out_goff = (long long)G * ch;
+    pa.B = B;
+    pa.T = (int)Ti;
+    pa.G = G;
+    pa.k = v->conv_post.taps;
+    pa.dil = 1;
+    pa.slope1 = 0.1f;
+    pa.in_inv_slope = 10.f;
+    pa.scale = 1.f;
+    pa.act = 0;
+    pa.lengths = lengths;
+    pa.len_mul = v->upp;
+    if (launch_voc_single(ch, pa, sms, s)) return 1;
+  } else {
     if (make_voc_a_map(&tmA, act[cur_in], ch, 7, 1, (int)Ti, B)) return 1;
     VocEpi ep = voc_epi();
     ep.out32 = wave;

@@ -37,6 +37,7 @@ struct VocPairArgs {
   const __half* x;         // guarded input [B][G + T + G][C], first element; stored LeakyReLU-activated
   const __half* add;       // optional raw addend, same geometry (running sum over the ResBlocks); may alias out
   __half* out;             // output, same geometry
+  float* out32;            // single-conv form only: when set, column 0 alone leaves as fp32 at out32[b * T + position] (conv_post: the waveform)
   const __half* w;         // packed weights: conv1 [k][C/8][C][8] then conv2 [k][C/8][C][8]
   const float* b1;
   const float* b2;
@@ -49,7 +50,7 @@ struct VocPairArgs {
   float slope1;            // LeakyReLU between the two convolutions
   float in_inv_slope;      // raw x = x >= 0 ? x : x * in_inv_slope
   float scale;             // applied after the sums
-  int act;                 // 0 none, 1 LeakyReLU(slope)
+  int act;                 // 0 none, 1 LeakyReLU(slope), 2 tanh
   float slope;
   uint32_t idesc;
   const int* lengths;      // optional [B] valid mel frames per utterance: positions >= lengths[b] * len_mul are zeros in both the
@@ -452,6 +453,12 @@ __global__ void __launch_bounds__((EW + 2) * 32, kMinCtas) voc_pair_kernel(const
 #pragma unroll
                   for (int u = 0; u < 8; ++u) v[u] = fmaxf(v[u], v[u] * a.slope);
                 }
+                if constexpr (kSingle) {
+                  if (a.out32 != nullptr) {                         // conv_post: tanh of the one real output channel, fp32
+                    if (cc == 0 && j == 0 && live) a.out32[(long long)b * a.T + pos] = pos < Tb ? tanhf(v[0]) : 0.f;
+                    continue;
+                  }
+                }
                 if (pos >= Tb) {                                    // ragged batch: past this utterance's end
 #pragma unroll
                   for (int u = 0; u < 8; ++u) v[u] = 0.f;
@@ -508,6 +515,15 @@ __global__ void k_voc_pack_pair(__half* __restrict__ dst, const float* __restric
   }
 }
 
+// One Conv1d weight [Cout, C, k] fp32 (Cout <= C) -> the single-conv image [k][C / 8][C rows][8], rows >= Cout zero
+__global__ void k_voc_pack_single(__half* __restrict__ dst, const float* __restrict__ w, int C, int Cout, int k) {
+  const int total = k * C * C;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c8 = i & 7, n = (i >> 3) % C, pk = (i >> 3) / C;
+    const int tap = pk / (C / 8), c = (pk - tap * (C / 8)) * 8 + c8;
+    dst[i] = __float2half_rn(n < Cout ? w[((long long)n * C + c) * k + tap] : 0.f);
+  }
+}
 // ConvTranspose1d weight [Cin, Cout, 2s] (stride s, padding s / 2) as the equivalent 3-tap convolution with N = s * Cout rows (see
 // k_voc_pack_convT), in the resident-tile image [tap j][Cin / 8][N][8]: row (phase r, co), tap j = input position q - 1 + j.
 __global__ void k_voc_pack_convT_planes(__half* __restrict__ dst, const float* __restrict__ src, int Cin, int Cout, int s) {
