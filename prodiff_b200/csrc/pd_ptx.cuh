@@ -301,6 +301,53 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
 }
 
 
+// Elect-issued forms: ALL lanes of a converged warp call these with warp-uniform operands; elect.sync picks the one lane that
+// issues.  The compiler then keeps descriptors and addresses in uniform registers (straight-line code) instead of wrapping the
+// tcgen05 instruction of an `if (lane == 0)` branch in a per-lane ELECT / R2UR.BROADCAST loop (~60 cycles per MMA, measured).
+// Descriptors are given as (low, high) 32-bit words.
+template <bool kPair>
+__device__ __forceinline__ void umma_f16_elect(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                               uint32_t accumulate) {
+  if constexpr (kPair) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "@q tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+template <bool kPair>
+__device__ __forceinline__ void umma_commit_elect_t(uint64_t* bar) {
+  if constexpr (kPair) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}" ::"r"(smem_u32(bar)),
+        "h"((uint16_t)3)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar))
+        : "memory");
+  }
+}
+
 // ------------------------------------------------------------------ descriptors
 // Shared-memory matrix descriptor for a K-major operand tile whose rows are 128 bytes (64 x 16-bit) wide and
 // laid out by TMA with CU_TENSOR_MAP_SWIZZLE_128B: 8-row groups of 1024 B (SBO), LBO unused for this layout.

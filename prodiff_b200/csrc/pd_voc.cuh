@@ -186,30 +186,34 @@ voc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && leader) {
-      uint32_t it = 0, ti = 0;
+    // MMA issue.  The whole warp runs the loop with warp-uniform values and ONE elected lane issues (inside the asm): an
+    // `if (lane == 0)` around tcgen05.mma makes the compiler broadcast every operand through an ELECT / R2UR loop, ~60-70 cycles
+    // per MMA -- as long as an N = 128 MMA itself, so the issuing thread, not the tensor pipe, set the pace of the 128-channel
+    // convolutions (ncu: the epilogue warps spent 45 % of their samples waiting for the accumulator).
+    if (leader) {
+      const uint32_t ring = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
+      const uint32_t tmem = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t idesc = sh.idesc;
+      constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO 1024, version 1, SWIZZLE_128B
+      uint32_t stage = 0, parity = 0, ti = 0;
       for (int tile = tile_first; tile < num_tiles; tile += tile_step, ++ti) {
         const uint32_t as = ti & 1u, aph = (ti >> 1) & 1u;
         mbar_wait(&tempty_bar[as], aph ^ 1u, 2);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * BN;
-        for (int kb = 0; kb < k_blocks; ++kb, ++it) {
-          const uint32_t stage = it % kStages, parity = (it / kStages) & 1u;
+        const uint32_t d_tmem = tmem + as * BN;
+#pragma unroll 1
+        for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&full_bar[stage], parity, 3);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
-          const uint64_t adesc = make_sw128_kmajor_desc(sa);
-          const uint64_t bdesc = make_sw128_kmajor_desc(sa + Cfg::kABytes);
+          const uint32_t a_lo = ((ring + stage * Cfg::kStageBytes) >> 4) & 0x3FFFu;
+          const uint32_t b_lo = ((ring + stage * Cfg::kStageBytes + Cfg::kABytes) >> 4) & 0x3FFFu;
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            if constexpr (kPair) umma_f16_2sm(d_tmem, desc_advance_k(adesc, k), desc_advance_k(bdesc, k), sh.idesc, (kb | k) != 0 ? 1u : 0u);
-            else umma_f16(d_tmem, desc_advance_k(adesc, k), desc_advance_k(bdesc, k), sh.idesc, (kb | k) != 0 ? 1u : 0u);
-          }
-          if constexpr (kPair) umma_commit_2sm(&empty_bar[stage]);
-          else umma_commit(&empty_bar[stage]);
+          for (int k = 0; k < kBlockK / 16; ++k)
+            umma_f16_elect<kPair>(d_tmem, a_lo + 2u * k, kDescHi, b_lo + 2u * k, kDescHi, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit_elect_t<kPair>(&empty_bar[stage]);
+          if (++stage == (uint32_t)kStages) { stage = 0; parity ^= 1u; }
         }
-        if constexpr (kPair) umma_commit_2sm(&tfull_bar[as]);
-        else umma_commit(&tfull_bar[as]);
+        umma_commit_elect_t<kPair>(&tfull_bar[as]);
       }
     }
   } else if (warp >= 2 + kEpiWarps) {
