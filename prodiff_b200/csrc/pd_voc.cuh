@@ -38,6 +38,9 @@ struct VocShape {
   int tap_groups;        // ceil(taps / g)
   int g;                 // taps per K block (C >= 64: 1, else 64 / C)
   uint32_t idesc;
+  long long* trace;      // debug (pd_debug_set_trace): CTA 0 stamps clock64() at [tile * 16 + slot] for its first 64 tiles -- 0 / 1 first / last
+                         // TMA issue, 2 accumulator stage free, 3 / 4 first / last operand block landed, 5 cycles the issuing warp spent
+                         // waiting for operand blocks, 6 epilogue sees the accumulator, 7 epilogue done
   // gather path (C < 64): the guarded activation buffer itself
   const __half* a_ptr;   // first element of the buffer (front guard of utterance 0)
   int a_C, a_taps, a_dil, a_G;
@@ -166,6 +169,10 @@ voc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int kb = 0; kb < k_blocks; ++kb, ++it) {
           const uint32_t stage = it % kStages, parity = (it / kStages) & 1u;
           mbar_wait(&empty_bar[stage], parity ^ 1u, 1);
+          if (sh.trace != nullptr && blockIdx.x == 0 && (kb == 0 || kb == k_blocks - 1)) {
+            const int tl = (tile - tile_first) / tile_step;
+            if (tl < 64) sh.trace[tl * 16 + (kb == 0 ? 0 : 1)] = clock64();
+          }
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           const int tg = kb / sh.cc_blocks, cc = kb - tg * sh.cc_blocks;
           if constexpr (kPair) {
@@ -200,11 +207,21 @@ voc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const uint32_t as = ti & 1u, aph = (ti >> 1) & 1u;
         mbar_wait(&tempty_bar[as], aph ^ 1u, 2);
         tc_fence_after();
+        const bool tr = sh.trace != nullptr && blockIdx.x == 0 && ti < 64u && lane == 0;
+        long long waited = 0;
+        if (tr) sh.trace[ti * 16 + 2] = clock64();
         const uint32_t d_tmem = tmem + as * BN;
 #pragma unroll 1
         for (int kb = 0; kb < k_blocks; ++kb) {
+          const long long w0 = tr ? clock64() : 0;
           mbar_wait(&full_bar[stage], parity, 3);
           tc_fence_after();
+          if (tr) {
+            const long long w1 = clock64();
+            waited += w1 - w0;
+            if (kb == 0) sh.trace[ti * 16 + 3] = w1;
+            if (kb == k_blocks - 1) { sh.trace[ti * 16 + 4] = w1; sh.trace[ti * 16 + 5] = waited; }
+          }
           const uint32_t a_lo = ((ring + stage * Cfg::kStageBytes) >> 4) & 0x3FFFu;
           const uint32_t b_lo = ((ring + stage * Cfg::kStageBytes + Cfg::kABytes) >> 4) & 0x3FFFu;
 #pragma unroll
@@ -388,6 +405,8 @@ voc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
       mbar_wait(&tfull_bar[as], aph, 4);
       tc_fence_after();
+      const bool etr = sh.trace != nullptr && blockIdx.x == 0 && ti < 64u && threadIdx.x == 64;
+      if (etr) sh.trace[ti * 16 + 6] = clock64();
       if (works) {
 #pragma unroll
         for (int ci = 0; ci < kChunks; ++ci) {
@@ -465,6 +484,7 @@ voc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
       tc_fence_before();
       __syncwarp();
+      if (etr) sh.trace[ti * 16 + 7] = clock64();
       if (lane == 0) {
         if constexpr (kPair) mbar_arrive_leader(&tempty_bar[as]);
         else mbar_arrive(&tempty_bar[as]);

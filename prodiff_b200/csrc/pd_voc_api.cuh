@@ -101,6 +101,7 @@ int launch_voc(const VocConv& cv, const CUtensorMap& a, const __half* abuf, int 
   sh.a_taps = cv.taps;
   sh.a_dil = cv.dil;
   sh.a_G = kVocG;
+  sh.trace = g_trace ? g_trace + 13 * 1024 : nullptr;
   const bool gather = cv.cin < 64;
   if (!gather && cv.bn >= 128 && voc_pair_mode() && B * sh.m_tiles_per_row >= 2) {
     sh.idesc = make_idesc(PD_FP16, cv.bn, 256);
