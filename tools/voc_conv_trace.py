@@ -24,12 +24,12 @@ lib.pd_debug_set_trace(buf.data_ptr())
 run(); torch.cuda.synchronize()
 lib.pd_debug_set_trace(None)
 t = buf[13 * 1024:14 * 1024].cpu().view(64, 16)
-names = ["tma_first", "tma_last", "acc_free", "first_block", "last_block", "waited_for_blocks", "epi_sees_acc", "epi_done"]
+names = ["tma_first", "tma_last", "acc_free", "first_block", "last_block", "waited_for_blocks", "epi_sees_acc", "epi_done", "a_tile_seen"]
 t0 = int(t[0, 2])
 rows = []
 for i in range(64):
     if int(t[i, 2]) == 0: break
-    rows.append({nm: (int(t[i, j]) - t0 if j != 5 else int(t[i, j])) for j, nm in enumerate(names)})
+    rows.append({nm: (int(t[i, j]) - t0 if j != 5 else int(t[i, j])) if int(t[i, j]) != 0 else 0 for j, nm in enumerate(names)})
 for r in rows[8:14]:
     print(" ".join(f"{a}={v}" for a, v in r.items()))
 if len(rows) > 12:
