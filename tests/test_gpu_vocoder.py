@@ -161,7 +161,8 @@ def test_batch_rows_equal_single_utterance_runs():
     assert float((full - ref).abs().max()) <= WAV_MAX_TOL
 
 
-def test_ragged_batch_rows_equal_single_utterance_runs():
+@pytest.mark.parametrize("fused", [1, 0], ids=["fused_rounds", "two_launch_rounds"])
+def test_ragged_batch_rows_equal_single_utterance_runs(fused):
     """A padded batch with per-utterance lengths (what batching the reference's one-segment-per-call inferer needs,
     handler/infer/handler.py:373-378): the generator's receptive field (~13 frames per side) would let whatever lies past
     an utterance's end leak into its last frames; with ``lengths`` every activation past the end is held at zero, so row b
@@ -175,18 +176,23 @@ def test_ragged_batch_rows_equal_single_utterance_runs():
     for b, n in enumerate(lens):           # the padding holds junk, as a sampler's ragged output may
         c[b, :, n:] = 37.0
         f0[b, n:] = 555.0
+    from prodiff_b200 import _lib
     gen = _build(h, state)
     upp = gen.upp
-    with torch.no_grad():
-        full = gen(c.cuda(), f0.cuda(), rand_ini=ri.cuda(), noise=nz.cuda(), lengths=lens).cpu()
-        for b, n in enumerate(lens):
-            one = gen(c[b:b + 1, :, :n].contiguous().cuda(), f0[b:b + 1, :n].contiguous().cuda(), rand_ini=ri.cuda(),
-                      noise=nz[b:b + 1, :n * upp].contiguous().cuda()).cpu()
-            assert torch.equal(full[b, 0, :n * upp], one[0, 0]), (b, float((full[b, 0, :n * upp] - one[0, 0]).abs().max()))
-            assert float(full[b, 0, n * upp:].abs().max()) == 0.0 if n < T else True
-        # and without lengths the junk does reach the last frames (the test would be vacuous otherwise)
-        plain = gen(c.cuda(), f0.cuda(), rand_ini=ri.cuda(), noise=nz.cuda()).cpu()
-        assert not torch.equal(plain[1, 0, :lens[1] * upp], full[1, 0, :lens[1] * upp])
+    prev = _lib.load().pd_set_voc_fused(fused)
+    try:
+        with torch.no_grad():
+            full = gen(c.cuda(), f0.cuda(), rand_ini=ri.cuda(), noise=nz.cuda(), lengths=lens).cpu()
+            for b, n in enumerate(lens):
+                one = gen(c[b:b + 1, :, :n].contiguous().cuda(), f0[b:b + 1, :n].contiguous().cuda(), rand_ini=ri.cuda(),
+                          noise=nz[b:b + 1, :n * upp].contiguous().cuda()).cpu()
+                assert torch.equal(full[b, 0, :n * upp], one[0, 0]), (b, float((full[b, 0, :n * upp] - one[0, 0]).abs().max()))
+                assert float(full[b, 0, n * upp:].abs().max()) == 0.0 if n < T else True
+            # and without lengths the junk does reach the last frames (the test would be vacuous otherwise)
+            plain = gen(c.cuda(), f0.cuda(), rand_ini=ri.cuda(), noise=nz.cuda()).cpu()
+            assert not torch.equal(plain[1, 0, :lens[1] * upp], full[1, 0, :lens[1] * upp])
+    finally:
+        _lib.load().pd_set_voc_fused(1 if prev != 0 else 0)
 
 
 def test_philox_noise_path_and_determinism():
