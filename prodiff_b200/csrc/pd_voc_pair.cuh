@@ -163,9 +163,9 @@ __global__ void __launch_bounds__((EW + 2) * 32, kMinCtas) voc_pair_kernel(const
   const VocPairSmem L = voc_pair_smem<C, NB, kRes, kXB, kMinCtas, kSingle>(a.k, a.dil);
   const uint32_t XPS = L.xr * 16, YPS = L.yr * 16;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar_off);
-  uint64_t* xfull = bars;             // [2]   NT arrivals: a gathered x tile is visible to the tensor core
+  uint64_t* xfull = bars;             // [2]   EW arrivals (one per warp): a gathered x tile is visible to the tensor core
   uint64_t* acc1 = bars + 2;          //       conv1 accumulators complete
-  uint64_t* yfull = bars + 3;         //       NT arrivals: the intermediate tile is in shared memory
+  uint64_t* yfull = bars + 3;         //       EW arrivals: the intermediate tile is in shared memory
   uint64_t* acc2 = bars + 4;          //       conv2 accumulators complete
   uint64_t* wfull = bars + 5;         // [kPairRingMax] (resident: [0] only)
   uint64_t* wempty = bars + 5 + kPairRingMax;
@@ -173,10 +173,10 @@ __global__ void __launch_bounds__((EW + 2) * 32, kMinCtas) voc_pair_kernel(const
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    mbar_init(&xfull[0], NT);
-    mbar_init(&xfull[1], NT);
+    mbar_init(&xfull[0], EW);   // one arrival per warp (after its lanes' proxy fences): an arrive is a shared-memory atomic, and 128
+    mbar_init(&xfull[1], EW);   // same-address arrivals per barrier per tile from 4 CTAs kept the SM's atomic unit busy
     mbar_init(acc1, 1);
-    mbar_init(yfull, NT);
+    mbar_init(yfull, EW);
     mbar_init(acc2, 1);
     for (int i = 0; i < kPairRingMax; ++i) {
       mbar_init(&wfull[i], 1);
@@ -313,7 +313,8 @@ __global__ void __launch_bounds__((EW + 2) * 32, kMinCtas) voc_pair_kernel(const
     auto publish_x = [&](uint32_t buf) {   // this thread's share of a gathered tile has landed: make it visible to the tensor core
       asm volatile("cp.async.wait_group 0;" ::: "memory");
       fence_proxy_async_smem();
-      mbar_arrive(&xfull[buf]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&xfull[buf]);
     };
     if (kAhead && (int)blockIdx.x < num_tiles) {
       gather(blockIdx.x, 0);
@@ -392,7 +393,8 @@ __global__ void __launch_bounds__((EW + 2) * 32, kMinCtas) voc_pair_kernel(const
         if (tid == 0) PD_PAIR_TRACE(3);
         fence_proxy_async_smem();
         tc_fence_before();
-        mbar_arrive(yfull);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(yfull);
         if (kAhead && tile + (int)gridDim.x < num_tiles) publish_x(buf ^ 1u);   // the next tile, gathered during the previous iteration
         if (tid == 0) PD_PAIR_TRACE(4);
         // ---- epilogue 2: output row r <-> position p0 + r; raw x from tile row r + h + hd
