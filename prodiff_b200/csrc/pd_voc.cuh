@@ -91,7 +91,7 @@ template <int BN, bool kPair = false> struct VocCfg {
   static constexpr uint32_t kBBytes = (kPair ? BN / 2 : BN) * kBlockK * 2;
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;
   static constexpr uint32_t kStagingBytes = kEpiWarps * 32 * kRowWords * 4;
-  static constexpr int kStagesFit = (int)((200u * 1024u - kStagingBytes) / kStageBytes);
+  static constexpr int kStagesFit = (int)((224u * 1024u - kStagingBytes) / kStageBytes);   // 227 KB per CTA less barriers and alignment slack
   static constexpr int kStages = kStagesFit < 8 ? kStagesFit : 8;
   static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 + 256;
 };
