@@ -700,16 +700,21 @@ __global__ void k_voc_transpose_src(float* __restrict__ dst, const float* __rest
   }
 }
 
-// zero a guarded activation buffer's guard rows ([B][G + T + G][C]): front and back G rows of every utterance
-__global__ void k_voc_zero_guards(__half* __restrict__ buf, int Tn, int C, int G, int B) {
-  const long long per = 2ll * G * C;
-  const long long total = per * B;
+// zero the guard rows of up to four guarded activation buffers of one geometry ([B][G + T + G][C]): front and back G rows of every
+// utterance, 16 bytes per thread (one launch per stage instead of one per buffer: the chain is launch-bound for a single utterance)
+struct VocGuardBufs { __half* p[4]; int n; };
+__global__ void k_voc_zero_guards(VocGuardBufs bufs, int Tn, int C, int G, int B) {
+  const long long per = 2ll * G * C / 8;        // 16-byte pieces per utterance (C is a multiple of 8)
+  const long long total = per * B * bufs.n;
+  const int c8n = C / 8;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int b = (int)(i / per);
-    const long long r = i - (long long)b * per;
-    const long long row = r / C, c = r - row * C;
+    const int which = (int)(i / (per * B));
+    const long long j = i - (long long)which * per * B;
+    const int b = (int)(j / per);
+    const long long r = j - (long long)b * per;
+    const long long row = r / c8n, c8 = r - row * c8n;
     const long long prow = row < G ? row : (long long)Tn + row;   // rows [0, G) and [G + T, G + T + G)
-    buf[((long long)b * (Tn + 2 * G) + prow) * C + c] = __float2half_rn(0.f);
+    *reinterpret_cast<uint4*>(bufs.p[which] + ((long long)b * (Tn + 2 * G) + prow) * C + c8 * 8) = make_uint4(0u, 0u, 0u, 0u);
   }
 }
 

@@ -460,9 +460,12 @@ extern "C" int pd_vocoder_forward(pd_vocoder* v, const float* c, const float* f0
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   const uint8_t* pk = v->packed;
   const int sms = v->sm_count, G = kVocG;
-  auto zero_guards = [&](__half* buf, long long Tn, int C) -> int {
-    const long long n = 2ll * G * C * B;
-    k_voc_zero_guards<<<(int)std::min<long long>((n + 255) / 256, 2048), 256, 0, s>>>(buf, (int)Tn, C, G, B);
+  auto zero_guards = [&](long long Tn, int C, __half* b0, __half* b1 = nullptr, __half* b2 = nullptr, __half* b3 = nullptr) -> int {
+    VocGuardBufs gb;
+    gb.p[0] = b0; gb.p[1] = b1; gb.p[2] = b2; gb.p[3] = b3;
+    gb.n = b3 ? 4 : (b2 ? 3 : (b1 ? 2 : 1));
+    const long long n = 2ll * G * C / 8 * B * gb.n;
+    k_voc_zero_guards<<<(int)std::min<long long>((n + 255) / 256, 2048), 256, 0, s>>>(gb, (int)Tn, C, G, B);
     PD_LAUNCH_CHECK("k_voc_zero_guards");
     return 0;
   };
@@ -478,7 +481,7 @@ extern "C" int pd_vocoder_forward(pd_vocoder* v, const float* c, const float* f0
   PD_LAUNCH_CHECK("k_voc_source");
   // ---- conv_pre (models.py:271) on the hand-off tensor c [B, M, T]; its output is stored LeakyReLU(0.1)-activated (:273)
   __half* mel = reinterpret_cast<__half*>(ws + L.mel);
-  if (zero_guards(mel, T, cf.num_mels)) return 1;
+  if (zero_guards(T, cf.num_mels, mel)) return 1;
   {
     const dim3 grid((T + 31) / 32, cf.num_mels / 32, B), block(32, 8);
     k_voc_mel_in<<<grid, block, 0, s>>>(mel, c, cf.num_mels, T, G, lengths);
@@ -491,7 +494,7 @@ extern "C" int pd_vocoder_forward(pd_vocoder* v, const float* c, const float* f0
   long long Ti = T;
   CUtensorMap tmA;
   {
-    if (zero_guards(act[cur_in], Ti, ch)) return 1;
+    if (zero_guards(Ti, ch, act[cur_in])) return 1;
     if (make_voc_a_map(&tmA, mel, cf.num_mels, 7, 1, T, B)) return 1;
     VocEpi ep = voc_epi();
     ep.out16 = act[cur_in] + (size_t)G * ch;
@@ -530,7 +533,7 @@ extern "C" int pd_vocoder_forward(pd_vocoder* v, const float* c, const float* f0
       PD_LAUNCH_CHECK("k_voc_srcconv");
     }
     // x = ups[i](leaky_relu(x)) + x_source (:274-277), stored activated for the ResBlocks' first convs
-    if (zero_guards(XL, To, co) || zero_guards(TMP, To, co) || zero_guards(CUR, To, co) || zero_guards(OUT, To, co)) return 1;
+    if (zero_guards(To, co, XL, TMP, CUR, OUT)) return 1;
     if (voc_fused_enabled() && voc_single_ok(ch, u)) {
       VocPairArgs pa;
       memset(&pa, 0, sizeof(pa));
